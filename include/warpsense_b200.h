@@ -1,0 +1,174 @@
+/*
+ * warpsense_b200.h -- C ABI of the B200-native TSDF hot path (libwarpsense_b200.so).
+ *
+ * Drop-in boundary for warpsense's two data-parallel hot paths.  The reference has no FFI layer:
+ * its callers use C++ classes.  Every entry point below names the reference
+ * interface it replaces (file:line under /root/reference); include/warpsense_b200.hpp rebuilds those
+ * classes (cuda::DeviceMap, cuda::DeviceMapMemWrapper, cuda::TSDFCuda, cuda::RegistrationCuda,
+ * cuda::TSDFMapping, cuda::TSDFRegistration) as header-only shims over this ABI.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types;
+ *   - every call returns WS_OK (0) or a negative error code; ws_last_error() gives the text;
+ *   - points are packed {int32 x,y,z} millimetres in the map frame (rmagine::Pointi, 12 bytes);
+ *   - TSDF entries are the reference's packed uint32 {int16 value | int16 weight << 16}
+ *     (include/map/tsdf.h:16-35); host grids use the reference's ring layout, x slowest, z fastest
+ *     (include/map/hdf5_local_map.h:140-151), index computed in 64 bit;
+ *   - 4x4 transforms are column-major float[16] (Eigen::Matrix4f storage), translation in mm;
+ *   - H is column-major int64[36], g int64[6] (rmagine::Matrix6x6l / Point6l);
+ *   - a handle is thread-compatible: callers serialise access exactly as the reference does with
+ *     TSDFMapping::mutex_ (src/warpsense/tsdf_mapping.cpp:67,73,93).
+ */
+#ifndef WARPSENSE_B200_H
+#define WARPSENSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WS_OK 0
+#define WS_ERR_INVALID (-1)   /* bad argument                                            */
+#define WS_ERR_CUDA (-2)      /* CUDA runtime failure (the reference exit(1)s here)      */
+#define WS_ERR_CAPACITY (-3)  /* scan too large (reference: > 1,000,000 points returns)  */
+#define WS_ERR_STATE (-4)     /* call order violated (e.g. reg step before prepare)      */
+
+#define WS_MAX_POINTS (1 << 24)
+
+typedef struct ws_handle ws_handle;
+
+typedef struct { int32_t x, y, z; } ws_point;   /* rmagine::Pointi */
+
+/* work counters of the last ws_update_tsdf (SURVEY.md 8d "work counters to print") */
+typedef struct {
+  int64_t n_points;
+  int64_t n_candidates;      /* C: candidate writes                                   */
+  int64_t n_touched;         /* T: distinct voxels that received a candidate (this rank's slab) */
+  int64_t n_written;         /* voxels whose stored entry was rewritten               */
+  int64_t n_touched_bricks;  /* 8x8x8 bricks streamed by the merge pass               */
+  int64_t n_parked;          /* voxels that needed a replay round                     */
+  int64_t n_rounds;          /* replay rounds that did work                           */
+} ws_update_counters;
+
+/* flags of ws_register_cloud */
+#define WS_REG_DEVICE_SOLVE 0   /* FP64 solve + pose update on the GPU, no per-iteration host round trip */
+#define WS_REG_HOST_SOLVE 1     /* reference structure: sums to the host every iteration (tsdf_registration.cpp:55-92) */
+
+/* ---- lifetime -------------------------------------------------------------------------------
+ * ws_create: cuda::TSDFCuda::TSDFCuda(existing_map, tau, max_weight, map_resolution)
+ *            (include/warpsense/cuda/update_tsdf.h:12, src/warpsense/cuda/update_tsdf.cu:130-141)
+ *            + cuda::RegistrationCuda::RegistrationCuda(map) (include/warpsense/cuda/registration.h:13).
+ * size[3] are the local-map side lengths as HDF5LocalMap stores them (odd; even sizes must already
+ * be s+1, src/map/hdf5_local_map.cpp:6-8).  The grid starts filled with (tau, 0) at pos 0,
+ * offset size/2 (hdf5_local_map.cpp:11-19).
+ * ws_create_sharded: same, but this handle holds only rank's x-slab of the ring (+1 halo column each
+ * side) out of `world` slabs -- one handle per GPU/process. */
+int ws_create(const int32_t size[3], int32_t tau, int32_t max_weight, int32_t map_resolution,
+              int32_t device, ws_handle **out);
+int ws_create_sharded(const int32_t size[3], int32_t tau, int32_t max_weight, int32_t map_resolution,
+                      int32_t device, int32_t rank, int32_t world, ws_handle **out);
+/* cuda::TSDFCuda::~TSDFCuda / RegistrationCuda::~RegistrationCuda (no cudaDeviceReset: the process may
+ * hold other handles; the reference resets in cleanup.cu:3-11) */
+void ws_destroy(ws_handle *h);
+const char *ws_last_error(const ws_handle *h);
+/* run all work of this handle on an existing CUDA stream (cudaStream_t); NULL restores the private one.
+ * The reference uses the legacy default stream with blocking copies (SURVEY.md 8b "Threading"). */
+int ws_set_stream(ws_handle *h, void *cuda_stream);
+void *ws_get_stream(ws_handle *h);
+int ws_sync(ws_handle *h);                         /* cudaDeviceSynchronize() calls of the reference */
+
+/* ---- map transfer ---------------------------------------------------------------------------
+ * cuda::DeviceMapMemWrapper::to_device / to_host / update_params
+ * (include/warpsense/cuda/device_map_wrapper.h:22-27, src/warpsense/cuda/device_map_wrapper.cu:35-92).
+ * `entries` is the host ring array of size[0]*size[1]*size[2] raw entries (HDF5LocalMap::get_data()). */
+int ws_map_upload(ws_handle *h, const uint32_t *entries, const int32_t size[3],
+                  const int32_t offset[3], const int32_t pos[3]);
+int ws_map_download(ws_handle *h, uint32_t *entries);
+int ws_map_set_params(ws_handle *h, const int32_t offset[3], const int32_t pos[3]);
+int ws_map_get_params(const ws_handle *h, int32_t size[3], int32_t offset[3], int32_t pos[3]);
+/* reset every voxel to (value, weight) and make it the default entry of unseen chunks --
+ * HDF5GlobalMap(name, initial_value, initial_weight) + HDF5LocalMap ctor fill
+ * (hdf5_global_map.cpp:24-27, hdf5_local_map.cpp:15-19) */
+int ws_map_fill(ws_handle *h, int32_t value, int32_t weight);
+/* single-voxel access in map (voxel) coordinates: DeviceMap::value_unchecked + in_bounds
+ * (include/warpsense/cuda/device_map.h:94-150); returns WS_ERR_INVALID when out of bounds */
+int ws_map_get_voxel(ws_handle *h, int32_t x, int32_t y, int32_t z, uint32_t *entry);
+int ws_map_set_voxel(ws_handle *h, int32_t x, int32_t y, int32_t z, uint32_t entry);
+
+/* ---- TSDF update ----------------------------------------------------------------------------
+ * cuda::TSDFCuda::update_tsdf(scan_points, scanner_pos, up)
+ * (include/warpsense/cuda/update_tsdf.h:14, src/warpsense/cuda/update_tsdf.cu:143-166); results equal
+ * the CPU path update_tsdf(...) of src/cpu/update_tsdf.cpp:397-564.  scanner_pos is in voxels, up is
+ * R*(0,0,32768) (src/warpsense/tsdf_mapping.cpp:77-85).  Blocking, like the reference.
+ * n > WS_MAX_POINTS returns WS_ERR_CAPACITY (reference: prints and returns, update_tsdf.cu:146-150). */
+int ws_update_tsdf(ws_handle *h, const ws_point *points, int64_t n,
+                   const int32_t scanner_pos[3], const int32_t up[3]);
+/* same with the points already in device memory (e.g. the cloud ws_register_cloud just transformed) */
+int ws_update_tsdf_device(ws_handle *h, const ws_point *device_points, int64_t n,
+                          const int32_t scanner_pos[3], const int32_t up[3]);
+int ws_get_update_counters(const ws_handle *h, ws_update_counters *out);
+
+/* ---- registration ---------------------------------------------------------------------------
+ * ws_reg_prepare: cuda::RegistrationCuda::prepare_registration(points)
+ *                 (include/warpsense/cuda/registration.h:15, src/warpsense/cuda/registration.cu:303-308).
+ * ws_reg_step:    cuda::RegistrationCuda::perform_registration(map_dev, pretransform, h, g, e, c, res)
+ *                 (registration.h:16-19, registration.cu:347-368): one accumulation pass for transform T.
+ *                 All points are used (the reference kernel silently stops at 65,536).
+ * ws_register_cloud: cuda::TSDFRegistration::register_cloud(cloud, pretransform)
+ *                 (include/warpsense/tsdf_registration.h:24, src/warpsense/tsdf_registration.cpp:29-96)
+ *                 following the CPU loop register_cloud(...) of src/cpu/registration.cpp:14-177
+ *                 (centre recomputed every iteration; cloud transformed in place at the end).
+ *                 `cloud` may be NULL to register the points given to ws_reg_prepare and leave the
+ *                 transformed cloud on the device (ws_reg_points_device). */
+int ws_reg_prepare(ws_handle *h, const ws_point *points, int64_t n);
+int ws_reg_step(ws_handle *h, const float T[16], int32_t map_resolution,
+                int64_t H[36], int64_t g[6], int32_t *err, int32_t *cnt);
+int ws_register_cloud(ws_handle *h, ws_point *cloud, int64_t n, const float pretransform[16],
+                      int32_t max_iterations, float it_weight_gradient, float epsilon,
+                      int32_t map_resolution, int32_t flags, float out_transform[16],
+                      int32_t *iterations);
+/* per-iteration sums of the last ws_register_cloud: 29 int64 per iteration
+ * (21 upper-triangle H row-major, 6 g, err, cnt); returns the number of iterations copied */
+int ws_reg_get_trace(ws_handle *h, int64_t *out, int32_t max_iterations);
+const ws_point *ws_reg_points_device(ws_handle *h, int64_t *n);
+
+/* multi-GPU registration building blocks (one handle per rank; the caller all-reduces the 29 sums,
+ * e.g. ncclAllReduce(int64, sum) on ws_reg_sums_device(), between the two calls -- SURVEY.md 8e) */
+int ws_reg_begin(ws_handle *h, const float pretransform[16]);
+int ws_reg_accumulate(ws_handle *h, int32_t map_resolution);           /* local 29 sums, async   */
+void *ws_reg_sums_device(ws_handle *h);                                /* int64[29] device ptr   */
+int ws_reg_solve(ws_handle *h, float it_weight_gradient, float epsilon);/* solve + pose update    */
+int ws_reg_finish(ws_handle *h, float out_transform[16], int32_t *iterations, int32_t *finished);
+
+/* test hook for the reduction shape (test/cuda.cpp:416-532): sums of n Jacobians with values */
+int ws_test_reduce(ws_handle *h, const int64_t *jacobis6, const int32_t *values, int64_t n,
+                   int64_t H[36], int64_t g[6], int32_t *err, int32_t *cnt);
+
+/* ---- local-map shift ------------------------------------------------------------------------
+ * HDF5LocalMap::shift(new_pos) on the device-resident grid (src/map/hdf5_local_map.cpp:53-118;
+ * today a whole-grid D2H + H2D round trip, src/warpsense/tsdf_mapping.cpp:115-123).  Leaving slabs are
+ * saved into an in-memory 64^3 chunk store (src/map/hdf5_global_map.cpp:53-137), entering slabs are
+ * loaded from it or default-filled. */
+int ws_shift(ws_handle *h, const int32_t new_pos[3]);
+/* HDF5LocalMap::write_back (hdf5_local_map.cpp:210-217): save the whole local map into the store */
+int ws_write_back(ws_handle *h);
+int64_t ws_store_num_chunks(const ws_handle *h);
+int ws_store_chunk_list(const ws_handle *h, int32_t *xyz, int64_t cap);
+/* copy one 64^3 chunk (index x*4096 + y*64 + z, hdf5_global_map.cpp:53-57); WS_ERR_INVALID if absent */
+int ws_store_get_chunk(const ws_handle *h, int32_t cx, int32_t cy, int32_t cz, uint32_t *out);
+
+/* ---- timing -------------------------------------------------------------------------------- */
+/* record cudaEvents around the hot kernels on the handle's stream (kind: 0 march, 1 merge, 2 reg) */
+int ws_profile_enable(ws_handle *h, int32_t on);
+int ws_profile_reset(ws_handle *h);
+/* sum of elapsed ms and launch count per kind since the last reset (synchronises the stream) */
+int ws_profile_get(ws_handle *h, int32_t kind, double *total_ms, int64_t *launches);
+
+const char *ws_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WARPSENSE_B200_H */

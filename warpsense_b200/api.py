@@ -1,0 +1,481 @@
+"""Host-side mirror of the reference's class interface for the hot path, over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference (paths under /root/reference):
+
+  HostLocalMap      ~ HDF5LocalMap's in-memory part   include/map/hdf5_local_map.h
+  DeviceMap         ~ cuda::DeviceMap                 include/warpsense/cuda/device_map.h:32-164
+  DeviceMapMemWrapper ~ cuda::DeviceMapMemWrapper     include/warpsense/cuda/device_map_wrapper.h:10-36
+  TSDFCuda          ~ cuda::TSDFCuda                  include/warpsense/cuda/update_tsdf.h:9-34
+  RegistrationCuda  ~ cuda::RegistrationCuda          include/warpsense/cuda/registration.h:10-45
+  TSDFMapping       ~ cuda::TSDFMapping               include/warpsense/tsdf_mapping.h:17-60
+  TSDFRegistration  ~ cuda::TSDFRegistration          include/warpsense/tsdf_registration.h:17-27
+
+Everything that touches voxels or points runs in libwarpsense_b200.so on the GPU; this file only
+marshals arguments.  (The same shims exist as C++ in include/warpsense_b200.hpp.)
+"""
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import lib as _lib
+from .fixedpoint import colmajor16, convert_pose_to_gpu, from_colmajor16, to_map
+from .params import Params
+
+_i32p = C.POINTER(C.c_int32)
+
+
+def _i3(v):
+    return np.ascontiguousarray(np.asarray(v, dtype=np.int32).reshape(3))
+
+
+def _pts(points):
+    p = np.asarray(points)
+    if p.dtype != np.int32 or not p.flags.c_contiguous:
+        p = np.ascontiguousarray(p, dtype=np.int32)
+    return p.reshape(-1, 3)
+
+
+def make_entry(value, weight):
+    """TSDFEntry(value, weight).raw()  (include/map/tsdf.h:16-57)."""
+    return (int(value) & 0xFFFF) | ((int(weight) & 0xFFFF) << 16)
+
+
+def entry_value(raw):
+    v = int(raw) & 0xFFFF
+    return v - 0x10000 if v >= 0x8000 else v
+
+
+def entry_weight(raw):
+    w = (int(raw) >> 16) & 0xFFFF
+    return w - 0x10000 if w >= 0x8000 else w
+
+
+class HostLocalMap:
+    """The in-memory part of HDF5LocalMap: ring array + size/pos/offset (hdf5_local_map.cpp:5-20).
+
+    Only storage and index arithmetic live here (the data contract of cuda::DeviceMap); updates,
+    lookups in bulk and shifts happen on the device."""
+
+    def __init__(self, sx, sy, sz, default_value, default_weight=0):
+        self.size = np.array([s if s % 2 == 1 else s + 1 for s in (int(sx), int(sy), int(sz))], np.int32)
+        self.pos = np.zeros(3, np.int32)
+        self.offset = (self.size // 2).astype(np.int32)
+        self.default_entry = make_entry(default_value, default_weight)
+        self.data = np.full(int(np.prod(self.size.astype(np.int64))), self.default_entry, dtype=np.uint32)
+
+    def get_size(self):
+        return self.size
+
+    def get_pos(self):
+        return self.pos
+
+    def get_offset(self):
+        return self.offset
+
+    def get_data(self):
+        return self.data
+
+    def in_bounds(self, x, y, z):
+        """hdf5_local_map.h:275-279"""
+        d = np.abs(np.array([x, y, z], np.int64) - self.pos)
+        return bool((d <= self.size // 2).all())
+
+    def get_index(self, x, y, z):
+        """hdf5_local_map.h:140-151 (64-bit)"""
+        r = (np.array([x, y, z], np.int64) - self.pos + self.offset + self.size) % self.size
+        return int((r[0] * self.size[1] + r[1]) * self.size[2] + r[2])
+
+    def value(self, x, y, z):
+        if not self.in_bounds(x, y, z):
+            raise IndexError("Index out of bounds: %d; %d; %d" % (x, y, z))   # std::out_of_range
+        raw = self.data[self.get_index(x, y, z)]
+        return entry_value(raw), entry_weight(raw)
+
+    def set_value(self, x, y, z, value, weight):
+        if not self.in_bounds(x, y, z):
+            raise IndexError("Index out of bounds: %d; %d; %d" % (x, y, z))
+        self.data[self.get_index(x, y, z)] = make_entry(value, weight)
+
+
+class DeviceMap:
+    """cuda::DeviceMap: a non-owning view {size, offset, data, pos} of a host ring array."""
+
+    def __init__(self, size_or_map, offset=None, data=None, pos=None):
+        if offset is None:
+            m = size_or_map
+            self.size_, self.offset_, self.data_, self.pos_ = m.get_size(), m.get_offset(), m.get_data(), m.get_pos()
+        else:
+            self.size_, self.offset_, self.data_, self.pos_ = size_or_map, offset, data, pos
+
+    def get_size(self):
+        return self.size_
+
+    def get_offset(self):
+        return self.offset_
+
+    def get_pos(self):
+        return self.pos_
+
+
+class _Handle:
+    """Owns one ws_handle (RAII like the reference's device wrappers; copy is not supported)."""
+
+    def __init__(self, size, tau, max_weight, map_resolution, device=0, rank=0, world=1):
+        self.L = _lib.load()
+        self.h = C.c_void_p()
+        s = _i3(size)
+        if world == 1:
+            rc = self.L.ws_create(s.ctypes.data_as(_i32p), int(tau), int(max_weight), int(map_resolution),
+                                  int(device), C.byref(self.h))
+        else:
+            rc = self.L.ws_create_sharded(s.ctypes.data_as(_i32p), int(tau), int(max_weight), int(map_resolution),
+                                          int(device), int(rank), int(world), C.byref(self.h))
+        if rc != _lib.WS_OK:
+            raise _lib.WarpsenseError(rc, "ws_create failed (bad arguments or no usable CUDA device)")
+        self.size = s.copy()
+        self.tau, self.max_weight, self.res = int(tau), int(max_weight), int(map_resolution)
+        self.device, self.rank, self.world = int(device), int(rank), int(world)
+
+    def check(self, rc):
+        if rc < 0:
+            raise _lib.WarpsenseError(rc, (self.L.ws_last_error(self.h) or b"").decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.ws_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceMapMemWrapper:
+    """cuda::DeviceMapMemWrapper: whole-grid host<->device transfers and the param-only update."""
+
+    def __init__(self, handle):
+        self._hd = handle
+
+    def to_device(self, existing_map):
+        """device_map_wrapper.cu:64-75"""
+        d = existing_map.data_
+        assert d.dtype == np.uint32 and d.flags.c_contiguous
+        s, o, p = _i3(existing_map.size_), _i3(existing_map.offset_), _i3(existing_map.pos_)
+        hd = self._hd
+        hd.check(hd.L.ws_map_upload(hd.h, d.ctypes.data, s.ctypes.data_as(_i32p), o.ctypes.data_as(_i32p),
+                                    p.ctypes.data_as(_i32p)))
+
+    def to_host(self, existing_map):
+        """device_map_wrapper.cu:77-92 (also returns the device-side pos/offset into the view)"""
+        d = existing_map.data_
+        assert d.dtype == np.uint32 and d.flags.c_contiguous and d.flags.writeable
+        hd = self._hd
+        hd.check(hd.L.ws_map_download(hd.h, d.ctypes.data))
+        s, o, p = np.zeros(3, np.int32), np.zeros(3, np.int32), np.zeros(3, np.int32)
+        hd.check(hd.L.ws_map_get_params(hd.h, s.ctypes.data_as(_i32p), o.ctypes.data_as(_i32p), p.ctypes.data_as(_i32p)))
+        existing_map.offset_[:] = o
+        existing_map.pos_[:] = p
+
+    def update_params(self, existing_map):
+        """device_map_wrapper.cu:35-43"""
+        o, p = _i3(existing_map.offset_), _i3(existing_map.pos_)
+        hd = self._hd
+        hd.check(hd.L.ws_map_set_params(hd.h, o.ctypes.data_as(_i32p), p.ctypes.data_as(_i32p)))
+
+    def params(self):
+        s, o, p = np.zeros(3, np.int32), np.zeros(3, np.int32), np.zeros(3, np.int32)
+        hd = self._hd
+        hd.check(hd.L.ws_map_get_params(hd.h, s.ctypes.data_as(_i32p), o.ctypes.data_as(_i32p), p.ctypes.data_as(_i32p)))
+        return s, o, p
+
+
+class TSDFCuda:
+    """cuda::TSDFCuda(existing_map, tau, max_weight, map_resolution) -- update_tsdf.h:9-34."""
+
+    n_max_points_ = _lib.WS_MAX_POINTS
+
+    def __init__(self, existing_map, tau, max_weight, map_resolution, device=0, rank=0, world=1, upload=True):
+        self._hd = _Handle(existing_map.size_, tau, max_weight, map_resolution, device, rank, world)
+        self._avg = DeviceMapMemWrapper(self._hd)
+        if upload:
+            self._avg.to_device(existing_map)
+        else:
+            self._avg.update_params(existing_map)
+
+    # -- reference surface --
+    def update_tsdf(self, scan_points, scanner_pos, up):
+        """update_tsdf.cu:169-183: ray-march the scan into the device map.  Blocking."""
+        p = _pts(scan_points)
+        sp, u = _i3(scanner_pos), _i3(up)
+        hd = self._hd
+        hd.check(hd.L.ws_update_tsdf(hd.h, p.ctypes.data, len(p), sp.ctypes.data_as(_i32p), u.ctypes.data_as(_i32p)))
+
+    def update_tsdf_result(self, result, scan_points, scanner_pos, up):
+        """update_tsdf.cu:143-166 overload: update, then copy the map into `result` (a DeviceMap view)."""
+        self.update_tsdf(scan_points, scanner_pos, up)
+        self._avg.to_host(result)
+
+    def update_tsdf_device(self, device_ptr, n, scanner_pos, up):
+        sp, u = _i3(scanner_pos), _i3(up)
+        hd = self._hd
+        hd.check(hd.L.ws_update_tsdf_device(hd.h, C.c_void_p(int(device_ptr)), int(n), sp.ctypes.data_as(_i32p),
+                                            u.ctypes.data_as(_i32p)))
+
+    def avg_map(self):
+        return self._avg
+
+    def new_map(self):
+        # the reference keeps a dense scratch grid (new_map_); here scratch keys live beside the map and
+        # only pos/offset matter to callers (tsdf_mapping.cpp:123)
+        return self._avg
+
+    def device_map(self):
+        return self._hd
+
+    # -- extras --
+    def counters(self):
+        c = _lib.UpdateCounters()
+        self._hd.check(self._hd.L.ws_get_update_counters(self._hd.h, C.byref(c)))
+        return c.as_dict()
+
+    def voxel(self, x, y, z):
+        e = C.c_uint32()
+        self._hd.check(self._hd.L.ws_map_get_voxel(self._hd.h, int(x), int(y), int(z), C.byref(e)))
+        return entry_value(e.value), entry_weight(e.value)
+
+    def set_voxel(self, x, y, z, value, weight):
+        self._hd.check(self._hd.L.ws_map_set_voxel(self._hd.h, int(x), int(y), int(z), make_entry(value, weight)))
+
+    def shift(self, new_pos):
+        p = _i3(new_pos)
+        self._hd.check(self._hd.L.ws_shift(self._hd.h, p.ctypes.data_as(_i32p)))
+
+    def write_back(self):
+        self._hd.check(self._hd.L.ws_write_back(self._hd.h))
+
+    def chunk_list(self):
+        hd = self._hd
+        n = int(hd.L.ws_store_num_chunks(hd.h))
+        out = np.zeros((max(n, 1), 3), np.int32)
+        k = hd.check(hd.L.ws_store_chunk_list(hd.h, out.ctypes.data_as(_i32p), n))
+        return [tuple(int(v) for v in out[i]) for i in range(k)]
+
+    def chunk(self, cx, cy, cz):
+        out = np.zeros(64 ** 3, np.uint32)
+        hd = self._hd
+        rc = hd.L.ws_store_get_chunk(hd.h, int(cx), int(cy), int(cz), out.ctypes.data_as(C.POINTER(C.c_uint32)))
+        return out if rc == _lib.WS_OK else None
+
+    def sync(self):
+        self._hd.check(self._hd.L.ws_sync(self._hd.h))
+
+    def profile(self, on=True):
+        self._hd.check(self._hd.L.ws_profile_enable(self._hd.h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._hd.check(self._hd.L.ws_profile_reset(self._hd.h))
+
+    def profile_get(self, kind):
+        ms, n = C.c_double(), C.c_int64()
+        self._hd.check(self._hd.L.ws_profile_get(self._hd.h, int(kind), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def close(self):
+        self._hd.close()
+
+
+class RegistrationCuda:
+    """cuda::RegistrationCuda(map) -- registration.h:10-45.  Shares the device map of a TSDFCuda."""
+
+    def __init__(self, tsdf):
+        self._hd = tsdf.device_map() if isinstance(tsdf, TSDFCuda) else tsdf
+        self.curr_n_points = 0
+
+    def prepare_registration(self, points):
+        """registration.cu:303-308"""
+        p = _pts(points)
+        hd = self._hd
+        hd.check(hd.L.ws_reg_prepare(hd.h, p.ctypes.data, len(p)))
+        self.curr_n_points = len(p)
+
+    def perform_registration(self, pretransform, map_resolution):
+        """registration.cu:347-368 -> (H 6x6 int64, g int64[6], e, c) for transform `pretransform`."""
+        T = colmajor16(pretransform)
+        H = np.zeros(36, np.int64)
+        g = np.zeros(6, np.int64)
+        e, c = C.c_int32(), C.c_int32()
+        hd = self._hd
+        hd.check(hd.L.ws_reg_step(hd.h, T.ctypes.data_as(C.POINTER(C.c_float)), int(map_resolution),
+                                  H.ctypes.data_as(C.POINTER(C.c_int64)), g.ctypes.data_as(C.POINTER(C.c_int64)),
+                                  C.byref(e), C.byref(c)))
+        return H.reshape(6, 6).T.copy(), g, e.value, c.value
+
+    def register_cloud(self, cloud, pretransform, max_iterations, it_weight_gradient, epsilon, map_resolution,
+                       host_solve=False, keep_on_device=False):
+        """The whole Gauss-Newton loop (src/cpu/registration.cpp:14-177).  `cloud` (int32 [n,3]) is
+        transformed IN PLACE; returns (total_transform 4x4 float32, iterations)."""
+        T = colmajor16(pretransform)
+        out = np.zeros(16, np.float32)
+        it = C.c_int32()
+        hd = self._hd
+        if keep_on_device:
+            ptr, n = None, self.curr_n_points
+        else:
+            assert cloud.dtype == np.int32 and cloud.flags.c_contiguous and cloud.flags.writeable
+            ptr, n = cloud.ctypes.data, len(cloud)
+            self.curr_n_points = n
+        hd.check(hd.L.ws_register_cloud(hd.h, ptr, int(n), T.ctypes.data_as(C.POINTER(C.c_float)),
+                                        int(max_iterations), float(it_weight_gradient), float(epsilon),
+                                        int(map_resolution),
+                                        _lib.WS_REG_HOST_SOLVE if host_solve else _lib.WS_REG_DEVICE_SOLVE,
+                                        out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(it)))
+        return from_colmajor16(out), it.value
+
+    def trace(self, max_iterations=256):
+        out = np.zeros((max_iterations, 29), np.int64)
+        hd = self._hd
+        n = hd.check(hd.L.ws_reg_get_trace(hd.h, out.ctypes.data_as(C.POINTER(C.c_int64)), int(max_iterations)))
+        return out[:n].copy()
+
+    def points_device(self):
+        n = C.c_int64()
+        ptr = self._hd.L.ws_reg_points_device(self._hd.h, C.byref(n))
+        return ptr, n.value
+
+    def test_reduce(self, jacobis, values):
+        """Reduction-shape hook (test/cuda.cpp:416-532)."""
+        J = np.ascontiguousarray(np.asarray(jacobis, np.int64).reshape(-1, 6))
+        v = np.ascontiguousarray(np.asarray(values, np.int32).reshape(-1))
+        H = np.zeros(36, np.int64)
+        g = np.zeros(6, np.int64)
+        e, c = C.c_int32(), C.c_int32()
+        hd = self._hd
+        hd.check(hd.L.ws_test_reduce(hd.h, J.ctypes.data_as(C.POINTER(C.c_int64)), v.ctypes.data_as(_i32p), len(J),
+                                     H.ctypes.data_as(C.POINTER(C.c_int64)), g.ctypes.data_as(C.POINTER(C.c_int64)),
+                                     C.byref(e), C.byref(c)))
+        return H.reshape(6, 6).T.copy(), g, e.value, c.value
+
+
+class TSDFMapping:
+    """cuda::TSDFMapping(params, local_map) -- tsdf_mapping.h:17-60, tsdf_mapping.cpp:13-205 (no ROS).
+
+    The reference serialises callers with a shared_mutex (update = exclusive, registration = shared);
+    a plain lock gives the same exclusion here.  The map-shift thread becomes an explicit, synchronous
+    `map_shift(pose)` that runs the shift ON THE DEVICE (ws_shift) instead of a D2H/H2D round trip."""
+
+    def __init__(self, params: Params, local_map: HostLocalMap, device=0, rank=0, world=1):
+        self.params_ = params
+        self.hdf5_local_map_ = local_map
+        self.cuda_map_ = DeviceMap(local_map)
+        self.tsdf_ = TSDFCuda(self.cuda_map_, params.map.tau, params.map.max_weight, params.map.resolution,
+                              device=device, rank=rank, world=world)
+        self.mutex_ = threading.RLock()
+        self.shifted_ = False
+        self.is_shifting_ = False
+        self._last_shift_pose = np.eye(4, dtype=np.float32)
+
+    def tsdf(self):
+        return self.tsdf_
+
+    def shifted(self):
+        return self.shifted_
+
+    def is_shifting(self):
+        return self.is_shifting_
+
+    def join_mapping_thread(self):
+        pass
+
+    def convert_pose_to_gpu(self, pose):
+        """tsdf_mapping.cpp:77-85"""
+        return convert_pose_to_gpu(pose, self.params_.map.resolution)
+
+    def update_tsdf(self, scan_points, pose_or_pos, up=None):
+        """update_tsdf(points, pose) / update_tsdf(points, pos, up) -- tsdf_mapping.cpp:62-75."""
+        if up is None:
+            pos, up = self.convert_pose_to_gpu(pose_or_pos)
+        else:
+            pos = pose_or_pos
+        with self.mutex_:
+            self.tsdf_.update_tsdf(scan_points, pos, up)
+
+    def preprocess_from_ros(self, cloud_xyz_m, pose):
+        """tsdf_mapping.cpp:145-163 without PCL: voxel-grid subsample at the map resolution (one
+        centroid per occupied leaf, like pcl::VoxelGrid), metres -> int millimetres, pose -> mm Matrix4f."""
+        res_m = self.params_.map.resolution / 1000.0
+        pts = np.asarray(cloud_xyz_m, dtype=np.float32).reshape(-1, 3)
+        if len(pts):
+            leaf = np.floor(pts / np.float32(res_m)).astype(np.int64)
+            leaf -= leaf.min(axis=0)
+            dims = leaf.max(axis=0) + 1
+            key = (leaf[:, 0] * dims[1] + leaf[:, 1]) * dims[2] + leaf[:, 2]
+            order = np.argsort(key, kind="stable")
+            ks = key[order]
+            first = np.concatenate([[True], ks[1:] != ks[:-1]])
+            idx = np.cumsum(first) - 1
+            n = int(idx[-1]) + 1
+            sums = np.zeros((n, 3), np.float64)
+            np.add.at(sums, idx, pts[order].astype(np.float64))
+            cnt = np.bincount(idx, minlength=n)[:, None]
+            cent = (sums / cnt).astype(np.float32)
+        else:
+            cent = pts
+        points_rm = np.trunc(cent * np.float32(1000.0)).astype(np.int32)
+        mm_pose = np.eye(4, dtype=np.float32)
+        P = np.asarray(pose, dtype=np.float64).reshape(4, 4)
+        mm_pose[:3, :3] = P[:3, :3].astype(np.float32)
+        mm_pose[:3, 3] = (P[:3, 3] * 1000.0).astype(np.float32)
+        return points_rm, mm_pose
+
+    def update_tsdf_from_ros(self, cloud_xyz_m, pose):
+        """tsdf_mapping.cpp:165-173: cloud in metres (sensor points already in the map frame), pose in
+        metres (Isometry3d as a 4x4)."""
+        points_rm, mm_pose = self.preprocess_from_ros(cloud_xyz_m, pose)
+        self.map_shift(mm_pose)
+        self.update_tsdf(points_rm, mm_pose)
+        return points_rm, mm_pose
+
+    def map_shift(self, current_pose):
+        """tsdf_mapping.cpp:97-136, one turn of the loop body, synchronous."""
+        d = (self._last_shift_pose[:3, 3] / 1000.0) - (np.asarray(current_pose, np.float32)[:3, 3] / 1000.0)
+        if float(np.linalg.norm(d)) < self.params_.map.shift:
+            return False
+        self.is_shifting_ = True
+        self._last_shift_pose = np.array(current_pose, dtype=np.float32)
+        pos = to_map(current_pose, self.params_.map.resolution)
+        with self.mutex_:
+            self.tsdf_.shift(pos)
+            _, o, p = self.tsdf_.avg_map().params()
+            self.hdf5_local_map_.offset[:] = o
+            self.hdf5_local_map_.pos[:] = p
+        self.shifted_ = True
+        self.is_shifting_ = False
+        return True
+
+    def get_tsdf_map(self):
+        """tsdf_mapping.cpp:138-143: bring the device map back into the host local map."""
+        with self.mutex_:
+            self.tsdf_.avg_map().to_host(self.cuda_map_)
+        return self.hdf5_local_map_
+
+    def close(self):
+        self.tsdf_.close()
+
+
+class TSDFRegistration(TSDFMapping):
+    """cuda::TSDFRegistration -- tsdf_registration.h:17-27, tsdf_registration.cpp:29-96."""
+
+    def __init__(self, params: Params, local_map: HostLocalMap, device=0, rank=0, world=1):
+        super().__init__(params, local_map, device=device, rank=rank, world=world)
+        self.reg_ = RegistrationCuda(self.tsdf_)
+
+    def register_cloud(self, cloud, pretransform, host_solve=False):
+        r = self.params_.registration
+        with self.mutex_:
+            T, _ = self.reg_.register_cloud(cloud, pretransform, r.max_iterations, r.it_weight_gradient, r.epsilon,
+                                            self.params_.map.resolution, host_solve=host_solve)
+        return T

@@ -1,0 +1,784 @@
+// capi.cu -- the C ABI of include/warpsense_b200.h over the kernels in this directory.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include "../../include/warpsense_b200.h"
+#include "ws_internal.h"
+
+static_assert(sizeof(ws_point) == sizeof(ws_pt), "point layout");
+#define WS_NSUM 29
+#define WS_TRACE_CAP 256
+#define WS_CHUNK 64
+
+namespace {
+
+struct DeviceGuard
+{
+  int prev = -1;
+  explicit DeviceGuard(int dev)
+  {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+template <typename F>
+int guarded(ws_handle *h, F &&f)
+{
+  if (!h) return WS_ERR_INVALID;
+  try
+  {
+    DeviceGuard dg(h->device);
+    return f();
+  }
+  catch (const std::invalid_argument &e) { h->last_error = e.what(); return WS_ERR_INVALID; }
+  catch (const std::length_error &e) { h->last_error = e.what(); return WS_ERR_CAPACITY; }
+  catch (const std::logic_error &e) { h->last_error = e.what(); return WS_ERR_STATE; }
+  catch (const std::exception &e) { h->last_error = e.what(); return WS_ERR_CUDA; }
+}
+
+void free_handle(ws_handle *h)
+{
+  if (!h) return;
+  DeviceGuard dg(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (auto &t : h->timers) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
+  cudaFree(h->g.grid); cudaFree(h->g.keys); cudaFree(h->g.brick_flag);
+  cudaFree(h->d_points); cudaFree(h->d_reg_points); cudaFree(h->d_brick_list);
+  cudaFree(h->d_counters); cudaFreeHost(h->h_counters);
+  cudaFree(h->d_pend_addr); cudaFree(h->d_pend_prev); cudaFree(h->d_pend_key);
+  cudaFree(h->d_acc); cudaFree(h->d_trace); cudaFreeHost(h->h_acc);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+void ensure_points(ws_pt **buf, size_t *cap, size_t n)
+{
+  if (n <= *cap) return;
+  size_t want = std::max<size_t>(n, 1 << 17);
+  if (*buf) WS_CUDA_OK(cudaFree(*buf));
+  *buf = nullptr; *cap = 0;
+  WS_CUDA_OK(cudaMalloc(buf, want * sizeof(ws_pt)));
+  *cap = want;
+}
+
+int create_impl(const int32_t size[3], int tau, int max_weight, int res, int device, int rank, int world, ws_handle **out)
+{
+  if (!out) return WS_ERR_INVALID;
+  *out = nullptr;
+  if (!size || size[0] < 1 || size[1] < 1 || size[2] < 1) return WS_ERR_INVALID;
+  if (size[0] % 2 == 0 || size[1] % 2 == 0 || size[2] % 2 == 0) return WS_ERR_INVALID;  // hdf5_local_map.cpp:6-8
+  if (tau < 1 || tau > 32767 || res < 2 || max_weight < 0 || max_weight > 32767) return WS_ERR_INVALID;
+  if (world < 1 || rank < 0 || rank >= world) return WS_ERR_INVALID;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return WS_ERR_CUDA;
+
+  ws_handle *h = new ws_handle();
+  h->device = device; h->tau = tau; h->max_weight = max_weight; h->res = res;
+  h->rank = rank; h->world = world;
+  h->default_entry = make_entry(tau, 0);
+  try
+  {
+    DeviceGuard dg(device);
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    GridDesc &g = h->g;
+    for (int a = 0; a < 3; a++)
+    {
+      g.size[a] = size[a]; g.half[a] = size[a] / 2; g.pos[a] = 0; g.offset[a] = size[a] / 2;
+      g.nb[a] = (size[a] + WS_BRICK - 1) / WS_BRICK;
+    }
+    if (g.nb[0] > WS_MAX_XBRICKS) throw std::invalid_argument("map too large along x");
+    // x-slab residency: this rank owns ring-x brick columns [c_lo, c_hi) plus the columns holding the
+    // rows just outside (the registration stencil reads x+-1)
+    const int c_lo = (int)((i64)g.nb[0] * rank / world), c_hi = (int)((i64)g.nb[0] * (rank + 1) / world);
+    if (c_hi <= c_lo) throw std::invalid_argument("more ranks than ring-x brick columns");
+    g.own_lo = c_lo * WS_BRICK;
+    g.own_hi = std::min(c_hi * WS_BRICK, g.size[0]);
+    g.full = (world == 1) ? 1 : 0;
+    for (int c = 0; c < WS_MAX_XBRICKS; c++) g.xslot[c] = -1;
+    std::vector<int> cols;
+    if (world == 1) for (int c = 0; c < g.nb[0]; c++) cols.push_back(c);
+    else
+    {
+      const int below = (g.own_lo - 1 + g.size[0]) % g.size[0], above = g.own_hi % g.size[0];
+      for (int c = c_lo; c < c_hi; c++) cols.push_back(c);
+      cols.push_back(below / WS_BRICK);
+      cols.push_back(above / WS_BRICK);
+      std::sort(cols.begin(), cols.end());
+      cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+    }
+    for (size_t s = 0; s < cols.size(); s++) g.xslot[cols[s]] = (short)s;
+    g.n_bricks = (i64)cols.size() * g.nb[1] * g.nb[2];
+    if (g.n_bricks >= (1ll << 31)) throw std::invalid_argument("map too large");
+    const size_t n_vox = (size_t)g.n_bricks * WS_BRICK_VOX;
+
+    WS_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+    WS_CUDA_OK(cudaMalloc(&g.grid, n_vox * sizeof(uint32_t)));
+    WS_CUDA_OK(cudaMalloc(&g.keys, n_vox * sizeof(u64)));
+    WS_CUDA_OK(cudaMalloc(&g.brick_flag, (size_t)g.n_bricks * sizeof(unsigned)));
+    WS_CUDA_OK(cudaMalloc(&h->d_brick_list, (size_t)g.n_bricks * sizeof(unsigned)));
+    WS_CUDA_OK(cudaMalloc(&h->d_counters, sizeof(UpdateCounters)));
+    WS_CUDA_OK(cudaMallocHost(&h->h_counters, sizeof(UpdateCounters)));
+    std::memset(h->h_counters, 0, sizeof(UpdateCounters));
+    size_t pcap = 8u << 20;
+    if (const char *env = std::getenv("WS_PENDING_CAP")) pcap = (size_t)std::strtoull(env, nullptr, 10);
+    pcap = std::min(pcap, n_vox);
+    pcap = std::max<size_t>(pcap, 1);
+    h->pending_cap = (unsigned)pcap;
+    WS_CUDA_OK(cudaMalloc(&h->d_pend_addr, pcap * sizeof(u64)));
+    WS_CUDA_OK(cudaMalloc(&h->d_pend_prev, pcap * sizeof(u64)));
+    WS_CUDA_OK(cudaMalloc(&h->d_pend_key, pcap * sizeof(u64)));
+    WS_CUDA_OK(cudaMalloc(&h->d_acc, sizeof(RegAccum) + 16 * sizeof(float)));
+    WS_CUDA_OK(cudaMemsetAsync(h->d_acc, 0, sizeof(RegAccum) + 16 * sizeof(float), h->stream));
+    WS_CUDA_OK(cudaMallocHost(&h->h_acc, sizeof(RegAccum)));
+    std::memset(h->h_acc, 0, sizeof(RegAccum));
+    h->trace_cap = WS_TRACE_CAP;
+    WS_CUDA_OK(cudaMalloc(&h->d_trace, (size_t)WS_TRACE_CAP * WS_NSUM * sizeof(u64)));
+    ws_launch_fill(h, h->default_entry);
+    WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+  }
+  catch (const std::invalid_argument &)
+  {
+    free_handle(h);
+    return WS_ERR_INVALID;
+  }
+  catch (const std::exception &)
+  {
+    free_handle(h);
+    return WS_ERR_CUDA;
+  }
+  *out = h;
+  return WS_OK;
+}
+
+// ---- chunk store (src/map/hdf5_global_map.cpp) -------------------------------------------------
+inline u64 chunk_key(int x, int y, int z)
+{
+  return ((u64)(uint32_t)(x + (1 << 20)) << 42) | ((u64)(uint32_t)(y + (1 << 20)) << 21) | (u64)(uint32_t)(z + (1 << 20));
+}
+inline void chunk_unkey(u64 k, int &x, int &y, int &z)
+{
+  x = (int)((k >> 42) & 0x1FFFFF) - (1 << 20);
+  y = (int)((k >> 21) & 0x1FFFFF) - (1 << 20);
+  z = (int)(k & 0x1FFFFF) - (1 << 20);
+}
+// include/map/util.h:5-12
+inline int floor_divide(int a, int b) { return (int)std::floor((float)a / (float)b); }
+
+// hdf5_global_map.cpp:59-137 (activate_chunk): default-filled on first use
+std::vector<uint32_t> &activate_chunk(ws_handle *h, int cx, int cy, int cz)
+{
+  auto it = h->store.find(chunk_key(cx, cy, cz));
+  if (it != h->store.end()) return it->second;
+  auto &v = h->store[chunk_key(cx, cy, cz)];
+  v.assign((size_t)WS_CHUNK * WS_CHUNK * WS_CHUNK, h->default_entry);
+  return v;
+}
+
+bool column_resident(const GridDesc &g, int x)
+{
+  if (g.full) return true;
+  return g.xslot[ring_coord(x, g.pos[0], g.offset[0], g.size[0]) >> 3] >= 0;
+}
+
+// hdf5_local_map.cpp:120-198 (save_load_area) on the device-resident grid, in x-slices of bounded size
+void save_load_area(ws_handle *h, const int bottom[3], const int top[3], bool save)
+{
+  int start[3], end[3];
+  for (int a = 0; a < 3; a++) { start[a] = std::min(bottom[a], top[a]); end[a] = std::max(bottom[a], top[a]); }
+  const i64 plane = (i64)(end[1] - start[1] + 1) * (end[2] - start[2] + 1);
+  const int max_nx = (int)std::max<i64>(1, (i64)(32 << 20) / plane);
+  uint32_t *d_buf = nullptr, *h_buf = nullptr;
+  const size_t cap = (size_t)plane * std::min(max_nx, end[0] - start[0] + 1);
+  WS_CUDA_OK(cudaMalloc(&d_buf, cap * sizeof(uint32_t)));
+  if (cudaMallocHost(&h_buf, cap * sizeof(uint32_t)) != cudaSuccess) { cudaFree(d_buf); throw std::runtime_error("cudaMallocHost(shift buffer)"); }
+  try
+  {
+    for (int x0 = start[0]; x0 <= end[0]; x0 += max_nx)
+    {
+      const int x1 = std::min(end[0], x0 + max_nx - 1);
+      const int lo[3] = { x0, start[1], start[2] };
+      const int ext[3] = { x1 - x0 + 1, end[1] - start[1] + 1, end[2] - start[2] + 1 };
+      const size_t n = (size_t)ext[0] * ext[1] * ext[2];
+      if (save)
+      {
+        ws_box_transfer(h, d_buf, lo, ext, true);
+        WS_CUDA_OK(cudaMemcpyAsync(h_buf, d_buf, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+      }
+      // chunk-wise traversal, as the reference does (touch each chunk once)
+      const int cs[3] = { floor_divide(lo[0], WS_CHUNK), floor_divide(lo[1], WS_CHUNK), floor_divide(lo[2], WS_CHUNK) };
+      const int ce[3] = { floor_divide(x1, WS_CHUNK), floor_divide(end[1], WS_CHUNK), floor_divide(end[2], WS_CHUNK) };
+      for (int cx = cs[0]; cx <= ce[0]; ++cx)
+        for (int cy = cs[1]; cy <= ce[1]; ++cy)
+          for (int cz = cs[2]; cz <= ce[2]; ++cz)
+          {
+            std::vector<uint32_t> &chunk = activate_chunk(h, cx, cy, cz);
+            const int xs = std::max(lo[0], cx * WS_CHUNK), xe = std::min(x1, cx * WS_CHUNK + WS_CHUNK - 1);
+            const int ys = std::max(lo[1], cy * WS_CHUNK), ye = std::min(end[1], cy * WS_CHUNK + WS_CHUNK - 1);
+            const int zs = std::max(lo[2], cz * WS_CHUNK), ze = std::min(end[2], cz * WS_CHUNK + WS_CHUNK - 1);
+            for (int x = xs; x <= xe; ++x)
+            {
+              if (!column_resident(h->g, x)) continue;
+              for (int y = ys; y <= ye; ++y)
+              {
+                const size_t brow = ((size_t)(x - lo[0]) * ext[1] + (size_t)(y - lo[1])) * ext[2];
+                const size_t crow = ((size_t)(x - cx * WS_CHUNK) * WS_CHUNK + (size_t)(y - cy * WS_CHUNK)) * WS_CHUNK;
+                for (int z = zs; z <= ze; ++z)
+                {
+                  if (save) chunk[crow + (z - cz * WS_CHUNK)] = h_buf[brow + (z - lo[2])];
+                  else h_buf[brow + (z - lo[2])] = chunk[crow + (z - cz * WS_CHUNK)];
+                }
+              }
+            }
+          }
+      if (!save)
+      {
+        WS_CUDA_OK(cudaMemcpyAsync(d_buf, h_buf, n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+        ws_box_transfer(h, d_buf, lo, ext, false);
+        WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+      }
+    }
+  }
+  catch (...)
+  {
+    cudaFree(d_buf); cudaFreeHost(h_buf);
+    throw;
+  }
+  cudaFree(d_buf); cudaFreeHost(h_buf);
+}
+
+void read_acc(ws_handle *h)
+{
+  WS_CUDA_OK(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(RegAccum), cudaMemcpyDeviceToHost, h->stream));
+  WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+}
+
+void sums_to_hg(const u64 sums[32], int64_t H[36], int64_t g[6], int32_t *err, int32_t *cnt)
+{
+  int k = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = i; j < 6; j++)
+    {
+      const int64_t v = (int64_t)sums[k++];
+      H[j * 6 + i] = v;
+      H[i * 6 + j] = v;
+    }
+  for (int i = 0; i < 6; i++) g[i] = (int64_t)sums[21 + i];
+  *err = (int32_t)(int64_t)sums[27];
+  *cnt = (int32_t)(int64_t)sums[28];
+}
+
+}  // namespace
+
+void ws_timer_begin(ws_handle *h, int kind)
+{
+  if (!h->profile) return;
+  if (h->timers_used >= h->timers.size())
+  {
+    if (h->timers.size() >= (1u << 16)) { h->timers_used = h->timers.size() + 1; return; }
+    WsTimer t;
+    if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) return;
+    h->timers.push_back(t);
+    h->timer_kind.push_back(kind);
+  }
+  h->timer_kind[h->timers_used] = kind;
+  cudaEventRecord(h->timers[h->timers_used].start, h->stream);
+}
+
+void ws_timer_end(ws_handle *h)
+{
+  if (!h->profile) return;
+  if (h->timers_used < h->timers.size())
+  {
+    cudaEventRecord(h->timers[h->timers_used].stop, h->stream);
+    h->timers_used++;
+  }
+}
+
+extern "C" {
+
+const char *ws_version(void) { return "warpsense_b200 0.1.0 (sm_100a)"; }
+
+int ws_create(const int32_t size[3], int32_t tau, int32_t max_weight, int32_t map_resolution, int32_t device, ws_handle **out)
+{
+  return create_impl(size, tau, max_weight, map_resolution, device, 0, 1, out);
+}
+
+int ws_create_sharded(const int32_t size[3], int32_t tau, int32_t max_weight, int32_t map_resolution,
+                      int32_t device, int32_t rank, int32_t world, ws_handle **out)
+{
+  return create_impl(size, tau, max_weight, map_resolution, device, rank, world, out);
+}
+
+void ws_destroy(ws_handle *h) { free_handle(h); }
+
+const char *ws_last_error(const ws_handle *h) { return h ? h->last_error.c_str() : "null handle"; }
+
+int ws_set_stream(ws_handle *h, void *cuda_stream)
+{
+  return guarded(h, [&]() {
+    WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    if (cuda_stream == nullptr)
+    {
+      if (!h->own_stream)
+      {
+        WS_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        h->own_stream = true;
+      }
+    }
+    else
+    {
+      if (h->own_stream) cudaStreamDestroy(h->stream);
+      h->own_stream = false;
+      h->stream = (cudaStream_t)cuda_stream;
+    }
+    return WS_OK;
+  });
+}
+
+void *ws_get_stream(ws_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+int ws_sync(ws_handle *h)
+{
+  return guarded(h, [&]() { WS_CUDA_OK(cudaStreamSynchronize(h->stream)); return WS_OK; });
+}
+
+int ws_map_upload(ws_handle *h, const uint32_t *entries, const int32_t size[3], const int32_t offset[3], const int32_t pos[3])
+{
+  return guarded(h, [&]() {
+    if (!entries || !size || !offset || !pos) throw std::invalid_argument("ws_map_upload: null argument");
+    for (int a = 0; a < 3; a++)
+      if (size[a] != h->g.size[a]) throw std::invalid_argument("ws_map_upload: size differs from the handle's map");
+    for (int a = 0; a < 3; a++)
+    {
+      if (offset[a] < 0 || offset[a] >= size[a]) throw std::invalid_argument("ws_map_upload: offset out of range");
+      h->g.offset[a] = offset[a]; h->g.pos[a] = pos[a];
+    }
+    ws_launch_upload(h, entries);
+    return WS_OK;
+  });
+}
+
+int ws_map_download(ws_handle *h, uint32_t *entries)
+{
+  return guarded(h, [&]() {
+    if (!entries) throw std::invalid_argument("ws_map_download: null argument");
+    ws_launch_download(h, entries);
+    return WS_OK;
+  });
+}
+
+int ws_map_set_params(ws_handle *h, const int32_t offset[3], const int32_t pos[3])
+{
+  return guarded(h, [&]() {
+    if (!offset || !pos) throw std::invalid_argument("ws_map_set_params: null argument");
+    for (int a = 0; a < 3; a++)
+    {
+      if (offset[a] < 0 || offset[a] >= h->g.size[a]) throw std::invalid_argument("ws_map_set_params: offset out of range");
+      h->g.offset[a] = offset[a]; h->g.pos[a] = pos[a];
+    }
+    return WS_OK;
+  });
+}
+
+int ws_map_get_params(const ws_handle *h, int32_t size[3], int32_t offset[3], int32_t pos[3])
+{
+  if (!h) return WS_ERR_INVALID;
+  for (int a = 0; a < 3; a++)
+  {
+    if (size) size[a] = h->g.size[a];
+    if (offset) offset[a] = h->g.offset[a];
+    if (pos) pos[a] = h->g.pos[a];
+  }
+  return WS_OK;
+}
+
+int ws_map_fill(ws_handle *h, int32_t value, int32_t weight)
+{
+  return guarded(h, [&]() {
+    h->default_entry = make_entry(value, weight);   // also what unseen chunks of the store hold
+    ws_launch_fill(h, h->default_entry);
+    WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return WS_OK;
+  });
+}
+
+static i64 voxel_addr(ws_handle *h, int x, int y, int z)
+{
+  const GridDesc &g = h->g;
+  if (!grid_in_bounds(g, x, y, z)) throw std::invalid_argument("voxel out of bounds");
+  const int rx = ring_coord(x, g.pos[0], g.offset[0], g.size[0]);
+  const int ry = ring_coord(y, g.pos[1], g.offset[1], g.size[1]);
+  const int rz = ring_coord(z, g.pos[2], g.offset[2], g.size[2]);
+  const i64 b = brick_of(g, rx, ry, rz);
+  if (b < 0) throw std::invalid_argument("voxel not resident on this rank");
+  return b * WS_BRICK_VOX + brick_local(rx, ry, rz);
+}
+
+int ws_map_get_voxel(ws_handle *h, int32_t x, int32_t y, int32_t z, uint32_t *entry)
+{
+  return guarded(h, [&]() {
+    if (!entry) throw std::invalid_argument("ws_map_get_voxel: null argument");
+    const i64 addr = voxel_addr(h, x, y, z);
+    WS_CUDA_OK(cudaMemcpyAsync(entry, h->g.grid + addr, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+    WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return WS_OK;
+  });
+}
+
+int ws_map_set_voxel(ws_handle *h, int32_t x, int32_t y, int32_t z, uint32_t entry)
+{
+  return guarded(h, [&]() {
+    const i64 addr = voxel_addr(h, x, y, z);
+    WS_CUDA_OK(cudaMemcpyAsync(h->g.grid + addr, &entry, sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+    WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return WS_OK;
+  });
+}
+
+static void check_update_args(int64_t n, const int32_t *scanner_pos, const int32_t *up)
+{
+  if (n < 0 || !scanner_pos || !up) throw std::invalid_argument("ws_update_tsdf: bad argument");
+  if (n > WS_MAX_POINTS) throw std::length_error("ws_update_tsdf: too many points (reference limit semantics, update_tsdf.cu:146-150)");
+}
+
+int ws_update_tsdf(ws_handle *h, const ws_point *points, int64_t n, const int32_t scanner_pos[3], const int32_t up[3])
+{
+  return guarded(h, [&]() {
+    check_update_args(n, scanner_pos, up);
+    if (n > 0 && !points) throw std::invalid_argument("ws_update_tsdf: null points");
+    ensure_points(&h->d_points, &h->points_cap, (size_t)n);
+    if (n > 0)
+      WS_CUDA_OK(cudaMemcpyAsync(h->d_points, points, (size_t)n * sizeof(ws_pt), cudaMemcpyHostToDevice, h->stream));
+    h->last_n_points = n;
+    ws_launch_update(h, h->d_points, (int)n, scanner_pos, up);
+    return WS_OK;
+  });
+}
+
+int ws_update_tsdf_device(ws_handle *h, const ws_point *device_points, int64_t n, const int32_t scanner_pos[3], const int32_t up[3])
+{
+  return guarded(h, [&]() {
+    check_update_args(n, scanner_pos, up);
+    if (n > 0 && !device_points) throw std::invalid_argument("ws_update_tsdf_device: null points");
+    h->last_n_points = n;
+    ws_launch_update(h, reinterpret_cast<const ws_pt *>(device_points), (int)n, scanner_pos, up);
+    return WS_OK;
+  });
+}
+
+int ws_get_update_counters(const ws_handle *h, ws_update_counters *out)
+{
+  if (!h || !out) return WS_ERR_INVALID;
+  const UpdateCounters &c = h->last_counters;
+  out->n_points = h->last_n_points;
+  out->n_candidates = (int64_t)c.n_candidates;
+  out->n_touched = (int64_t)c.n_touched;
+  out->n_written = (int64_t)c.n_written;
+  out->n_touched_bricks = c.n_touched_bricks;
+  out->n_parked = c.n_parked;
+  out->n_rounds = c.rounds;
+  return WS_OK;
+}
+
+int ws_reg_prepare(ws_handle *h, const ws_point *points, int64_t n)
+{
+  return guarded(h, [&]() {
+    if (n < 0 || (n > 0 && !points)) throw std::invalid_argument("ws_reg_prepare: bad argument");
+    if (n > WS_MAX_POINTS) throw std::length_error("ws_reg_prepare: too many points");
+    ensure_points(&h->d_reg_points, &h->reg_points_cap, (size_t)n);
+    if (n > 0)
+      WS_CUDA_OK(cudaMemcpyAsync(h->d_reg_points, points, (size_t)n * sizeof(ws_pt), cudaMemcpyHostToDevice, h->stream));
+    h->reg_n = (int)n;
+    return WS_OK;
+  });
+}
+
+int ws_reg_step(ws_handle *h, const float T[16], int32_t map_resolution, int64_t H[36], int64_t g[6], int32_t *err, int32_t *cnt)
+{
+  return guarded(h, [&]() {
+    if (!T || !H || !g || !err || !cnt || map_resolution < 1) throw std::invalid_argument("ws_reg_step: bad argument");
+    ws_launch_reg_reset(h, T, 0.f);
+    ws_launch_reg_iteration(h, h->reg_n, map_resolution, 0, 0.f, 0.f);
+    read_acc(h);
+    sums_to_hg(h->h_acc->sums, H, g, err, cnt);
+    return WS_OK;
+  });
+}
+
+int ws_register_cloud(ws_handle *h, ws_point *cloud, int64_t n, const float pretransform[16], int32_t max_iterations,
+                      float it_weight_gradient, float epsilon, int32_t map_resolution, int32_t flags,
+                      float out_transform[16], int32_t *iterations)
+{
+  return guarded(h, [&]() {
+    if (!pretransform || !out_transform || map_resolution < 1 || max_iterations < 0)
+      throw std::invalid_argument("ws_register_cloud: bad argument");
+    if (cloud)
+    {
+      if (n < 0) throw std::invalid_argument("ws_register_cloud: bad point count");
+      if (n > WS_MAX_POINTS) throw std::length_error("ws_register_cloud: too many points");
+      ensure_points(&h->d_reg_points, &h->reg_points_cap, (size_t)n);
+      if (n > 0)
+        WS_CUDA_OK(cudaMemcpyAsync(h->d_reg_points, cloud, (size_t)n * sizeof(ws_pt), cudaMemcpyHostToDevice, h->stream));
+      h->reg_n = (int)n;
+    }
+    const int np = h->reg_n;
+    ws_launch_reg_reset(h, pretransform, 0.f);
+    int it_done = 0;
+    h->last_reg_host = (flags & WS_REG_HOST_SOLVE) != 0;
+    h->host_trace.clear();
+    if (!h->last_reg_host)
+    {
+      // GN iterations back to back on the device; look at `finished` only every 32 launches
+      while (it_done < max_iterations)
+      {
+        const int batch = std::min(32, max_iterations - it_done);
+        for (int i = 0; i < batch; i++) ws_launch_reg_iteration(h, np, map_resolution, 1, it_weight_gradient, epsilon);
+        it_done += batch;
+        if (it_done < max_iterations)
+        {
+          read_acc(h);
+          if (h->h_acc->finished) break;
+        }
+      }
+      ws_launch_transform_cloud(h, h->d_reg_points, np);
+      read_acc(h);
+      it_done = (int)h->h_acc->iterations;
+      std::memcpy(out_transform, h->h_acc->T, 16 * sizeof(float));
+    }
+    else
+    {
+      // the reference's structure: sums to the host, FP64 solve there (tsdf_registration.cpp:55-92)
+      float T[16];
+      std::memcpy(T, pretransform, sizeof(T));
+      float alpha = 0.f;
+      float prev[4] = { 0, 0, 0, 0 };
+      bool finished = false;
+      for (int i = 0; i < max_iterations && !finished; i++)
+      {
+        ws_launch_reg_iteration(h, np, map_resolution, 0, 0.f, 0.f);
+        read_acc(h);
+        int64_t H[36], g[6]; int32_t e, c;
+        sums_to_hg(h->h_acc->sums, H, g, &e, &c);
+        for (int k = 0; k < WS_NSUM; k++) h->host_trace.push_back((i64)h->h_acc->sums[k]);
+        const float errv = [&]() { double xi[6]; ws_host_solve((const i64 *)H, (const i64 *)g, e, c, alpha, T, xi); return (float)e / c; }();
+        alpha += it_weight_gradient;
+        if (fabs(errv - prev[2]) < epsilon && fabs(errv - prev[0]) < epsilon) finished = true;
+        prev[0] = prev[1]; prev[1] = prev[2]; prev[2] = prev[3]; prev[3] = errv;
+        it_done = i + 1;
+        ws_launch_reg_reset(h, T, alpha);
+      }
+      ws_launch_transform_cloud(h, h->d_reg_points, np);
+      std::memcpy(out_transform, T, sizeof(T));
+    }
+    if (cloud && np > 0)
+      WS_CUDA_OK(cudaMemcpyAsync(cloud, h->d_reg_points, (size_t)np * sizeof(ws_pt), cudaMemcpyDeviceToHost, h->stream));
+    WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    WS_CUDA_OK(cudaGetLastError());
+    h->last_reg_iterations = it_done;
+    if (iterations) *iterations = it_done;
+    return WS_OK;
+  });
+}
+
+int ws_reg_get_trace(ws_handle *h, int64_t *out, int32_t max_iterations)
+{
+  if (!h || !out) return WS_ERR_INVALID;
+  int n = std::min(h->last_reg_iterations, (int)max_iterations);
+  int rc = guarded(h, [&]() {
+    if (h->last_reg_host)
+    {
+      n = std::min<int>(n, (int)(h->host_trace.size() / WS_NSUM));
+      std::memcpy(out, h->host_trace.data(), (size_t)n * WS_NSUM * sizeof(int64_t));
+    }
+    else
+    {
+      n = std::min(n, h->trace_cap);
+      if (n > 0)
+      {
+        WS_CUDA_OK(cudaMemcpyAsync(out, h->d_trace, (size_t)n * WS_NSUM * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+      }
+    }
+    return WS_OK;
+  });
+  return rc == WS_OK ? n : rc;
+}
+
+const ws_point *ws_reg_points_device(ws_handle *h, int64_t *n)
+{
+  if (!h) return nullptr;
+  if (n) *n = h->reg_n;
+  return reinterpret_cast<const ws_point *>(h->d_reg_points);
+}
+
+int ws_reg_begin(ws_handle *h, const float pretransform[16])
+{
+  return guarded(h, [&]() {
+    if (!pretransform) throw std::invalid_argument("ws_reg_begin: null argument");
+    ws_launch_reg_reset(h, pretransform, 0.f);
+    h->last_reg_host = false;
+    return WS_OK;
+  });
+}
+
+int ws_reg_accumulate(ws_handle *h, int32_t map_resolution)
+{
+  return guarded(h, [&]() {
+    if (map_resolution < 1) throw std::invalid_argument("ws_reg_accumulate: bad resolution");
+    ws_launch_reg_iteration(h, h->reg_n, map_resolution, 0, 0.f, 0.f);
+    return WS_OK;
+  });
+}
+
+void *ws_reg_sums_device(ws_handle *h) { return h ? (void *)h->d_acc->sums : nullptr; }
+
+int ws_reg_solve(ws_handle *h, float it_weight_gradient, float epsilon)
+{
+  return guarded(h, [&]() { ws_launch_reg_solve(h, it_weight_gradient, epsilon); return WS_OK; });
+}
+
+int ws_reg_finish(ws_handle *h, float out_transform[16], int32_t *iterations, int32_t *finished)
+{
+  return guarded(h, [&]() {
+    ws_launch_transform_cloud(h, h->d_reg_points, h->reg_n);
+    read_acc(h);
+    if (out_transform) std::memcpy(out_transform, h->h_acc->T, 16 * sizeof(float));
+    if (iterations) *iterations = (int32_t)h->h_acc->iterations;
+    if (finished) *finished = (int32_t)h->h_acc->finished;
+    h->last_reg_iterations = (int)h->h_acc->iterations;
+    return WS_OK;
+  });
+}
+
+int ws_test_reduce(ws_handle *h, const int64_t *jacobis6, const int32_t *values, int64_t n, int64_t H[36], int64_t g[6], int32_t *err, int32_t *cnt)
+{
+  return guarded(h, [&]() {
+    if (n < 0 || (n > 0 && (!jacobis6 || !values)) || !H || !g || !err || !cnt) throw std::invalid_argument("ws_test_reduce: bad argument");
+    i64 *d_j = nullptr; int *d_v = nullptr;
+    const float I[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    ws_launch_reg_reset(h, I, 0.f);
+    WS_CUDA_OK(cudaMalloc(&d_j, std::max<size_t>(1, (size_t)n * 6 * sizeof(i64))));
+    WS_CUDA_OK(cudaMalloc(&d_v, std::max<size_t>(1, (size_t)n * sizeof(int))));
+    if (n > 0)
+    {
+      WS_CUDA_OK(cudaMemcpyAsync(d_j, jacobis6, (size_t)n * 6 * sizeof(i64), cudaMemcpyHostToDevice, h->stream));
+      WS_CUDA_OK(cudaMemcpyAsync(d_v, values, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    ws_launch_test_reduce(h, d_j, d_v, (int)n);
+    read_acc(h);
+    cudaFree(d_j); cudaFree(d_v);
+    sums_to_hg(h->h_acc->sums, H, g, err, cnt);
+    return WS_OK;
+  });
+}
+
+int ws_shift(ws_handle *h, const int32_t new_pos[3])
+{
+  return guarded(h, [&]() {
+    if (!new_pos) throw std::invalid_argument("ws_shift: null argument");
+    GridDesc &g = h->g;
+    int diff[3];
+    for (int a = 0; a < 3; a++)
+    {
+      diff[a] = new_pos[a] - g.pos[a];
+      if (std::abs(diff[a]) > g.size[a]) throw std::invalid_argument("ws_shift: shift larger than the map (hdf5_local_map.cpp:63-65)");
+    }
+    for (int axis = 0; axis < 3; axis++)                                    // hdf5_local_map.cpp:68-117
+    {
+      if (diff[axis] == 0) continue;
+      int start[3], end[3];
+      for (int a = 0; a < 3; a++) { start[a] = g.pos[a] - g.half[a]; end[a] = g.pos[a] + g.half[a]; }
+      if (diff[axis] > 0) end[axis] = start[axis] + diff[axis] - 1;
+      else start[axis] = end[axis] + diff[axis] + 1;
+      save_load_area(h, start, end, true);
+
+      g.pos[axis] += diff[axis];
+      g.offset[axis] = (g.offset[axis] + diff[axis] + g.size[axis]) % g.size[axis];
+
+      for (int a = 0; a < 3; a++) { start[a] = g.pos[a] - g.half[a]; end[a] = g.pos[a] + g.half[a]; }
+      if (diff[axis] > 0) start[axis] = end[axis] - (diff[axis] - 1);
+      else end[axis] = start[axis] - diff[axis] - 1;
+      save_load_area(h, start, end, false);
+    }
+    return WS_OK;
+  });
+}
+
+int ws_write_back(ws_handle *h)
+{
+  return guarded(h, [&]() {
+    int start[3], end[3];
+    for (int a = 0; a < 3; a++) { start[a] = h->g.pos[a] - h->g.half[a]; end[a] = h->g.pos[a] + h->g.half[a]; }
+    save_load_area(h, start, end, true);
+    return WS_OK;
+  });
+}
+
+int64_t ws_store_num_chunks(const ws_handle *h) { return h ? (int64_t)h->store.size() : 0; }
+
+int ws_store_chunk_list(const ws_handle *h, int32_t *xyz, int64_t cap)
+{
+  if (!h || !xyz) return WS_ERR_INVALID;
+  int64_t k = 0;
+  for (const auto &kv : h->store)
+  {
+    if (k >= cap) break;
+    int x, y, z;
+    chunk_unkey(kv.first, x, y, z);
+    xyz[3 * k] = x; xyz[3 * k + 1] = y; xyz[3 * k + 2] = z;
+    k++;
+  }
+  return (int)k;
+}
+
+int ws_store_get_chunk(const ws_handle *h, int32_t cx, int32_t cy, int32_t cz, uint32_t *out)
+{
+  if (!h || !out) return WS_ERR_INVALID;
+  auto it = h->store.find(chunk_key(cx, cy, cz));
+  if (it == h->store.end()) return WS_ERR_INVALID;
+  std::memcpy(out, it->second.data(), it->second.size() * sizeof(uint32_t));
+  return WS_OK;
+}
+
+int ws_profile_enable(ws_handle *h, int32_t on)
+{
+  if (!h) return WS_ERR_INVALID;
+  h->profile = on != 0;
+  return WS_OK;
+}
+
+int ws_profile_reset(ws_handle *h)
+{
+  return guarded(h, [&]() {
+    WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->timers_used = 0;
+    return WS_OK;
+  });
+}
+
+int ws_profile_get(ws_handle *h, int32_t kind, double *total_ms, int64_t *launches)
+{
+  return guarded(h, [&]() {
+    WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    double tot = 0.0;
+    int64_t cnt = 0;
+    const size_t used = std::min(h->timers_used, h->timers.size());
+    for (size_t i = 0; i < used; i++)
+    {
+      if (h->timer_kind[i] != kind) continue;
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, h->timers[i].start, h->timers[i].stop) == cudaSuccess) { tot += ms; cnt++; }
+    }
+    if (total_ms) *total_ms = tot;
+    if (launches) *launches = cnt;
+    return WS_OK;
+  });
+}
+
+}  // extern "C"

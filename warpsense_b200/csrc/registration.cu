@@ -1,0 +1,402 @@
+// registration.cu -- Point-to-TSDF registration inner loop for sm_100a.
+//
+// Replaces RegistrationCuda::perform_registration (src/warpsense/cuda/registration.cu:15-368 under
+// /root/reference: calc_jacobis_krnl + h_g_e_reduction_krnl + host finish) with ONE fused kernel per
+// Gauss-Newton iteration whose sums equal the reference's CPU path (src/cpu/registration.cpp:52-118)
+// bit for bit: fixed-point transform -> centre + 6 face-neighbour gather from the bricked grid ->
+// gated central differences -> 6x int64 Jacobian -> warp-shuffle reduction of the 21 upper-triangle
+// H terms, 6 g terms, error and count -> 29 int64 atomics per block.  The last block to finish also
+// runs the damped FP64 6x6 solve and the Rodrigues update (registration.cpp:128-157,
+// include/warpsense/registration/util.h:5-39), so the next iteration starts with no host round trip.
+// All sums are integers, hence exact and independent of reduction order and of the GPU count.
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include "ws_internal.h"
+
+#define FULL 0xFFFFFFFFu
+#define WS_NSUM 29
+
+namespace {
+
+// include/util/util.h:8-11
+WS_HD void to_int_mat(const float T[16], int M[16])
+{
+  for (int i = 0; i < 16; i++) M[i] = (int)(T[i] * (float)WS_MR);
+}
+
+// include/util/util.h:13-18 (column-major M)
+WS_HD void transform_point(const int M[16], int x, int y, int z, int out[3])
+{
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+  {
+    int acc = wadd(wadd(wadd(wmul(M[r], x), wmul(M[4 + r], y)), wmul(M[8 + r], z)), M[12 + r]);
+    out[r] = div_mr32(acc);
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// FP64 damped solve + pose update, compiled for host and device from one source so the two agree.
+// Mirrors Eigen's PartialPivLU-based Matrix<double,6,6>::inverse().
+WS_HD void inverse6(const double A[36], double inv[36])
+{
+  double lu[6][6];
+  int perm[6];
+  for (int r = 0; r < 6; r++) { perm[r] = r; for (int c = 0; c < 6; c++) lu[r][c] = A[c * 6 + r]; }
+  for (int k = 0; k < 6; k++)
+  {
+    int piv = k; double best = fabs(lu[k][k]);
+    for (int r = k + 1; r < 6; r++) if (fabs(lu[r][k]) > best) { best = fabs(lu[r][k]); piv = r; }
+    if (piv != k)
+    {
+      for (int c = 0; c < 6; c++) { double t = lu[k][c]; lu[k][c] = lu[piv][c]; lu[piv][c] = t; }
+      int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+    }
+    for (int r = k + 1; r < 6; r++) lu[r][k] /= lu[k][k];
+    for (int r = k + 1; r < 6; r++)
+      for (int c = k + 1; c < 6; c++) lu[r][c] -= lu[r][k] * lu[k][c];
+  }
+  for (int col = 0; col < 6; col++)
+  {
+    double y[6];
+    for (int r = 0; r < 6; r++) y[r] = (perm[r] == col) ? 1.0 : 0.0;
+    for (int r = 0; r < 6; r++)
+      for (int c = 0; c < r; c++) y[r] -= lu[r][c] * y[c];
+    for (int r = 5; r >= 0; r--)
+    {
+      for (int c = r + 1; c < 6; c++) y[r] -= lu[r][c] * y[c];
+      y[r] /= lu[r][r];
+    }
+    for (int r = 0; r < 6; r++) inv[col * 6 + r] = y[r];
+  }
+}
+
+// include/warpsense/registration/util.h:5-39
+WS_HD void xi_to_transform(const double xi[6], const int center[3], float out[16])
+{
+  double theta = sqrt(xi[0] * xi[0] + xi[1] * xi[1] + xi[2] * xi[2]);
+  double l[3] = { xi[0] / theta, xi[1] / theta, xi[2] / theta };
+  float L[3][3] = { { 0.f, (float)(-l[2]), (float)l[1] },
+                    { (float)l[2], 0.f, (float)(-l[0]) },
+                    { (float)(-l[1]), (float)l[0], 0.f } };
+  float s = (float)sin(theta);
+  float c1 = (float)(1 - cos(theta));
+  float A[3][3], R[3][3];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) A[i][j] = c1 * L[i][j];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++)
+    {
+      float b = A[i][0] * L[0][j];
+      b = b + A[i][1] * L[1][j];
+      b = b + A[i][2] * L[2][j];
+      float id = (i == j) ? 1.f : 0.f;
+      R[i][j] = (id + s * L[i][j]) + b;
+    }
+  float oc[3] = { -(float)center[0], -(float)center[1], -(float)center[2] };
+  float xf[3] = { (float)xi[3], (float)xi[4], (float)xi[5] };
+  for (int i = 0; i < 16; i++) out[i] = 0.f;
+  for (int i = 0; i < 3; i++)
+  {
+    for (int j = 0; j < 3; j++) out[j * 4 + i] = R[i][j];
+    float shift = R[i][0] * oc[0];
+    shift = shift + R[i][1] * oc[1];
+    shift = shift + R[i][2] * oc[2];
+    shift = shift + 0.f * 1.f;
+    out[12 + i] = (shift + (float)center[i]) + xf[i];
+  }
+  out[15] = 1.f;
+}
+
+// registration.cpp:128-145.  H column-major 6x6.  T updated in place; returns err / cnt.
+WS_HD float gn_solve(const i64 H[36], const i64 g[6], int err, int cnt, float alpha, float T[16], double xi_out[6])
+{
+  int center[3] = { (int)T[12], (int)T[13], (int)T[14] };
+  double hf[36], gf[6], inv[36], xi[6];
+  for (int i = 0; i < 36; i++) hf[i] = (double)H[i];
+  for (int i = 0; i < 6; i++) gf[i] = (double)g[i];
+  double damp = (double)(alpha * (float)cnt);
+  for (int i = 0; i < 6; i++) hf[i * 6 + i] += damp * 1.0;
+  inverse6(hf, inv);
+  for (int r = 0; r < 6; r++)
+  {
+    double acc = 0.0;
+    for (int k = 0; k < 6; k++) acc += (-inv[k * 6 + r]) * gf[k];
+    xi[r] = acc;
+  }
+  float X[16], N[16];
+  xi_to_transform(xi, center, X);
+  for (int c = 0; c < 4; c++)
+    for (int r = 0; r < 4; r++)
+    {
+      float acc = X[0 * 4 + r] * T[c * 4 + 0];
+      acc = acc + X[1 * 4 + r] * T[c * 4 + 1];
+      acc = acc + X[2 * 4 + r] * T[c * 4 + 2];
+      acc = acc + X[3 * 4 + r] * T[c * 4 + 3];
+      N[c * 4 + r] = acc;
+    }
+  for (int i = 0; i < 16; i++) T[i] = N[i];
+  if (xi_out) for (int i = 0; i < 6; i++) xi_out[i] = xi[i];
+  return (float)err / cnt;
+}
+
+void ws_host_solve(const i64 H[36], const i64 g[6], int err, int cnt, float alpha, float T[16], double xi_out[6])
+{
+  gn_solve(H, g, err, cnt, alpha, T, xi_out);
+}
+
+namespace {
+
+// expand the 21 upper-triangle sums (row-major, i <= j) into a column-major symmetric 6x6
+WS_HD void expand_h(const u64 sums[WS_NSUM], i64 H[36], i64 g[6])
+{
+  int k = 0;
+  for (int i = 0; i < 6; i++)
+    for (int j = i; j < 6; j++)
+    {
+      i64 v = (i64)sums[k++];
+      H[j * 6 + i] = v;
+      H[i * 6 + j] = v;
+    }
+  for (int i = 0; i < 6; i++) g[i] = (i64)sums[21 + i];
+}
+
+// H += J J^T (upper triangle), g += J v, err += |v|, cnt += 1   (registration.cpp:104-107)
+WS_D void accumulate_point(i64 sum[WS_NSUM], const i64 J[6], const int cv)
+{
+  int k = 0;
+#pragma unroll
+  for (int a = 0; a < 6; a++)
+#pragma unroll
+    for (int b = a; b < 6; b++) sum[k++] += J[a] * J[b];
+#pragma unroll
+  for (int a = 0; a < 6; a++) sum[21 + a] += J[a] * cv;
+  sum[27] += cv < 0 ? -cv : cv;
+  sum[28] += 1;
+}
+
+// warp-shuffle reduction of the 29 exact sums, one shared-memory atomic per warp, 29 global atomics per
+// block; returns true in the block that arrives last (its thread 0 may then read the complete sums)
+WS_D bool reduce_and_commit(const i64 sum[WS_NSUM], u64 *s_sum, bool *s_last, RegAccum *acc)
+{
+#pragma unroll
+  for (int i = 0; i < WS_NSUM; i++)
+  {
+    i64 v = sum[i];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(FULL, v, o);
+    if ((threadIdx.x & 31) == 0 && v != 0) atomicAdd(&s_sum[i], (u64)v);
+  }
+  __syncthreads();
+  if (threadIdx.x < WS_NSUM && s_sum[threadIdx.x] != 0ull) atomicAdd(&acc->sums[threadIdx.x], s_sum[threadIdx.x]);
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    const unsigned t = atomicAdd(&acc->ticket, 1u);
+    *s_last = (t == gridDim.x - 1);
+    __threadfence();
+  }
+  __syncthreads();
+  return *s_last;
+}
+
+// one thread: finish a Gauss-Newton iteration from the complete sums (registration.cpp:128-157)
+__device__ void finish_iteration(RegAccum *acc, u64 *trace, int trace_cap, float it_weight_gradient, float epsilon)
+{
+  u64 sums[WS_NSUM];
+  for (int i = 0; i < WS_NSUM; i++) sums[i] = ((volatile u64 *)acc->sums)[i];
+  const unsigned it = acc->iterations;
+  if (trace && (int)it < trace_cap)
+    for (int i = 0; i < WS_NSUM; i++) trace[(size_t)it * WS_NSUM + i] = sums[i];
+  i64 H[36], g[6];
+  expand_h(sums, H, g);
+  const int err = (int)(i64)sums[27];
+  const int cnt = (int)(i64)sums[28];
+  float T[16];
+  for (int i = 0; i < 16; i++) T[i] = acc->T[i];
+  const float e = gn_solve(H, g, err, cnt, acc->alpha, T, nullptr);
+  for (int i = 0; i < 16; i++) acc->T[i] = T[i];
+  acc->alpha += it_weight_gradient;                                                    // :141
+  if (fabs(e - acc->prev_err[2]) < epsilon && fabs(e - acc->prev_err[0]) < epsilon)    // :146-150
+    acc->finished = 1u;
+  acc->prev_err[0] = acc->prev_err[1];                                                 // :151-155
+  acc->prev_err[1] = acc->prev_err[2];
+  acc->prev_err[2] = acc->prev_err[3];
+  acc->prev_err[3] = e;
+  acc->iterations = it + 1;
+  for (int i = 0; i < WS_NSUM; i++) acc->sums[i] = 0ull;
+}
+
+__global__ void __launch_bounds__(256, 2)
+reg_accum_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const int n, const FastDiv div_res,
+                 RegAccum *__restrict__ acc, u64 *__restrict__ trace, const int trace_cap,
+                 const int fused_solve, const float it_weight_gradient, const float epsilon)
+{
+  if (acc->finished) return;
+
+  __shared__ u64 s_sum[WS_NSUM];
+  __shared__ bool s_last;
+  if (threadIdx.x < WS_NSUM) s_sum[threadIdx.x] = 0ull;
+  __syncthreads();
+
+  float T[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) T[i] = acc->T[i];
+  int M[16];
+  to_int_mat(T, M);                                                                    // :54
+  const int cx = (int)T[12], cy = (int)T[13], cz = (int)T[14];                         // :52
+
+  i64 sum[WS_NSUM];
+#pragma unroll
+  for (int i = 0; i < WS_NSUM; i++) sum[i] = 0;
+
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+  {
+    const ws_pt p = pts[j];
+    int q[3];
+    transform_point(M, p.x, p.y, p.z, q);                                              // :63
+    const int bx = fd_sdiv(q[0], div_res), by = fd_sdiv(q[1], div_res), bz = fd_sdiv(q[2], div_res);  // :65
+    const int px = wsub(q[0], cx), py = wsub(q[1], cy), pz = wsub(q[2], cz);           // :66
+
+    // centre and all six face neighbours must be inside the map (:68-81 throw otherwise)
+    int dx = bx - g.pos[0], dy = by - g.pos[1], dz = bz - g.pos[2];
+    dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy; dz = dz < 0 ? -dz : dz;
+    if (dx > g.half[0] || dy > g.half[1] || dz > g.half[2]) continue;
+    const int rx = ring_coord(bx, g.pos[0], g.offset[0], g.size[0]);
+    if (rx < g.own_lo || rx >= g.own_hi) continue;       // another rank sums this point
+    const int ry = ring_coord(by, g.pos[1], g.offset[1], g.size[1]);
+    const int rz = ring_coord(bz, g.pos[2], g.offset[2], g.size[2]);
+    const uint32_t cur = g.grid[brick_of(g, rx, ry, rz) * WS_BRICK_VOX + brick_local(rx, ry, rz)];
+    if (entry_weight(cur) == 0) continue;                                              // :71-74
+    if (dx > g.half[0] - 1 || dy > g.half[1] - 1 || dz > g.half[2] - 1) continue;
+
+    const int rxn = rx + 1 == g.size[0] ? 0 : rx + 1, rxl = rx == 0 ? g.size[0] - 1 : rx - 1;
+    const int ryn = ry + 1 == g.size[1] ? 0 : ry + 1, ryl = ry == 0 ? g.size[1] - 1 : ry - 1;
+    const int rzn = rz + 1 == g.size[2] ? 0 : rz + 1, rzl = rz == 0 ? g.size[2] - 1 : rz - 1;
+    const uint32_t xn = g.grid[brick_of(g, rxn, ry, rz) * WS_BRICK_VOX + brick_local(rxn, ry, rz)];
+    const uint32_t xl = g.grid[brick_of(g, rxl, ry, rz) * WS_BRICK_VOX + brick_local(rxl, ry, rz)];
+    const uint32_t yn = g.grid[brick_of(g, rx, ryn, rz) * WS_BRICK_VOX + brick_local(rx, ryn, rz)];
+    const uint32_t yl = g.grid[brick_of(g, rx, ryl, rz) * WS_BRICK_VOX + brick_local(rx, ryl, rz)];
+    const uint32_t zn = g.grid[brick_of(g, rx, ry, rzn) * WS_BRICK_VOX + brick_local(rx, ry, rzn)];
+    const uint32_t zl = g.grid[brick_of(g, rx, ry, rzl) * WS_BRICK_VOX + brick_local(rx, ry, rzl)];
+
+    int gr[3] = { 0, 0, 0 };                                                           // :83-96
+    {
+      int v1 = entry_value(xn), v0 = entry_value(xl);
+      if (entry_weight(xn) != 0 && entry_weight(xl) != 0 && !((v1 > 0 && v0 < 0) || (v1 < 0 && v0 > 0))) gr[0] = (v1 - v0) / 2;
+      v1 = entry_value(yn); v0 = entry_value(yl);
+      if (entry_weight(yn) != 0 && entry_weight(yl) != 0 && !((v1 > 0 && v0 < 0) || (v1 < 0 && v0 > 0))) gr[1] = (v1 - v0) / 2;
+      v1 = entry_value(zn); v0 = entry_value(zl);
+      if (entry_weight(zn) != 0 && entry_weight(zl) != 0 && !((v1 > 0 && v0 < 0) || (v1 < 0 && v0 > 0))) gr[2] = (v1 - v0) / 2;
+    }
+    i64 J[6];                                                                          // :98 (cross in int32)
+    J[0] = wsub(wmul(py, gr[2]), wmul(pz, gr[1]));
+    J[1] = wsub(wmul(pz, gr[0]), wmul(px, gr[2]));
+    J[2] = wsub(wmul(px, gr[1]), wmul(py, gr[0]));
+    J[3] = gr[0]; J[4] = gr[1]; J[5] = gr[2];
+    accumulate_point(sum, J, entry_value(cur));
+  }
+
+  const bool last = reduce_and_commit(sum, s_sum, &s_last, acc);
+  if (last && threadIdx.x == 0)
+  {
+    acc->ticket = 0u;
+    if (fused_solve) finish_iteration(acc, trace, trace_cap, it_weight_gradient, epsilon);
+  }
+}
+
+// test/cuda.cpp:416-532 shape: reduce caller-supplied Jacobians/values through the same code path
+__global__ void __launch_bounds__(256)
+test_reduce_kernel(const i64 *__restrict__ jac, const int *__restrict__ values, const int n, RegAccum *__restrict__ acc)
+{
+  __shared__ u64 s_sum[WS_NSUM];
+  __shared__ bool s_last;
+  if (threadIdx.x < WS_NSUM) s_sum[threadIdx.x] = 0ull;
+  __syncthreads();
+  i64 sum[WS_NSUM];
+#pragma unroll
+  for (int i = 0; i < WS_NSUM; i++) sum[i] = 0;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+  {
+    i64 J[6];
+    for (int a = 0; a < 6; a++) J[a] = jac[(size_t)j * 6 + a];
+    accumulate_point(sum, J, values[j]);
+  }
+  const bool last = reduce_and_commit(sum, s_sum, &s_last, acc);
+  if (last && threadIdx.x == 0) acc->ticket = 0u;
+}
+
+__global__ void reg_solve_kernel(RegAccum *acc, u64 *trace, int trace_cap, float it_weight_gradient, float epsilon)
+{
+  if (acc->finished) return;
+  finish_iteration(acc, trace, trace_cap, it_weight_gradient, epsilon);
+}
+
+__global__ void reg_reset_kernel(RegAccum *acc, const float *T, float alpha0)
+{
+  const int t = threadIdx.x;
+  if (t < 32) acc->sums[t] = 0ull;
+  if (t < 16) acc->T[t] = T[t];
+  if (t < 4) acc->prev_err[t] = 0.f;
+  if (t == 0) { acc->ticket = 0u; acc->finished = 0u; acc->iterations = 0u; acc->alpha = alpha0; }
+}
+
+// registration.cpp:164-174 : apply the final transform to the cloud in place
+__global__ void __launch_bounds__(256)
+transform_cloud_kernel(ws_pt *pts, int n, const RegAccum *acc)
+{
+  float T[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) T[i] = acc->T[i];
+  int M[16];
+  to_int_mat(T, M);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+  {
+    const ws_pt p = pts[j];
+    int q[3];
+    transform_point(M, p.x, p.y, p.z, q);
+    ws_pt o; o.x = q[0]; o.y = q[1]; o.z = q[2];
+    pts[j] = o;
+  }
+}
+
+}  // namespace
+
+void ws_launch_reg_reset(ws_handle *h, const float T[16], float alpha0)
+{
+  // T is staged through the pinned mirror so the copy is asynchronous on the handle's stream
+  std::memcpy(h->h_acc->T, T, 16 * sizeof(float));
+  float *d_T_stage = reinterpret_cast<float *>(reinterpret_cast<char *>(h->d_acc) + sizeof(RegAccum));
+  WS_CUDA_OK(cudaMemcpyAsync(d_T_stage, h->h_acc->T, 16 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  reg_reset_kernel<<<1, 32, 0, h->stream>>>(h->d_acc, d_T_stage, alpha0);
+}
+
+void ws_launch_reg_iteration(ws_handle *h, int n, int res, int fused_solve, float it_weight_gradient, float epsilon)
+{
+  int blocks = (n + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  ws_timer_begin(h, WS_TIMER_REG);
+  reg_accum_kernel<<<blocks, 256, 0, h->stream>>>(h->g, h->d_reg_points, n, make_fastdiv((unsigned)res), h->d_acc,
+                                                  h->d_trace, h->trace_cap, fused_solve, it_weight_gradient, epsilon);
+  ws_timer_end(h);
+}
+
+void ws_launch_reg_solve(ws_handle *h, float it_weight_gradient, float epsilon)
+{
+  reg_solve_kernel<<<1, 1, 0, h->stream>>>(h->d_acc, h->d_trace, h->trace_cap, it_weight_gradient, epsilon);
+}
+
+void ws_launch_test_reduce(ws_handle *h, const i64 *d_jacobis, const int *d_values, int n)
+{
+  int blocks = (n + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  test_reduce_kernel<<<blocks, 256, 0, h->stream>>>(d_jacobis, d_values, n, h->d_acc);
+}
+
+void ws_launch_transform_cloud(ws_handle *h, ws_pt *d_pts, int n)
+{
+  if (n <= 0) return;
+  transform_cloud_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(d_pts, n, h->d_acc);
+}

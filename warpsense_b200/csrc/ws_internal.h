@@ -1,0 +1,132 @@
+// ws_internal.h -- host-side state of one map handle and the launcher prototypes (not part of the ABI).
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "ws_common.cuh"
+
+struct UpdateParams
+{
+  int tau, max_weight, res, weight_epsilon, dz_per_distance;
+  int pos_mm[3];       // scanner_pos * map_resolution (update_tsdf.cpp:410)
+  i64 up[3];
+  FastDiv div_res;     // / map_resolution
+  FastDiv div_weps;    // / (tau - weight_epsilon)
+  int half_res;        // map_resolution / 2
+  int n_points;
+  int far_only;        // rounds >= 2: start each ray where interpolated candidates can first occur
+  int far_len;         // first march length worth visiting when far_only
+};
+
+// device-side work counters / status of one update (kept in one small device buffer)
+struct UpdateCounters
+{
+  unsigned long long n_candidates;
+  unsigned long long n_touched;
+  unsigned long long n_written;
+  unsigned n_touched_bricks;
+  unsigned n_pending;        // voxels whose winner is an interpolated candidate below tau
+  unsigned n_pending_next;
+  unsigned pending_overflow;
+  unsigned error;            // bit 0: seq field overflow (too many march/fan steps)
+  unsigned rounds;
+  unsigned n_parked;         // voxels parked by the merge pass (before any replay round)
+};
+
+struct RegAccum           // 29 exact sums + bookkeeping, device resident
+{
+  u64 sums[32];            // [0..20] H upper triangle row-major, [21..26] g, [27] err, [28] cnt
+  unsigned ticket;
+  unsigned finished;
+  unsigned iterations;
+  float alpha;
+  float prev_err[4];
+  float T[16];             // current total transform, column-major
+};
+
+struct WsTimer
+{
+  cudaEvent_t start, stop;
+};
+
+struct ws_handle
+{
+  int device = 0;
+  int tau = 0, max_weight = 0, res = 0;
+  int rank = 0, world = 1;
+  GridDesc g{};
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+
+  // scan points
+  ws_pt *d_points = nullptr;      // update_tsdf staging
+  size_t points_cap = 0;
+  ws_pt *d_reg_points = nullptr;  // registration cloud
+  size_t reg_points_cap = 0;
+  int reg_n = 0;
+
+  // update scratch
+  unsigned *d_brick_list = nullptr;     // touched resident brick ids
+  UpdateCounters *d_counters = nullptr;
+  UpdateCounters *h_counters = nullptr; // pinned
+  // pending (interpolated winner) resolution
+  unsigned pending_cap = 0;
+  u64 *d_pend_addr = nullptr;           // voxel address of each pending slot
+  u64 *d_pend_prev = nullptr;           // key of the current (interpolated) winner
+  u64 *d_pend_key = nullptr;            // atomicMin target of the next round
+  unsigned *d_pend_list[2] = {nullptr, nullptr};
+
+  // registration
+  RegAccum *d_acc = nullptr;
+  u64 *d_trace = nullptr;               // [max_trace][29]
+  int trace_cap = 0;
+  RegAccum *h_acc = nullptr;            // pinned
+
+  // timing of the dominant kernels (cudaEvents on `stream`)
+  bool profile = false;
+  std::vector<WsTimer> timers;
+  std::vector<int> timer_kind;
+  size_t timers_used = 0;
+
+  UpdateCounters last_counters{};
+  int64_t last_n_points = 0;
+  std::string last_error;
+  int sm_count = 148;
+
+  // registration trace of the last ws_register_cloud when the host solved (device mode: d_trace)
+  std::vector<i64> host_trace;
+  int last_reg_iterations = 0;
+  bool last_reg_host = false;
+
+  // in-memory global chunk store (src/map/hdf5_global_map.cpp): 64^3 raw entries per chunk
+  std::unordered_map<u64, std::vector<uint32_t>> store;
+  uint32_t default_entry = 0;
+};
+
+// update_tsdf.cu
+void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3]);
+// registration.cu
+void ws_launch_reg_reset(ws_handle *h, const float T[16], float alpha0);
+void ws_launch_reg_iteration(ws_handle *h, int n, int res, int fused_solve, float it_weight_gradient, float epsilon);
+void ws_launch_reg_solve(ws_handle *h, float it_weight_gradient, float epsilon);
+void ws_launch_transform_cloud(ws_handle *h, ws_pt *d_pts, int n);
+void ws_host_solve(const i64 H[36], const i64 g[6], int err, int cnt, float alpha, float T[16], double xi_out[6]);
+// map_ops.cu
+void ws_launch_fill(ws_handle *h, uint32_t entry);
+void ws_launch_upload(ws_handle *h, const uint32_t *d_linear);
+void ws_launch_download(ws_handle *h, uint32_t *d_linear);
+void ws_box_transfer(ws_handle *h, uint32_t *d_buf, const int lo[3], const int ext[3], bool pack);
+void ws_launch_test_reduce(ws_handle *h, const i64 *d_jacobis, const int *d_values, int n);
+
+#define WS_TIMER_MARCH 0
+#define WS_TIMER_MERGE 1
+#define WS_TIMER_REG 2
+void ws_timer_begin(ws_handle *h, int kind);
+void ws_timer_end(ws_handle *h);
+
+#define WS_CUDA_OK(expr)                                                                            \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess) throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
