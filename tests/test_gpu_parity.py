@@ -11,7 +11,7 @@ import pytest
 from helpers import assert_same_grid, device_grid, make_pair, random_cloud
 from oracle import oracle as orc
 from warpsense_b200 import api, fixedpoint as fp, lib
-from warpsense_b200.synth import ScanStream
+from warpsense_b200.synth import ScanStream, frame_pose
 
 pytestmark = pytest.mark.gpu
 
@@ -75,7 +75,7 @@ def test_g4_transform_point_device():
         assert np.array_equal(out, T)
     rng = np.random.default_rng(5)
     cloud = random_cloud(rng, 5000, -30000, 30000)
-    T = ScanStream(8, 8, 64, 100).pose(37)
+    T = frame_pose(37)
     want = orc.transform_points(cloud, orc.to_int_mat(T))
     reg.register_cloud(cloud, T, 0, 0.1, 0.0, 64)
     assert np.array_equal(cloud, want)
