@@ -123,6 +123,8 @@ int ws_get_update_counters(const ws_handle *h, ws_update_counters *out);
  *                 `cloud` may be NULL to register the points given to ws_reg_prepare and leave the
  *                 transformed cloud on the device (ws_reg_points_device). */
 int ws_reg_prepare(ws_handle *h, const ws_point *points, int64_t n);
+/* same, the cloud already being in device memory (device-to-device copy on the handle's stream) */
+int ws_reg_prepare_device(ws_handle *h, const ws_point *device_points, int64_t n);
 int ws_reg_step(ws_handle *h, const float T[16], int32_t map_resolution,
                 int64_t H[36], int64_t g[6], int32_t *err, int32_t *cnt);
 int ws_register_cloud(ws_handle *h, ws_point *cloud, int64_t n, const float pretransform[16],
@@ -165,6 +167,9 @@ int ws_profile_enable(ws_handle *h, int32_t on);
 int ws_profile_reset(ws_handle *h);
 /* sum of elapsed ms and launch count per kind since the last reset (synchronises the stream) */
 int ws_profile_get(ws_handle *h, int32_t kind, double *total_ms, int64_t *launches);
+
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t ws_launch_count(const ws_handle *h);
 
 const char *ws_version(void);
 

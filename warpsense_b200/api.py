@@ -273,6 +273,12 @@ class TSDFCuda:
     def sync(self):
         self._hd.check(self._hd.L.ws_sync(self._hd.h))
 
+    def set_stream(self, cuda_stream):
+        self._hd.check(self._hd.L.ws_set_stream(self._hd.h, C.c_void_p(int(cuda_stream) if cuda_stream else None)))
+
+    def launch_count(self):
+        return int(self._hd.L.ws_launch_count(self._hd.h))
+
     def profile(self, on=True):
         self._hd.check(self._hd.L.ws_profile_enable(self._hd.h, 1 if on else 0))
 
@@ -301,6 +307,11 @@ class RegistrationCuda:
         hd = self._hd
         hd.check(hd.L.ws_reg_prepare(hd.h, p.ctypes.data, len(p)))
         self.curr_n_points = len(p)
+
+    def prepare_registration_device(self, device_ptr, n):
+        hd = self._hd
+        hd.check(hd.L.ws_reg_prepare_device(hd.h, C.c_void_p(int(device_ptr)), int(n)))
+        self.curr_n_points = int(n)
 
     def perform_registration(self, pretransform, map_resolution):
         """registration.cu:347-368 -> (H 6x6 int64, g int64[6], e, c) for transform `pretransform`."""

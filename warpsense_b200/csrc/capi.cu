@@ -499,6 +499,19 @@ int ws_reg_prepare(ws_handle *h, const ws_point *points, int64_t n)
   });
 }
 
+int ws_reg_prepare_device(ws_handle *h, const ws_point *device_points, int64_t n)
+{
+  return guarded(h, [&]() {
+    if (n < 0 || (n > 0 && !device_points)) throw std::invalid_argument("ws_reg_prepare_device: bad argument");
+    if (n > WS_MAX_POINTS) throw std::length_error("ws_reg_prepare_device: too many points");
+    ensure_points(&h->d_reg_points, &h->reg_points_cap, (size_t)n);
+    if (n > 0)
+      WS_CUDA_OK(cudaMemcpyAsync(h->d_reg_points, device_points, (size_t)n * sizeof(ws_pt), cudaMemcpyDeviceToDevice, h->stream));
+    h->reg_n = (int)n;
+    return WS_OK;
+  });
+}
+
 int ws_reg_step(ws_handle *h, const float T[16], int32_t map_resolution, int64_t H[36], int64_t g[6], int32_t *err, int32_t *cnt)
 {
   return guarded(h, [&]() {
@@ -745,6 +758,8 @@ int ws_store_get_chunk(const ws_handle *h, int32_t cx, int32_t cy, int32_t cz, u
   std::memcpy(out, it->second.data(), it->second.size() * sizeof(uint32_t));
   return WS_OK;
 }
+
+int64_t ws_launch_count(const ws_handle *h) { return h ? h->launches : 0; }
 
 int ws_profile_enable(ws_handle *h, int32_t on)
 {

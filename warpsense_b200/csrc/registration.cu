@@ -371,6 +371,7 @@ void ws_launch_reg_reset(ws_handle *h, const float T[16], float alpha0)
   float *d_T_stage = reinterpret_cast<float *>(reinterpret_cast<char *>(h->d_acc) + sizeof(RegAccum));
   WS_CUDA_OK(cudaMemcpyAsync(d_T_stage, h->h_acc->T, 16 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   reg_reset_kernel<<<1, 32, 0, h->stream>>>(h->d_acc, d_T_stage, alpha0);
+  h->launches++;
 }
 
 void ws_launch_reg_iteration(ws_handle *h, int n, int res, int fused_solve, float it_weight_gradient, float epsilon)
@@ -381,11 +382,13 @@ void ws_launch_reg_iteration(ws_handle *h, int n, int res, int fused_solve, floa
   reg_accum_kernel<<<blocks, 256, 0, h->stream>>>(h->g, h->d_reg_points, n, make_fastdiv((unsigned)res), h->d_acc,
                                                   h->d_trace, h->trace_cap, fused_solve, it_weight_gradient, epsilon);
   ws_timer_end(h);
+  h->launches++;
 }
 
 void ws_launch_reg_solve(ws_handle *h, float it_weight_gradient, float epsilon)
 {
   reg_solve_kernel<<<1, 1, 0, h->stream>>>(h->d_acc, h->d_trace, h->trace_cap, it_weight_gradient, epsilon);
+  h->launches++;
 }
 
 void ws_launch_test_reduce(ws_handle *h, const i64 *d_jacobis, const int *d_values, int n)
@@ -393,10 +396,12 @@ void ws_launch_test_reduce(ws_handle *h, const i64 *d_jacobis, const int *d_valu
   int blocks = (n + 255) / 256;
   if (blocks < 1) blocks = 1;
   test_reduce_kernel<<<blocks, 256, 0, h->stream>>>(d_jacobis, d_values, n, h->d_acc);
+  h->launches++;
 }
 
 void ws_launch_transform_cloud(ws_handle *h, ws_pt *d_pts, int n)
 {
   if (n <= 0) return;
   transform_cloud_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(d_pts, n, h->d_acc);
+  h->launches++;
 }

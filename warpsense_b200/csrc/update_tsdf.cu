@@ -395,8 +395,8 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
     ws_timer_begin(h, WS_TIMER_MARCH);
     march_kernel<true><<<blocks, 256, 0, s>>>(h->g, P, d_pts, h->d_brick_list, h->d_counters, nullptr, nullptr);
     ws_timer_end(h);
-    int dev_sms = 148;
-    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device);
+    h->launches += 2;
+    const int dev_sms = h->sm_count;
     ws_timer_begin(h, WS_TIMER_MERGE);
     merge_kernel<<<dev_sms * 8, 256, 0, s>>>(h->g, P, h->d_brick_list, h->d_counters, h->pending_cap,
                                             h->d_pend_addr, h->d_pend_prev, h->d_pend_key);
@@ -412,6 +412,7 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
       resolve_kernel<<<dev_sms * 4, 256, 0, s>>>(h->g, P2, h->d_counters, h->pending_cap,
                                                  h->d_pend_addr, h->d_pend_prev, h->d_pend_key);
       round_advance_kernel<<<1, 1, 0, s>>>(h->d_counters);
+      h->launches += 3;
     }
     WS_CUDA_OK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
     WS_CUDA_OK(cudaStreamSynchronize(s));
@@ -425,6 +426,7 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
       resolve_kernel<<<dev_sms * 4, 256, 0, s>>>(h->g, P2, h->d_counters, h->pending_cap,
                                                  h->d_pend_addr, h->d_pend_prev, h->d_pend_key);
       round_advance_kernel<<<1, 1, 0, s>>>(h->d_counters);
+      h->launches += 3;
       WS_CUDA_OK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
       WS_CUDA_OK(cudaStreamSynchronize(s));
     }

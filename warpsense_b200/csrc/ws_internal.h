@@ -93,6 +93,7 @@ struct ws_handle
   int64_t last_n_points = 0;
   std::string last_error;
   int sm_count = 148;
+  int64_t launches = 0;   // kernels launched by this handle
 
   // registration trace of the last ws_register_cloud when the host solved (device mode: d_trace)
   std::vector<i64> host_trace;

@@ -65,6 +65,7 @@ def _signatures():
         "ws_update_tsdf_device": (C.c_int, [hp, vp, C.c_int64, i32p, i32p]),
         "ws_get_update_counters": (C.c_int, [hp, C.POINTER(UpdateCounters)]),
         "ws_reg_prepare": (C.c_int, [hp, vp, C.c_int64]),
+        "ws_reg_prepare_device": (C.c_int, [hp, vp, C.c_int64]),
         "ws_reg_step": (C.c_int, [hp, f32p, C.c_int32, i64p, i64p, i32p, i32p]),
         "ws_register_cloud": (C.c_int, [hp, vp, C.c_int64, f32p, C.c_int32, C.c_float, C.c_float,
                                         C.c_int32, C.c_int32, f32p, i32p]),
@@ -81,6 +82,7 @@ def _signatures():
         "ws_store_num_chunks": (C.c_int64, [hp]),
         "ws_store_chunk_list": (C.c_int, [hp, i32p, C.c_int64]),
         "ws_store_get_chunk": (C.c_int, [hp, C.c_int32, C.c_int32, C.c_int32, u32p]),
+        "ws_launch_count": (C.c_int64, [hp]),
         "ws_profile_enable": (C.c_int, [hp, C.c_int32]),
         "ws_profile_reset": (C.c_int, [hp]),
         "ws_profile_get": (C.c_int, [hp, C.c_int32, C.POINTER(C.c_double), i64p]),
