@@ -326,7 +326,8 @@ def run_native(args):
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 ms = float(t.item())
             kern = {name: tsdf.profile_get(kind) for name, kind in
-                    (("march", lib.TIMER_MARCH), ("merge", lib.TIMER_MERGE), ("reg", lib.TIMER_REG))}
+                    (("march", lib.TIMER_MARCH), ("merge", lib.TIMER_MERGE), ("reg", lib.TIMER_REG),
+                     ("replay", lib.TIMER_REPLAY))}
             tsdf.profile(False)
             return ms, clocks, kern, tsdf.launch_count() - launches0, last
 
@@ -344,9 +345,10 @@ def run_native(args):
         march_ms = kern["march"][0] / max(1, K)
         merge_ms = kern["merge"][0] / max(1, K)
         reg_ms = kern["reg"][0] / max(1, K)
+        replay_ms = kern["replay"][0] / max(1, K)
         upd_bytes = 12 * N + 8 * T_vox
         peak, peak_src = peaks()
-        upd_ms = march_ms + merge_ms
+        upd_ms = march_ms + merge_ms + replay_ms
         achieved = upd_bytes / (upd_ms / 1000.0) / 1e9 if upd_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -360,12 +362,12 @@ def run_native(args):
                             "update_tsdf -> counters D2H"},
             "gpu_launches": launches,
             "roofline": {
-                "bound": "hbm", "kernel": "update_tsdf = march_kernel<true> + merge_kernel (per scan)",
+                "bound": "hbm", "kernel": "update_tsdf = march_kernel + brick_list/merge_kernel + replay_kernel (per scan)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                 "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_scan": upd_bytes,
                 "formula": "12*N + 8*T (SURVEY.md 8d), N=%d points, T=%d touched voxels, C=%d candidates" % (N, T_vox, C_cand),
-                "kernel_ms_per_scan": {"march": march_ms, "merge": merge_ms, "reg_20_iterations": reg_ms,
+                "kernel_ms_per_scan": {"march": march_ms, "merge": merge_ms, "replay": replay_ms, "reg_20_iterations": reg_ms,
                                        "step_total": ms_dev / K},
                 "reg_bytes_per_scan": None,
             },

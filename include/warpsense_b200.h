@@ -162,7 +162,8 @@ int ws_store_chunk_list(const ws_handle *h, int32_t *xyz, int64_t cap);
 int ws_store_get_chunk(const ws_handle *h, int32_t cx, int32_t cy, int32_t cz, uint32_t *out);
 
 /* ---- timing -------------------------------------------------------------------------------- */
-/* record cudaEvents around the hot kernels on the handle's stream (kind: 0 march, 1 merge, 2 reg) */
+/* record cudaEvents around the hot kernels on the handle's stream (kind: 0 march, 1 brick list + merge, 2 registration
+ * iteration, 3 replay) */
 int ws_profile_enable(ws_handle *h, int32_t on);
 int ws_profile_reset(ws_handle *h);
 /* sum of elapsed ms and launch count per kind since the last reset (synchronises the stream) */

@@ -50,6 +50,8 @@ void free_handle(ws_handle *h)
   cudaFree(h->d_points); cudaFree(h->d_reg_points); cudaFree(h->d_brick_list);
   cudaFree(h->d_counters); cudaFreeHost(h->h_counters);
   cudaFree(h->d_pend_addr); cudaFree(h->d_pend_prev); cudaFree(h->d_pend_key);
+  cudaFree(h->d_active[0]); cudaFree(h->d_active[1]);
+  cudaFree(h->d_rec); cudaFree(h->d_list); cudaFree(h->d_chunk_fill);
   cudaFree(h->d_acc); cudaFree(h->d_trace); cudaFreeHost(h->h_acc);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -124,7 +126,7 @@ int create_impl(const int32_t size[3], int tau, int max_weight, int res, int dev
     WS_CUDA_OK(cudaMalloc(&h->d_counters, sizeof(UpdateCounters)));
     WS_CUDA_OK(cudaMallocHost(&h->h_counters, sizeof(UpdateCounters)));
     std::memset(h->h_counters, 0, sizeof(UpdateCounters));
-    size_t pcap = 8u << 20;
+    size_t pcap = 16u << 20;
     if (const char *env = std::getenv("WS_PENDING_CAP")) pcap = (size_t)std::strtoull(env, nullptr, 10);
     pcap = std::min(pcap, n_vox);
     pcap = std::max<size_t>(pcap, 1);
@@ -132,6 +134,16 @@ int create_impl(const int32_t size[3], int tau, int max_weight, int res, int dev
     WS_CUDA_OK(cudaMalloc(&h->d_pend_addr, pcap * sizeof(u64)));
     WS_CUDA_OK(cudaMalloc(&h->d_pend_prev, pcap * sizeof(u64)));
     WS_CUDA_OK(cudaMalloc(&h->d_pend_key, pcap * sizeof(u64)));
+    WS_CUDA_OK(cudaMalloc(&h->d_active[0], pcap * sizeof(unsigned)));
+    WS_CUDA_OK(cudaMalloc(&h->d_active[1], pcap * sizeof(unsigned)));
+    // far-field candidate record: starts at WS_RECORD_CAP records (default: half a record per voxel, between
+    // 1 Mi and 32 Mi; 16 bytes each, and as much again for the replay list) and grows on demand up to
+    // WS_RECORD_MAX records (default 2 Gi)
+    size_t rcap = std::min<size_t>(32u << 20, std::max<size_t>(1u << 20, n_vox / 2)), rmax = (size_t)2 << 30;
+    if (const char *env = std::getenv("WS_RECORD_CAP")) rcap = (size_t)std::strtoull(env, nullptr, 10);
+    if (const char *env = std::getenv("WS_RECORD_MAX")) rmax = (size_t)std::strtoull(env, nullptr, 10);
+    rmax = std::max(rmax, rcap);
+    ws_update_alloc(h, std::max<size_t>(1, rcap / WS_REC_CHUNK), std::max<size_t>(1, rmax / WS_REC_CHUNK));
     WS_CUDA_OK(cudaMalloc(&h->d_acc, sizeof(RegAccum) + 16 * sizeof(float)));
     WS_CUDA_OK(cudaMemsetAsync(h->d_acc, 0, sizeof(RegAccum) + 16 * sizeof(float), h->stream));
     WS_CUDA_OK(cudaMallocHost(&h->h_acc, sizeof(RegAccum)));

@@ -4,23 +4,41 @@
 // /root/reference) with kernels whose RESULT equals the reference's CPU path
 // (src/cpu/update_tsdf.cpp:397-564), which is the parity target.
 //
-// Pipeline per scan (all on one stream, no host round trip in the common case):
-//   1. march_kernel<true>   one warp per ray, lanes stride over the res/2 march steps; every candidate
-//                           (voxel, value, real|interpolated, order) becomes ONE 64-bit atomicMin on the
-//                           voxel's key -- see ws_common.cuh / DESIGN.md for why min over
-//                           (|value|, interpolated, order) reproduces the sequential rule at :508-512;
-//                           first touch of a brick appends it to the touched-brick list.
-//   2. merge_kernel         persistent blocks stream the touched bricks (4 KB keys + 2 KB entries each),
-//                           fold final winners into the grid (:542-560), reset the keys, and park the
-//                           rare voxels whose winner is an interpolated candidate below tau ("pending").
-//   3. march_kernel<false> + resolve_kernel, repeated while pending voxels remain: replay only the far
-//                           part of the rays against the pending voxels, restricted to candidates later
-//                           in the reference's order than the current winner.
+// Pipeline per scan (one stream, one host synchronisation at the end to fetch the work counters):
+//   1. march_kernel<true>   persistent warps, one ray per warp at a time (rays are fetched from a global
+//                           counter).  Lanes stride over the res/2 march steps; the steps that survive the
+//                           reference's "same (x,y) column as the previous step" filter (:455-458) are
+//                           compacted through a per-warp shared-memory queue so the expensive part (value,
+//                           weight, fan of interpolated voxels, addressing) runs with full lanes.  Every
+//                           candidate (voxel, value, real|interpolated, order) is ONE 64-bit atomicMin
+//                           (RED, no return) on the voxel's key -- see ws_common.cuh / DESIGN.md for why
+//                           min over (|value|, interpolated, order) reproduces the sequential rule at
+//                           :508-512 -- plus a plain store that flags the voxel's 8x8x8 brick.
+//                           Far-field candidates (the only ones that can meet an interpolated winner)
+//                           are also appended to a record list in 64-entry chunks owned by the warp.
+//   2. brick_list_kernel    touched-brick flags -> compact list (and flags reset for the next scan).
+//   3. merge_kernel         streams the touched bricks (4 KB keys + 2 KB entries each), folds final
+//                           winners into the grid (:542-560), resets the keys, and parks the voxels whose
+//                           winner is an interpolated candidate below tau ("pending").
+//   4. replay_kernel        cooperative (grid-synchronised).  Round 1 streams the record list once and
+//                           keeps, per pending voxel, the minimum key among the candidates that follow the
+//                           parked winner in the reference's order; those candidates are also compacted
+//                           into a short list that later rounds stream instead.  Rounds repeat on the
+//                           device until every pending voxel has its final winner.
+// If the record list overflows its buffer the host grows it and regenerates it with march_kernel<false>
+// (far part of every ray, no atomics) before running replay_kernel again.
+#include <cooperative_groups.h>
 #include <stdexcept>
 #include "ws_internal.h"
 
+namespace cg = cooperative_groups;
+
 #define FULL 0xFFFFFFFFu
 #define PEND_DONE 0xFFFFFFFFFFFFFFFFull
+#define MARCH_WARPS 8
+#define MARCH_THREADS (MARCH_WARPS * 32)
+#define QCAP 64
+#define RAY_BATCH 4
 
 namespace {
 
@@ -29,48 +47,59 @@ struct Ray
   int p[3];
   int d[3];
   int distance;
-  i64 iv[3];
+  int iv[3];
   FastDiv div_dist;
   int n_steps;
-  bool valid;
 };
 
-// per-ray setup: update_tsdf.cpp:420-446
-WS_D Ray ray_setup(const GridDesc &g, const UpdateParams &P, const ws_pt pt)
+// per-ray setup (update_tsdf.cpp:420-446), computed cooperatively: the two rounds of 64-bit divisions
+// (normalised direction + division magic, normalised interpolation vector) run once per warp with one
+// component per lane instead of seven times in every lane.  Warp-uniform result.
+WS_D bool ray_setup_warp(const GridDesc &g, const UpdateParams &P, const ws_pt pt, const int lane, Ray &r)
 {
-  Ray r;
-  r.valid = false;
-  r.n_steps = 0;
   r.p[0] = pt.x; r.p[1] = pt.y; r.p[2] = pt.z;
 #pragma unroll
-  for (int a = 0; a < 3; a++) r.d[a] = wsub(r.p[a], P.pos_mm[a]);                               // :422
-  int sq = wadd(wadd(wmul(r.d[0], r.d[0]), wmul(r.d[1], r.d[1])), wmul(r.d[2], r.d[2]));
-  if (sq <= 0) return r;             // distance == 0 (:424) or int32 norm overflow (out of contract)
+  for (int a = 0; a < 3; a++) r.d[a] = wsub(r.p[a], P.pos_mm[a]);                                // :422
+  const int sq = wadd(wadd(wmul(r.d[0], r.d[0]), wmul(r.d[1], r.d[1])), wmul(r.d[2], r.d[2]));
+  if (sq <= 0) return false;          // distance == 0 (:424) or int32 norm overflow (out of contract)
   r.distance = isqrt31(sq);                                                                      // :423
-  if (r.distance == 0) return r;
+  if (r.distance == 0) return false;
   if (!grid_in_bounds(g, fd_sdiv(r.p[0], P.div_res), fd_sdiv(r.p[1], P.div_res), fd_sdiv(r.p[2], P.div_res)))
-    return r;                                                                                    // :430-434
+    return false;                                                                                // :430-434
+
+  // lanes 0..2: |d[a]| * MR / distance (:438); lane 3: floor((2^64-1) / distance) for the division magic
+  const int dl = lane == 0 ? r.d[0] : (lane == 1 ? r.d[1] : r.d[2]);
+  const u64 adl = (u64)(dl < 0 ? 0u - (unsigned)dl : (unsigned)dl);
+  const u64 num1 = lane == 3 ? ~0ull : (adl << WS_MR_SHIFT);
+  const u64 q1 = num1 / (u64)(unsigned)r.distance;
+  const i64 nds = dl < 0 ? -(i64)q1 : (i64)q1;
   i64 nd[3], c1[3];
-#pragma unroll
-  for (int a = 0; a < 3; a++) nd[a] = ((i64)r.d[a] * WS_MR) / r.distance;                        // :438
+  nd[0] = __shfl_sync(FULL, nds, 0);
+  nd[1] = __shfl_sync(FULL, nds, 1);
+  nd[2] = __shfl_sync(FULL, nds, 2);
+  r.div_dist.d = (unsigned)r.distance;
+  r.div_dist.M = r.distance <= 1 ? 0ull : __shfl_sync(FULL, q1, 3) + 1ull;
+
   c1[0] = div_mr64(nd[1] * P.up[2] - nd[2] * P.up[1]);                                           // :439
   c1[1] = div_mr64(nd[2] * P.up[0] - nd[0] * P.up[2]);
   c1[2] = div_mr64(nd[0] * P.up[1] - nd[1] * P.up[0]);
-  i64 iv0 = nd[1] * c1[2] - nd[2] * c1[1];
-  i64 iv1 = nd[2] * c1[0] - nd[0] * c1[2];
-  i64 iv2 = nd[0] * c1[1] - nd[1] * c1[0];
-  i64 isq = (i64)((u64)iv0 * (u64)iv0 + (u64)iv1 * (u64)iv1 + (u64)iv2 * (u64)iv2);
-  i64 inorm = __double2ll_rz(sqrt(__ll2double_rn(isq)));                                         // :440 (FP64, like Eigen)
-  if (inorm <= 0) return r;                                                                      // :441-445
-  r.iv[0] = (iv0 * WS_MR) / inorm;                                                               // :446
-  r.iv[1] = (iv1 * WS_MR) / inorm;
-  r.iv[2] = (iv2 * WS_MR) / inorm;
-  r.div_dist.d = (unsigned)r.distance;
-  r.div_dist.M = r.distance <= 1 ? 0ull : (~0ull) / (unsigned)r.distance + 1ull;
+  const i64 iv0 = nd[1] * c1[2] - nd[2] * c1[1];
+  const i64 iv1 = nd[2] * c1[0] - nd[0] * c1[2];
+  const i64 iv2 = nd[0] * c1[1] - nd[1] * c1[0];
+  const i64 isq = (i64)((u64)iv0 * (u64)iv0 + (u64)iv1 * (u64)iv1 + (u64)iv2 * (u64)iv2);
+  const i64 inorm = __double2ll_rz(sqrt(__ll2double_rn(isq)));                                   // :440 (FP64, like Eigen)
+  if (inorm <= 0) return false;                                                                  // :441-445
+  // lanes 0..2: (iv[a] * MR) / inorm, truncating (:446)
+  const i64 il = lane == 0 ? iv0 : (lane == 1 ? iv1 : iv2);
+  const i64 num2 = il * WS_MR;
+  const u64 q2 = (u64)(num2 < 0 ? -num2 : num2) / (u64)inorm;
+  const i64 ivs = num2 < 0 ? -(i64)q2 : (i64)q2;
+  r.iv[0] = (int)__shfl_sync(FULL, ivs, 0);
+  r.iv[1] = (int)__shfl_sync(FULL, ivs, 1);
+  r.iv[2] = (int)__shfl_sync(FULL, ivs, 2);
   // len = 1, 1+h, ... <= distance + tau  (:450)
   r.n_steps = (r.distance + P.tau - 1) / P.half_res + 1;
-  r.valid = true;
-  return r;
+  return true;
 }
 
 WS_D void step_index(const UpdateParams &P, const Ray &r, int len, int proj[3], int idx[3])
@@ -83,28 +112,128 @@ WS_D void step_index(const UpdateParams &P, const Ray &r, int len, int proj[3], 
   }
 }
 
-template <bool FIRST>
-__global__ void __launch_bounds__(256)
-march_kernel(const GridDesc g, const UpdateParams P, const ws_pt *__restrict__ pts,
-             unsigned *__restrict__ brick_list, UpdateCounters *__restrict__ ctr,
-             const u64 *__restrict__ pend_prev, u64 *__restrict__ pend_key)
+// in-bounds voxel -> ring coordinate; t = v - pos + offset lies in (-size, 2*size)
+WS_D int ring_fast(int v, int base, int size)
 {
-  if (!FIRST && ctr->n_pending == 0) return;   // nothing parked: the replay round is a no-op
+  int t = v + base;
+  t += (t < 0) ? size : 0;
+  t -= (t >= size) ? size : 0;
+  return t;
+}
 
-  const int lane = threadIdx.x & 31;
-  const int ray_id = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  unsigned n_cand = 0;
-  unsigned err = 0;
+// Record writer.  The record is a sequence of 64-entry chunks with a fill count each.  A warp reserves
+// WS_REC_SPAN consecutive chunks at a time (one same-address atomic per 2048 records -- the allocation
+// counter is a single L2 word, and same-address atomics serialise), fills them in order, and on its way
+// out zeroes the fill counts of the chunks it reserved but did not use.
+struct RecWriter
+{
+  unsigned cur;        // chunk being filled
+  unsigned span_end;   // end of the span `cur` belongs to
+  unsigned next_span;  // next reserved span (valid in lane 0 once the atomic has returned)
+  int fill;            // entries in `cur`
+};
 
-  if (ray_id < P.n_points)
+WS_D void rec_init(RecWriter &w, UpdateCounters *ctr, int lane)
+{
+  unsigned b = 0;
+  if (lane == 0) b = atomicAdd(&ctr->n_chunks, 2u * WS_REC_SPAN);
+  b = __shfl_sync(FULL, b, 0);
+  w.cur = b; w.span_end = b + WS_REC_SPAN; w.next_span = b + WS_REC_SPAN; w.fill = 0;
+}
+
+// warp-collective append of one record per lane with want == true
+WS_D void rec_append(RecWriter &w, const bool want, const u64 key, const u64 addr, const int lane,
+                     Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill, const unsigned cap_chunks,
+                     UpdateCounters *__restrict__ ctr)
+{
+  const unsigned m = __ballot_sync(FULL, want);
+  if (m == 0u) return;
+  const int n = __popc(m);
+  const int slot = w.fill + __popc(m & ((1u << lane) - 1u));
+  // the chunk after `cur`: the next one of the span, or the first one of the next span
+  unsigned after = w.cur + 1u;
+  const bool span_done = after == w.span_end;
+  if (w.fill + n >= WS_REC_CHUNK && span_done) after = __shfl_sync(FULL, w.next_span, 0);
+  if (want)
   {
-    const ws_pt pt = pts[ray_id];
-    const Ray r = ray_setup(g, P, pt);
-    if (r.valid)
+    const unsigned chunk = slot < WS_REC_CHUNK ? w.cur : after;
+    if (chunk < cap_chunks)
     {
-      int start = 0;
-      if (!FIRST && P.far_only && P.far_len > 1) start = (P.far_len - 1) / P.half_res;
+      Rec e; e.key = key; e.ref = addr;
+      rec[(size_t)chunk * WS_REC_CHUNK + (unsigned)(slot & (WS_REC_CHUNK - 1))] = e;
+    }
+  }
+  w.fill += n;
+  if (w.fill >= WS_REC_CHUNK)
+  {
+    if (lane == 0)
+    {
+      if (w.cur < cap_chunks) chunk_fill[w.cur] = WS_REC_CHUNK;
+      else ctr->rec_overflow = 1u;
+    }
+    w.cur = after;
+    w.fill -= WS_REC_CHUNK;
+    if (span_done)
+    {
+      w.span_end = after + WS_REC_SPAN;
+      if (lane == 0) w.next_span = atomicAdd(&ctr->n_chunks, (unsigned)WS_REC_SPAN);   // consumed a span later
+    }
+  }
+}
+
+WS_D void rec_finish(RecWriter &w, const int lane, unsigned *__restrict__ chunk_fill, const unsigned cap_chunks,
+                     UpdateCounters *__restrict__ ctr)
+{
+  const unsigned next_span = __shfl_sync(FULL, w.next_span, 0);
+  if (lane == 0)
+  {
+    if (w.cur < cap_chunks) chunk_fill[w.cur] = (unsigned)w.fill;
+    else if (w.fill > 0) ctr->rec_overflow = 1u;
+  }
+  // unused remainder of the current span and the whole reserved next span
+  for (unsigned c = w.cur + 1u + (unsigned)lane; c < w.span_end; c += 32u)
+    if (c < cap_chunks) chunk_fill[c] = 0u;
+  for (unsigned c = next_span + (unsigned)lane; c < next_span + WS_REC_SPAN; c += 32u)
+    if (c < cap_chunks) chunk_fill[c] = 0u;
+}
+
+// ATOMIC: the scan's first pass (candidate keys + brick flags + record).  !ATOMIC: regenerate the record
+// only (far part of every ray), used when the record buffer had to grow.
+template <bool ATOMIC>
+__global__ void __launch_bounds__(MARCH_THREADS, 3)
+march_kernel(const GridDesc g, const UpdateParams P, const ws_pt *__restrict__ pts,
+             UpdateCounters *__restrict__ ctr, Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill,
+             const unsigned cap_chunks)
+{
+  __shared__ int4 s_q[MARCH_WARPS][QCAP][2];
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  int4 (*q)[2] = s_q[wib];
+  const unsigned lt = (1u << lane) - 1u;
+  const int total_warps = gridDim.x * MARCH_WARPS;
+
+  RecWriter rw;
+  rec_init(rw, ctr, lane);
+
+  unsigned long long n_cand = 0ull;
+  unsigned err = 0u;
+  const int base_x = g.offset[0] - g.pos[0], base_y = g.offset[1] - g.pos[1], base_z = g.offset[2] - g.pos[2];
+
+  // rays are fetched RAY_BATCH at a time (again: one same-address atomic per fetch); the next batch is
+  // requested when the current one starts and consumed when it is done
+  int batch = (blockIdx.x * MARCH_WARPS + wib) * RAY_BATCH;
+  unsigned nxt = 0;
+  for (int ray_id = batch; ray_id < P.n_points; )
+  {
+    if (ray_id == batch && lane == 0) nxt = atomicAdd(&ctr->ray_counter, (unsigned)RAY_BATCH);
+
+    Ray r;
+    const ws_pt pt = pts[ray_id];
+    if (ray_setup_warp(g, P, pt, lane, r))
+    {
       if (r.n_steps > (1 << WS_SEQ_MARCH_BITS)) err |= 1u;
+      int start = 0;
+      if (!ATOMIC && P.far_len > 1) start = (P.far_len - 1) / P.half_res;
 
       int carry_x = 0, carry_y = 0;
       if (start > 0 && start < r.n_steps)
@@ -114,114 +243,161 @@ march_kernel(const GridDesc g, const UpdateParams P, const ws_pt *__restrict__ p
         carry_x = ix[0]; carry_y = ix[1];
       }
 
-      for (int base = start; base < r.n_steps; base += 32)
+      int qn = 0, qh = 0;                     // queue fill / head (warp-uniform)
+      for (int base = start; base < r.n_steps || qn > 0; base += 32)
       {
-        const int i = base + lane;
+        if (base < r.n_steps)
+        {
+          const int i = base + lane;
+          const int len = 1 + i * P.half_res;
+          int proj[3], index[3];
+          step_index(P, r, len, proj, index);
+
+          int px = __shfl_up_sync(FULL, index[0], 1);
+          int py = __shfl_up_sync(FULL, index[1], 1);
+          if (lane == 0) { px = carry_x; py = carry_y; }
+          carry_x = __shfl_sync(FULL, index[0], 31);
+          carry_y = __shfl_sync(FULL, index[1], 31);
+
+          bool active = i < r.n_steps;
+          if (i > 0 && index[0] == px && index[1] == py) active = false;                         // :455-458
+          if (active && !grid_in_bounds(g, index[0], index[1], index[2])) active = false;        // :460-463
+          const unsigned m = __ballot_sync(FULL, active);
+          if (active)
+          {
+            const int pos = (qh + qn + __popc(m & lt)) & (QCAP - 1);
+            q[pos][0] = make_int4(proj[0], proj[1], proj[2], i);
+            q[pos][1] = make_int4(index[0], index[1], index[2], 0);
+          }
+          qn += __popc(m);
+          __syncwarp();
+          if (qn < 32 && base + 32 < r.n_steps) continue;     // keep filling
+        }
+        if (qn == 0) continue;
+
+        // ---- heavy part: up to 32 compacted march steps, one per lane ---------------------------
+        const int take = qn < 32 ? qn : 32;
+        bool have = lane < take;
+        const int4 qa = q[(qh + lane) & (QCAP - 1)][0];
+        const int4 qb = q[(qh + lane) & (QCAP - 1)][1];
+        __syncwarp();
+        qh = (qh + take) & (QCAP - 1);
+        qn -= take;
+
+        const int i = qa.w;
         const int len = 1 + i * P.half_res;
-        int proj[3], index[3];
-        step_index(P, r, len, proj, index);
-
-        int px = __shfl_up_sync(FULL, index[0], 1);
-        int py = __shfl_up_sync(FULL, index[1], 1);
-        if (lane == 0) { px = carry_x; py = carry_y; }
-        carry_x = __shfl_sync(FULL, index[0], 31);
-        carry_y = __shfl_sync(FULL, index[1], 31);
-
-        bool active = i < r.n_steps;
-        if (i > 0 && index[0] == px && index[1] == py) active = false;                           // :455-458
-        if (active && !grid_in_bounds(g, index[0], index[1], index[2])) active = false;          // :460-463
-        if (!active) continue;
-
         // distance of the hit to the centre of the marched voxel (:466-472)
-        int tcx = wadd(wmul(index[0], P.res), P.half_res);
-        int tcy = wadd(wmul(index[1], P.res), P.half_res);
-        int tcz = wadd(wmul(index[2], P.res), P.half_res);
-        int ex = wsub(r.p[0], tcx), ey = wsub(r.p[1], tcy), ez = wsub(r.p[2], tcz);
-        int vsq = wadd(wadd(wmul(ex, ex), wmul(ey, ey)), wmul(ez, ez));
+        const int tcx = wadd(wmul(qb.x, P.res), P.half_res);
+        const int tcy = wadd(wmul(qb.y, P.res), P.half_res);
+        const int tcz = wadd(wmul(qb.z, P.res), P.half_res);
+        const int ex = wsub(r.p[0], tcx), ey = wsub(r.p[1], tcy), ez = wsub(r.p[2], tcz);
+        const int vsq = wadd(wadd(wmul(ex, ex), wmul(ey, ey)), wmul(ez, ez));
         int value = vsq < 0 ? P.tau : isqrt31(vsq);
         value = value < P.tau ? value : P.tau;
         if (len > r.distance) value = -value;
 
         int weight = WS_WR;                                                                      // :475-479
         if (value < -P.weight_epsilon) weight = (int)fd_udiv((unsigned)(WS_WR * (P.tau + value)), P.div_weps);
-        if (weight == 0) continue;                                                               // :480-483
+        if (weight == 0) have = false;                                                           // :480-483
 
         const int delta_z = div_mr32(wmul(P.dz_per_distance, len));                              // :485
         const int iter_steps = fd_sdiv(delta_z * 2, P.div_res) + 1;                              // :486
         const int mid = fd_sdiv(delta_z, P.div_res);                                             // :487
-        int lowest[3];
-#pragma unroll
-        for (int a = 0; a < 3; a++) lowest[a] = wsub(proj[a], (int)div_mr64((i64)delta_z * r.iv[a]));   // :488
-        if (iter_steps > (1 << WS_SEQ_STEP_BITS)) err |= 1u;
+        const int low_x = wsub(qa.x, (int)div_mr64((i64)delta_z * r.iv[0]));                     // :488
+        const int low_y = wsub(qa.y, (int)div_mr64((i64)delta_z * r.iv[1]));
+        const int low_z = wsub(qa.z, (int)div_mr64((i64)delta_z * r.iv[2]));
+        if (have && iter_steps > (1 << WS_SEQ_STEP_BITS)) err |= 1u;
+        const bool far = len >= P.far_len;
+        const int max_steps = __reduce_max_sync(FULL, have ? iter_steps : 0);
+        unsigned last_brick = 0xFFFFFFFFu;
 
-        for (int step = 0; step < iter_steps; ++step)                                            // :491
+        for (int step = 0; step < max_steps; ++step)                                             // :491
         {
-          int v[3];
-          const i64 sr = (i64)wmul(step, P.res);
-#pragma unroll
-          for (int a = 0; a < 3; a++)
-            v[a] = fd_sdiv(wadd(lowest[a], (int)div_mr64(sr * r.iv[a])), P.div_res);             // :493
-          if (!grid_in_bounds(g, v[0], v[1], v[2])) continue;                                    // :495-498
-          n_cand++;
+          bool valid = have && step < iter_steps;
+          const int sr = wmul(step, P.res);
+          const int vx = fd_sdiv(wadd(low_x, (int)div_mr64((i64)sr * r.iv[0])), P.div_res);      // :493
+          const int vy = fd_sdiv(wadd(low_y, (int)div_mr64((i64)sr * r.iv[1])), P.div_res);
+          const int vz = fd_sdiv(wadd(low_z, (int)div_mr64((i64)sr * r.iv[2])), P.div_res);
+          if (!grid_in_bounds(g, vx, vy, vz)) valid = false;                                     // :495-498
+          if (valid) n_cand++;
 
-          const int rx = ring_coord(v[0], g.pos[0], g.offset[0], g.size[0]);
-          const int ry = ring_coord(v[1], g.pos[1], g.offset[1], g.size[1]);
-          const int rz = ring_coord(v[2], g.pos[2], g.offset[2], g.size[2]);
-          const i64 brick = brick_of(g, rx, ry, rz);
-          if (brick < 0) continue;                       // column lives on another rank
-          const i64 addr = brick * WS_BRICK_VOX + brick_local(rx, ry, rz);
-          const bool interp = step != mid;                                                       // :503-506
-          const u64 seq = make_seq((unsigned)ray_id, (unsigned)i, (unsigned)step);
-          const u64 key = make_key(value, interp, seq);
-
-          if (FIRST)
+          u64 key = 0ull, addr = 0ull;
+          bool resident = false;
+          if (valid)
           {
-            atomicMin(&g.keys[addr], key);                                                       // :508-512
-            // first touch of a brick: publish it for the merge pass (one probe per distinct brick per warp)
-            const unsigned m = __match_any_sync(__activemask(), (unsigned)brick);
-            if ((__ffs(m) - 1) == lane && __ldcg(&g.brick_flag[brick]) == 0u)
+            const int rx = ring_fast(vx, base_x, g.size[0]);
+            const int ry = ring_fast(vy, base_y, g.size[1]);
+            const int rz = ring_fast(vz, base_z, g.size[2]);
+            const i64 brick = brick_of(g, rx, ry, rz);
+            if (brick >= 0)                                // else: the column lives on another rank
             {
-              if (atomicExch(&g.brick_flag[brick], 1u) == 0u)
-                brick_list[atomicAdd(&ctr->n_touched_bricks, 1u)] = (unsigned)brick;
+              resident = true;
+              addr = (u64)brick * WS_BRICK_VOX + (u64)brick_local(rx, ry, rz);
+              const u64 seq = make_seq((unsigned)ray_id, (unsigned)i, (unsigned)step);
+              key = make_key(value, step != mid, seq);                                           // :503-506
+              if (ATOMIC)
+              {
+                atomicMin(&g.keys[addr], key);                                                   // :508-512
+                if ((unsigned)brick != last_brick)
+                {
+                  g.brick_flag[brick] = 1u;
+                  last_brick = (unsigned)brick;
+                }
+              }
             }
           }
-          else
-          {
-            const u64 cur = __ldcg(&g.keys[addr]);
-            if (key_is_pending(cur))
-            {
-              const unsigned slot = (unsigned)(cur & 0xFFFFFFFFull);
-              if (seq > key_seq(pend_prev[slot])) atomicMin(&pend_key[slot], key);
-            }
-          }
+          rec_append(rw, resident && far, key, addr, lane, rec, chunk_fill, cap_chunks, ctr);
         }
       }
     }
+    if (++ray_id == batch + RAY_BATCH)
+    {
+      batch = total_warps * RAY_BATCH + (int)__shfl_sync(FULL, nxt, 0);
+      ray_id = batch;
+    }
   }
 
-  if (FIRST)
+  rec_finish(rw, lane, chunk_fill, cap_chunks, ctr);
+  if (ATOMIC)
   {
-    // candidate counter (work statistics): warp shuffle, then one atomic per warp leader
+    // candidate counter (work statistics): warp shuffle, then one atomic per warp
     for (int o = 16; o > 0; o >>= 1) n_cand += __shfl_down_sync(FULL, n_cand, o);
-    __shared__ unsigned s_cand;
-    if (threadIdx.x == 0) s_cand = 0;
-    __syncthreads();
-    if (lane == 0 && n_cand) atomicAdd(&s_cand, n_cand);
-    __syncthreads();
-    if (threadIdx.x == 0 && s_cand) atomicAdd(&ctr->n_candidates, (unsigned long long)s_cand);
+    if (lane == 0 && n_cand) atomicAdd(&ctr->n_candidates, n_cand);
   }
   if (err) atomicOr(&ctr->error, err);
 }
 
-// final winner -> grid entry (update_tsdf.cpp:542-560); returns 1 if the entry changed
-WS_D unsigned apply_winner(const GridDesc &g, const UpdateParams &P, i64 addr, u64 key)
+// touched-brick flags -> compact list; flags are reset for the next scan
+__global__ void __launch_bounds__(256)
+brick_list_kernel(const GridDesc g, unsigned *__restrict__ brick_list, UpdateCounters *__restrict__ ctr)
+{
+  const int lane = threadIdx.x & 31;
+  const i64 stride = (i64)gridDim.x * blockDim.x;
+  const i64 n_round = (g.n_bricks + 31) & ~31ll;
+  for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < n_round; b += stride)
+  {
+    const bool set = b < g.n_bricks && g.brick_flag[b] != 0u;
+    const unsigned m = __ballot_sync(FULL, set);
+    if (m == 0u) continue;
+    unsigned first = 0;
+    if (lane == 0) first = atomicAdd(&ctr->n_touched_bricks, (unsigned)__popc(m));
+    first = __shfl_sync(FULL, first, 0);
+    if (set)
+    {
+      brick_list[first + (unsigned)__popc(m & ((1u << lane) - 1u))] = (unsigned)b;
+      g.brick_flag[b] = 0u;
+    }
+  }
+}
+
+// final winner -> grid entry (update_tsdf.cpp:542-560); returns 1 if the reference writes the entry
+WS_D unsigned apply_winner_to(uint32_t *slot, const uint32_t e, const UpdateParams &P, const u64 key)
 {
   const int value = key_value(key);
   int weight = tsdf_weight(value, P.tau, P.weight_epsilon);
   if (key_interpolated(key)) weight = -weight;
-  const uint32_t e = g.grid[addr];
   const uint32_t n = merge_entry(e, value, weight, P.max_weight);
-  if (n != e) g.grid[addr] = n;
+  if (n != e) *slot = n;
   const int ew = entry_weight(e);
   return ((weight > 0 && ew > 0) || (weight != 0 && ew <= 0)) ? 1u : 0u;
 }
@@ -235,118 +411,249 @@ WS_D bool winner_is_final(u64 key, int tau)
 
 __global__ void __launch_bounds__(256)
 merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict__ brick_list,
-             UpdateCounters *__restrict__ ctr, unsigned pending_cap,
+             UpdateCounters *__restrict__ ctr, const unsigned pending_cap,
              u64 *__restrict__ pend_addr, u64 *__restrict__ pend_prev, u64 *__restrict__ pend_key)
 {
   const unsigned n_tb = ctr->n_touched_bricks;
+  const int lane = threadIdx.x & 31;
   unsigned touched = 0, written = 0;
-  for (unsigned bi = blockIdx.x; bi < n_tb; bi += gridDim.x)
+  // two bricks per turn; all four loads of a thread are in flight before the first is used
+  for (unsigned bi = blockIdx.x; bi < n_tb; bi += 2u * gridDim.x)
   {
-    const i64 brick = brick_list[bi];
-    const i64 base = brick * WS_BRICK_VOX + 2 * threadIdx.x;
-    const ulonglong2 kk = *reinterpret_cast<const ulonglong2 *>(&g.keys[base]);
-    const u64 k2[2] = { kk.x, kk.y };
+    i64 base[2];
+    ulonglong2 kk[2];
+    uint2 ee[2];
+    bool live[2];
 #pragma unroll
-    for (int j = 0; j < 2; j++)
+    for (int u = 0; u < 2; u++)
     {
-      const u64 k = k2[j];
-      const bool occupied = k != WS_KEY_EMPTY;
-      const bool fin = occupied && winner_is_final(k, P.tau);
-      const bool park = occupied && !fin;
-      const i64 addr = base + j;
-      if (occupied) touched++;
-      if (fin)
+      const unsigned b = bi + (unsigned)u * gridDim.x;
+      live[u] = b < n_tb;
+      base[u] = (i64)brick_list[live[u] ? b : bi] * WS_BRICK_VOX + 2 * threadIdx.x;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+    {
+      kk[u] = __ldcs(reinterpret_cast<const ulonglong2 *>(&g.keys[base[u]]));
+      ee[u] = *reinterpret_cast<const uint2 *>(&g.grid[base[u]]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++)
+    {
+      const u64 k2[2] = { live[u] ? kk[u].x : WS_KEY_EMPTY, live[u] ? kk[u].y : WS_KEY_EMPTY };
+      const uint32_t e2[2] = { ee[u].x, ee[u].y };
+      bool parked[2] = { false, false };
+#pragma unroll
+      for (int j = 0; j < 2; j++)
       {
-        written += apply_winner(g, P, addr, k);
-        g.keys[addr] = WS_KEY_EMPTY;
-      }
-      // parked voxels: one slot counter bump per warp
-      const unsigned pm = __ballot_sync(FULL, park);
-      if (pm)
-      {
-        const int lane = threadIdx.x & 31;
-        unsigned first = 0;
-        if (lane == (__ffs(pm) - 1)) first = atomicAdd(&ctr->n_pending, (unsigned)__popc(pm));
-        first = __shfl_sync(FULL, first, __ffs(pm) - 1);
-        if (park)
+        const u64 k = k2[j];
+        const bool occupied = k != WS_KEY_EMPTY;
+        const bool fin = occupied && winner_is_final(k, P.tau);
+        const bool park = occupied && !fin;
+        const i64 addr = base[u] + j;
+        parked[j] = park;
+        if (occupied) touched++;
+        if (fin) written += apply_winner_to(&g.grid[addr], e2[j], P, k);
+        // parked voxels: one slot counter bump per warp
+        const unsigned pm = __ballot_sync(FULL, park);
+        if (pm)
         {
-          const unsigned slot = first + (unsigned)__popc(pm & ((1u << lane) - 1u));
-          if (slot < pending_cap)
+          unsigned first = 0;
+          if (lane == (__ffs(pm) - 1)) first = atomicAdd(&ctr->n_pending, (unsigned)__popc(pm));
+          first = __shfl_sync(FULL, first, __ffs(pm) - 1);
+          if (park)
           {
-            pend_addr[slot] = (u64)addr;
-            pend_prev[slot] = k;
-            pend_key[slot] = WS_KEY_EMPTY;
-            g.keys[addr] = WS_KEY_PENDING_TAG | (u64)slot;
-          }
-          else
-          {
-            atomicAdd(&ctr->pending_overflow, 1u);
-            g.keys[addr] = WS_KEY_EMPTY;
+            const unsigned slot = first + (unsigned)__popc(pm & ((1u << lane) - 1u));
+            if (slot < pending_cap)
+            {
+              pend_addr[slot] = (u64)addr;
+              pend_prev[slot] = k;
+              pend_key[slot] = WS_KEY_EMPTY;
+              g.keys[addr] = WS_KEY_PENDING_TAG | (u64)slot;
+            }
+            else
+            {
+              atomicAdd(&ctr->pending_overflow, 1u);
+              g.keys[addr] = WS_KEY_EMPTY;
+            }
           }
         }
       }
+      // reset the keys of this thread's two voxels: one 16-byte store unless one of them stays parked
+      if (k2[0] != WS_KEY_EMPTY || k2[1] != WS_KEY_EMPTY)
+      {
+        if (!parked[0] && !parked[1])
+          *reinterpret_cast<ulonglong2 *>(&g.keys[base[u]]) = make_ulonglong2(WS_KEY_EMPTY, WS_KEY_EMPTY);
+        else
+        {
+          if (!parked[0] && k2[0] != WS_KEY_EMPTY) g.keys[base[u]] = WS_KEY_EMPTY;
+          if (!parked[1] && k2[1] != WS_KEY_EMPTY) g.keys[base[u] + 1] = WS_KEY_EMPTY;
+        }
+      }
     }
-    if (threadIdx.x == 0) g.brick_flag[brick] = 0u;
   }
   for (int o = 16; o > 0; o >>= 1)
   {
     touched += __shfl_down_sync(FULL, touched, o);
     written += __shfl_down_sync(FULL, written, o);
   }
-  if ((threadIdx.x & 31) == 0)
+  if (lane == 0)
   {
     if (touched) atomicAdd(&ctr->n_touched, (unsigned long long)touched);
     if (written) atomicAdd(&ctr->n_written, (unsigned long long)written);
   }
 }
 
-// after a replay round: settle every parked voxel that now has its final winner
-__global__ void __launch_bounds__(256)
-resolve_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict__ ctr, unsigned pending_cap,
-               u64 *__restrict__ pend_addr, u64 *__restrict__ pend_prev, u64 *__restrict__ pend_key)
+// one parked voxel after a replay round: settled, or restart after the new (still interpolated) winner
+WS_D bool resolve_slot(const GridDesc &g, const UpdateParams &P, const unsigned s,
+                       u64 *__restrict__ pend_addr, u64 *__restrict__ pend_prev, u64 *__restrict__ pend_key,
+                       unsigned &written)
 {
-  unsigned n = ctr->n_pending;
-  if (n > pending_cap) n = pending_cap;
-  unsigned written = 0, still = 0;
-  for (unsigned s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
+  const u64 addr = pend_addr[s];
+  if (addr == PEND_DONE) return false;
+  const u64 k2 = pend_key[s];
+  u64 fin;
+  if (k2 == WS_KEY_EMPTY) fin = pend_prev[s];            // nothing later in the order: the parked winner stands
+  else if (winner_is_final(k2, P.tau)) fin = k2;
+  else
   {
-    const u64 addr = pend_addr[s];
-    if (addr == PEND_DONE) continue;
-    const u64 k2 = pend_key[s];
-    u64 fin;
-    if (k2 == WS_KEY_EMPTY) fin = pend_prev[s];          // nothing later in the order: the parked winner stands
-    else if (winner_is_final(k2, P.tau)) fin = k2;
-    else
+    pend_prev[s] = k2;                                   // still interpolated: restart after it
+    pend_key[s] = WS_KEY_EMPTY;
+    return true;
+  }
+  written += apply_winner_to(&g.grid[addr], g.grid[addr], P, fin);
+  g.keys[addr] = WS_KEY_EMPTY;
+  pend_addr[s] = PEND_DONE;
+  return false;
+}
+
+WS_D void list_append(const bool want, const Rec e, const int lane, Rec *__restrict__ list, unsigned *counter)
+{
+  const unsigned m = __ballot_sync(FULL, want);
+  if (m == 0u) return;
+  unsigned first = 0;
+  if (lane == 0) first = atomicAdd(counter, (unsigned)__popc(m));
+  first = __shfl_sync(FULL, first, 0);
+  if (want) list[first + (unsigned)__popc(m & ((1u << lane) - 1u))] = e;
+}
+
+// Cooperative launch: settles every parked voxel on the device (see the file header, step 4).
+__global__ void __launch_bounds__(256)
+replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict__ ctr, const unsigned pending_cap,
+              u64 *__restrict__ pend_addr, u64 *__restrict__ pend_prev, u64 *__restrict__ pend_key,
+              const Rec *__restrict__ rec, const unsigned *__restrict__ chunk_fill, const unsigned cap_chunks,
+              Rec *__restrict__ list, unsigned *__restrict__ active0, unsigned *__restrict__ active1)
+{
+  cg::grid_group grid = cg::this_grid();
+  unsigned n_pend = ctr->n_pending;
+  if (n_pend > pending_cap) n_pend = pending_cap;
+  if (n_pend == 0u || ctr->rec_overflow != 0u || ctr->pending_overflow != 0u) return;   // grid-uniform
+
+  const int lane = threadIdx.x & 31;
+  const unsigned gthread = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned gthreads = gridDim.x * blockDim.x;
+  const unsigned gwarp = gthread >> 5, gwarps = gthreads >> 5;
+  unsigned written = 0;
+
+  // ---- round 1, candidates: the record, one warp per pair of 64-entry chunks.  Four independent
+  // record -> key -> parked-winner chains per lane are in flight at a time (the pass is latency bound).
+  unsigned n_chunks = ctr->n_chunks;
+  if (n_chunks > cap_chunks) n_chunks = cap_chunks;
+  for (unsigned c0 = gwarp * 2u; c0 < n_chunks; c0 += gwarps * 2u)
+  {
+    Rec rr[4];
+    bool ok[4];
+    u64 kv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
     {
-      pend_prev[s] = k2;                                 // still interpolated: restart after it
-      pend_key[s] = WS_KEY_EMPTY;
-      still++;
-      continue;
+      const unsigned c = c0 + (unsigned)(u >> 1);
+      const unsigned j = (unsigned)(u & 1) * 32u + (unsigned)lane;
+      ok[u] = c < n_chunks && j < chunk_fill[c < n_chunks ? c : c0];
+      rr[u].key = 0ull; rr[u].ref = 0ull;
+      if (ok[u]) rr[u] = rec[(size_t)c * WS_REC_CHUNK + j];
     }
-    written += apply_winner(g, P, (i64)addr, fin);
-    g.keys[addr] = WS_KEY_EMPTY;
-    pend_addr[s] = PEND_DONE;
+#pragma unroll
+    for (int u = 0; u < 4; u++) kv[u] = ok[u] ? __ldcg(&g.keys[rr[u].ref]) : WS_KEY_EMPTY;
+    u64 thr[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+    {
+      ok[u] = ok[u] && key_is_pending(kv[u]);
+      thr[u] = ok[u] ? pend_prev[(unsigned)(kv[u] & 0xFFFFFFFFull)] : 0ull;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+    {
+      const unsigned slot = (unsigned)(kv[u] & 0xFFFFFFFFull);
+      const bool hit = ok[u] && key_seq(rr[u].key) > key_seq(thr[u]);
+      if (hit) atomicMin(&pend_key[slot], rr[u].key);
+      Rec e; e.key = rr[u].key; e.ref = (u64)slot;
+      list_append(hit, e, lane, list, &ctr->n_list);
+    }
   }
-  for (int o = 16; o > 0; o >>= 1)
+  grid.sync();
+
+  // ---- rounds: resolve, then offer the short list to what is still pending ----------------------
+  for (unsigned round = 1;; round++)
   {
-    written += __shfl_down_sync(FULL, written, o);
-    still += __shfl_down_sync(FULL, still, o);
+    unsigned *act_out = (round & 1u) ? active1 : active0;
+    const unsigned *act_in = (round & 1u) ? active0 : active1;
+    unsigned *n_out = &ctr->n_active[round & 1u];
+    const unsigned n_in = round == 1u ? n_pend : ctr->n_active[(round & 1u) ^ 1u];
+    const unsigned n_in_round = (n_in + 31u) & ~31u;
+    for (unsigned t = gthread; t < n_in_round; t += gthreads)
+    {
+      bool still = false;
+      unsigned s = 0;
+      if (t < n_in)
+      {
+        s = round == 1u ? t : act_in[t];
+        still = resolve_slot(g, P, s, pend_addr, pend_prev, pend_key, written);
+      }
+      const unsigned m = __ballot_sync(FULL, still);
+      if (m)
+      {
+        unsigned first = 0;
+        if (lane == 0) first = atomicAdd(n_out, (unsigned)__popc(m));
+        first = __shfl_sync(FULL, first, 0);
+        if (still) act_out[first + (unsigned)__popc(m & ((1u << lane) - 1u))] = s;
+      }
+    }
+    grid.sync();
+    const unsigned n_still = *((volatile unsigned *)n_out);
+    if (gthread == 0)
+    {
+      ctr->rounds = round;
+      ctr->n_active[(round & 1u) ^ 1u] = 0u;      // next round's output counter (its readers are done)
+    }
+    if (n_still == 0u) break;
+    const unsigned n_list = ctr->n_list;
+    for (unsigned t = gthread; t < n_list; t += gthreads)
+    {
+      const Rec e = list[t];
+      const unsigned slot = (unsigned)e.ref;
+      if (pend_addr[slot] != PEND_DONE && key_seq(e.key) > key_seq(pend_prev[slot])) atomicMin(&pend_key[slot], e.key);
+    }
+    grid.sync();
   }
-  if ((threadIdx.x & 31) == 0)
+
+  for (int o = 16; o > 0; o >>= 1) written += __shfl_down_sync(FULL, written, o);
+  if (lane == 0 && written) atomicAdd(&ctr->n_written, (unsigned long long)written);
+  if (gthread == 0)
   {
-    if (written) atomicAdd(&ctr->n_written, (unsigned long long)written);
-    if (still) atomicAdd(&ctr->n_pending_next, still);
+    ctr->n_parked = n_pend;
+    ctr->n_pending = 0u;
   }
 }
 
-// one thread: roll the pending counters over to the next replay round
-__global__ void round_advance_kernel(UpdateCounters *ctr)
+// between a record overflow and its regeneration
+__global__ void rec_reset_kernel(UpdateCounters *ctr)
 {
-  if (ctr->n_pending == 0) return;
-  if (ctr->rounds == 0) ctr->n_parked = ctr->n_pending;
-  ctr->rounds += 1;
-  if (ctr->n_pending_next == 0) ctr->n_pending = 0;   // everything settled: later rounds become no-ops
-  ctr->n_pending_next = 0;
+  ctr->n_chunks = 0u;
+  ctr->rec_overflow = 0u;
+  ctr->ray_counter = 0u;
+  ctr->n_list = 0u;
 }
 
 }  // namespace
@@ -361,6 +668,37 @@ static int far_start_len(int res, int dz)
   long long L0 = (need + dz - 1) / dz;
   long long fl = L0 - 10LL * res - 16;
   return fl < 1 ? 1 : (int)(fl > 0x7fffffff ? 0x7fffffff : fl);
+}
+
+static void ensure_record(ws_handle *h, size_t chunks)
+{
+  if (chunks <= h->rec_cap_chunks) return;
+  WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_rec); cudaFree(h->d_list); cudaFree(h->d_chunk_fill);
+  h->d_rec = nullptr; h->d_list = nullptr; h->d_chunk_fill = nullptr; h->rec_cap_chunks = 0;
+  WS_CUDA_OK(cudaMalloc(&h->d_rec, chunks * WS_REC_CHUNK * sizeof(Rec)));
+  WS_CUDA_OK(cudaMalloc(&h->d_list, chunks * WS_REC_CHUNK * sizeof(Rec)));
+  WS_CUDA_OK(cudaMalloc(&h->d_chunk_fill, chunks * sizeof(unsigned)));
+  h->rec_cap_chunks = chunks;
+}
+
+static void launch_replay(ws_handle *h, const UpdateParams &P)
+{
+  if (h->replay_blocks == 0)
+  {
+    int per_sm = 0;
+    WS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, replay_kernel, 256, 0));
+    if (per_sm < 1) throw std::runtime_error("replay_kernel does not fit on an SM");
+    if (per_sm > 4) per_sm = 4;
+    h->replay_blocks = per_sm * h->sm_count;
+  }
+  unsigned cap_chunks = (unsigned)h->rec_cap_chunks;
+  void *args[] = { (void *)&h->g, (void *)&P, (void *)&h->d_counters, (void *)&h->pending_cap,
+                   (void *)&h->d_pend_addr, (void *)&h->d_pend_prev, (void *)&h->d_pend_key,
+                   (void *)&h->d_rec, (void *)&h->d_chunk_fill, (void *)&cap_chunks,
+                   (void *)&h->d_list, (void *)&h->d_active[0], (void *)&h->d_active[1] };
+  WS_CUDA_OK(cudaLaunchCooperativeKernel((const void *)replay_kernel, dim3(h->replay_blocks), dim3(256), args, 0, h->stream));
+  h->launches++;
 }
 
 void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3])
@@ -383,52 +721,48 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
   P.div_weps = make_fastdiv((unsigned)(P.tau - P.weight_epsilon > 0 ? P.tau - P.weight_epsilon : 1));
   P.half_res = h->res / 2;
   P.n_points = n;
-  P.far_only = 0;
   P.far_len = far_start_len(h->res, P.dz_per_distance);
 
   cudaStream_t s = h->stream;
   WS_CUDA_OK(cudaMemsetAsync(h->d_counters, 0, sizeof(UpdateCounters), s));
   if (n > 0)
   {
-    const int rays_per_block = 8;
-    const int blocks = (n + rays_per_block - 1) / rays_per_block;
+    const int march_blocks = h->sm_count * 3;
+    unsigned cap_chunks = (unsigned)h->rec_cap_chunks;
     ws_timer_begin(h, WS_TIMER_MARCH);
-    march_kernel<true><<<blocks, 256, 0, s>>>(h->g, P, d_pts, h->d_brick_list, h->d_counters, nullptr, nullptr);
+    march_kernel<true><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, d_pts, h->d_counters, h->d_rec,
+                                                              h->d_chunk_fill, cap_chunks);
     ws_timer_end(h);
-    h->launches += 2;
-    const int dev_sms = h->sm_count;
     ws_timer_begin(h, WS_TIMER_MERGE);
-    merge_kernel<<<dev_sms * 8, 256, 0, s>>>(h->g, P, h->d_brick_list, h->d_counters, h->pending_cap,
-                                            h->d_pend_addr, h->d_pend_prev, h->d_pend_key);
-    ws_timer_end(h);
-    // replay rounds for parked voxels; each is a no-op (early exit) once nothing is parked
-    UpdateParams P2 = P;
-    P2.far_only = 1;
-    const int fixed_rounds = 3;
-    for (int r = 0; r < fixed_rounds; r++)
-    {
-      march_kernel<false><<<blocks, 256, 0, s>>>(h->g, P2, d_pts, h->d_brick_list, h->d_counters,
-                                                 h->d_pend_prev, h->d_pend_key);
-      resolve_kernel<<<dev_sms * 4, 256, 0, s>>>(h->g, P2, h->d_counters, h->pending_cap,
+    brick_list_kernel<<<h->sm_count * 4, 256, 0, s>>>(h->g, h->d_brick_list, h->d_counters);
+    merge_kernel<<<h->sm_count * 8, 256, 0, s>>>(h->g, P, h->d_brick_list, h->d_counters, h->pending_cap,
                                                  h->d_pend_addr, h->d_pend_prev, h->d_pend_key);
-      round_advance_kernel<<<1, 1, 0, s>>>(h->d_counters);
-      h->launches += 3;
-    }
+    ws_timer_end(h);
+    h->launches += 3;
+    ws_timer_begin(h, WS_TIMER_REPLAY);
+    launch_replay(h, P);
+    ws_timer_end(h);
     WS_CUDA_OK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
     WS_CUDA_OK(cudaStreamSynchronize(s));
-    // extremely deep chains of interpolated winners: keep replaying until settled
+    // the record did not fit: grow it, regenerate it from the far part of every ray, settle again
     int guard = 0;
-    while (h->h_counters->n_pending != 0 && h->h_counters->pending_overflow == 0)
+    while (h->h_counters->rec_overflow != 0u && h->h_counters->pending_overflow == 0u)
     {
-      if (++guard > 100000) throw std::runtime_error("update_tsdf: replay rounds do not converge");
-      march_kernel<false><<<blocks, 256, 0, s>>>(h->g, P2, d_pts, h->d_brick_list, h->d_counters,
-                                                 h->d_pend_prev, h->d_pend_key);
-      resolve_kernel<<<dev_sms * 4, 256, 0, s>>>(h->g, P2, h->d_counters, h->pending_cap,
-                                                 h->d_pend_addr, h->d_pend_prev, h->d_pend_key);
-      round_advance_kernel<<<1, 1, 0, s>>>(h->d_counters);
-      h->launches += 3;
+      if (++guard > 8) throw std::runtime_error("update_tsdf: candidate record keeps overflowing");
+      size_t want = (size_t)h->h_counters->n_chunks + (size_t)h->h_counters->n_chunks / 4 + 1024;
+      if (want > h->rec_max_chunks) want = h->rec_max_chunks;
+      if (want <= h->rec_cap_chunks)
+        throw std::runtime_error("update_tsdf: candidate record exceeds WS_RECORD_MAX");
+      ensure_record(h, want);
+      cap_chunks = (unsigned)h->rec_cap_chunks;
+      rec_reset_kernel<<<1, 1, 0, s>>>(h->d_counters);
+      march_kernel<false><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, d_pts, h->d_counters, h->d_rec,
+                                                                 h->d_chunk_fill, cap_chunks);
+      h->launches += 2;
+      launch_replay(h, P);
       WS_CUDA_OK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
       WS_CUDA_OK(cudaStreamSynchronize(s));
+      h->record_regrows++;
     }
   }
   else
@@ -440,6 +774,14 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
   h->last_counters = *h->h_counters;
   if (h->last_counters.pending_overflow)
     throw std::runtime_error("update_tsdf: pending-voxel capacity exceeded (raise WS_PENDING_CAP)");
+  if (h->last_counters.n_pending != 0u)
+    throw std::runtime_error("update_tsdf: parked voxels were left unsettled");
   if (h->last_counters.error & 1u)
     throw std::runtime_error("update_tsdf: ray too long for the candidate order field (march steps > 32768 or fan > 64)");
+}
+
+void ws_update_alloc(ws_handle *h, size_t initial_chunks, size_t max_chunks)
+{
+  h->rec_max_chunks = max_chunks;
+  ensure_record(h, initial_chunks < max_chunks ? initial_chunks : max_chunks);
 }

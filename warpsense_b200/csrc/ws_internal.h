@@ -1,5 +1,6 @@
 // ws_internal.h -- host-side state of one map handle and the launcher prototypes (not part of the ABI).
 #pragma once
+#include <cstddef>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -15,9 +16,17 @@ struct UpdateParams
   FastDiv div_weps;    // / (tau - weight_epsilon)
   int half_res;        // map_resolution / 2
   int n_points;
-  int far_only;        // rounds >= 2: start each ray where interpolated candidates can first occur
-  int far_len;         // first march length worth visiting when far_only
+  int far_len;         // march lengths >= far_len can meet an interpolated winner: their candidates are recorded
 };
+
+// one recorded candidate: its key and the voxel address (record) or the pending slot (replay list)
+struct Rec
+{
+  u64 key;
+  u64 ref;
+};
+#define WS_REC_CHUNK 64    // records per chunk; a chunk belongs to one warp of the march kernel
+#define WS_REC_SPAN 16     // chunks a warp reserves per allocation
 
 // device-side work counters / status of one update (kept in one small device buffer)
 struct UpdateCounters
@@ -32,7 +41,18 @@ struct UpdateCounters
   unsigned error;            // bit 0: seq field overflow (too many march/fan steps)
   unsigned rounds;
   unsigned n_parked;         // voxels parked by the merge pass (before any replay round)
+  unsigned pad0[19];
+  unsigned ray_counter;      // dynamic ray fetch of the persistent march warps (own 128-byte line)
+  unsigned pad1[31];
+  unsigned n_chunks;         // record chunks handed out (own 128-byte line)
+  unsigned pad2[31];
+  unsigned rec_overflow;     // the record did not fit its buffer
+  unsigned n_list;           // entries of the replay list (round-1 survivors)
+  unsigned n_active[2];      // still-pending slots, ping-pong between replay rounds
 };
+
+static_assert(offsetof(UpdateCounters, ray_counter) == 128 && offsetof(UpdateCounters, n_chunks) == 256,
+              "hot counters live on their own 128-byte lines");
 
 struct RegAccum           // 29 exact sums + bookkeeping, device resident
 {
@@ -75,7 +95,14 @@ struct ws_handle
   u64 *d_pend_addr = nullptr;           // voxel address of each pending slot
   u64 *d_pend_prev = nullptr;           // key of the current (interpolated) winner
   u64 *d_pend_key = nullptr;            // atomicMin target of the next round
-  unsigned *d_pend_list[2] = {nullptr, nullptr};
+  unsigned *d_active[2] = {nullptr, nullptr};   // still-pending slot lists (ping-pong)
+  // far-field candidate record + replay list (same capacity), 64-entry chunks
+  Rec *d_rec = nullptr;
+  Rec *d_list = nullptr;
+  unsigned *d_chunk_fill = nullptr;
+  size_t rec_cap_chunks = 0, rec_max_chunks = 0;
+  int replay_blocks = 0;                // cooperative grid of replay_kernel
+  int64_t record_regrows = 0;
 
   // registration
   RegAccum *d_acc = nullptr;
@@ -107,6 +134,7 @@ struct ws_handle
 
 // update_tsdf.cu
 void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3]);
+void ws_update_alloc(ws_handle *h, size_t initial_chunks, size_t max_chunks);
 // registration.cu
 void ws_launch_reg_reset(ws_handle *h, const float T[16], float alpha0);
 void ws_launch_reg_iteration(ws_handle *h, int n, int res, int fused_solve, float it_weight_gradient, float epsilon);
@@ -123,6 +151,7 @@ void ws_launch_test_reduce(ws_handle *h, const i64 *d_jacobis, const int *d_valu
 #define WS_TIMER_MARCH 0
 #define WS_TIMER_MERGE 1
 #define WS_TIMER_REG 2
+#define WS_TIMER_REPLAY 3
 void ws_timer_begin(ws_handle *h, int kind);
 void ws_timer_end(ws_handle *h);
 

@@ -19,7 +19,7 @@ WS_MAX_POINTS = 1 << 24
 WS_REG_DEVICE_SOLVE = 0
 WS_REG_HOST_SOLVE = 1
 
-TIMER_MARCH, TIMER_MERGE, TIMER_REG = 0, 1, 2
+TIMER_MARCH, TIMER_MERGE, TIMER_REG, TIMER_REPLAY = 0, 1, 2, 3
 
 
 class UpdateCounters(C.Structure):
