@@ -373,6 +373,8 @@ def run_native(args):
             },
             "work": {"N": N, "C": C_cand, "T": T_vox, "touched_bricks": counters["n_touched_bricks"],
                      "parked": counters["n_parked"], "replay_rounds": counters["n_rounds"],
+                     "replay_list": counters["n_list"], "record_chunks": counters["n_record_chunks"],
+                     "replay_phase_us": [v / 1000.0 for v in counters["replay_phase_ns"]],
                      "iterations": GN_ITERS, "V": int(np.prod(np.array(size, np.int64)))},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -50,6 +50,9 @@ typedef struct {
   int64_t n_touched_bricks;  /* 8x8x8 bricks streamed by the merge pass               */
   int64_t n_parked;          /* voxels that needed a replay round                     */
   int64_t n_rounds;          /* replay rounds that did work                           */
+  int64_t n_list;            /* recorded candidates that followed a parked winner (replay list) */
+  int64_t n_record_chunks;   /* 64-entry chunks of the far-field candidate record handed out   */
+  int64_t replay_phase_ns[3];/* replay kernel: record pass, first resolve, remaining rounds    */
 } ws_update_counters;
 
 /* flags of ws_register_cloud */

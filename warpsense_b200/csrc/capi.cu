@@ -52,7 +52,7 @@ void free_handle(ws_handle *h)
   cudaFree(h->d_pend_addr); cudaFree(h->d_pend_prev); cudaFree(h->d_pend_key);
   cudaFree(h->d_active[0]); cudaFree(h->d_active[1]);
   cudaFree(h->d_rec); cudaFree(h->d_list); cudaFree(h->d_chunk_fill);
-  cudaFree(h->d_acc); cudaFree(h->d_trace); cudaFreeHost(h->h_acc);
+  cudaFree(h->d_acc); cudaFree(h->d_trace); cudaFreeHost(h->h_acc); cudaFree(h->d_reg_partials);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -495,6 +495,9 @@ int ws_get_update_counters(const ws_handle *h, ws_update_counters *out)
   out->n_touched_bricks = c.n_touched_bricks;
   out->n_parked = c.n_parked;
   out->n_rounds = c.rounds;
+  out->n_list = c.n_list;
+  out->n_record_chunks = c.n_chunks;
+  for (int i = 0; i < 3; i++) out->replay_phase_ns[i] = (int64_t)(c.t_phase[i + 1] - c.t_phase[i]);
   return WS_OK;
 }
 
@@ -559,18 +562,8 @@ int ws_register_cloud(ws_handle *h, ws_point *cloud, int64_t n, const float pret
     h->host_trace.clear();
     if (!h->last_reg_host)
     {
-      // GN iterations back to back on the device; look at `finished` only every 32 launches
-      while (it_done < max_iterations)
-      {
-        const int batch = std::min(32, max_iterations - it_done);
-        for (int i = 0; i < batch; i++) ws_launch_reg_iteration(h, np, map_resolution, 1, it_weight_gradient, epsilon);
-        it_done += batch;
-        if (it_done < max_iterations)
-        {
-          read_acc(h);
-          if (h->h_acc->finished) break;
-        }
-      }
+      // every Gauss-Newton iteration inside one persistent cooperative kernel (registration.cu)
+      if (max_iterations > 0) ws_launch_reg_loop(h, np, map_resolution, max_iterations, it_weight_gradient, epsilon);
       ws_launch_transform_cloud(h, h->d_reg_points, np);
       read_acc(h);
       it_done = (int)h->h_acc->iterations;

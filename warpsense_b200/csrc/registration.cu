@@ -9,10 +9,13 @@
 // runs the damped FP64 6x6 solve and the Rodrigues update (registration.cpp:128-157,
 // include/warpsense/registration/util.h:5-39), so the next iteration starts with no host round trip.
 // All sums are integers, hence exact and independent of reduction order and of the GPU count.
+#include <cooperative_groups.h>
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include "ws_internal.h"
+
+namespace cg = cooperative_groups;
 
 #define FULL 0xFFFFFFFFu
 #define WS_NSUM 29
@@ -307,6 +310,320 @@ reg_accum_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const int n, c
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent Gauss-Newton loop: ALL iterations of register_cloud in one cooperative kernel, one grid
+// synchronisation per iteration.
+//   * every thread keeps its points in registers across iterations;
+//   * per iteration each block reduces its 29 exact sums (register butterfly + shared memory) and stores
+//     them as one row of `partials`; after grid.sync() EVERY block adds up all rows and runs the same
+//     deterministic FP64 solve (warp 0), so each block owns the next transform without a second barrier;
+//   * the solve is inverse6()/gn_solve() above with the row operations spread over six lanes and the six
+//     columns of the inverse over six lanes: operation order per element unchanged, results bit-identical.
+#define REG_THREADS 256
+#define REG_PTS 2
+#define REG_NSLOT 32
+
+struct RegLoopParams
+{
+  int n;
+  FastDiv div_res;
+  int max_iterations;
+  float it_weight_gradient;
+  float epsilon;
+};
+
+// one point's contribution for int transform M / centre c (registration.cpp:63-107); all seven voxel
+// loads are issued together
+WS_D void accumulate_cloud_point(const GridDesc &g, const int M[16], const int cx, const int cy, const int cz,
+                                 const FastDiv div_res, const ws_pt p, i64 sum[WS_NSUM])
+{
+  int q[3];
+  transform_point(M, p.x, p.y, p.z, q);                                                  // :63
+  const int bx = fd_sdiv(q[0], div_res), by = fd_sdiv(q[1], div_res), bz = fd_sdiv(q[2], div_res);  // :65
+  const int px = wsub(q[0], cx), py = wsub(q[1], cy), pz = wsub(q[2], cz);               // :66
+  int dx = bx - g.pos[0], dy = by - g.pos[1], dz = bz - g.pos[2];
+  dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy; dz = dz < 0 ? -dz : dz;
+  if (dx > g.half[0] || dy > g.half[1] || dz > g.half[2]) return;                        // :68 throws
+  const int rx = ring_coord(bx, g.pos[0], g.offset[0], g.size[0]);
+  if (rx < g.own_lo || rx >= g.own_hi) return;             // another rank sums this point
+  const int ry = ring_coord(by, g.pos[1], g.offset[1], g.size[1]);
+  const int rz = ring_coord(bz, g.pos[2], g.offset[2], g.size[2]);
+  const bool inner = !(dx > g.half[0] - 1 || dy > g.half[1] - 1 || dz > g.half[2] - 1);  // :76-81 throw otherwise
+  const int rxn = rx + 1 == g.size[0] ? 0 : rx + 1, rxl = rx == 0 ? g.size[0] - 1 : rx - 1;
+  const int ryn = ry + 1 == g.size[1] ? 0 : ry + 1, ryl = ry == 0 ? g.size[1] - 1 : ry - 1;
+  const int rzn = rz + 1 == g.size[2] ? 0 : rz + 1, rzl = rz == 0 ? g.size[2] - 1 : rz - 1;
+  const uint32_t cur = g.grid[brick_of(g, rx, ry, rz) * WS_BRICK_VOX + brick_local(rx, ry, rz)];
+  uint32_t xn = 0, xl = 0, yn = 0, yl = 0, zn = 0, zl = 0;
+  if (inner)
+  {
+    xn = g.grid[brick_of(g, rxn, ry, rz) * WS_BRICK_VOX + brick_local(rxn, ry, rz)];
+    xl = g.grid[brick_of(g, rxl, ry, rz) * WS_BRICK_VOX + brick_local(rxl, ry, rz)];
+    yn = g.grid[brick_of(g, rx, ryn, rz) * WS_BRICK_VOX + brick_local(rx, ryn, rz)];
+    yl = g.grid[brick_of(g, rx, ryl, rz) * WS_BRICK_VOX + brick_local(rx, ryl, rz)];
+    zn = g.grid[brick_of(g, rx, ry, rzn) * WS_BRICK_VOX + brick_local(rx, ry, rzn)];
+    zl = g.grid[brick_of(g, rx, ry, rzl) * WS_BRICK_VOX + brick_local(rx, ry, rzl)];
+  }
+  if (entry_weight(cur) == 0 || !inner) return;                                          // :71-74
+
+  int gr[3] = { 0, 0, 0 };                                                               // :83-96
+  {
+    int v1 = entry_value(xn), v0 = entry_value(xl);
+    if (entry_weight(xn) != 0 && entry_weight(xl) != 0 && !((v1 > 0 && v0 < 0) || (v1 < 0 && v0 > 0))) gr[0] = (v1 - v0) / 2;
+    v1 = entry_value(yn); v0 = entry_value(yl);
+    if (entry_weight(yn) != 0 && entry_weight(yl) != 0 && !((v1 > 0 && v0 < 0) || (v1 < 0 && v0 > 0))) gr[1] = (v1 - v0) / 2;
+    v1 = entry_value(zn); v0 = entry_value(zl);
+    if (entry_weight(zn) != 0 && entry_weight(zl) != 0 && !((v1 > 0 && v0 < 0) || (v1 < 0 && v0 > 0))) gr[2] = (v1 - v0) / 2;
+  }
+  i64 J[6];                                                                              // :98 (cross in int32)
+  J[0] = wsub(wmul(py, gr[2]), wmul(pz, gr[1]));
+  J[1] = wsub(wmul(pz, gr[0]), wmul(px, gr[2]));
+  J[2] = wsub(wmul(px, gr[1]), wmul(py, gr[0]));
+  J[3] = gr[0]; J[4] = gr[1]; J[5] = gr[2];
+  accumulate_point(sum, J, entry_value(cur));
+}
+
+// warp butterfly over 32 slots: afterwards lane l holds the warp total of slot l
+WS_D i64 warp_transpose_reduce(i64 v[REG_NSLOT], const int lane)
+{
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1)
+  {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; i++)
+    {
+      const i64 send = upper ? v[i] : v[i + half];
+      const i64 keep = upper ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(FULL, send, half);
+    }
+  }
+  return v[0];
+}
+
+struct GnState
+{
+  float T[16];
+  float alpha;
+  float prev_err[4];
+  unsigned finished;
+  unsigned iterations;
+};
+
+// warp 0 of a block: damped solve + pose update from the complete sums (registration.cpp:128-157),
+// arithmetic identical to gn_solve()/inverse6() (same operations, same order per element)
+WS_D void warp_gn_solve(const u64 *s_total, GnState *st, double *s_lu, int *s_perm, double *s_inv, double *s_xi,
+                        const float it_weight_gradient, const float epsilon, const int lane)
+{
+  const int r = lane < 6 ? lane : 5;
+  const int err = (int)(i64)s_total[27];
+  const int cnt = (int)(i64)s_total[28];
+  const double damp = (double)(st->alpha * (float)cnt);
+  // row r of hf (symmetric: H[j*6+i] = H[i*6+j] = upper(i<=j))
+  double row[6];
+#pragma unroll
+  for (int c = 0; c < 6; c++)
+  {
+    const int i = r < c ? r : c, j = r < c ? c : r;
+    const int k = i * 6 - (i * (i - 1)) / 2 + (j - i);          // index of (i<=j) in the row-major upper triangle
+    row[c] = (double)(i64)s_total[k];
+    if (c == r) row[c] += damp * 1.0;
+  }
+  int prow = r;
+#pragma unroll
+  for (int k = 0; k < 6; k++)
+  {
+    // partial pivoting: first row (lowest index >= k) with the largest |lu[r][k]|
+    double best = (lane < 6 && lane >= k) ? fabs(row[k]) : -1.0;
+    int bidx = lane;
+#pragma unroll
+    for (int o = 4; o >= 1; o >>= 1)
+    {
+      const double ob = __shfl_xor_sync(FULL, best, o);
+      const int oi = __shfl_xor_sync(FULL, bidx, o);
+      if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    const int piv = __shfl_sync(FULL, bidx, 0);
+    // swap rows k and piv
+    const int src = lane == k ? piv : (lane == piv ? k : lane);
+#pragma unroll
+    for (int c = 0; c < 6; c++) row[c] = __shfl_sync(FULL, row[c], src);
+    prow = __shfl_sync(FULL, prow, src);
+    // eliminate below the pivot
+    double prk[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) prk[c] = __shfl_sync(FULL, row[c], k);
+    if (lane < 6 && lane > k)
+    {
+      row[k] /= prk[k];
+#pragma unroll
+      for (int c = k + 1; c < 6; c++) row[c] -= row[k] * prk[c];
+    }
+  }
+  if (lane < 6)
+  {
+#pragma unroll
+    for (int c = 0; c < 6; c++) s_lu[lane * 6 + c] = row[c];
+    s_perm[lane] = prow;
+  }
+  __syncwarp();
+  // column `lane` of the inverse
+  if (lane < 6)
+  {
+    double y[6];
+#pragma unroll
+    for (int rr = 0; rr < 6; rr++) y[rr] = (s_perm[rr] == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int rr = 0; rr < 6; rr++)
+#pragma unroll
+      for (int c = 0; c < rr; c++) y[rr] -= s_lu[rr * 6 + c] * y[c];
+#pragma unroll
+    for (int rr = 5; rr >= 0; rr--)
+    {
+#pragma unroll
+      for (int c = rr + 1; c < 6; c++) y[rr] -= s_lu[rr * 6 + c] * y[c];
+      y[rr] /= s_lu[rr * 6 + rr];
+    }
+#pragma unroll
+    for (int rr = 0; rr < 6; rr++) s_inv[lane * 6 + rr] = y[rr];
+  }
+  __syncwarp();
+  if (lane < 6)
+  {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) acc += (-s_inv[k * 6 + lane]) * (double)(i64)s_total[21 + k];
+    s_xi[lane] = acc;
+  }
+  __syncwarp();
+  if (lane == 0)
+  {
+    const int center[3] = { (int)st->T[12], (int)st->T[13], (int)st->T[14] };
+    double xi[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) xi[i] = s_xi[i];
+    float X[16], N[16];
+    xi_to_transform(xi, center, X);
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+#pragma unroll
+      for (int rr = 0; rr < 4; rr++)
+      {
+        float acc = X[0 * 4 + rr] * st->T[c * 4 + 0];
+        acc = acc + X[1 * 4 + rr] * st->T[c * 4 + 1];
+        acc = acc + X[2 * 4 + rr] * st->T[c * 4 + 2];
+        acc = acc + X[3 * 4 + rr] * st->T[c * 4 + 3];
+        N[c * 4 + rr] = acc;
+      }
+#pragma unroll
+    for (int i = 0; i < 16; i++) st->T[i] = N[i];
+    const float e = (float)err / cnt;
+    st->alpha += it_weight_gradient;                                                      // :141
+    if (fabs(e - st->prev_err[2]) < epsilon && fabs(e - st->prev_err[0]) < epsilon)       // :146-150
+      st->finished = 1u;
+    st->prev_err[0] = st->prev_err[1];                                                    // :151-155
+    st->prev_err[1] = st->prev_err[2];
+    st->prev_err[2] = st->prev_err[3];
+    st->prev_err[3] = e;
+    st->iterations += 1u;
+  }
+}
+
+__global__ void __launch_bounds__(REG_THREADS)
+reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopParams rp,
+                RegAccum *__restrict__ acc, u64 *__restrict__ partials, u64 *__restrict__ trace, const int trace_cap)
+{
+  cg::grid_group grid = cg::this_grid();
+  __shared__ u64 s_w[REG_THREADS / 32][REG_NSLOT];
+  __shared__ u64 s_total[REG_NSLOT];
+  __shared__ GnState s_st;
+  __shared__ double s_lu[36], s_inv[36], s_xi[6];
+  __shared__ int s_perm[6];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gthread = blockIdx.x * REG_THREADS + tid;
+  const int gthreads = gridDim.x * REG_THREADS;
+
+  if (tid < 16) s_st.T[tid] = acc->T[tid];
+  if (tid < 4) s_st.prev_err[tid] = 0.f;
+  if (tid == 0) { s_st.alpha = acc->alpha; s_st.finished = 0u; s_st.iterations = 0u; }
+
+  ws_pt my[REG_PTS];
+#pragma unroll
+  for (int k = 0; k < REG_PTS; k++)
+  {
+    const int j = gthread + k * gthreads;
+    my[k].x = 0; my[k].y = 0; my[k].z = 0;
+    if (j < rp.n) my[k] = pts[j];
+  }
+  __syncthreads();
+
+  for (int it = 0; it < rp.max_iterations; it++)
+  {
+    float T[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) T[i] = s_st.T[i];
+    int M[16];
+    to_int_mat(T, M);                                                                    // :54
+    const int cx = (int)T[12], cy = (int)T[13], cz = (int)T[14];                         // :52
+
+    i64 sum[REG_NSLOT];
+#pragma unroll
+    for (int i = 0; i < REG_NSLOT; i++) sum[i] = 0;
+#pragma unroll
+    for (int k = 0; k < REG_PTS; k++)
+      if (gthread + k * gthreads < rp.n) accumulate_cloud_point(g, M, cx, cy, cz, rp.div_res, my[k], sum);
+    for (int j = gthread + REG_PTS * gthreads; j < rp.n; j += gthreads)   // clouds larger than the register cache
+      accumulate_cloud_point(g, M, cx, cy, cz, rp.div_res, pts[j], sum);
+
+    const i64 mine = warp_transpose_reduce(sum, lane);
+    s_w[warp][lane] = (u64)mine;
+    __syncthreads();
+    u64 *row = partials + ((size_t)(it & 1) * gridDim.x + blockIdx.x) * REG_NSLOT;
+    if (tid < REG_NSLOT)
+    {
+      u64 a = 0ull;
+#pragma unroll
+      for (int w = 0; w < REG_THREADS / 32; w++) a += s_w[w][tid];
+      row[tid] = a;
+    }
+    __threadfence();
+    grid.sync();
+
+    // every block: total over all blocks' rows
+    {
+      const u64 *base = partials + (size_t)(it & 1) * gridDim.x * REG_NSLOT;
+      u64 a = 0ull;
+      for (int b = warp; b < (int)gridDim.x; b += REG_THREADS / 32) a += __ldcg(&base[(size_t)b * REG_NSLOT + lane]);
+      s_w[warp][lane] = a;
+    }
+    __syncthreads();
+    if (tid < REG_NSLOT)
+    {
+      u64 a = 0ull;
+#pragma unroll
+      for (int w = 0; w < REG_THREADS / 32; w++) a += s_w[w][tid];
+      s_total[tid] = a;
+      if (blockIdx.x == 0 && trace && it < trace_cap && tid < WS_NSUM) trace[(size_t)it * WS_NSUM + tid] = a;
+    }
+    __syncthreads();
+    if (warp == 0) warp_gn_solve(s_total, &s_st, s_lu, s_perm, s_inv, s_xi, rp.it_weight_gradient, rp.epsilon, lane);
+    __syncthreads();
+    if (s_st.finished) break;
+  }
+
+  if (blockIdx.x == 0)
+  {
+    if (tid < 16) acc->T[tid] = s_st.T[tid];
+    if (tid < 4) acc->prev_err[tid] = s_st.prev_err[tid];
+    if (tid == 0)
+    {
+      acc->alpha = s_st.alpha;
+      acc->finished = s_st.finished;
+      acc->iterations = s_st.iterations;
+    }
+  }
+}
+
 // test/cuda.cpp:416-532 shape: reduce caller-supplied Jacobians/values through the same code path
 __global__ void __launch_bounds__(256)
 test_reduce_kernel(const i64 *__restrict__ jac, const int *__restrict__ values, const int n, RegAccum *__restrict__ acc)
@@ -381,6 +698,32 @@ void ws_launch_reg_iteration(ws_handle *h, int n, int res, int fused_solve, floa
   ws_timer_begin(h, WS_TIMER_REG);
   reg_accum_kernel<<<blocks, 256, 0, h->stream>>>(h->g, h->d_reg_points, n, make_fastdiv((unsigned)res), h->d_acc,
                                                   h->d_trace, h->trace_cap, fused_solve, it_weight_gradient, epsilon);
+  ws_timer_end(h);
+  h->launches++;
+}
+
+void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float it_weight_gradient, float epsilon)
+{
+  if (h->reg_loop_blocks == 0)
+  {
+    int per_sm = 0;
+    WS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reg_loop_kernel, REG_THREADS, 0));
+    if (per_sm < 1) throw std::runtime_error("reg_loop_kernel does not fit on an SM");
+    if (per_sm > 2) per_sm = 2;
+    h->reg_loop_blocks = per_sm * h->sm_count;
+    WS_CUDA_OK(cudaMalloc(&h->d_reg_partials, (size_t)2 * h->reg_loop_blocks * REG_NSLOT * sizeof(u64)));
+  }
+  RegLoopParams rp;
+  rp.n = n;
+  rp.div_res = make_fastdiv((unsigned)res);
+  rp.max_iterations = max_iterations;
+  rp.it_weight_gradient = it_weight_gradient;
+  rp.epsilon = epsilon;
+  void *args[] = { (void *)&h->g, (void *)&h->d_reg_points, (void *)&rp, (void *)&h->d_acc,
+                   (void *)&h->d_reg_partials, (void *)&h->d_trace, (void *)&h->trace_cap };
+  ws_timer_begin(h, WS_TIMER_REG);
+  WS_CUDA_OK(cudaLaunchCooperativeKernel((const void *)reg_loop_kernel, dim3(h->reg_loop_blocks), dim3(REG_THREADS),
+                                         args, 0, h->stream));
   ws_timer_end(h);
   h->launches++;
 }

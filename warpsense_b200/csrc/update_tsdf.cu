@@ -42,6 +42,13 @@ namespace cg = cooperative_groups;
 
 namespace {
 
+WS_D unsigned long long global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct Ray
 {
   int p[3];
@@ -554,6 +561,7 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
   const unsigned gthreads = gridDim.x * blockDim.x;
   const unsigned gwarp = gthread >> 5, gwarps = gthreads >> 5;
   unsigned written = 0;
+  if (gthread == 0) ctr->t_phase[0] = global_ns();
 
   // ---- round 1, candidates: the record, one warp per pair of 64-entry chunks.  Four independent
   // record -> key -> parked-winner chains per lane are in flight at a time (the pass is latency bound).
@@ -593,6 +601,7 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
     }
   }
   grid.sync();
+  if (gthread == 0) ctr->t_phase[1] = global_ns();
 
   // ---- rounds: resolve, then offer the short list to what is still pending ----------------------
   for (unsigned round = 1;; round++)
@@ -624,6 +633,7 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
     const unsigned n_still = *((volatile unsigned *)n_out);
     if (gthread == 0)
     {
+      if (round == 1u) ctr->t_phase[2] = global_ns();
       ctr->rounds = round;
       ctr->n_active[(round & 1u) ^ 1u] = 0u;      // next round's output counter (its readers are done)
     }
@@ -644,6 +654,7 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
   {
     ctr->n_parked = n_pend;
     ctr->n_pending = 0u;
+    ctr->t_phase[3] = global_ns();
   }
 }
 

@@ -49,6 +49,7 @@ struct UpdateCounters
   unsigned rec_overflow;     // the record did not fit its buffer
   unsigned n_list;           // entries of the replay list (round-1 survivors)
   unsigned n_active[2];      // still-pending slots, ping-pong between replay rounds
+  unsigned long long t_phase[4];   // %globaltimer at the replay kernel's phase boundaries (diagnostics)
 };
 
 static_assert(offsetof(UpdateCounters, ray_counter) == 128 && offsetof(UpdateCounters, n_chunks) == 256,
@@ -109,6 +110,8 @@ struct ws_handle
   u64 *d_trace = nullptr;               // [max_trace][29]
   int trace_cap = 0;
   RegAccum *h_acc = nullptr;            // pinned
+  u64 *d_reg_partials = nullptr;        // [2][reg_loop_blocks][32] per-block sums of the persistent GN loop
+  int reg_loop_blocks = 0;
 
   // timing of the dominant kernels (cudaEvents on `stream`)
   bool profile = false;
@@ -139,6 +142,7 @@ void ws_update_alloc(ws_handle *h, size_t initial_chunks, size_t max_chunks);
 void ws_launch_reg_reset(ws_handle *h, const float T[16], float alpha0);
 void ws_launch_reg_iteration(ws_handle *h, int n, int res, int fused_solve, float it_weight_gradient, float epsilon);
 void ws_launch_reg_solve(ws_handle *h, float it_weight_gradient, float epsilon);
+void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float it_weight_gradient, float epsilon);
 void ws_launch_transform_cloud(ws_handle *h, ws_pt *d_pts, int n);
 void ws_host_solve(const i64 H[36], const i64 g[6], int err, int cnt, float alpha, float T[16], double xi_out[6]);
 // map_ops.cu

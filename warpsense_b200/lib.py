@@ -25,10 +25,12 @@ TIMER_MARCH, TIMER_MERGE, TIMER_REG, TIMER_REPLAY = 0, 1, 2, 3
 class UpdateCounters(C.Structure):
     _fields_ = [("n_points", C.c_int64), ("n_candidates", C.c_int64), ("n_touched", C.c_int64),
                 ("n_written", C.c_int64), ("n_touched_bricks", C.c_int64), ("n_parked", C.c_int64),
-                ("n_rounds", C.c_int64)]
+                ("n_rounds", C.c_int64), ("n_list", C.c_int64), ("n_record_chunks", C.c_int64),
+                ("replay_phase_ns", C.c_int64 * 3)]
 
     def as_dict(self):
-        return {k: int(getattr(self, k)) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        return {k: (int(v) if isinstance(v, int) else [int(x) for x in v]) for k, v in d.items()}
 
 
 class WarpsenseError(RuntimeError):
