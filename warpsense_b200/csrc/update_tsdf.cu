@@ -416,13 +416,17 @@ WS_D bool winner_is_final(u64 key, int tau)
   return !key_interpolated(key) || key_abs_value(key) >= tau;
 }
 
+#define PEND_SEEN_FLAG 0x8000000000000000ull   // pend_addr: the stored entry has weight > 0
+
 __global__ void __launch_bounds__(256)
 merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict__ brick_list,
              UpdateCounters *__restrict__ ctr, const unsigned pending_cap,
              u64 *__restrict__ pend_addr, u64 *__restrict__ pend_prev, u64 *__restrict__ pend_key)
 {
+  __shared__ unsigned s_cnt[8][4];
+  __shared__ unsigned s_base;
   const unsigned n_tb = ctr->n_touched_bricks;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned touched = 0, written = 0;
   // two bricks per turn; all four loads of a thread are in flight before the first is used
   for (unsigned bi = blockIdx.x; bi < n_tb; bi += 2u * gridDim.x)
@@ -444,60 +448,81 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
       kk[u] = __ldcs(reinterpret_cast<const ulonglong2 *>(&g.keys[base[u]]));
       ee[u] = *reinterpret_cast<const uint2 *>(&g.grid[base[u]]);
     }
+    // pass 1: fold final winners, find the voxels to park (keys left over from an earlier scan's parking
+    // carry the PENDING tag: they are larger than any candidate, so they count as empty)
+    unsigned pm[4];
+    u64 kq[4];
 #pragma unroll
     for (int u = 0; u < 2; u++)
     {
-      const u64 k2[2] = { live[u] ? kk[u].x : WS_KEY_EMPTY, live[u] ? kk[u].y : WS_KEY_EMPTY };
+      const u64 k2[2] = { kk[u].x, kk[u].y };
       const uint32_t e2[2] = { ee[u].x, ee[u].y };
-      bool parked[2] = { false, false };
+      bool parked[2];
 #pragma unroll
       for (int j = 0; j < 2; j++)
       {
         const u64 k = k2[j];
-        const bool occupied = k != WS_KEY_EMPTY;
+        const bool occupied = live[u] && key_is_candidate(k);
         const bool fin = occupied && winner_is_final(k, P.tau);
-        const bool park = occupied && !fin;
-        const i64 addr = base[u] + j;
-        parked[j] = park;
+        parked[j] = occupied && !fin;
+        kq[u * 2 + j] = k;
         if (occupied) touched++;
-        if (fin) written += apply_winner_to(&g.grid[addr], e2[j], P, k);
-        // parked voxels: one slot counter bump per warp
-        const unsigned pm = __ballot_sync(FULL, park);
-        if (pm)
+        if (fin) written += apply_winner_to(&g.grid[base[u] + j], e2[j], P, k);
+        pm[u * 2 + j] = __ballot_sync(FULL, parked[j]);
+      }
+      if (live[u])
+      {
+        // keys: reset everything that is not parked (one 16-byte store when neither voxel is)
+        const bool o0 = k2[0] != WS_KEY_EMPTY, o1 = k2[1] != WS_KEY_EMPTY;
+        if (o0 || o1)
         {
-          unsigned first = 0;
-          if (lane == (__ffs(pm) - 1)) first = atomicAdd(&ctr->n_pending, (unsigned)__popc(pm));
-          first = __shfl_sync(FULL, first, __ffs(pm) - 1);
-          if (park)
+          if (!parked[0] && !parked[1])
+            *reinterpret_cast<ulonglong2 *>(&g.keys[base[u]]) = make_ulonglong2(WS_KEY_EMPTY, WS_KEY_EMPTY);
+          else
           {
-            const unsigned slot = first + (unsigned)__popc(pm & ((1u << lane) - 1u));
-            if (slot < pending_cap)
-            {
-              pend_addr[slot] = (u64)addr;
-              pend_prev[slot] = k;
-              pend_key[slot] = WS_KEY_EMPTY;
-              g.keys[addr] = WS_KEY_PENDING_TAG | (u64)slot;
-            }
-            else
-            {
-              atomicAdd(&ctr->pending_overflow, 1u);
-              g.keys[addr] = WS_KEY_EMPTY;
-            }
+            if (!parked[0] && o0) g.keys[base[u]] = WS_KEY_EMPTY;
+            if (!parked[1] && o1) g.keys[base[u] + 1] = WS_KEY_EMPTY;
           }
         }
+        // parked bitmap of this warp's 64 voxels (always written: the words may hold an earlier scan's bits)
+        if (lane == 0)
+          *reinterpret_cast<uint2 *>(&g.park_bits[park_word((u64)base[u])]) = make_uint2(pm[u * 2], pm[u * 2 + 1]);
       }
-      // reset the keys of this thread's two voxels: one 16-byte store unless one of them stays parked
-      if (k2[0] != WS_KEY_EMPTY || k2[1] != WS_KEY_EMPTY)
+    }
+    // pass 2: slots for the parked voxels -- ONE global atomic per block and turn
+    if (lane < 4) s_cnt[warp][lane] = (unsigned)__popc(pm[lane]);
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      unsigned tot = 0;
+      for (int w = 0; w < 8; w++)
+        for (int q = 0; q < 4; q++) { const unsigned c = s_cnt[w][q]; s_cnt[w][q] = tot; tot += c; }
+      s_base = tot ? atomicAdd(&ctr->n_pending, tot) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+    {
+      if (pm[q] & (1u << lane))
       {
-        if (!parked[0] && !parked[1])
-          *reinterpret_cast<ulonglong2 *>(&g.keys[base[u]]) = make_ulonglong2(WS_KEY_EMPTY, WS_KEY_EMPTY);
+        const unsigned slot = s_base + s_cnt[warp][q] + (unsigned)__popc(pm[q] & ((1u << lane) - 1u));
+        const i64 addr = base[q >> 1] + (q & 1);
+        const uint32_t e = (q & 1) ? ee[q >> 1].y : ee[q >> 1].x;
+        if (slot < pending_cap)
+        {
+          pend_addr[slot] = (u64)addr | (entry_weight(e) > 0 ? PEND_SEEN_FLAG : 0ull);
+          pend_prev[slot] = kq[q];
+          pend_key[slot] = WS_KEY_EMPTY;
+          g.keys[addr] = WS_KEY_PENDING_TAG | (u64)slot;
+        }
         else
         {
-          if (!parked[0] && k2[0] != WS_KEY_EMPTY) g.keys[base[u]] = WS_KEY_EMPTY;
-          if (!parked[1] && k2[1] != WS_KEY_EMPTY) g.keys[base[u] + 1] = WS_KEY_EMPTY;
+          atomicAdd(&ctr->pending_overflow, 1u);
+          g.keys[addr] = WS_KEY_EMPTY;
         }
       }
     }
+    __syncthreads();
   }
   for (int o = 16; o > 0; o >>= 1)
   {
@@ -516,8 +541,8 @@ WS_D bool resolve_slot(const GridDesc &g, const UpdateParams &P, const unsigned 
                        u64 *__restrict__ pend_addr, u64 *__restrict__ pend_prev, u64 *__restrict__ pend_key,
                        unsigned &written)
 {
-  const u64 addr = pend_addr[s];
-  if (addr == PEND_DONE) return false;
+  const u64 pa = pend_addr[s];
+  if (pa == PEND_DONE) return false;
   const u64 k2 = pend_key[s];
   u64 fin;
   if (k2 == WS_KEY_EMPTY) fin = pend_prev[s];            // nothing later in the order: the parked winner stands
@@ -528,20 +553,52 @@ WS_D bool resolve_slot(const GridDesc &g, const UpdateParams &P, const unsigned 
     pend_key[s] = WS_KEY_EMPTY;
     return true;
   }
-  written += apply_winner_to(&g.grid[addr], g.grid[addr], P, fin);
-  g.keys[addr] = WS_KEY_EMPTY;
+  // an interpolated (negative-weight) winner never changes an entry that already has weight > 0
+  // (update_tsdf.cpp:546-557): no grid access at all for those
+  if (!(key_interpolated(fin) && (pa & PEND_SEEN_FLAG)))
+  {
+    const u64 addr = pa & ~PEND_SEEN_FLAG;
+    written += apply_winner_to(&g.grid[addr], g.grid[addr], P, fin);
+  }
+  // the voxel's key keeps its PENDING tag: the next scan's atomicMin / merge treat it as empty
   pend_addr[s] = PEND_DONE;
   return false;
 }
 
-WS_D void list_append(const bool want, const Rec e, const int lane, Rec *__restrict__ list, unsigned *counter)
+// replay list writer: a warp reserves WS_LIST_SPAN entries at a time (one same-address atomic per span) and
+// pads what it does not use with entries whose slot is LIST_NONE
+#define WS_LIST_SPAN 128
+#define LIST_NONE 0xFFFFFFFFFFFFFFFFull
+struct ListWriter
+{
+  unsigned base, used;
+};
+
+WS_D void list_pad(ListWriter &w, const int lane, Rec *__restrict__ list)
+{
+  for (unsigned t = w.used + (unsigned)lane; t < WS_LIST_SPAN; t += 32u)
+  {
+    Rec e; e.key = 0ull; e.ref = LIST_NONE;
+    list[w.base + t] = e;
+  }
+  w.used = WS_LIST_SPAN;
+}
+
+WS_D void list_append(ListWriter &w, const bool want, const Rec e, const int lane, Rec *__restrict__ list, unsigned *counter)
 {
   const unsigned m = __ballot_sync(FULL, want);
   if (m == 0u) return;
-  unsigned first = 0;
-  if (lane == 0) first = atomicAdd(counter, (unsigned)__popc(m));
-  first = __shfl_sync(FULL, first, 0);
-  if (want) list[first + (unsigned)__popc(m & ((1u << lane) - 1u))] = e;
+  const unsigned n = (unsigned)__popc(m);
+  if (w.used + n > WS_LIST_SPAN)
+  {
+    if (w.used < WS_LIST_SPAN) list_pad(w, lane, list);
+    unsigned b = 0;
+    if (lane == 0) b = atomicAdd(counter, (unsigned)WS_LIST_SPAN);
+    w.base = __shfl_sync(FULL, b, 0);
+    w.used = 0;
+  }
+  if (want) list[w.base + w.used + (unsigned)__popc(m & ((1u << lane) - 1u))] = e;
+  w.used += n;
 }
 
 // Cooperative launch: settles every parked voxel on the device (see the file header, step 4).
@@ -564,14 +621,19 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
   if (gthread == 0) ctr->t_phase[0] = global_ns();
 
   // ---- round 1, candidates: the record, one warp per pair of 64-entry chunks.  Four independent
-  // record -> key -> parked-winner chains per lane are in flight at a time (the pass is latency bound).
+  // record -> parked bit -> key -> parked-winner chains per lane are in flight at a time (the pass is
+  // latency bound); the parked bitmap (1 bit per voxel, L2 resident) spares the key lookup for the ~80 %
+  // of the records whose voxel is not parked.
   unsigned n_chunks = ctr->n_chunks;
   if (n_chunks > cap_chunks) n_chunks = cap_chunks;
+  ListWriter lw;
+  lw.base = 0u; lw.used = WS_LIST_SPAN;
   for (unsigned c0 = gwarp * 2u; c0 < n_chunks; c0 += gwarps * 2u)
   {
     Rec rr[4];
     bool ok[4];
     u64 kv[4];
+    unsigned pw[4];
 #pragma unroll
     for (int u = 0; u < 4; u++)
     {
@@ -582,7 +644,13 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
       if (ok[u]) rr[u] = rec[(size_t)c * WS_REC_CHUNK + j];
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) kv[u] = ok[u] ? __ldcg(&g.keys[rr[u].ref]) : WS_KEY_EMPTY;
+    for (int u = 0; u < 4; u++) pw[u] = ok[u] ? __ldcg(&g.park_bits[park_word(rr[u].ref)]) : 0u;
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+    {
+      ok[u] = ok[u] && ((pw[u] >> park_bit(rr[u].ref)) & 1u);
+      kv[u] = ok[u] ? __ldcg(&g.keys[rr[u].ref]) : WS_KEY_EMPTY;
+    }
     u64 thr[4];
 #pragma unroll
     for (int u = 0; u < 4; u++)
@@ -597,9 +665,10 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
       const bool hit = ok[u] && key_seq(rr[u].key) > key_seq(thr[u]);
       if (hit) atomicMin(&pend_key[slot], rr[u].key);
       Rec e; e.key = rr[u].key; e.ref = (u64)slot;
-      list_append(hit, e, lane, list, &ctr->n_list);
+      list_append(lw, hit, e, lane, list, &ctr->n_list);
     }
   }
+  if (lw.used < WS_LIST_SPAN) list_pad(lw, lane, list);
   grid.sync();
   if (gthread == 0) ctr->t_phase[1] = global_ns();
 
@@ -642,6 +711,7 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
     for (unsigned t = gthread; t < n_list; t += gthreads)
     {
       const Rec e = list[t];
+      if (e.ref == LIST_NONE) continue;
       const unsigned slot = (unsigned)e.ref;
       if (pend_addr[slot] != PEND_DONE && key_seq(e.key) > key_seq(pend_prev[slot])) atomicMin(&pend_key[slot], e.key);
     }
@@ -688,7 +758,10 @@ static void ensure_record(ws_handle *h, size_t chunks)
   cudaFree(h->d_rec); cudaFree(h->d_list); cudaFree(h->d_chunk_fill);
   h->d_rec = nullptr; h->d_list = nullptr; h->d_chunk_fill = nullptr; h->rec_cap_chunks = 0;
   WS_CUDA_OK(cudaMalloc(&h->d_rec, chunks * WS_REC_CHUNK * sizeof(Rec)));
-  WS_CUDA_OK(cudaMalloc(&h->d_list, chunks * WS_REC_CHUNK * sizeof(Rec)));
+  // replay list: every record can land in it, spans are padded (< 32 of 128 entries) and every warp of the
+  // replay grid (<= 4 blocks x 8 warps per SM) may leave one span partly used
+  const size_t list_entries = chunks * WS_REC_CHUNK * 3 / 2 + (size_t)h->sm_count * 4 * 8 * WS_LIST_SPAN;
+  WS_CUDA_OK(cudaMalloc(&h->d_list, list_entries * sizeof(Rec)));
   WS_CUDA_OK(cudaMalloc(&h->d_chunk_fill, chunks * sizeof(unsigned)));
   h->rec_cap_chunks = chunks;
 }

@@ -89,6 +89,7 @@ struct GridDesc
   uint32_t *grid;   // n_bricks * 512 TSDF entries  {int16 value | int16 weight << 16}
   u64 *keys;        // n_bricks * 512 candidate keys (all-ones when idle)
   unsigned *brick_flag;  // per resident brick: touched by the current scan
+  unsigned *park_bits;   // 1 bit per voxel: parked by the current scan's merge pass (valid for touched bricks)
   short xslot[WS_MAX_XBRICKS];  // ring-x brick column -> resident slot, -1 if not resident
 };
 
@@ -149,6 +150,11 @@ WS_HD u64 make_key(int value, bool interpolated, u64 seq)
   u64 ord = interpolated ? (WS_SEQ_MAX - seq) : seq;
   return ((u64)av << 47) | ((u64)(interpolated ? 1 : 0) << 46) | (ord << 1) | (u64)(value < 0 ? 1 : 0);
 }
+
+// bit of voxel `addr` in park_bits: a warp of the merge pass owns 64 consecutive voxels (two per lane) and
+// stores one ballot word per voxel parity
+WS_HD size_t park_word(u64 addr) { return (size_t)((addr >> 6) * 2ull + (addr & 1ull)); }
+WS_HD unsigned park_bit(u64 addr) { return (unsigned)((addr >> 1) & 31ull); }
 
 WS_HD bool key_is_candidate(u64 k) { return (k >> 62) == 0; }
 WS_HD bool key_is_pending(u64 k) { return (k >> 62) == 2; }
