@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--beams", type=int, default=128)
     ap.add_argument("--cols", type=int, default=1024)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA kernels")
     ap.add_argument("--update-only", action="store_true", help="BASELINE configs[1]: update_tsdf without registration")
     return ap.parse_args()
 
@@ -379,10 +380,60 @@ def run_native(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, frames, s)
-        print(json.dumps(line))
     tsdf.close()
+    if rank == 0:
+        if world == 1 and not args.no_ref_cuda:
+            try:
+                line["reference_cuda_same_gpu"] = reference_cuda(args, frames, s)
+            except Exception as exc:   # the secondary baseline must never take the bench line down
+                line["reference_cuda_same_gpu"] = {"unavailable": repr(exc)[:200]}
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def reference_cuda(args, frames, s, scans=5):
+    """Secondary baseline: the REFERENCE's own CUDA kernels (src/warpsense/cuda/*.cu, recompiled unmodified
+    for sm_100a into oracle/_ref/libws_refcuda.so) on this same GPU, through the reference's own classes
+    (blocking copies, default stream).  Not the parity target: different collision rule, sensor origin and
+    bounds, and its registration kernels only look at the first 65,536 points."""
+    from oracle import refcuda
+    from oracle import oracle as orc
+    from warpsense_b200 import fixedpoint as fp
+    if not refcuda.available():
+        return {"unavailable": "oracle/_ref/libws_refcuda.so not built (needs /root/reference at build time)"}
+    side, res = args.grid, args.res
+    r = refcuda.RefCuda((side, side, side), TAU, MAX_WEIGHT, res)
+    pos, up = fp.convert_pose_to_gpu(frames[0]["pose"], res)
+    r.set_points(frames[0]["points_map"])
+    r.update(pos, up)
+    t_upd, t_reg = [], []
+    I = np.eye(4, dtype=np.float32)
+    for k in range(1, min(scans, len(frames) - 1) + 1):
+        f = frames[k]
+        r.set_points(f["points_prior"])
+        if not args.update_only:
+            t0 = time.perf_counter()
+            r.reg_prepare()
+            T, alpha = I.copy(), 0.0
+            for _ in range(GN_ITERS):
+                H, g, e, c = r.reg_step(fp.colmajor16(T))
+                if c > 0:
+                    T, _, _ = orc.reg_solve(H.reshape(6, 6).T, g, e, c, alpha, T)
+                alpha += IT_WEIGHT
+            t_reg.append(time.perf_counter() - t0)
+        pos, up = fp.convert_pose_to_gpu(f["pose"], res)
+        r.set_points(f["points_map"])
+        t0 = time.perf_counter()
+        r.update(pos, up)
+        t_upd.append(time.perf_counter() - t0)
+    r.close()
+    upd = statistics.median(t_upd)
+    reg = statistics.median(t_reg) if t_reg else 0.0
+    return {"value": 1.0 / (upd + reg), "unit": UNIT, "update_ms": 1000.0 * upd, "reg_20_iterations_ms": 1000.0 * reg,
+            "kind": "reference CUDA kernels recompiled for sm_100a, reference classes, host buffers (e2e-like)",
+            "note": "not the parity target; registration covers only the first 65,536 points; the 6x6 solve "
+                    "between iterations runs on the host as in tsdf_registration.cpp:67-69", "scans": len(t_upd)}
 
 
 def cpu_baseline(args, frames, s):
