@@ -1,0 +1,386 @@
+// warpsense_b200.hpp -- the reference's hot-path classes as header-only C++17 shims over the C ABI of
+// warpsense_b200.h.  Same names, argument meaning and error behaviour as the reference (citations are
+// file:line under /root/reference), minus ROS / PCL / Eigen / HighFive types:
+//
+//   rmagine::Pointi            include/warpsense/math/vector3.h:416      packed {int x, y, z}
+//   Matrix4f                   Eigen::Matrix4f storage                   column-major float[16]
+//   HostLocalMap               HDF5LocalMap's in-memory part             include/map/hdf5_local_map.h
+//   cuda::DeviceMap            include/warpsense/cuda/device_map.h:32-164
+//   cuda::DeviceMapMemWrapper  include/warpsense/cuda/device_map_wrapper.h:10-36
+//   cuda::TSDFCuda             include/warpsense/cuda/update_tsdf.h:9-34
+//   cuda::RegistrationCuda     include/warpsense/cuda/registration.h:10-45
+//   cuda::TSDFMapping          include/warpsense/tsdf_mapping.h:17-60
+//   cuda::TSDFRegistration     include/warpsense/tsdf_registration.h:17-27
+//
+// Everything that touches voxels or points runs in libwarpsense_b200.so on the GPU; this header only
+// marshals arguments.  CUDA failures throw std::runtime_error (the reference prints and exit(1)s,
+// include/warpsense/cuda/common.cuh:10-21).
+#pragma once
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "warpsense_b200.h"
+
+namespace rmagine
+{
+struct Pointi
+{
+  int x = 0, y = 0, z = 0;
+  Pointi() = default;
+  Pointi(int x_, int y_, int z_) : x(x_), y(y_), z(z_) {}
+};
+static_assert(sizeof(Pointi) == sizeof(ws_point), "rmagine::Pointi must be 12 packed bytes");
+}  // namespace rmagine
+
+namespace warpsense_b200
+{
+constexpr int WEIGHT_RESOLUTION = 64;       // include/warpsense/consts.h:9-10
+constexpr int MATRIX_RESOLUTION = 32768;    // include/warpsense/consts.h:12-13
+
+struct Matrix4f    // column-major, like Eigen::Matrix4f
+{
+  float m[16];
+  static Matrix4f Identity()
+  {
+    Matrix4f r{};
+    for (int i = 0; i < 4; i++) r.m[i * 4 + i] = 1.f;
+    return r;
+  }
+  float &operator()(int row, int col) { return m[col * 4 + row]; }
+  float operator()(int row, int col) const { return m[col * 4 + row]; }
+};
+
+// TSDFEntry (include/map/tsdf.h:16-57)
+struct TSDFEntry
+{
+  uint32_t raw = 0;
+  TSDFEntry() = default;
+  TSDFEntry(int value, int weight) : raw((uint32_t)(uint16_t)(int16_t)value | ((uint32_t)(uint16_t)(int16_t)weight << 16)) {}
+  int value() const { return (int16_t)(raw & 0xFFFFu); }
+  int weight() const { return (int16_t)(raw >> 16); }
+};
+
+// include/params/map_params.h:49-106, registration_params.h:22-30 (unit scaling included)
+struct MapParams
+{
+  int resolution = 64;
+  int tau = 600;           // int(max_distance * 1000)
+  int max_weight = 640;    // max_weight * WEIGHT_RESOLUTION
+  float shift = 3.0f;      // metres the sensor must move before the local map is shifted
+  int size[3] = { 313, 313, 79 };
+  static MapParams from_ros(float max_distance_m, int max_weight, const float size_m[3], int resolution_mm, float shift_m)
+  {
+    MapParams p;
+    p.resolution = resolution_mm;
+    p.tau = (int)(max_distance_m * 1000.f);
+    p.max_weight = max_weight * WEIGHT_RESOLUTION;
+    p.shift = shift_m;
+    for (int a = 0; a < 3; a++) p.size[a] = (int)size_m[a] * 1000 / resolution_mm;
+    return p;
+  }
+};
+struct RegistrationParams
+{
+  int max_iterations = 200;
+  float it_weight_gradient = 0.1f;
+  float epsilon = 0.03f;
+};
+struct Params
+{
+  MapParams map;
+  RegistrationParams registration;
+};
+
+// The in-memory part of HDF5LocalMap (src/map/hdf5_local_map.cpp:5-20): ring array + size/pos/offset.
+class HostLocalMap
+{
+public:
+  using Ptr = std::shared_ptr<HostLocalMap>;
+  HostLocalMap(int sx, int sy, int sz, int default_value, int default_weight)
+  {
+    const int s[3] = { sx, sy, sz };
+    for (int a = 0; a < 3; a++)
+    {
+      size_[a] = s[a] % 2 == 1 ? s[a] : s[a] + 1;        // hdf5_local_map.cpp:6-8
+      pos_[a] = 0;
+      offset_[a] = size_[a] / 2;
+    }
+    data_.assign((size_t)size_[0] * size_[1] * size_[2], TSDFEntry(default_value, default_weight));
+  }
+  int *get_size() { return size_; }
+  int *get_pos() { return pos_; }
+  int *get_offset() { return offset_; }
+  TSDFEntry *get_data() { return data_.data(); }
+  bool in_bounds(int x, int y, int z) const                // hdf5_local_map.h:275-279
+  {
+    return std::abs(x - pos_[0]) <= size_[0] / 2 && std::abs(y - pos_[1]) <= size_[1] / 2 && std::abs(z - pos_[2]) <= size_[2] / 2;
+  }
+  TSDFEntry &value(int x, int y, int z)                    // hdf5_local_map.h:140-181 (64-bit index)
+  {
+    if (!in_bounds(x, y, z)) throw std::out_of_range("Index out of bounds");
+    auto ov = [](int v, int m) { return ((v % m) + m) % m; };
+    const int64_t i = ((int64_t)ov(x - pos_[0] + offset_[0], size_[0]) * size_[1] + ov(y - pos_[1] + offset_[1], size_[1])) * size_[2] +
+                      ov(z - pos_[2] + offset_[2], size_[2]);
+    return data_[(size_t)i];
+  }
+
+private:
+  int size_[3], pos_[3], offset_[3];
+  std::vector<TSDFEntry> data_;
+};
+
+inline void ws_check(ws_handle *h, int rc, const char *what)
+{
+  if (rc < 0) throw std::runtime_error(std::string(what) + ": " + (h ? ws_last_error(h) : "no handle") + " (code " + std::to_string(rc) + ")");
+}
+
+// include/util/util.h:8-18,52-56 (host helpers used to prepare the call arguments)
+inline void to_int_mat(const Matrix4f &mat, int out[16])
+{
+  for (int i = 0; i < 16; i++) out[i] = (int)(mat.m[i] * (float)MATRIX_RESOLUTION);
+}
+inline rmagine::Pointi transform_point(const rmagine::Pointi &p, const int M[16])
+{
+  int r[3];
+  for (int i = 0; i < 3; i++)
+  {
+    const int32_t acc = (int32_t)((uint32_t)M[i] * (uint32_t)p.x + (uint32_t)M[4 + i] * (uint32_t)p.y + (uint32_t)M[8 + i] * (uint32_t)p.z + (uint32_t)M[12 + i]);
+    r[i] = acc / MATRIX_RESOLUTION;
+  }
+  return rmagine::Pointi(r[0], r[1], r[2]);
+}
+inline rmagine::Pointi to_map(const Matrix4f &pose, int map_resolution)
+{
+  return rmagine::Pointi((int)std::floor(pose.m[12] / map_resolution), (int)std::floor(pose.m[13] / map_resolution),
+                         (int)std::floor(pose.m[14] / map_resolution));
+}
+}  // namespace warpsense_b200
+
+namespace cuda
+{
+using warpsense_b200::HostLocalMap;
+using warpsense_b200::Matrix4f;
+using warpsense_b200::Params;
+using warpsense_b200::TSDFEntry;
+using warpsense_b200::ws_check;
+
+// cuda::DeviceMap: a non-owning view {size, offset, data, pos} of a host ring array (device_map.h:32-66)
+struct DeviceMap
+{
+  DeviceMap(int *size, int *offset, TSDFEntry *data, int *pos) : size_(size), offset_(offset), data_(data), pos_(pos) {}
+  explicit DeviceMap(const std::shared_ptr<HostLocalMap> &map)
+      : size_(map->get_size()), offset_(map->get_offset()), data_(map->get_data()), pos_(map->get_pos()) {}
+  DeviceMap() = default;
+  const int *get_size() const { return size_; }
+  const int *get_offset() const { return offset_; }
+  const int *get_pos() const { return pos_; }
+  int *size_ = nullptr, *offset_ = nullptr;
+  TSDFEntry *data_ = nullptr;
+  int *pos_ = nullptr;
+};
+
+// device_map_wrapper.h:10-36 over a shared ws_handle
+struct DeviceMapMemWrapper
+{
+  explicit DeviceMapMemWrapper(ws_handle *h) : h_(h) {}
+  void to_device(const DeviceMap &m)                               // device_map_wrapper.cu:64-75
+  {
+    ws_check(h_, ws_map_upload(h_, reinterpret_cast<const uint32_t *>(m.data_), m.size_, m.offset_, m.pos_), "to_device");
+  }
+  void to_host(const DeviceMap &m)                                 // device_map_wrapper.cu:77-92
+  {
+    ws_check(h_, ws_map_download(h_, reinterpret_cast<uint32_t *>(m.data_)), "to_host");
+    int32_t s[3];
+    ws_check(h_, ws_map_get_params(h_, s, m.offset_, m.pos_), "to_host");
+  }
+  void update_params(const DeviceMap &m)                           // device_map_wrapper.cu:35-43
+  {
+    ws_check(h_, ws_map_set_params(h_, m.offset_, m.pos_), "update_params");
+  }
+  ws_handle *dev() const { return h_; }
+  ws_handle *h_;
+};
+
+// update_tsdf.h:9-34
+class TSDFCuda
+{
+public:
+  explicit TSDFCuda(const DeviceMap &existing_map, int tau, int max_weight, int map_resolution, int device = 0)
+  {
+    const int rc = ws_create(existing_map.size_, tau, max_weight, map_resolution, device, &h_);
+    if (rc != WS_OK) throw std::runtime_error("TSDFCuda: ws_create failed (bad arguments or no usable CUDA device)");
+    avg_map_.reset(new DeviceMapMemWrapper(h_));
+    avg_map_->to_device(existing_map);
+  }
+  TSDFCuda(const TSDFCuda &) = delete;
+  TSDFCuda &operator=(const TSDFCuda &) = delete;
+  ~TSDFCuda() { ws_destroy(h_); }
+
+  // update_tsdf.cu:169-183; more than n_max_points_ points: prints and returns, like update_tsdf.cu:146-150
+  void update_tsdf(const std::vector<rmagine::Pointi> &scan_points, const rmagine::Pointi &scanner_pos, const rmagine::Pointi &up)
+  {
+    const int32_t sp[3] = { scanner_pos.x, scanner_pos.y, scanner_pos.z }, u[3] = { up.x, up.y, up.z };
+    const int rc = ws_update_tsdf(h_, reinterpret_cast<const ws_point *>(scan_points.data()), (int64_t)scan_points.size(), sp, u);
+    if (rc == WS_ERR_CAPACITY) { std::fprintf(stderr, "Too many points in scan (%zu)\n", scan_points.size()); return; }
+    ws_check(h_, rc, "update_tsdf");
+  }
+  void update_tsdf(DeviceMap &result, const std::vector<rmagine::Pointi> &scan_points, const rmagine::Pointi &scanner_pos, const rmagine::Pointi &up)
+  {
+    update_tsdf(scan_points, scanner_pos, up);                     // update_tsdf.cu:143-166
+    avg_map_->to_host(result);
+  }
+  ws_handle *device_map() { return h_; }
+  DeviceMapMemWrapper &avg_map() { return *avg_map_; }
+  DeviceMapMemWrapper &new_map() { return *avg_map_; }             // scratch keys live beside the map here
+  ws_update_counters counters() const
+  {
+    ws_update_counters c;
+    ws_get_update_counters(h_, &c);
+    return c;
+  }
+  static constexpr int n_max_points_ = WS_MAX_POINTS;
+
+private:
+  ws_handle *h_ = nullptr;
+  std::unique_ptr<DeviceMapMemWrapper> avg_map_;
+};
+
+// registration.h:10-45 (shares the device map of a TSDFCuda)
+class RegistrationCuda
+{
+public:
+  explicit RegistrationCuda(ws_handle *map) : h_(map) {}
+  void prepare_registration(const std::vector<rmagine::Pointi> &points)          // registration.cu:303-308
+  {
+    ws_check(h_, ws_reg_prepare(h_, reinterpret_cast<const ws_point *>(points.data()), (int64_t)points.size()), "prepare_registration");
+  }
+  // registration.cu:347-368; H column-major int64[36] (rmagine::Matrix6x6l storage), g int64[6]
+  void perform_registration(const Matrix4f *pretransform, int64_t H[36], int64_t g[6], int &e, int &c, int map_resolution)
+  {
+    int32_t ee = 0, cc = 0;
+    ws_check(h_, ws_reg_step(h_, pretransform->m, map_resolution, H, g, &ee, &cc), "perform_registration");
+    e = ee; c = cc;
+  }
+  ws_handle *h_;
+};
+
+// tsdf_mapping.h:17-60 without ROS: the map-shift thread becomes an explicit synchronous map_shift(pose)
+class TSDFMapping
+{
+public:
+  explicit TSDFMapping(const Params &params, HostLocalMap::Ptr &local_map, int device = 0)
+      : params_(params), hdf5_local_map_(local_map), cuda_map_(local_map),
+        tsdf_(new TSDFCuda(cuda_map_, params.map.tau, params.map.max_weight, params.map.resolution, device)),
+        last_shift_pose_(Matrix4f::Identity())
+  {
+    shifted_ = false;
+    is_shifting_ = false;
+  }
+  virtual ~TSDFMapping() = default;
+
+  void update_tsdf(const std::vector<rmagine::Pointi> &scan_points, const rmagine::Pointi &pos_rm, const rmagine::Pointi &up_rm)
+  {
+    std::unique_lock<std::shared_mutex> lock(mutex_);              // tsdf_mapping.cpp:71-75
+    tsdf_->update_tsdf(scan_points, pos_rm, up_rm);
+  }
+  void update_tsdf(const std::vector<rmagine::Pointi> &scan_points, const Matrix4f &pose)
+  {
+    rmagine::Pointi pos_rm, up_rm;                                 // tsdf_mapping.cpp:62-69
+    convert_pose_to_gpu(pose, pos_rm, up_rm);
+    std::unique_lock<std::shared_mutex> lock(mutex_);
+    tsdf_->update_tsdf(scan_points, pos_rm, up_rm);
+  }
+  void update_tsdf(DeviceMap &result, const std::vector<rmagine::Pointi> &scan_points, const Matrix4f &pose)
+  {
+    rmagine::Pointi pos_rm, up_rm;                                 // tsdf_mapping.cpp:87-95
+    convert_pose_to_gpu(pose, pos_rm, up_rm);
+    std::unique_lock<std::shared_mutex> lock(mutex_);
+    tsdf_->update_tsdf(result, scan_points, pos_rm, up_rm);
+  }
+  // tsdf_mapping.cpp:77-85
+  void convert_pose_to_gpu(const Matrix4f &pose, rmagine::Pointi &pos_rm, rmagine::Pointi &up_rm) const
+  {
+    int M[16], R[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };   // Matrix4i::Identity() ...
+    warpsense_b200::to_int_mat(pose, M);
+    for (int c = 0; c < 3; c++)                                               // ... with the int rotation block
+      for (int r = 0; r < 3; r++) R[c * 4 + r] = M[c * 4 + r];
+    up_rm = warpsense_b200::transform_point(rmagine::Pointi(0, 0, warpsense_b200::MATRIX_RESOLUTION), R);
+    pos_rm = warpsense_b200::to_map(pose, params_.map.resolution);
+  }
+  // one turn of the map-shift loop (tsdf_mapping.cpp:97-136), the shift itself running on the device
+  bool map_shift(const Matrix4f &current_pose)
+  {
+    float d2 = 0.f;
+    for (int a = 0; a < 3; a++)
+    {
+      const float d = last_shift_pose_.m[12 + a] / 1000.f - current_pose.m[12 + a] / 1000.f;
+      d2 += d * d;
+    }
+    if (std::sqrt(d2) < params_.map.shift) return false;
+    is_shifting_ = true;
+    last_shift_pose_ = current_pose;
+    const rmagine::Pointi p = warpsense_b200::to_map(current_pose, params_.map.resolution);
+    {
+      std::unique_lock<std::shared_mutex> lock(mutex_);
+      const int32_t np[3] = { p.x, p.y, p.z };
+      ws_check(tsdf_->device_map(), ws_shift(tsdf_->device_map(), np), "map_shift");
+      int32_t s[3];
+      ws_map_get_params(tsdf_->device_map(), s, hdf5_local_map_->get_offset(), hdf5_local_map_->get_pos());
+    }
+    shifted_ = true;
+    is_shifting_ = false;
+    return true;
+  }
+  void get_tsdf_map()                                              // tsdf_mapping.cpp:138-143
+  {
+    std::shared_lock<std::shared_mutex> lock(mutex_);
+    tsdf_->avg_map().to_host(cuda_map_);
+  }
+  const std::unique_ptr<TSDFCuda> &tsdf() const { return tsdf_; }
+  std::unique_ptr<TSDFCuda> &tsdf() { return tsdf_; }
+  void join_mapping_thread() {}
+  std::atomic<bool> &shifted() { return shifted_; }
+  std::atomic<bool> &is_shifting() { return is_shifting_; }
+
+protected:
+  const Params &params_;
+  HostLocalMap::Ptr &hdf5_local_map_;
+  DeviceMap cuda_map_;
+  std::unique_ptr<TSDFCuda> tsdf_;
+  std::shared_mutex mutex_;
+  std::atomic<bool> shifted_, is_shifting_;
+  Matrix4f last_shift_pose_;
+};
+
+// tsdf_registration.h:17-27
+struct TSDFRegistration : public TSDFMapping
+{
+  explicit TSDFRegistration(const Params &params, HostLocalMap::Ptr &local_map, int device = 0)
+      : TSDFMapping(params, local_map, device), reg_(new RegistrationCuda(tsdf_->device_map())) {}
+
+  // tsdf_registration.cpp:29-96, following the CPU loop (src/cpu/registration.cpp:14-177): the cloud is
+  // transformed in place and the total transform returned.  All iterations run in one persistent kernel.
+  Matrix4f register_cloud(std::vector<rmagine::Pointi> &cloud, const Matrix4f &pretransform, int *iterations = nullptr)
+  {
+    Matrix4f out{};
+    int32_t it = 0;
+    std::shared_lock<std::shared_mutex> lock(mutex_);
+    ws_check(tsdf_->device_map(),
+             ws_register_cloud(tsdf_->device_map(), reinterpret_cast<ws_point *>(cloud.data()), (int64_t)cloud.size(), pretransform.m,
+                               params_.registration.max_iterations, params_.registration.it_weight_gradient,
+                               params_.registration.epsilon, params_.map.resolution, WS_REG_DEVICE_SOLVE, out.m, &it),
+             "register_cloud");
+    if (iterations) *iterations = it;
+    return out;
+  }
+  std::unique_ptr<RegistrationCuda> reg_;
+};
+}  // namespace cuda

@@ -1,0 +1,92 @@
+// C++ host-side test of include/warpsense_b200.hpp: the reference's own known-answer test for update_tsdf
+// (test/map.cpp:9-90 == test/cuda.cpp:268-347 under /root/reference, "G1") and a registration round trip,
+// written against the reference's class names.  Needs a CUDA device; built and run by tests/test_cpp_shim.py.
+#include <cstdio>
+#include <cstdlib>
+#include "warpsense_b200.hpp"
+
+#define CHECK(cond)                                                              \
+  do {                                                                           \
+    if (!(cond)) { std::fprintf(stderr, "CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); return 1; } \
+  } while (0)
+
+// include/warpsense/test/common.h:16-26
+static int calc_weight(int value, int tau, int eps)
+{
+  int weight = warpsense_b200::WEIGHT_RESOLUTION;
+  if (value < -eps) weight = warpsense_b200::WEIGHT_RESOLUTION * (tau + value) / (tau - eps);
+  return weight;
+}
+
+int main()
+{
+  using namespace warpsense_b200;
+  // ---- G1: one point, res 1000, tau 3000, 21^3 map -------------------------------------------------
+  {
+    Params params;
+    params.map.resolution = 1000; params.map.tau = 3000; params.map.max_weight = 10 * WEIGHT_RESOLUTION;
+    auto local_map = std::make_shared<HostLocalMap>(20, 20, 20, params.map.tau, 0);
+    cuda::TSDFMapping gpu(params, local_map);
+    std::vector<rmagine::Pointi> scan = { rmagine::Pointi(5500, 500, 500) };
+    gpu.update_tsdf(scan, Matrix4f::Identity());
+    gpu.get_tsdf_map();
+    const int want[9] = { 0, 3000, 3000, 2000, 1000, 0, -1000, -2000, 3000 };
+    const int eps = params.map.tau / 10;
+    for (int k = 1; k <= 7; k++)
+    {
+      const TSDFEntry e = local_map->value(k, 0, 0);
+      CHECK(e.value() == want[k]);
+      CHECK(e.weight() == calc_weight(want[k], params.map.tau, eps));
+    }
+    CHECK(local_map->value(8, 0, 0).value() == 3000 && local_map->value(8, 0, 0).weight() == 0);
+    const ws_update_counters c = gpu.tsdf()->counters();
+    CHECK(c.n_candidates == 8 && c.n_touched == 8);
+  }
+  // ---- registration: build a wall, shift the cloud by (+120, -80, 0) mm, register it back ------------------
+  {
+    Params params;
+    params.map.resolution = 64; params.map.tau = 600; params.map.max_weight = 10 * WEIGHT_RESOLUTION;
+    params.registration.max_iterations = 50; params.registration.epsilon = 0.f;
+    auto local_map = std::make_shared<HostLocalMap>(128, 128, 64, params.map.tau, 0);
+    cuda::TSDFRegistration gpu(params, local_map);
+    std::vector<rmagine::Pointi> scan;
+    for (int a = -40; a <= 40; a++)
+      for (int b = -12; b <= 12; b++)
+      {
+        scan.emplace_back(2500, a * 40, b * 40);      // wall x = 2.5 m
+        scan.emplace_back(a * 40, 2200, b * 40);      // wall y = 2.2 m
+        scan.emplace_back(-2300, a * 40, b * 40);
+        scan.emplace_back(a * 40, -2600, b * 40);
+      }
+    gpu.update_tsdf(scan, Matrix4f::Identity());
+    std::vector<rmagine::Pointi> cloud = scan;
+    for (auto &p : cloud) { p.x += 120; p.y -= 80; }
+    int it = 0;
+    const Matrix4f T = gpu.register_cloud(cloud, Matrix4f::Identity(), &it);
+    std::printf("register_cloud: %d iterations, t = (%.1f, %.1f, %.1f) mm\n", it, T(0, 3), T(1, 3), T(2, 3));
+    CHECK(it == 50);
+    CHECK(std::fabs(T(0, 3) + 120.f) < 25.f && std::fabs(T(1, 3) - 80.f) < 25.f);
+    // the cloud came back transformed in place (src/cpu/registration.cpp:168-174)
+    long err = 0;
+    for (size_t i = 0; i < cloud.size(); i++) err += std::labs(cloud[i].x - scan[i].x) + std::labs(cloud[i].y - scan[i].y);
+    CHECK(err / (long)cloud.size() < 40);
+    // single accumulation step through RegistrationCuda
+    gpu.reg_->prepare_registration(scan);
+    int64_t H[36], g[6]; int e = 0, c = 0;
+    const Matrix4f I = Matrix4f::Identity();
+    gpu.reg_->perform_registration(&I, H, g, e, c, params.map.resolution);
+    CHECK(c > 1000);
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) CHECK(H[i * 6 + j] == H[j * 6 + i]);
+    // map shift on the device keeps voxels addressable at the same world coordinates
+    const TSDFEntry before = [&] { gpu.get_tsdf_map(); return local_map->value(39, 0, 0); }();
+    Matrix4f pose = Matrix4f::Identity();
+    pose(0, 3) = 3500.f;                                // 3.5 m > params.map.shift (3 m)
+    CHECK(gpu.map_shift(pose));
+    gpu.get_tsdf_map();
+    CHECK(local_map->get_pos()[0] == 54);               // floor(3500 / 64)
+    const TSDFEntry after = local_map->value(39, 0, 0);
+    CHECK(before.raw == after.raw);
+  }
+  std::printf("cpp shim ok\n");
+  return 0;
+}
