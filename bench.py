@@ -253,13 +253,9 @@ def run_native(args):
             T, _ = reg.register_cloud(None, np.eye(4, dtype=np.float32), GN_ITERS, IT_WEIGHT, EPSILON, res,
                                       keep_on_device=True)
             return T
-        hd.check(hd.L.ws_reg_begin(hd.h, I16.ctypes.data_as(f32p)))
-        for _ in range(GN_ITERS):
-            hd.check(hd.L.ws_reg_accumulate(hd.h, res))
-            dist.all_reduce(sums)                      # int64 sum: exact, identical on every rank
-            hd.check(hd.L.ws_reg_solve(hd.h, IT_WEIGHT, EPSILON))
-        hd.check(hd.L.ws_reg_finish(hd.h, Tout.ctypes.data_as(f32p), C.byref(it_out), C.byref(fin_out)))
-        return fp.from_colmajor16(Tout)
+        T, _ = reg.register_cloud_sharded(np.eye(4, dtype=np.float32), GN_ITERS, IT_WEIGHT, EPSILON, res,
+                                          lambda _r: dist.all_reduce(sums))   # int64 sum: exact, same on every rank
+        return T
 
     def step_device(k, dev_cloud):
         f = frames[k]

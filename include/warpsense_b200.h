@@ -144,8 +144,17 @@ const ws_point *ws_reg_points_device(ws_handle *h, int64_t *n);
 int ws_reg_begin(ws_handle *h, const float pretransform[16]);
 int ws_reg_accumulate(ws_handle *h, int32_t map_resolution);           /* local 29 sums, async   */
 void *ws_reg_sums_device(ws_handle *h);                                /* int64[29] device ptr   */
+int ws_reg_sums_get(ws_handle *h, int64_t sums[29]);                   /* host copies of the same  */
+int ws_reg_sums_set(ws_handle *h, const int64_t sums[29]);             /* (MPI / test reductions)  */
 int ws_reg_solve(ws_handle *h, float it_weight_gradient, float epsilon);/* solve + pose update    */
+int ws_reg_peek(ws_handle *h, int32_t *iterations, int32_t *finished);  /* progress so far (synchronises) */
 int ws_reg_finish(ws_handle *h, float out_transform[16], int32_t *iterations, int32_t *finished);
+
+/* Host-only (no GPU needed): the x-slab of rank `rank` out of `world` for a map of ring side size_x --
+ * owned ring-x rows [own_lo, own_hi) and the resident 8-row brick columns (owned + one halo row each
+ * side); returns the number of resident columns or WS_ERR_INVALID. */
+int ws_slab_layout(int32_t size_x, int32_t rank, int32_t world, int32_t *own_lo, int32_t *own_hi,
+                   int32_t *resident_cols, int32_t cap);
 
 /* test hook for the reduction shape (test/cuda.cpp:416-532): sums of n Jacobians with values */
 int ws_test_reduce(ws_handle *h, const int64_t *jacobis6, const int32_t *values, int64_t n,

@@ -1,0 +1,178 @@
+"""x-slab sharding of the ring over ranks.
+
+CPU (`not gpu`): the slab layout is a partition with one-row halos; a world_size-2 gloo run of the
+registration exchange (oracle partial sums of each rank's slab -> all_reduce(int64[29]) -> identical solve)
+reproduces the single-process oracle trace bit for bit.
+GPU: the same map held as 2 or 3 sharded handles (one per "rank", all on cuda:0) gives bit-identical voxels,
+sums and poses to the oracle -- the NCCL all-reduce is replaced by a host-side sum of ws_reg_sums_get()."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from warpsense_b200 import api, fixedpoint as fp
+from warpsense_b200.synth import ScanStream
+
+MR = fp.MATRIX_RESOLUTION
+
+
+# ----------------------------------------------------------------------------- host logic
+@pytest.mark.parametrize("size_x,world", [(5, 1), (21, 2), (129, 2), (129, 3), (513, 2), (513, 4), (513, 8), (2049, 8), (65, 8)])
+def test_slab_layout_is_a_partition_with_halos(size_x, world):
+    owned = np.zeros(size_x, np.int32)
+    for r in range(world):
+        lo, hi, cols = api.slab_layout(size_x, r, world)
+        assert 0 <= lo < hi <= size_x and lo % 8 == 0
+        owned[lo:hi] += 1
+        resident = set()
+        for c in cols:
+            resident.update(range(c * 8, min(c * 8 + 8, size_x)))
+        need = set(range(lo, hi))
+        if world > 1:
+            need |= {(lo - 1) % size_x, hi % size_x}        # the registration stencil reads x+-1 (ring wrap)
+        assert need <= resident
+    assert (owned == 1).all(), "every ring-x row is owned by exactly one rank"
+
+
+def test_slab_layout_rejects_more_ranks_than_columns():
+    with pytest.raises(ValueError):
+        api.slab_layout(17, 0, 4)      # 3 brick columns, 4 ranks: rank 0 gets none
+
+
+def _owned_mask(points, T, res, om, lo, hi):
+    """Points whose centre voxel's ring-x row lies in [lo, hi) (the rank that sums them)."""
+    q = fp.transform_points(points, fp.to_int_mat(T))
+    vx = (np.sign(q[:, 0]) * (np.abs(q[:, 0]) // res)).astype(np.int64)       # trunc toward zero (registration.cpp:65)
+    size, pos, off = int(om.size[0]), int(om.pos[0]), int(om.offset[0])
+    inb = np.abs(vx - pos) <= size // 2
+    rx = (vx - pos + off + size) % size
+    return inb & (rx >= lo) & (rx < hi)
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        res, tau, mw, side = 100, 1000, 640, 96
+        s = ScanStream(16, 128, side, res)
+        om = orc.LocalMap(side, side, side, tau, 0)
+        for k in range(2):
+            f = s.frame(k)
+            pos, up = fp.convert_pose_to_gpu(f["pose"], res)
+            orc.update_tsdf(om, f["points_map"], pos, up, tau, mw, res)
+        om.set_state(list(om.pos), [9, 40, 48])              # ring origin away from the array origin
+        cloud = s.frame(2, prior_pose=s.pose(1))["points_prior"]
+        lo, hi, _ = api.slab_layout(int(om.size[0]), rank, world)
+        T, alpha = np.eye(4, dtype=np.float32), 0.0
+        trace = []
+        for it in range(6):
+            mask = _owned_mask(cloud, T, res, om, lo, hi)
+            H, g, e, c = orc.reg_step(om, cloud[mask], T, res)
+            # but points are transformed by the FULL cloud's T: reg_step does that per point, so a subset is exact
+            sums = np.concatenate([H[np.triu_indices(6)], g, [e, c]]).astype(np.int64)
+            t = torch.from_numpy(sums)
+            dist.all_reduce(t)                                # the one exchange step of the path
+            tot = t.numpy()
+            Hf = np.zeros((6, 6), np.int64)
+            Hf[np.triu_indices(6)] = tot[:21]
+            Hf = Hf + Hf.T - np.diag(np.diag(Hf))
+            T, _, _ = orc.reg_solve(Hf, tot[21:27], int(tot[27]), int(tot[28]), alpha, T)
+            alpha += 0.1
+            trace.append(tot.copy())
+        # single-process oracle for comparison (same on every rank)
+        oT, oit, otr = orc.register_cloud(om, cloud.copy(), np.eye(4, dtype=np.float32), 6, 0.1, 0.0, res, trace=True)
+        ok = np.array_equal(np.array(trace), otr) and np.array_equal(T, oT)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (ok, T.tobytes()))
+        if rank == 0:
+            out.put((all(g[0] for g in gathered), len({g[1] for g in gathered})))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_registration_exchange_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    all_ok, distinct_T = out.get(timeout=10)
+    assert all_ok, "all-reduced partial sums differ from the single-process oracle trace"
+    assert distinct_T == 1, "ranks disagree on the transform"
+
+
+# ----------------------------------------------------------------------------- GPU: sharded handles
+def _slab_rows(hm_size, lo, hi):
+    row = int(hm_size[1]) * int(hm_size[2])
+    return slice(lo * row, hi * row)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_handles_match_oracle_on_one_gpu(world):
+    res, tau, mw, side = 100, 1000, 640, 96
+    s = ScanStream(32, 256, side, res)
+    om = orc.LocalMap(side, side, side, tau, 0)
+    hm = api.HostLocalMap(side, side, side, tau, 0)
+    ranks = []
+    for r in range(world):
+        t = api.TSDFCuda(api.DeviceMap(hm), tau, mw, res, device=0, rank=r, world=world)
+        ranks.append((t, api.RegistrationCuda(t)))
+    # ---- update: no exchange; every rank marches the whole scan into its slab ----
+    for k in range(3):
+        f = s.frame(k)
+        pos, up = fp.convert_pose_to_gpu(f["pose"], res)
+        st = orc.update_tsdf(om, f["points_map"], pos, up, tau, mw, res)
+        touched = 0
+        for t, _ in ranks:
+            t.update_tsdf(f["points_map"], pos, up)
+            c = t.counters()
+            assert c["n_candidates"] == st["n_candidates"]      # every rank sees every candidate
+            touched += c["n_touched"]
+        assert touched >= st["n_touched"]                        # halo columns are updated twice
+    for r, (t, _) in enumerate(ranks):
+        lo, hi, _ = api.slab_layout(int(hm.size[0]), r, world)
+        back = api.HostLocalMap(side, side, side, tau, 0)
+        t.avg_map().to_host(api.DeviceMap(back))
+        sl = _slab_rows(hm.size, lo, hi)
+        assert np.array_equal(back.data[sl], om.data[sl]), "rank %d slab differs from the oracle" % r
+    # ---- registration: host-side sum of the 29 int64 stands in for ncclAllReduce ----
+    cloud = s.frame(3, prior_pose=s.pose(2))["points_prior"].copy()
+    oT, oit, otr = orc.register_cloud(om, cloud.copy(), np.eye(4, dtype=np.float32), 8, 0.1, 0.0, res, trace=True)
+    for _, reg in ranks:
+        reg.prepare_registration(cloud)
+    hds = [reg._hd for _, reg in ranks]
+    I16 = fp.colmajor16(np.eye(4, dtype=np.float32))
+    import ctypes as C
+    f32p = C.POINTER(C.c_float)
+    for hd in hds:
+        hd.check(hd.L.ws_reg_begin(hd.h, I16.ctypes.data_as(f32p)))
+    for it in range(8):
+        for hd in hds:
+            hd.check(hd.L.ws_reg_accumulate(hd.h, res))
+        tot = sum(reg.sums_get() for _, reg in ranks)
+        assert np.array_equal(tot, otr[it]), "iteration %d: summed slab sums differ from the oracle" % it
+        for (_, reg), hd in zip(ranks, hds):
+            reg.sums_set(tot)
+            hd.check(hd.L.ws_reg_solve(hd.h, 0.1, 0.0))
+    out = np.zeros(16, np.float32)
+    Ts = []
+    for hd in hds:
+        it_, fin_ = C.c_int32(), C.c_int32()
+        hd.check(hd.L.ws_reg_finish(hd.h, out.ctypes.data_as(f32p), C.byref(it_), C.byref(fin_)))
+        assert it_.value == 8
+        Ts.append(fp.from_colmajor16(out).copy())
+    for T in Ts:
+        assert np.array_equal(T, Ts[0])
+        assert np.abs(T[:3, :3] - oT[:3, :3]).max() <= 1e-4 and np.abs(T[:3, 3] - oT[:3, 3]).max() <= 0.1
+    for t, _ in ranks:
+        t.close()

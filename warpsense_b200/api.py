@@ -118,6 +118,17 @@ class DeviceMap:
         return self.pos_
 
 
+def slab_layout(size_x, rank, world):
+    """Host-only: (own_lo, own_hi, resident brick columns) of rank's ring-x slab (ws_slab_layout)."""
+    L = _lib.load()
+    lo, hi = C.c_int32(), C.c_int32()
+    cols = np.zeros(512, np.int32)
+    n = L.ws_slab_layout(int(size_x), int(rank), int(world), C.byref(lo), C.byref(hi), cols.ctypes.data_as(_i32p), 512)
+    if n < 0:
+        raise ValueError("no slab for rank %d of %d with ring side %d" % (rank, world, size_x))
+    return lo.value, hi.value, [int(c) for c in cols[:n]]
+
+
 class _Handle:
     """Owns one ws_handle (RAII like the reference's device wrappers; copy is not supported)."""
 
@@ -344,6 +355,43 @@ class RegistrationCuda:
                                         int(map_resolution),
                                         _lib.WS_REG_HOST_SOLVE if host_solve else _lib.WS_REG_DEVICE_SOLVE,
                                         out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(it)))
+        return from_colmajor16(out), it.value
+
+    # -- multi-GPU: one handle per rank, the caller supplies the exchange step --
+    def sums_device_ptr(self):
+        """Device address of this rank's int64[29] Gauss-Newton sums (what the all-reduce operates on)."""
+        return int(self._hd.L.ws_reg_sums_device(self._hd.h))
+
+    def sums_get(self):
+        out = np.zeros(29, np.int64)
+        self._hd.check(self._hd.L.ws_reg_sums_get(self._hd.h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
+    def sums_set(self, sums):
+        a = np.ascontiguousarray(sums, dtype=np.int64).reshape(29)
+        self._hd.check(self._hd.L.ws_reg_sums_set(self._hd.h, a.ctypes.data_as(C.POINTER(C.c_int64))))
+
+    def register_cloud_sharded(self, pretransform, max_iterations, it_weight_gradient, epsilon, map_resolution,
+                               allreduce, check_every=8):
+        """register_cloud over an x-slab sharded map: every rank calls this with the same cloud (staged with
+        prepare_registration*) and an `allreduce(self)` that sums the int64[29] at sums_device_ptr() over all
+        ranks (e.g. torch.distributed.all_reduce on a view of it).  Integer sums: bit-identical on every
+        rank for any rank count, so each rank runs the identical solve.  Returns (T, iterations)."""
+        hd = self._hd
+        f32p = C.POINTER(C.c_float)
+        T0 = colmajor16(pretransform)
+        hd.check(hd.L.ws_reg_begin(hd.h, T0.ctypes.data_as(f32p)))
+        it, fin = C.c_int32(), C.c_int32()
+        for i in range(int(max_iterations)):
+            hd.check(hd.L.ws_reg_accumulate(hd.h, int(map_resolution)))
+            allreduce(self)
+            hd.check(hd.L.ws_reg_solve(hd.h, float(it_weight_gradient), float(epsilon)))
+            if epsilon > 0 and (i + 1) % check_every == 0 and i + 1 < max_iterations:
+                hd.check(hd.L.ws_reg_peek(hd.h, C.byref(it), C.byref(fin)))
+                if fin.value:
+                    break
+        out = np.zeros(16, np.float32)
+        hd.check(hd.L.ws_reg_finish(hd.h, out.ctypes.data_as(f32p), C.byref(it), C.byref(fin)))
         return from_colmajor16(out), it.value
 
     def trace(self, max_iterations=256):

@@ -67,6 +67,29 @@ void ensure_points(ws_pt **buf, size_t *cap, size_t n)
   *cap = want;
 }
 
+// Host-only: which ring-x rows rank `rank` of `world` owns and which brick columns it keeps resident
+// (contiguous slabs in ring coordinates + one halo row each side).
+bool slab_layout(int size_x, int rank, int world, int *own_lo, int *own_hi, std::vector<int> &cols)
+{
+  const int nbx = (size_x + WS_BRICK - 1) / WS_BRICK;
+  const int c_lo = (int)((i64)nbx * rank / world), c_hi = (int)((i64)nbx * (rank + 1) / world);
+  if (c_hi <= c_lo) return false;
+  *own_lo = c_lo * WS_BRICK;
+  *own_hi = std::min(c_hi * WS_BRICK, size_x);
+  cols.clear();
+  if (world == 1) for (int c = 0; c < nbx; c++) cols.push_back(c);
+  else
+  {
+    const int below = (*own_lo - 1 + size_x) % size_x, above = *own_hi % size_x;
+    for (int c = c_lo; c < c_hi; c++) cols.push_back(c);
+    cols.push_back(below / WS_BRICK);
+    cols.push_back(above / WS_BRICK);
+    std::sort(cols.begin(), cols.end());
+    cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+  }
+  return true;
+}
+
 int create_impl(const int32_t size[3], int tau, int max_weight, int res, int device, int rank, int world, ws_handle **out)
 {
   if (!out) return WS_ERR_INVALID;
@@ -95,23 +118,11 @@ int create_impl(const int32_t size[3], int tau, int max_weight, int res, int dev
     if (g.nb[0] > WS_MAX_XBRICKS) throw std::invalid_argument("map too large along x");
     // x-slab residency: this rank owns ring-x brick columns [c_lo, c_hi) plus the columns holding the
     // rows just outside (the registration stencil reads x+-1)
-    const int c_lo = (int)((i64)g.nb[0] * rank / world), c_hi = (int)((i64)g.nb[0] * (rank + 1) / world);
-    if (c_hi <= c_lo) throw std::invalid_argument("more ranks than ring-x brick columns");
-    g.own_lo = c_lo * WS_BRICK;
-    g.own_hi = std::min(c_hi * WS_BRICK, g.size[0]);
+    std::vector<int> cols;
+    if (!slab_layout(g.size[0], rank, world, &g.own_lo, &g.own_hi, cols))
+      throw std::invalid_argument("more ranks than ring-x brick columns");
     g.full = (world == 1) ? 1 : 0;
     for (int c = 0; c < WS_MAX_XBRICKS; c++) g.xslot[c] = -1;
-    std::vector<int> cols;
-    if (world == 1) for (int c = 0; c < g.nb[0]; c++) cols.push_back(c);
-    else
-    {
-      const int below = (g.own_lo - 1 + g.size[0]) % g.size[0], above = g.own_hi % g.size[0];
-      for (int c = c_lo; c < c_hi; c++) cols.push_back(c);
-      cols.push_back(below / WS_BRICK);
-      cols.push_back(above / WS_BRICK);
-      std::sort(cols.begin(), cols.end());
-      cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
-    }
     for (size_t s = 0; s < cols.size(); s++) g.xslot[cols[s]] = (short)s;
     g.n_bricks = (i64)cols.size() * g.nb[1] * g.nb[2];
     if (g.n_bricks >= (1ll << 31)) throw std::invalid_argument("map too large");
@@ -658,9 +669,52 @@ int ws_reg_accumulate(ws_handle *h, int32_t map_resolution)
 
 void *ws_reg_sums_device(ws_handle *h) { return h ? (void *)h->d_acc->sums : nullptr; }
 
+int ws_reg_sums_get(ws_handle *h, int64_t sums[29])
+{
+  return guarded(h, [&]() {
+    if (!sums) throw std::invalid_argument("ws_reg_sums_get: null argument");
+    WS_CUDA_OK(cudaMemcpyAsync(sums, h->d_acc->sums, WS_NSUM * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return WS_OK;
+  });
+}
+
+int ws_reg_sums_set(ws_handle *h, const int64_t sums[29])
+{
+  return guarded(h, [&]() {
+    if (!sums) throw std::invalid_argument("ws_reg_sums_set: null argument");
+    WS_CUDA_OK(cudaMemcpyAsync(h->d_acc->sums, sums, WS_NSUM * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    return WS_OK;
+  });
+}
+
+int ws_slab_layout(int32_t size_x, int32_t rank, int32_t world, int32_t *own_lo, int32_t *own_hi,
+                   int32_t *resident_cols, int32_t cap)
+{
+  if (size_x < 1 || world < 1 || rank < 0 || rank >= world || !own_lo || !own_hi) return WS_ERR_INVALID;
+  std::vector<int> cols;
+  int lo = 0, hi = 0;
+  if (!slab_layout(size_x, rank, world, &lo, &hi, cols)) return WS_ERR_INVALID;
+  *own_lo = lo; *own_hi = hi;
+  if (resident_cols)
+    for (size_t i = 0; i < cols.size() && (int)i < cap; i++) resident_cols[i] = cols[i];
+  return (int)cols.size();
+}
+
 int ws_reg_solve(ws_handle *h, float it_weight_gradient, float epsilon)
 {
   return guarded(h, [&]() { ws_launch_reg_solve(h, it_weight_gradient, epsilon); return WS_OK; });
+}
+
+int ws_reg_peek(ws_handle *h, int32_t *iterations, int32_t *finished)
+{
+  return guarded(h, [&]() {
+    read_acc(h);
+    if (iterations) *iterations = (int32_t)h->h_acc->iterations;
+    if (finished) *finished = (int32_t)h->h_acc->finished;
+    return WS_OK;
+  });
 }
 
 int ws_reg_finish(ws_handle *h, float out_transform[16], int32_t *iterations, int32_t *finished)

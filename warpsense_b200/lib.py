@@ -76,7 +76,11 @@ def _signatures():
         "ws_reg_begin": (C.c_int, [hp, f32p]),
         "ws_reg_accumulate": (C.c_int, [hp, C.c_int32]),
         "ws_reg_sums_device": (vp, [hp]),
+        "ws_reg_sums_get": (C.c_int, [hp, i64p]),
+        "ws_reg_sums_set": (C.c_int, [hp, i64p]),
+        "ws_slab_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p, C.c_int32]),
         "ws_reg_solve": (C.c_int, [hp, C.c_float, C.c_float]),
+        "ws_reg_peek": (C.c_int, [hp, i32p, i32p]),
         "ws_reg_finish": (C.c_int, [hp, f32p, i32p, i32p]),
         "ws_test_reduce": (C.c_int, [hp, i64p, i32p, C.c_int64, i64p, i64p, i32p, i32p]),
         "ws_shift": (C.c_int, [hp, i32p]),
