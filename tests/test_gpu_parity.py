@@ -133,6 +133,47 @@ def test_update_tsdf_random_clouds(size, res, tau, n, spread, spos):
         assert_same_grid(om, tsdf, hm, "scan %d" % scan)
 
 
+@pytest.mark.parametrize("case", [0, 2, 3])
+def test_update_tsdf_general_arithmetic_path(case, monkeypatch):
+    """WS_MARCH_GENERAL=1 switches the march's 32-bit fast path (march_math.cuh) off: the literal wrapping
+    arithmetic must give the same grids as the oracle (and therefore as the fast path)."""
+    monkeypatch.setenv("WS_MARCH_GENERAL", "1")
+    test_update_tsdf_random_clouds(*CASES[case])
+
+
+def test_update_tsdf_far_from_origin_and_long_rays():
+    """Rays the fast path must refuse: a map 3,000 km from the origin (|coordinate| * res >= 2^31) and rays
+    long enough for d * len to wrap int32, which the reference's arithmetic does too (update_tsdf.cpp:452)."""
+    rng = np.random.default_rng(21)
+    up = np.array([0, 0, MR], np.int32)
+    # (a) far from the origin, coarse voxels
+    tau, res, mw = 3000, 1000, 640
+    om, hm, tsdf = make_pair((21, 21, 21), tau, mw, res)
+    spos = [3000, -2999, 2500]
+    om.set_state(spos, [10, 10, 10])
+    hm.pos[:] = spos
+    tsdf.avg_map().update_params(api.DeviceMap(hm))
+    centre = np.array(spos, np.int64) * res
+    for scan in range(2):
+        pts = (centre + rng.integers(-9000, 9000, size=(300, 3))).astype(np.int32)
+        st = orc.update_tsdf(om, pts, spos, up, tau, mw, res)
+        tsdf.update_tsdf(pts, spos, up)
+        c = tsdf.counters()
+        assert (c["n_candidates"], c["n_touched"]) == (st["n_candidates"], st["n_touched"])
+        assert_same_grid(om, tsdf, hm, "far map, scan %d" % scan)
+    tsdf.close()
+    # (b) 45 m rays through a long thin map: d * len exceeds 2^31 near the far end (d^2 still fits int32)
+    tau, res, mw = 1000, 100, 640
+    om, hm, tsdf = make_pair((513, 17, 17), tau, mw, res)
+    spos = (-230, 0, 0)
+    pts = np.stack([rng.integers(22000, 23000, 200), rng.integers(-700, 700, 200), rng.integers(-700, 700, 200)], 1).astype(np.int32)
+    st = orc.update_tsdf(om, pts, spos, up, tau, mw, res)
+    tsdf.update_tsdf(pts, spos, up)
+    c = tsdf.counters()
+    assert (c["n_candidates"], c["n_touched"]) == (st["n_candidates"], st["n_touched"])
+    assert_same_grid(om, tsdf, hm, "long rays")
+
+
 def test_update_tsdf_tilted_up_vector_and_shifted_ring():
     """Non-trivial up vector (rolled sensor) and a map whose ring origin is not at the array origin."""
     rng = np.random.default_rng(77)

@@ -1,0 +1,109 @@
+// march_math.cuh -- exact 32-bit arithmetic of the ray march's fast path (host + device, unit-tested on the
+// host by tests/cpp/test_march_math.cu against the plain C formulas of update_tsdf.cpp:450-506).
+//
+// The reference marches `len = 1, 1+h, ...` and computes, per step and axis,
+//     proj = pos + (d * len) / distance        (int32, truncating)            update_tsdf.cpp:452
+//     idx  = proj / res                        (truncating)                   update_tsdf.cpp:453
+// Done literally that is two 64-bit magic divisions per axis and step.  Here:
+//   * (|d| * len) / distance advances by a DDA: a lane that handles steps i, i+32, i+64 ... keeps the
+//     quotient and the remainder and adds the (warp-uniform) quotient/remainder of |d|*32*h / distance;
+//   * x / res uses a 32-bit magic (one IMAD.HI) that is exact for |x| < 2^32 / res.
+// Both need bounded operands; `ray_is_small` states the bounds, rays outside them take the general path
+// (64-bit magics, wrapping int32 products, exactly like the oracle).
+#pragma once
+#include "ws_common.cuh"
+
+struct FastDiv32
+{
+  unsigned M;   // floor(2^32 / d) + 1
+  unsigned d;
+};
+
+static inline FastDiv32 make_fastdiv32(unsigned d)
+{
+  FastDiv32 f;
+  f.d = d;
+  f.M = d <= 1 ? 0u : (unsigned)((1ull << 32) / d) + 1u;
+  return f;
+}
+
+WS_HD unsigned ws_umulhi(unsigned a, unsigned b)
+{
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (unsigned)(((u64)a * (u64)b) >> 32);
+#endif
+}
+
+// n / d for n * d < 2^32, d >= 2
+WS_HD unsigned fd32_udiv(unsigned n, const FastDiv32 f) { return ws_umulhi(n, f.M); }
+
+// truncating n / d for |n| * d < 2^32, d >= 2
+WS_HD int fd32_sdiv(int n, const FastDiv32 f)
+{
+  const unsigned a = n < 0 ? 0u - (unsigned)n : (unsigned)n;
+  const int q = (int)ws_umulhi(a, f.M);
+  return n < 0 ? -q : q;
+}
+
+// floor(n / dist) and the remainder from a double-precision reciprocal: the estimate is within +-1
+// for n < 2^46 (relative error of fl(n * fl(1/dist)) <= 2^-52), one correction step makes it exact.
+WS_HD void divrem_rcp(unsigned n, unsigned dist, double rdist, unsigned &q, unsigned &rem)
+{
+  unsigned qe = (unsigned)((double)n * rdist);
+  int r = (int)(n - qe * dist);            // exact in wrap-around arithmetic: |true remainder| < 2 * dist
+  if (r < 0) { qe--; r += (int)dist; }
+  else if (r >= (int)dist) { qe++; r -= (int)dist; }
+  q = qe; rem = (unsigned)r;
+}
+
+// the same for a 64-bit numerator below 2^46 (quotient only)
+WS_HD u64 div_rcp64(u64 n, unsigned dist, double rdist)
+{
+  u64 qe = (u64)((double)n * rdist);
+  i64 r = (i64)(n - qe * (u64)dist);
+  if (r < 0) qe--;
+  else if (r >= (i64)dist) qe++;
+  return qe;
+}
+
+// DDA state of one axis: |d| * len = q * distance + rem
+struct DdaAxis
+{
+  unsigned q, rem;     // per lane
+  unsigned dq, drem;   // per 32 steps (warp-uniform)
+};
+
+WS_HD void dda_init(DdaAxis &s, unsigned absd, unsigned len0, unsigned stride_len, unsigned dist, double rdist)
+{
+  divrem_rcp(absd * len0, dist, rdist, s.q, s.rem);
+  divrem_rcp(absd * stride_len, dist, rdist, s.dq, s.drem);
+}
+
+WS_HD void dda_advance(DdaAxis &s, unsigned dist)
+{
+  s.q += s.dq;
+  s.rem += s.drem;
+  if (s.rem >= dist) { s.rem -= dist; s.q++; }
+}
+
+// Bounds under which the fast path is exact for a ray (all products below fit int32 without wrapping and
+// every dividend of a 32-bit magic division stays below 2^32 / res):
+//   max|d| * (distance + tau + 32*h + 1) < 2^31      DDA numerators incl. one stride beyond the last step
+//   dz * (distance + tau)               < 2^30       delta_z < 2^15: delta_z*iv and step*res*iv fit int32
+//   |p|, |pos| < coord_lim                            (host: coord_lim = 2^31 / res - tau - 70*res - 2^16)
+WS_HD bool ray_is_small(const int d[3], const int p[3], int distance, int tau, int half_res, int dz, int coord_lim)
+{
+  unsigned m = 0, c = 0;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+  {
+    const unsigned ad = d[a] < 0 ? 0u - (unsigned)d[a] : (unsigned)d[a];
+    const unsigned ap = p[a] < 0 ? 0u - (unsigned)p[a] : (unsigned)p[a];
+    m = ad > m ? ad : m;
+    c = ap > c ? ap : c;
+  }
+  const i64 L = (i64)distance + tau + 32ll * half_res + 1;
+  return coord_lim > 0 && c < (unsigned)coord_lim && (i64)m * L < (1ll << 31) && (i64)dz * L < (1ll << 30);
+}

@@ -28,8 +28,10 @@
 // If the record list overflows its buffer the host grows it and regenerates it with march_kernel<false>
 // (far part of every ray, no atomics) before running replay_kernel again.
 #include <cooperative_groups.h>
+#include <cstdlib>
 #include <stdexcept>
 #include "ws_internal.h"
+#include "march_math.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -49,20 +51,27 @@ WS_D unsigned long long global_ns()
   return t;
 }
 
+// include/map/hdf5_local_map.h:275-279, |v - pos| <= size/2 per axis, as 0 <= v - lo <= size - 1
+WS_D bool box_in_bounds(const UpdateParams &P, int x, int y, int z)
+{
+  return (unsigned)x - (unsigned)P.lo[0] <= (unsigned)P.ext[0] && (unsigned)y - (unsigned)P.lo[1] <= (unsigned)P.ext[1] &&
+         (unsigned)z - (unsigned)P.lo[2] <= (unsigned)P.ext[2];
+}
+
 struct Ray
 {
   int p[3];
   int d[3];
   int distance;
   int iv[3];
-  FastDiv div_dist;
   int n_steps;
+  bool small;          // march_math.cuh: the 32-bit fast path is exact for this ray
 };
 
-// per-ray setup (update_tsdf.cpp:420-446), computed cooperatively: the two rounds of 64-bit divisions
-// (normalised direction + division magic, normalised interpolation vector) run once per warp with one
-// component per lane instead of seven times in every lane.  Warp-uniform result.
-WS_D bool ray_setup_warp(const GridDesc &g, const UpdateParams &P, const ws_pt pt, const int lane, Ray &r)
+// per-ray setup (update_tsdf.cpp:420-446), every lane redundantly (warp-uniform result, no shuffles).
+// The truncating 64-bit divisions of the reference run as FP64 estimates with an exact integer
+// correction (march_math.cuh) wherever their operands are below 2^46, which they are for any sane ray.
+WS_D bool ray_setup(const UpdateParams &P, const ws_pt pt, Ray &r)
 {
   r.p[0] = pt.x; r.p[1] = pt.y; r.p[2] = pt.z;
 #pragma unroll
@@ -71,61 +80,55 @@ WS_D bool ray_setup_warp(const GridDesc &g, const UpdateParams &P, const ws_pt p
   if (sq <= 0) return false;          // distance == 0 (:424) or int32 norm overflow (out of contract)
   r.distance = isqrt31(sq);                                                                      // :423
   if (r.distance == 0) return false;
-  if (!grid_in_bounds(g, fd_sdiv(r.p[0], P.div_res), fd_sdiv(r.p[1], P.div_res), fd_sdiv(r.p[2], P.div_res)))
+  if (!box_in_bounds(P, fd_sdiv(r.p[0], P.div_res), fd_sdiv(r.p[1], P.div_res), fd_sdiv(r.p[2], P.div_res)))
     return false;                                                                                // :430-434
+  r.small = ray_is_small(r.d, r.p, r.distance, P.tau, P.half_res, P.dz_per_distance, P.coord_lim);
 
-  // lanes 0..2: |d[a]| * MR / distance (:438); lane 3: floor((2^64-1) / distance) for the division magic
-  const int dl = lane == 0 ? r.d[0] : (lane == 1 ? r.d[1] : r.d[2]);
-  const u64 adl = (u64)(dl < 0 ? 0u - (unsigned)dl : (unsigned)dl);
-  const u64 num1 = lane == 3 ? ~0ull : (adl << WS_MR_SHIFT);
-  const u64 q1 = num1 / (u64)(unsigned)r.distance;
-  const i64 nds = dl < 0 ? -(i64)q1 : (i64)q1;
+  const double rdist = 1.0 / (double)r.distance;
   i64 nd[3], c1[3];
-  nd[0] = __shfl_sync(FULL, nds, 0);
-  nd[1] = __shfl_sync(FULL, nds, 1);
-  nd[2] = __shfl_sync(FULL, nds, 2);
-  r.div_dist.d = (unsigned)r.distance;
-  r.div_dist.M = r.distance <= 1 ? 0ull : __shfl_sync(FULL, q1, 3) + 1ull;
-
+#pragma unroll
+  for (int a = 0; a < 3; a++)                                                                    // :438
+  {
+    const u64 ad = (u64)(r.d[a] < 0 ? 0u - (unsigned)r.d[a] : (unsigned)r.d[a]);
+    const i64 q = (i64)div_rcp64(ad << WS_MR_SHIFT, (unsigned)r.distance, rdist);
+    nd[a] = r.d[a] < 0 ? -q : q;
+  }
   c1[0] = div_mr64(nd[1] * P.up[2] - nd[2] * P.up[1]);                                           // :439
   c1[1] = div_mr64(nd[2] * P.up[0] - nd[0] * P.up[2]);
   c1[2] = div_mr64(nd[0] * P.up[1] - nd[1] * P.up[0]);
-  const i64 iv0 = nd[1] * c1[2] - nd[2] * c1[1];
-  const i64 iv1 = nd[2] * c1[0] - nd[0] * c1[2];
-  const i64 iv2 = nd[0] * c1[1] - nd[1] * c1[0];
-  const i64 isq = (i64)((u64)iv0 * (u64)iv0 + (u64)iv1 * (u64)iv1 + (u64)iv2 * (u64)iv2);
-  const i64 inorm = __double2ll_rz(sqrt(__ll2double_rn(isq)));                                   // :440 (FP64, like Eigen)
+  i64 iv[3];
+  iv[0] = nd[1] * c1[2] - nd[2] * c1[1];
+  iv[1] = nd[2] * c1[0] - nd[0] * c1[2];
+  iv[2] = nd[0] * c1[1] - nd[1] * c1[0];
+  const i64 isq = (i64)((u64)iv[0] * (u64)iv[0] + (u64)iv[1] * (u64)iv[1] + (u64)iv[2] * (u64)iv[2]);
+  const double fnorm = sqrt(__ll2double_rn(isq));
+  const i64 inorm = __double2ll_rz(fnorm);                                                       // :440 (FP64, like Eigen)
   if (inorm <= 0) return false;                                                                  // :441-445
-  // lanes 0..2: (iv[a] * MR) / inorm, truncating (:446)
-  const i64 il = lane == 0 ? iv0 : (lane == 1 ? iv1 : iv2);
-  const i64 num2 = il * WS_MR;
-  const u64 q2 = (u64)(num2 < 0 ? -num2 : num2) / (u64)inorm;
-  const i64 ivs = num2 < 0 ? -(i64)q2 : (i64)q2;
-  r.iv[0] = (int)__shfl_sync(FULL, ivs, 0);
-  r.iv[1] = (int)__shfl_sync(FULL, ivs, 1);
-  r.iv[2] = (int)__shfl_sync(FULL, ivs, 2);
+#pragma unroll
+  for (int a = 0; a < 3; a++)                                                                    // :446
+  {
+    const i64 num = iv[a] * WS_MR;
+    const u64 an = (u64)(num < 0 ? -num : num);
+    u64 q;
+    // a correctly rounded FP64 quotient of integers below 2^52 truncates to the exact integer quotient
+    if (an < (1ull << 52)) q = (u64)__double2ll_rz(__ll2double_rn((i64)an) / __ll2double_rn(inorm));
+    else q = an / (u64)inorm;
+    r.iv[a] = (int)(num < 0 ? -(i64)q : (i64)q);
+  }
   // len = 1, 1+h, ... <= distance + tau  (:450)
-  r.n_steps = (r.distance + P.tau - 1) / P.half_res + 1;
+  r.n_steps = (int)fd_udiv((unsigned)(r.distance + P.tau - 1), P.div_half) + 1;
   return true;
 }
 
-WS_D void step_index(const UpdateParams &P, const Ray &r, int len, int proj[3], int idx[3])
+// general (wrapping, 64-bit magic) projection of one march step
+WS_D void step_index(const UpdateParams &P, const Ray &r, const FastDiv div_dist, int len, int proj[3], int idx[3])
 {
 #pragma unroll
   for (int a = 0; a < 3; a++)
   {
-    proj[a] = wadd(P.pos_mm[a], fd_sdiv(wmul(r.d[a], len), r.div_dist));                         // :452
+    proj[a] = wadd(P.pos_mm[a], fd_sdiv(wmul(r.d[a], len), div_dist));                           // :452
     idx[a] = fd_sdiv(proj[a], P.div_res);                                                        // :453
   }
-}
-
-// in-bounds voxel -> ring coordinate; t = v - pos + offset lies in (-size, 2*size)
-WS_D int ring_fast(int v, int base, int size)
-{
-  int t = v + base;
-  t += (t < 0) ? size : 0;
-  t -= (t >= size) ? size : 0;
-  return t;
 }
 
 // Record writer.  The record is a sequence of 64-entry chunks with a fill count each.  A warp reserves
@@ -204,6 +207,201 @@ WS_D void rec_finish(RecWriter &w, const int lane, unsigned *__restrict__ chunk_
     if (c < cap_chunks) chunk_fill[c] = 0u;
 }
 
+struct MarchCtx
+{
+  RecWriter rw;
+  unsigned n_cand;
+  unsigned err;
+};
+
+// One ray, one warp.  FAST: march_math.cuh (DDA projection, 32-bit magics, int32 fan arithmetic); !FAST: the
+// literal wrapping arithmetic of the oracle.  Both produce identical candidates wherever FAST is allowed.
+template <bool ATOMIC, bool FAST>
+WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, const int ray_id, const int lane,
+                    int4 (*q)[2], MarchCtx &cx, Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill,
+                    const unsigned cap_chunks, UpdateCounters *__restrict__ ctr)
+{
+  const unsigned lt = (1u << lane) - 1u;
+  if (r.n_steps > (1 << WS_SEQ_MARCH_BITS)) cx.err |= 1u;
+  int start = 0;
+  if (!ATOMIC && P.far_len > 1) start = (P.far_len - 1) / P.half_res;
+
+  FastDiv div_dist;
+  div_dist.d = (unsigned)r.distance; div_dist.M = 0ull;
+  DdaAxis dda[3];
+  if (FAST)
+  {
+    const double rdist = 1.0 / (double)r.distance;
+    const unsigned len0 = 1u + (unsigned)(start + lane) * (unsigned)P.half_res;
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+      dda_init(dda[a], r.d[a] < 0 ? 0u - (unsigned)r.d[a] : (unsigned)r.d[a], len0, 32u * (unsigned)P.half_res,
+               (unsigned)r.distance, rdist);
+  }
+  else if (r.distance > 1) div_dist.M = (~0ull) / (u64)(unsigned)r.distance + 1ull;
+
+  int carry_x = 0, carry_y = 0;
+  if (start > 0 && start < r.n_steps)     // record regeneration only: the step before `start` seeds the column filter
+  {
+    FastDiv dd = div_dist;
+    if (FAST && r.distance > 1) dd.M = (~0ull) / (u64)(unsigned)r.distance + 1ull;
+    int pj[3], ix[3];
+    step_index(P, r, dd, 1 + (start - 1) * P.half_res, pj, ix);
+    carry_x = ix[0]; carry_y = ix[1];
+  }
+
+  int qn = 0, qh = 0;                     // queue fill / head (warp-uniform)
+  for (int base = start; base < r.n_steps || qn > 0; base += 32)
+  {
+    if (base < r.n_steps)
+    {
+      const int i = base + lane;
+      int proj[3], index[3];
+      if (FAST)
+      {
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+        {
+          proj[a] = P.pos_mm[a] + (r.d[a] < 0 ? -(int)dda[a].q : (int)dda[a].q);                 // :452
+          index[a] = fd32_sdiv(proj[a], P.div_res32);                                            // :453
+          dda_advance(dda[a], (unsigned)r.distance);
+        }
+      }
+      else step_index(P, r, div_dist, 1 + i * P.half_res, proj, index);
+
+      int px = __shfl_up_sync(FULL, index[0], 1);
+      int py = __shfl_up_sync(FULL, index[1], 1);
+      if (lane == 0) { px = carry_x; py = carry_y; }
+      carry_x = __shfl_sync(FULL, index[0], 31);
+      carry_y = __shfl_sync(FULL, index[1], 31);
+
+      bool active = i < r.n_steps;
+      if (i > 0 && index[0] == px && index[1] == py) active = false;                             // :455-458
+      if (!box_in_bounds(P, index[0], index[1], index[2])) active = false;                       // :460-463
+      const unsigned m = __ballot_sync(FULL, active);
+      if (active)
+      {
+        const int pos = (qh + qn + __popc(m & lt)) & (QCAP - 1);
+        q[pos][0] = make_int4(proj[0], proj[1], proj[2], i);
+        q[pos][1] = make_int4(index[0], index[1], index[2], 0);
+      }
+      qn += __popc(m);
+      __syncwarp();
+      if (qn < 32 && base + 32 < r.n_steps) continue;     // keep filling
+    }
+    if (qn == 0) continue;
+
+    // ---- heavy part: up to 32 compacted march steps, one per lane ---------------------------
+    const int take = qn < 32 ? qn : 32;
+    bool have = lane < take;
+    const int4 qa = q[(qh + lane) & (QCAP - 1)][0];
+    const int4 qb = q[(qh + lane) & (QCAP - 1)][1];
+    __syncwarp();
+    qh = (qh + take) & (QCAP - 1);
+    qn -= take;
+
+    const int i = qa.w;
+    const int len = 1 + i * P.half_res;
+    // distance of the hit to the centre of the marched voxel (:466-472)
+    const int tcx = wadd(wmul(qb.x, P.res), P.half_res);
+    const int tcy = wadd(wmul(qb.y, P.res), P.half_res);
+    const int tcz = wadd(wmul(qb.z, P.res), P.half_res);
+    const int ex = wsub(r.p[0], tcx), ey = wsub(r.p[1], tcy), ez = wsub(r.p[2], tcz);
+    const int vsq = wadd(wadd(wmul(ex, ex), wmul(ey, ey)), wmul(ez, ez));
+    int value = vsq < 0 ? P.tau : isqrt31(vsq);
+    value = value < P.tau ? value : P.tau;
+    if (len > r.distance) value = -value;
+
+    int weight = WS_WR;                                                                          // :475-479
+    if (value < -P.weight_epsilon) weight = (int)fd_udiv((unsigned)(WS_WR * (P.tau + value)), P.div_weps);
+    if (weight == 0) have = false;                                                               // :480-483
+
+    const int delta_z = div_mr32(wmul(P.dz_per_distance, len));                                  // :485
+    int iter_steps, mid, low_x, low_y, low_z;
+    if (FAST)
+    {
+      iter_steps = (int)fd32_udiv((unsigned)(delta_z * 2), P.div_res32) + 1;                     // :486
+      mid = (int)fd32_udiv((unsigned)delta_z, P.div_res32);                                      // :487
+      low_x = qa.x - div_mr32(delta_z * r.iv[0]);                                                // :488
+      low_y = qa.y - div_mr32(delta_z * r.iv[1]);
+      low_z = qa.z - div_mr32(delta_z * r.iv[2]);
+    }
+    else
+    {
+      iter_steps = fd_sdiv(delta_z * 2, P.div_res) + 1;
+      mid = fd_sdiv(delta_z, P.div_res);
+      low_x = wsub(qa.x, (int)div_mr64((i64)delta_z * r.iv[0]));
+      low_y = wsub(qa.y, (int)div_mr64((i64)delta_z * r.iv[1]));
+      low_z = wsub(qa.z, (int)div_mr64((i64)delta_z * r.iv[2]));
+    }
+    if (have && iter_steps > (1 << WS_SEQ_STEP_BITS)) cx.err |= 1u;
+    const bool far = len >= P.far_len;
+    const int max_steps = __reduce_max_sync(FULL, have ? iter_steps : 0);
+    unsigned last_brick = 0xFFFFFFFFu;
+
+    // keys of this march step's fan: real candidate at `mid`, interpolated ones around it (:503-506)
+    const unsigned av = (unsigned)(value < 0 ? -value : value);
+    const u64 seq0 = make_seq((unsigned)ray_id, (unsigned)i, 0u);
+    const u64 kbase = ((u64)av << 47) | (u64)(value < 0 ? 1 : 0);
+    const u64 key_real0 = kbase | (seq0 << 1);
+    const u64 key_int0 = kbase | (1ull << 46) | ((WS_SEQ_MAX - seq0) << 1);
+
+    for (int step = 0; step < max_steps; ++step)                                                 // :491
+    {
+      bool valid = have && step < iter_steps;
+      const int sr = wmul(step, P.res);
+      int vx, vy, vz;
+      if (FAST)
+      {
+        vx = fd32_sdiv(low_x + div_mr32(sr * r.iv[0]), P.div_res32);                             // :493
+        vy = fd32_sdiv(low_y + div_mr32(sr * r.iv[1]), P.div_res32);
+        vz = fd32_sdiv(low_z + div_mr32(sr * r.iv[2]), P.div_res32);
+      }
+      else
+      {
+        vx = fd_sdiv(wadd(low_x, (int)div_mr64((i64)sr * r.iv[0])), P.div_res);
+        vy = fd_sdiv(wadd(low_y, (int)div_mr64((i64)sr * r.iv[1])), P.div_res);
+        vz = fd_sdiv(wadd(low_z, (int)div_mr64((i64)sr * r.iv[2])), P.div_res);
+      }
+      // in bounds (:495-498) <=> 0 <= v - lo <= size - 1 per axis
+      const unsigned tx = (unsigned)vx - (unsigned)P.lo[0];
+      const unsigned ty = (unsigned)vy - (unsigned)P.lo[1];
+      const unsigned tz = (unsigned)vz - (unsigned)P.lo[2];
+      if (tx > (unsigned)P.ext[0] || ty > (unsigned)P.ext[1] || tz > (unsigned)P.ext[2]) valid = false;
+      if (valid) cx.n_cand++;
+
+      u64 key = 0ull, addr = 0ull;
+      bool resident = false;
+      if (valid)
+      {
+        // ring coordinates (hdf5_local_map.h:140-151): (v - pos + offset) mod size
+        int rx = (int)tx + P.ringc[0]; rx -= rx >= g.size[0] ? g.size[0] : 0;
+        int ry = (int)ty + P.ringc[1]; ry -= ry >= g.size[1] ? g.size[1] : 0;
+        int rz = (int)tz + P.ringc[2]; rz -= rz >= g.size[2] ? g.size[2] : 0;
+        const int slot = g.full ? (rx >> 3) : (int)g.xslot[rx >> 3];
+        if (slot >= 0)                                 // else: the column lives on another rank
+        {
+          resident = true;
+          const unsigned brick = (unsigned)((slot * g.nb[1] + (ry >> 3)) * g.nb[2] + (rz >> 3));
+          addr = (u64)brick * WS_BRICK_VOX + (u64)brick_local(rx, ry, rz);
+          const u64 s2 = (u64)(unsigned)step << 1;
+          key = step == mid ? key_real0 + s2 : key_int0 - s2;
+          if (ATOMIC)
+          {
+            atomicMin(&g.keys[addr], key);                                                       // :508-512
+            if (brick != last_brick)
+            {
+              g.brick_flag[brick] = 1u;
+              last_brick = brick;
+            }
+          }
+        }
+      }
+      rec_append(cx.rw, resident && far, key, addr, lane, rec, chunk_fill, cap_chunks, ctr);
+    }
+  }
+}
+
 // ATOMIC: the scan's first pass (candidate keys + brick flags + record).  !ATOMIC: regenerate the record
 // only (far part of every ray), used when the record buffer had to grow.
 template <bool ATOMIC>
@@ -216,15 +414,12 @@ march_kernel(const GridDesc g, const UpdateParams P, const ws_pt *__restrict__ p
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   int4 (*q)[2] = s_q[wib];
-  const unsigned lt = (1u << lane) - 1u;
   const int total_warps = gridDim.x * MARCH_WARPS;
 
-  RecWriter rw;
-  rec_init(rw, ctr, lane);
-
-  unsigned long long n_cand = 0ull;
-  unsigned err = 0u;
-  const int base_x = g.offset[0] - g.pos[0], base_y = g.offset[1] - g.pos[1], base_z = g.offset[2] - g.pos[2];
+  MarchCtx cx;
+  rec_init(cx.rw, ctr, lane);
+  cx.n_cand = 0u;
+  cx.err = 0u;
 
   // rays are fetched RAY_BATCH at a time (again: one same-address atomic per fetch); the next batch is
   // requested when the current one starts and consumed when it is done
@@ -236,126 +431,10 @@ march_kernel(const GridDesc g, const UpdateParams P, const ws_pt *__restrict__ p
 
     Ray r;
     const ws_pt pt = pts[ray_id];
-    if (ray_setup_warp(g, P, pt, lane, r))
+    if (ray_setup(P, pt, r))
     {
-      if (r.n_steps > (1 << WS_SEQ_MARCH_BITS)) err |= 1u;
-      int start = 0;
-      if (!ATOMIC && P.far_len > 1) start = (P.far_len - 1) / P.half_res;
-
-      int carry_x = 0, carry_y = 0;
-      if (start > 0 && start < r.n_steps)
-      {
-        int pj[3], ix[3];
-        step_index(P, r, 1 + (start - 1) * P.half_res, pj, ix);
-        carry_x = ix[0]; carry_y = ix[1];
-      }
-
-      int qn = 0, qh = 0;                     // queue fill / head (warp-uniform)
-      for (int base = start; base < r.n_steps || qn > 0; base += 32)
-      {
-        if (base < r.n_steps)
-        {
-          const int i = base + lane;
-          const int len = 1 + i * P.half_res;
-          int proj[3], index[3];
-          step_index(P, r, len, proj, index);
-
-          int px = __shfl_up_sync(FULL, index[0], 1);
-          int py = __shfl_up_sync(FULL, index[1], 1);
-          if (lane == 0) { px = carry_x; py = carry_y; }
-          carry_x = __shfl_sync(FULL, index[0], 31);
-          carry_y = __shfl_sync(FULL, index[1], 31);
-
-          bool active = i < r.n_steps;
-          if (i > 0 && index[0] == px && index[1] == py) active = false;                         // :455-458
-          if (active && !grid_in_bounds(g, index[0], index[1], index[2])) active = false;        // :460-463
-          const unsigned m = __ballot_sync(FULL, active);
-          if (active)
-          {
-            const int pos = (qh + qn + __popc(m & lt)) & (QCAP - 1);
-            q[pos][0] = make_int4(proj[0], proj[1], proj[2], i);
-            q[pos][1] = make_int4(index[0], index[1], index[2], 0);
-          }
-          qn += __popc(m);
-          __syncwarp();
-          if (qn < 32 && base + 32 < r.n_steps) continue;     // keep filling
-        }
-        if (qn == 0) continue;
-
-        // ---- heavy part: up to 32 compacted march steps, one per lane ---------------------------
-        const int take = qn < 32 ? qn : 32;
-        bool have = lane < take;
-        const int4 qa = q[(qh + lane) & (QCAP - 1)][0];
-        const int4 qb = q[(qh + lane) & (QCAP - 1)][1];
-        __syncwarp();
-        qh = (qh + take) & (QCAP - 1);
-        qn -= take;
-
-        const int i = qa.w;
-        const int len = 1 + i * P.half_res;
-        // distance of the hit to the centre of the marched voxel (:466-472)
-        const int tcx = wadd(wmul(qb.x, P.res), P.half_res);
-        const int tcy = wadd(wmul(qb.y, P.res), P.half_res);
-        const int tcz = wadd(wmul(qb.z, P.res), P.half_res);
-        const int ex = wsub(r.p[0], tcx), ey = wsub(r.p[1], tcy), ez = wsub(r.p[2], tcz);
-        const int vsq = wadd(wadd(wmul(ex, ex), wmul(ey, ey)), wmul(ez, ez));
-        int value = vsq < 0 ? P.tau : isqrt31(vsq);
-        value = value < P.tau ? value : P.tau;
-        if (len > r.distance) value = -value;
-
-        int weight = WS_WR;                                                                      // :475-479
-        if (value < -P.weight_epsilon) weight = (int)fd_udiv((unsigned)(WS_WR * (P.tau + value)), P.div_weps);
-        if (weight == 0) have = false;                                                           // :480-483
-
-        const int delta_z = div_mr32(wmul(P.dz_per_distance, len));                              // :485
-        const int iter_steps = fd_sdiv(delta_z * 2, P.div_res) + 1;                              // :486
-        const int mid = fd_sdiv(delta_z, P.div_res);                                             // :487
-        const int low_x = wsub(qa.x, (int)div_mr64((i64)delta_z * r.iv[0]));                     // :488
-        const int low_y = wsub(qa.y, (int)div_mr64((i64)delta_z * r.iv[1]));
-        const int low_z = wsub(qa.z, (int)div_mr64((i64)delta_z * r.iv[2]));
-        if (have && iter_steps > (1 << WS_SEQ_STEP_BITS)) err |= 1u;
-        const bool far = len >= P.far_len;
-        const int max_steps = __reduce_max_sync(FULL, have ? iter_steps : 0);
-        unsigned last_brick = 0xFFFFFFFFu;
-
-        for (int step = 0; step < max_steps; ++step)                                             // :491
-        {
-          bool valid = have && step < iter_steps;
-          const int sr = wmul(step, P.res);
-          const int vx = fd_sdiv(wadd(low_x, (int)div_mr64((i64)sr * r.iv[0])), P.div_res);      // :493
-          const int vy = fd_sdiv(wadd(low_y, (int)div_mr64((i64)sr * r.iv[1])), P.div_res);
-          const int vz = fd_sdiv(wadd(low_z, (int)div_mr64((i64)sr * r.iv[2])), P.div_res);
-          if (!grid_in_bounds(g, vx, vy, vz)) valid = false;                                     // :495-498
-          if (valid) n_cand++;
-
-          u64 key = 0ull, addr = 0ull;
-          bool resident = false;
-          if (valid)
-          {
-            const int rx = ring_fast(vx, base_x, g.size[0]);
-            const int ry = ring_fast(vy, base_y, g.size[1]);
-            const int rz = ring_fast(vz, base_z, g.size[2]);
-            const i64 brick = brick_of(g, rx, ry, rz);
-            if (brick >= 0)                                // else: the column lives on another rank
-            {
-              resident = true;
-              addr = (u64)brick * WS_BRICK_VOX + (u64)brick_local(rx, ry, rz);
-              const u64 seq = make_seq((unsigned)ray_id, (unsigned)i, (unsigned)step);
-              key = make_key(value, step != mid, seq);                                           // :503-506
-              if (ATOMIC)
-              {
-                atomicMin(&g.keys[addr], key);                                                   // :508-512
-                if ((unsigned)brick != last_brick)
-                {
-                  g.brick_flag[brick] = 1u;
-                  last_brick = (unsigned)brick;
-                }
-              }
-            }
-          }
-          rec_append(rw, resident && far, key, addr, lane, rec, chunk_fill, cap_chunks, ctr);
-        }
-      }
+      if (r.small) march_ray<ATOMIC, true>(g, P, r, ray_id, lane, q, cx, rec, chunk_fill, cap_chunks, ctr);
+      else march_ray<ATOMIC, false>(g, P, r, ray_id, lane, q, cx, rec, chunk_fill, cap_chunks, ctr);
     }
     if (++ray_id == batch + RAY_BATCH)
     {
@@ -364,14 +443,15 @@ march_kernel(const GridDesc g, const UpdateParams P, const ws_pt *__restrict__ p
     }
   }
 
-  rec_finish(rw, lane, chunk_fill, cap_chunks, ctr);
+  rec_finish(cx.rw, lane, chunk_fill, cap_chunks, ctr);
   if (ATOMIC)
   {
     // candidate counter (work statistics): warp shuffle, then one atomic per warp
+    unsigned long long n_cand = cx.n_cand;
     for (int o = 16; o > 0; o >>= 1) n_cand += __shfl_down_sync(FULL, n_cand, o);
     if (lane == 0 && n_cand) atomicAdd(&ctr->n_candidates, n_cand);
   }
-  if (err) atomicOr(&ctr->error, err);
+  if (cx.err) atomicOr(&ctr->error, cx.err);
 }
 
 // touched-brick flags -> compact list; flags are reset for the next scan
@@ -804,6 +884,23 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
   P.div_res = make_fastdiv((unsigned)h->res);
   P.div_weps = make_fastdiv((unsigned)(P.tau - P.weight_epsilon > 0 ? P.tau - P.weight_epsilon : 1));
   P.half_res = h->res / 2;
+  P.div_half = make_fastdiv((unsigned)P.half_res);
+  P.div_res32 = make_fastdiv32((unsigned)h->res);
+  // fast-path bound on |coordinate| (march_math.cuh): every dividend of a 32-bit magic stays below 2^32 / res
+  {
+    const long long lim = (1ll << 31) / h->res - P.tau - (1ll << 17);
+    P.coord_lim = lim > 0 ? (int)lim : 0;
+    for (int a = 0; a < 3; a++)
+      if (std::llabs((long long)P.pos_mm[a]) >= lim) P.coord_lim = 0;
+    if (std::getenv("WS_MARCH_GENERAL")) P.coord_lim = 0;   // tests: force the literal-arithmetic path
+  }
+  for (int a = 0; a < 3; a++)
+  {
+    const GridDesc &g = h->g;
+    P.lo[a] = g.pos[a] - g.half[a];
+    P.ext[a] = g.size[a] - 1;
+    P.ringc[a] = (int)((((long long)g.offset[a] - g.half[a]) % g.size[a] + g.size[a]) % g.size[a]);
+  }
   P.n_points = n;
   P.far_len = far_start_len(h->res, P.dz_per_distance);
 

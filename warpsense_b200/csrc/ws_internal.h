@@ -6,6 +6,7 @@
 #include <unordered_map>
 #include <vector>
 #include "ws_common.cuh"
+#include "march_math.cuh"
 
 struct UpdateParams
 {
@@ -17,6 +18,13 @@ struct UpdateParams
   int half_res;        // map_resolution / 2
   int n_points;
   int far_len;         // march lengths >= far_len can meet an interpolated winner: their candidates are recorded
+  // fast path of the march (march_math.cuh)
+  FastDiv div_half;    // / (map_resolution / 2)
+  FastDiv32 div_res32; // / map_resolution, 32-bit magic
+  int coord_lim;       // |coordinate| bound of the 32-bit magic divisions, 0 = fast path off
+  int lo[3];           // lowest in-bounds voxel per axis (pos - size/2)
+  int ext[3];          // size - 1
+  int ringc[3];        // ring coordinate of voxel lo: (offset - size/2) mod size
 };
 
 // one recorded candidate: its key and the voxel address (record) or the pending slot (replay list)
