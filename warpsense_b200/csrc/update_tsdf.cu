@@ -37,10 +37,17 @@ namespace cg = cooperative_groups;
 
 #define FULL 0xFFFFFFFFu
 #define PEND_DONE 0xFFFFFFFFFFFFFFFFull
+#ifndef MARCH_WARPS
 #define MARCH_WARPS 8
+#endif
+#ifndef MARCH_CTAS
+#define MARCH_CTAS 3          // CTAs per SM (register budget 65536 / (CTAS * THREADS))
+#endif
 #define MARCH_THREADS (MARCH_WARPS * 32)
 #define QCAP 64
-#define RAY_BATCH 4
+#ifndef RAY_BATCH
+#define RAY_BATCH 1          // same-box A/B on B200: 1 -> 0.77 ms, 2 -> 0.79, 4 -> 0.91, 8 -> 1.07 (tail of long rays)
+#endif
 
 namespace {
 
@@ -218,7 +225,7 @@ struct MarchCtx
 // literal wrapping arithmetic of the oracle.  Both produce identical candidates wherever FAST is allowed.
 template <bool ATOMIC, bool FAST>
 WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, const int ray_id, const int lane,
-                    int4 (*q)[2], MarchCtx &cx, Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill,
+                    int4 *qa_s, int4 *qb_s, MarchCtx &cx, Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill,
                     const unsigned cap_chunks, UpdateCounters *__restrict__ ctr)
 {
   const unsigned lt = (1u << lane) - 1u;
@@ -282,8 +289,8 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
       if (active)
       {
         const int pos = (qh + qn + __popc(m & lt)) & (QCAP - 1);
-        q[pos][0] = make_int4(proj[0], proj[1], proj[2], i);
-        q[pos][1] = make_int4(index[0], index[1], index[2], 0);
+        qa_s[pos] = make_int4(proj[0], proj[1], proj[2], i);
+        qb_s[pos] = make_int4(index[0], index[1], index[2], 0);
       }
       qn += __popc(m);
       __syncwarp();
@@ -294,29 +301,68 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
     // ---- heavy part: up to 32 compacted march steps, one per lane ---------------------------
     const int take = qn < 32 ? qn : 32;
     bool have = lane < take;
-    const int4 qa = q[(qh + lane) & (QCAP - 1)][0];
-    const int4 qb = q[(qh + lane) & (QCAP - 1)][1];
+    const int4 qa = qa_s[(qh + lane) & (QCAP - 1)];
+    const int4 qb = qb_s[(qh + lane) & (QCAP - 1)];
     __syncwarp();
     qh = (qh + take) & (QCAP - 1);
     qn -= take;
 
     const int i = qa.w;
     const int len = 1 + i * P.half_res;
-    // distance of the hit to the centre of the marched voxel (:466-472)
+    // distance of the hit to the centre of the marched voxel (:466-472), clamped to tau; the square root is
+    // skipped when the whole warp is farther than tau from the hit (free space, most of every ray)
     const int tcx = wadd(wmul(qb.x, P.res), P.half_res);
     const int tcy = wadd(wmul(qb.y, P.res), P.half_res);
     const int tcz = wadd(wmul(qb.z, P.res), P.half_res);
     const int ex = wsub(r.p[0], tcx), ey = wsub(r.p[1], tcy), ez = wsub(r.p[2], tcz);
     const int vsq = wadd(wadd(wmul(ex, ex), wmul(ey, ey)), wmul(ez, ez));
-    int value = vsq < 0 ? P.tau : isqrt31(vsq);
-    value = value < P.tau ? value : P.tau;
+    int value = P.tau;
+    if (__any_sync(FULL, (unsigned)vsq < (unsigned)P.tau_sq))       // vsq < 0 (wrapped) reads as "far" too
+    {
+      const int root = isqrt31(vsq < 0 ? 0 : vsq);
+      if ((unsigned)vsq < (unsigned)P.tau_sq) value = root < P.tau ? root : P.tau;
+    }
     if (len > r.distance) value = -value;
 
-    int weight = WS_WR;                                                                          // :475-479
-    if (value < -P.weight_epsilon) weight = (int)fd_udiv((unsigned)(WS_WR * (P.tau + value)), P.div_weps);
-    if (weight == 0) have = false;                                                               // :480-483
+    if (value <= P.zero_weight_max) have = false;       // weight == 0 (:475-483); the merge recomputes the weight
 
     const int delta_z = div_mr32(wmul(P.dz_per_distance, len));                                  // :485
+
+    // ---- near field: every step of this batch has a fan of exactly one voxel (iter_steps == 1, mid == 0)
+    // and lies before the recorded range, so there is no fan loop and no record
+    if (FAST && ATOMIC && 1 + __shfl_sync(FULL, qa.w, take - 1) * P.half_res < P.far_len)
+    {
+      const int vx = fd32_sdiv(qa.x - div_mr32(delta_z * r.iv[0]), P.div_res32);                 // :488,:493
+      const int vy = fd32_sdiv(qa.y - div_mr32(delta_z * r.iv[1]), P.div_res32);
+      const int vz = fd32_sdiv(qa.z - div_mr32(delta_z * r.iv[2]), P.div_res32);
+      const unsigned tx = (unsigned)vx - (unsigned)P.lo[0];
+      const unsigned ty = (unsigned)vy - (unsigned)P.lo[1];
+      const unsigned tz = (unsigned)vz - (unsigned)P.lo[2];
+      if (tx > (unsigned)P.ext[0] || ty > (unsigned)P.ext[1] || tz > (unsigned)P.ext[2]) have = false;   // :495-498
+      unsigned brick = 0xFFFFFFFFu;
+      if (have)
+      {
+        cx.n_cand++;
+        int rx = (int)tx + P.ringc[0]; rx -= rx >= g.size[0] ? g.size[0] : 0;
+        int ry = (int)ty + P.ringc[1]; ry -= ry >= g.size[1] ? g.size[1] : 0;
+        int rz = (int)tz + P.ringc[2]; rz -= rz >= g.size[2] ? g.size[2] : 0;
+        const int slot = g.full ? (rx >> 3) : (int)g.xslot[rx >> 3];
+        if (slot >= 0)
+        {
+          brick = (unsigned)((slot * g.nb[1] + (ry >> 3)) * g.nb[2] + (rz >> 3));
+          const u64 addr = (u64)brick * WS_BRICK_VOX + (u64)brick_local(rx, ry, rz);
+          const unsigned av = (unsigned)(value < 0 ? -value : value);
+          const u64 key = ((u64)av << 47) | (make_seq((unsigned)ray_id, (unsigned)i, 0u) << 1) | (u64)(value < 0 ? 1 : 0);
+#ifndef WHATIF_NOATOM
+          atomicMin(&g.keys[addr], key);                                                         // :508-512
+#endif
+        }
+      }
+      // consecutive lanes are consecutive march steps: mostly the same brick, flag it once
+      const unsigned prev_brick = __shfl_up_sync(FULL, brick, 1);
+      if (brick != 0xFFFFFFFFu && (lane == 0 || brick != prev_brick)) g.brick_flag[brick] = 1u;
+      continue;
+    }
     int iter_steps, mid, low_x, low_y, low_z;
     if (FAST)
     {
@@ -388,7 +434,9 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
           key = step == mid ? key_real0 + s2 : key_int0 - s2;
           if (ATOMIC)
           {
+#ifndef WHATIF_NOATOM
             atomicMin(&g.keys[addr], key);                                                       // :508-512
+#endif
             if (brick != last_brick)
             {
               g.brick_flag[brick] = 1u;
@@ -397,7 +445,9 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
           }
         }
       }
+#ifndef WHATIF_NOREC
       rec_append(cx.rw, resident && far, key, addr, lane, rec, chunk_fill, cap_chunks, ctr);
+#endif
     }
   }
 }
@@ -405,15 +455,15 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
 // ATOMIC: the scan's first pass (candidate keys + brick flags + record).  !ATOMIC: regenerate the record
 // only (far part of every ray), used when the record buffer had to grow.
 template <bool ATOMIC>
-__global__ void __launch_bounds__(MARCH_THREADS, 3)
+__global__ void __launch_bounds__(MARCH_THREADS, MARCH_CTAS)
 march_kernel(const GridDesc g, const UpdateParams P, const ws_pt *__restrict__ pts,
              UpdateCounters *__restrict__ ctr, Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill,
              const unsigned cap_chunks)
 {
-  __shared__ int4 s_q[MARCH_WARPS][QCAP][2];
+  __shared__ int4 s_qa[MARCH_WARPS][QCAP], s_qb[MARCH_WARPS][QCAP];   // per-warp queue of surviving march steps
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
-  int4 (*q)[2] = s_q[wib];
+  int4 *qa_s = s_qa[wib], *qb_s = s_qb[wib];
   const int total_warps = gridDim.x * MARCH_WARPS;
 
   MarchCtx cx;
@@ -433,8 +483,8 @@ march_kernel(const GridDesc g, const UpdateParams P, const ws_pt *__restrict__ p
     const ws_pt pt = pts[ray_id];
     if (ray_setup(P, pt, r))
     {
-      if (r.small) march_ray<ATOMIC, true>(g, P, r, ray_id, lane, q, cx, rec, chunk_fill, cap_chunks, ctr);
-      else march_ray<ATOMIC, false>(g, P, r, ray_id, lane, q, cx, rec, chunk_fill, cap_chunks, ctr);
+      if (r.small) march_ray<ATOMIC, true>(g, P, r, ray_id, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
+      else march_ray<ATOMIC, false>(g, P, r, ray_id, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
     }
     if (++ray_id == batch + RAY_BATCH)
     {
@@ -883,8 +933,12 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
   }
   P.div_res = make_fastdiv((unsigned)h->res);
   P.div_weps = make_fastdiv((unsigned)(P.tau - P.weight_epsilon > 0 ? P.tau - P.weight_epsilon : 1));
+  // largest value whose weight (:475-479) truncates to 0: such march steps are skipped (:480-483)
+  P.zero_weight_max = -P.tau - 1;
+  for (int v = -P.tau; v < -P.weight_epsilon && tsdf_weight(v, P.tau, P.weight_epsilon) == 0; v++) P.zero_weight_max = v;
   P.half_res = h->res / 2;
   P.div_half = make_fastdiv((unsigned)P.half_res);
+  P.tau_sq = P.tau * P.tau;
   P.div_res32 = make_fastdiv32((unsigned)h->res);
   // fast-path bound on |coordinate| (march_math.cuh): every dividend of a 32-bit magic stays below 2^32 / res
   {
@@ -908,7 +962,7 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
   WS_CUDA_OK(cudaMemsetAsync(h->d_counters, 0, sizeof(UpdateCounters), s));
   if (n > 0)
   {
-    const int march_blocks = h->sm_count * 3;
+    const int march_blocks = h->sm_count * MARCH_CTAS;
     unsigned cap_chunks = (unsigned)h->rec_cap_chunks;
     ws_timer_begin(h, WS_TIMER_MARCH);
     march_kernel<true><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, d_pts, h->d_counters, h->d_rec,

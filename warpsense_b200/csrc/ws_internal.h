@@ -21,6 +21,8 @@ struct UpdateParams
   // fast path of the march (march_math.cuh)
   FastDiv div_half;    // / (map_resolution / 2)
   FastDiv32 div_res32; // / map_resolution, 32-bit magic
+  int tau_sq;          // tau * tau (tau <= 32767)
+  int zero_weight_max; // march steps with value <= this have weight 0 and are skipped
   int coord_lim;       // |coordinate| bound of the 32-bit magic divisions, 0 = fast path off
   int lo[3];           // lowest in-bounds voxel per axis (pos - size/2)
   int ext[3];          // size - 1

@@ -103,8 +103,8 @@ def load(build_if_needed=True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if build_if_needed and _build.needs_build():
+    path = os.environ.get("WS_LIB_PATH") or _build.LIB_PATH     # WS_LIB_PATH: A/B runs of alternative builds (tools/)
+    if path == _build.LIB_PATH and build_if_needed and _build.needs_build():
         _build.build_library()
     if not os.path.exists(path):
         raise RuntimeError("libwarpsense_b200.so is missing: run `python -m warpsense_b200.build` "
