@@ -47,7 +47,7 @@ void free_handle(ws_handle *h)
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto &t : h->timers) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
   cudaFree(h->g.grid); cudaFree(h->g.keys); cudaFree(h->g.brick_flag); cudaFree(h->g.park_bits);
-  cudaFree(h->d_points); cudaFree(h->d_reg_points); cudaFree(h->d_brick_list);
+  cudaFree(h->d_points); cudaFree(h->d_rays); cudaFree(h->d_reg_points); cudaFree(h->d_brick_list);
   cudaFree(h->d_counters); cudaFreeHost(h->h_counters);
   cudaFree(h->d_pend_addr); cudaFree(h->d_pend_prev); cudaFree(h->d_pend_key);
   cudaFree(h->d_active[0]); cudaFree(h->d_active[1]);

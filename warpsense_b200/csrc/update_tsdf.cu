@@ -28,8 +28,10 @@
 // If the record list overflows its buffer the host grows it and regenerates it with march_kernel<false>
 // (far part of every ray, no atomics) before running replay_kernel again.
 #include <cooperative_groups.h>
+#include <algorithm>
 #include <cstdlib>
 #include <stdexcept>
+#include <vector>
 #include "ws_internal.h"
 #include "march_math.cuh"
 
@@ -65,6 +67,16 @@ WS_D bool box_in_bounds(const UpdateParams &P, int x, int y, int z)
          (unsigned)z - (unsigned)P.lo[2] <= (unsigned)P.ext[2];
 }
 
+// atomicAdd by ONE lane whose result is consumed much later.  Plain atomicAdd() in divergent code is
+// warp-aggregated by the compiler, which appends a SHFL of the result right behind the ATOMG and so
+// waits for the full L2 round trip on the spot (18 % of all stall samples of the march kernel).
+WS_D unsigned atom_add_async(unsigned *addr, unsigned v)
+{
+  unsigned old;
+  asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(addr), "r"(v) : "memory");
+  return old;
+}
+
 struct Ray
 {
   int p[3];
@@ -74,6 +86,29 @@ struct Ray
   int n_steps;
   bool small;          // march_math.cuh: the 32-bit fast path is exact for this ray
 };
+
+// What the set-up pass leaves per ray for the march warps: six 16-byte words, staged in shared memory
+#define RAY_WORDS 6
+struct __align__(16) RaySetup
+{
+  int p[3], distance;  // word 0
+  int d[3], n_steps;   // word 1
+  int iv[3], flags;    // word 2: bit 0 = small (fast path), bits 1.. = ray index
+  int seg[4];          // word 3: march-step ranges [seg[0], seg[1]) and [seg[2], seg[3]) this rank has to process
+  unsigned dq[3], pad0;    // word 4: DDA increments of 32 march steps per axis (fast path), quotient ...
+  unsigned drem[3], pad1;  // word 5: ... and remainder of |d| * 32 * h / distance
+};
+static_assert(sizeof(RaySetup) == 16 * RAY_WORDS, "RaySetup layout");
+
+// read one staged word; volatile asm so the compiler neither hoists it out of the march loops nor keeps the
+// per-ray constants in registers across them (register pressure made it re-derive loop invariants in FP64)
+WS_D int4 lds_word(const int4 *p)
+{
+  int4 v;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)));
+  return v;
+}
 
 // per-ray setup (update_tsdf.cpp:420-446), every lane redundantly (warp-uniform result, no shuffles).
 // The truncating 64-bit divisions of the reference run as FP64 estimates with an exact integer
@@ -128,12 +163,12 @@ WS_D bool ray_setup(const UpdateParams &P, const ws_pt pt, Ray &r)
 }
 
 // general (wrapping, 64-bit magic) projection of one march step
-WS_D void step_index(const UpdateParams &P, const Ray &r, const FastDiv div_dist, int len, int proj[3], int idx[3])
+WS_D void step_index(const UpdateParams &P, const int d[3], const FastDiv div_dist, int len, int proj[3], int idx[3])
 {
 #pragma unroll
   for (int a = 0; a < 3; a++)
   {
-    proj[a] = wadd(P.pos_mm[a], fd_sdiv(wmul(r.d[a], len), div_dist));                           // :452
+    proj[a] = wadd(P.pos_mm[a], fd_sdiv(wmul(d[a], len), div_dist));                             // :452
     idx[a] = fd_sdiv(proj[a], P.div_res);                                                        // :453
   }
 }
@@ -193,7 +228,7 @@ WS_D void rec_append(RecWriter &w, const bool want, const u64 key, const u64 add
     if (span_done)
     {
       w.span_end = after + WS_REC_SPAN;
-      if (lane == 0) w.next_span = atomicAdd(&ctr->n_chunks, (unsigned)WS_REC_SPAN);   // consumed a span later
+      if (lane == 0) w.next_span = atom_add_async(&ctr->n_chunks, (unsigned)WS_REC_SPAN);   // consumed a span later
     }
   }
 }
@@ -224,43 +259,55 @@ struct MarchCtx
 // One ray, one warp.  FAST: march_math.cuh (DDA projection, 32-bit magics, int32 fan arithmetic); !FAST: the
 // literal wrapping arithmetic of the oracle.  Both produce identical candidates wherever FAST is allowed.
 template <bool ATOMIC, bool FAST>
-WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, const int ray_id, const int lane,
+WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const int4 *ray_s, const int start,
+                    const int end, const int lane,
                     int4 *qa_s, int4 *qb_s, MarchCtx &cx, Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill,
                     const unsigned cap_chunks, UpdateCounters *__restrict__ ctr)
 {
   const unsigned lt = (1u << lane) - 1u;
-  if (r.n_steps > (1 << WS_SEQ_MARCH_BITS)) cx.err |= 1u;
-  int start = 0;
-  if (!ATOMIC && P.far_len > 1) start = (P.far_len - 1) / P.half_res;
+  // the step loop keeps only the direction and the distance in registers; the hit point, the interpolation
+  // vector and the ray index are re-read from the staged set-up where the heavy part needs them
+  int dvec[3], distance;
+  {
+    const int4 w0 = lds_word(ray_s + 0), w1 = lds_word(ray_s + 1);
+    distance = w0.w;
+    dvec[0] = w1.x; dvec[1] = w1.y; dvec[2] = w1.z;
+    if (w1.w > (1 << WS_SEQ_MARCH_BITS)) cx.err |= 1u;
+  }
 
   FastDiv div_dist;
-  div_dist.d = (unsigned)r.distance; div_dist.M = 0ull;
+  div_dist.d = (unsigned)distance; div_dist.M = 0ull;
   DdaAxis dda[3];
   if (FAST)
   {
-    const double rdist = 1.0 / (double)r.distance;
+    const double rdist = 1.0 / (double)distance;
     const unsigned len0 = 1u + (unsigned)(start + lane) * (unsigned)P.half_res;
+    const int4 w4 = lds_word(ray_s + 4), w5 = lds_word(ray_s + 5);
+    const unsigned dq[3] = { (unsigned)w4.x, (unsigned)w4.y, (unsigned)w4.z };
+    const unsigned dr[3] = { (unsigned)w5.x, (unsigned)w5.y, (unsigned)w5.z };
 #pragma unroll
     for (int a = 0; a < 3; a++)
-      dda_init(dda[a], r.d[a] < 0 ? 0u - (unsigned)r.d[a] : (unsigned)r.d[a], len0, 32u * (unsigned)P.half_res,
-               (unsigned)r.distance, rdist);
+    {
+      divrem_rcp((dvec[a] < 0 ? 0u - (unsigned)dvec[a] : (unsigned)dvec[a]) * len0, (unsigned)distance, rdist, dda[a].q, dda[a].rem);
+      dda[a].dq = dq[a]; dda[a].drem = dr[a];
+    }
   }
-  else if (r.distance > 1) div_dist.M = (~0ull) / (u64)(unsigned)r.distance + 1ull;
+  else if (distance > 1) div_dist.M = (~0ull) / (u64)(unsigned)distance + 1ull;
 
   int carry_x = 0, carry_y = 0;
-  if (start > 0 && start < r.n_steps)     // record regeneration only: the step before `start` seeds the column filter
+  if (start > 0)                          // a range that starts inside the ray: the step before it seeds the column filter
   {
     FastDiv dd = div_dist;
-    if (FAST && r.distance > 1) dd.M = (~0ull) / (u64)(unsigned)r.distance + 1ull;
+    if (FAST && distance > 1) dd.M = (~0ull) / (u64)(unsigned)distance + 1ull;
     int pj[3], ix[3];
-    step_index(P, r, dd, 1 + (start - 1) * P.half_res, pj, ix);
+    step_index(P, dvec, dd, 1 + (start - 1) * P.half_res, pj, ix);
     carry_x = ix[0]; carry_y = ix[1];
   }
 
   int qn = 0, qh = 0;                     // queue fill / head (warp-uniform)
-  for (int base = start; base < r.n_steps || qn > 0; base += 32)
+  for (int base = start; base < end || qn > 0; base += 32)
   {
-    if (base < r.n_steps)
+    if (base < end)
     {
       const int i = base + lane;
       int proj[3], index[3];
@@ -269,12 +316,12 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
 #pragma unroll
         for (int a = 0; a < 3; a++)
         {
-          proj[a] = P.pos_mm[a] + (r.d[a] < 0 ? -(int)dda[a].q : (int)dda[a].q);                 // :452
+          proj[a] = P.pos_mm[a] + (dvec[a] < 0 ? -(int)dda[a].q : (int)dda[a].q);                // :452
           index[a] = fd32_sdiv(proj[a], P.div_res32);                                            // :453
-          dda_advance(dda[a], (unsigned)r.distance);
+          dda_advance(dda[a], (unsigned)distance);
         }
       }
-      else step_index(P, r, div_dist, 1 + i * P.half_res, proj, index);
+      else step_index(P, dvec, div_dist, 1 + i * P.half_res, proj, index);
 
       int px = __shfl_up_sync(FULL, index[0], 1);
       int py = __shfl_up_sync(FULL, index[1], 1);
@@ -282,7 +329,7 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
       carry_x = __shfl_sync(FULL, index[0], 31);
       carry_y = __shfl_sync(FULL, index[1], 31);
 
-      bool active = i < r.n_steps;
+      bool active = i < end;
       if (i > 0 && index[0] == px && index[1] == py) active = false;                             // :455-458
       if (!box_in_bounds(P, index[0], index[1], index[2])) active = false;                       // :460-463
       const unsigned m = __ballot_sync(FULL, active);
@@ -294,7 +341,7 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
       }
       qn += __popc(m);
       __syncwarp();
-      if (qn < 32 && base + 32 < r.n_steps) continue;     // keep filling
+      if (qn < 32 && base + 32 < end) continue;           // keep filling
     }
     if (qn == 0) continue;
 
@@ -307,6 +354,10 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
     qh = (qh + take) & (QCAP - 1);
     qn -= take;
 
+    const int4 w0 = lds_word(ray_s + 0), w2 = lds_word(ray_s + 2);
+    const int rp[3] = { w0.x, w0.y, w0.z };
+    const int riv[3] = { w2.x, w2.y, w2.z };
+    const int ray_id = w2.w >> 1;
     const int i = qa.w;
     const int len = 1 + i * P.half_res;
     // distance of the hit to the centre of the marched voxel (:466-472), clamped to tau; the square root is
@@ -314,7 +365,7 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
     const int tcx = wadd(wmul(qb.x, P.res), P.half_res);
     const int tcy = wadd(wmul(qb.y, P.res), P.half_res);
     const int tcz = wadd(wmul(qb.z, P.res), P.half_res);
-    const int ex = wsub(r.p[0], tcx), ey = wsub(r.p[1], tcy), ez = wsub(r.p[2], tcz);
+    const int ex = wsub(rp[0], tcx), ey = wsub(rp[1], tcy), ez = wsub(rp[2], tcz);
     const int vsq = wadd(wadd(wmul(ex, ex), wmul(ey, ey)), wmul(ez, ez));
     int value = P.tau;
     if (__any_sync(FULL, (unsigned)vsq < (unsigned)P.tau_sq))       // vsq < 0 (wrapped) reads as "far" too
@@ -322,7 +373,7 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
       const int root = isqrt31(vsq < 0 ? 0 : vsq);
       if ((unsigned)vsq < (unsigned)P.tau_sq) value = root < P.tau ? root : P.tau;
     }
-    if (len > r.distance) value = -value;
+    if (len > distance) value = -value;
 
     if (value <= P.zero_weight_max) have = false;       // weight == 0 (:475-483); the merge recomputes the weight
 
@@ -332,9 +383,9 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
     // and lies before the recorded range, so there is no fan loop and no record
     if (FAST && ATOMIC && 1 + __shfl_sync(FULL, qa.w, take - 1) * P.half_res < P.far_len)
     {
-      const int vx = fd32_sdiv(qa.x - div_mr32(delta_z * r.iv[0]), P.div_res32);                 // :488,:493
-      const int vy = fd32_sdiv(qa.y - div_mr32(delta_z * r.iv[1]), P.div_res32);
-      const int vz = fd32_sdiv(qa.z - div_mr32(delta_z * r.iv[2]), P.div_res32);
+      const int vx = fd32_sdiv(qa.x - div_mr32(delta_z * riv[0]), P.div_res32);                 // :488,:493
+      const int vy = fd32_sdiv(qa.y - div_mr32(delta_z * riv[1]), P.div_res32);
+      const int vz = fd32_sdiv(qa.z - div_mr32(delta_z * riv[2]), P.div_res32);
       const unsigned tx = (unsigned)vx - (unsigned)P.lo[0];
       const unsigned ty = (unsigned)vy - (unsigned)P.lo[1];
       const unsigned tz = (unsigned)vz - (unsigned)P.lo[2];
@@ -342,13 +393,13 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
       unsigned brick = 0xFFFFFFFFu;
       if (have)
       {
-        cx.n_cand++;
         int rx = (int)tx + P.ringc[0]; rx -= rx >= g.size[0] ? g.size[0] : 0;
         int ry = (int)ty + P.ringc[1]; ry -= ry >= g.size[1] ? g.size[1] : 0;
         int rz = (int)tz + P.ringc[2]; rz -= rz >= g.size[2] ? g.size[2] : 0;
         const int slot = g.full ? (rx >> 3) : (int)g.xslot[rx >> 3];
         if (slot >= 0)
         {
+          cx.n_cand++;
           brick = (unsigned)((slot * g.nb[1] + (ry >> 3)) * g.nb[2] + (rz >> 3));
           const u64 addr = (u64)brick * WS_BRICK_VOX + (u64)brick_local(rx, ry, rz);
           const unsigned av = (unsigned)(value < 0 ? -value : value);
@@ -368,17 +419,17 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
     {
       iter_steps = (int)fd32_udiv((unsigned)(delta_z * 2), P.div_res32) + 1;                     // :486
       mid = (int)fd32_udiv((unsigned)delta_z, P.div_res32);                                      // :487
-      low_x = qa.x - div_mr32(delta_z * r.iv[0]);                                                // :488
-      low_y = qa.y - div_mr32(delta_z * r.iv[1]);
-      low_z = qa.z - div_mr32(delta_z * r.iv[2]);
+      low_x = qa.x - div_mr32(delta_z * riv[0]);                                                // :488
+      low_y = qa.y - div_mr32(delta_z * riv[1]);
+      low_z = qa.z - div_mr32(delta_z * riv[2]);
     }
     else
     {
       iter_steps = fd_sdiv(delta_z * 2, P.div_res) + 1;
       mid = fd_sdiv(delta_z, P.div_res);
-      low_x = wsub(qa.x, (int)div_mr64((i64)delta_z * r.iv[0]));
-      low_y = wsub(qa.y, (int)div_mr64((i64)delta_z * r.iv[1]));
-      low_z = wsub(qa.z, (int)div_mr64((i64)delta_z * r.iv[2]));
+      low_x = wsub(qa.x, (int)div_mr64((i64)delta_z * riv[0]));
+      low_y = wsub(qa.y, (int)div_mr64((i64)delta_z * riv[1]));
+      low_z = wsub(qa.z, (int)div_mr64((i64)delta_z * riv[2]));
     }
     if (have && iter_steps > (1 << WS_SEQ_STEP_BITS)) cx.err |= 1u;
     const bool far = len >= P.far_len;
@@ -399,22 +450,21 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
       int vx, vy, vz;
       if (FAST)
       {
-        vx = fd32_sdiv(low_x + div_mr32(sr * r.iv[0]), P.div_res32);                             // :493
-        vy = fd32_sdiv(low_y + div_mr32(sr * r.iv[1]), P.div_res32);
-        vz = fd32_sdiv(low_z + div_mr32(sr * r.iv[2]), P.div_res32);
+        vx = fd32_sdiv(low_x + div_mr32(sr * riv[0]), P.div_res32);                             // :493
+        vy = fd32_sdiv(low_y + div_mr32(sr * riv[1]), P.div_res32);
+        vz = fd32_sdiv(low_z + div_mr32(sr * riv[2]), P.div_res32);
       }
       else
       {
-        vx = fd_sdiv(wadd(low_x, (int)div_mr64((i64)sr * r.iv[0])), P.div_res);
-        vy = fd_sdiv(wadd(low_y, (int)div_mr64((i64)sr * r.iv[1])), P.div_res);
-        vz = fd_sdiv(wadd(low_z, (int)div_mr64((i64)sr * r.iv[2])), P.div_res);
+        vx = fd_sdiv(wadd(low_x, (int)div_mr64((i64)sr * riv[0])), P.div_res);
+        vy = fd_sdiv(wadd(low_y, (int)div_mr64((i64)sr * riv[1])), P.div_res);
+        vz = fd_sdiv(wadd(low_z, (int)div_mr64((i64)sr * riv[2])), P.div_res);
       }
       // in bounds (:495-498) <=> 0 <= v - lo <= size - 1 per axis
       const unsigned tx = (unsigned)vx - (unsigned)P.lo[0];
       const unsigned ty = (unsigned)vy - (unsigned)P.lo[1];
       const unsigned tz = (unsigned)vz - (unsigned)P.lo[2];
       if (tx > (unsigned)P.ext[0] || ty > (unsigned)P.ext[1] || tz > (unsigned)P.ext[2]) valid = false;
-      if (valid) cx.n_cand++;
 
       u64 key = 0ull, addr = 0ull;
       bool resident = false;
@@ -428,6 +478,7 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
         if (slot >= 0)                                 // else: the column lives on another rank
         {
           resident = true;
+          cx.n_cand++;
           const unsigned brick = (unsigned)((slot * g.nb[1] + (ry >> 3)) * g.nb[2] + (rz >> 3));
           addr = (u64)brick * WS_BRICK_VOX + (u64)brick_local(rx, ry, rz);
           const u64 s2 = (u64)(unsigned)step << 1;
@@ -452,45 +503,174 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const Ray &r, cons
   }
 }
 
+// March steps of a ray whose candidates can land in a resident x column (multi-GPU slabs): the ray's x
+// coordinate is monotone in the step index, so every resident x interval (already widened by the fan's
+// reach, UpdateParams::xiv_*) maps to one contiguous step range.  Conservative by two steps either side;
+// the exact per-candidate residency test stays in the march.
+WS_D void ray_segments(const UpdateParams &P, const Ray &r, int seg[4])
+{
+  seg[0] = 0; seg[1] = r.n_steps; seg[2] = 0; seg[3] = 0;
+  if (P.n_xiv <= 0) return;                          // everything resident
+  seg[1] = 0;
+  int n = 0;
+  for (int k = 0; k < P.n_xiv && n < 2; k++)
+  {
+    const double x0 = (double)P.xiv_lo[k] - (double)P.pos_mm[0], x1 = (double)P.xiv_hi[k] - (double)P.pos_mm[0];
+    int i0 = 0, i1 = r.n_steps;
+    if (r.d[0] == 0)
+    {
+      if (!(x0 <= 0.0 && 0.0 < x1)) continue;
+    }
+    else
+    {
+      const double s = (double)r.distance / (double)r.d[0];
+      double l0 = x0 * s, l1 = x1 * s;               // lengths at which the ray crosses the interval ends
+      if (l0 > l1) { const double t = l0; l0 = l1; l1 = t; }
+      const double h = (double)P.half_res;
+      const double f0 = floor((l0 - 1.0) / h) - 2.0, f1 = ceil((l1 - 1.0) / h) + 3.0;
+      if (f1 <= 0.0 || f0 >= (double)r.n_steps) continue;
+      i0 = f0 < 0.0 ? 0 : (int)f0;
+      i1 = f1 > (double)r.n_steps ? r.n_steps : (int)f1;
+    }
+    if (i0 >= i1) continue;
+    if (n == 1 && i0 <= seg[1] && i1 >= seg[0])      // touches the first range: merge
+    {
+      seg[0] = i0 < seg[0] ? i0 : seg[0];
+      seg[1] = i1 > seg[1] ? i1 : seg[1];
+      continue;
+    }
+    seg[2 * n] = i0; seg[2 * n + 1] = i1;
+    n++;
+  }
+}
+
+// Set-up pass: one THREAD per ray (the march needs the result warp-uniform; computing it there costs every
+// lane of a warp the same ~600 instructions).  Rays without work on this rank get empty step ranges.
+__global__ void __launch_bounds__(256)
+setup_kernel(const UpdateParams P, const ws_pt *__restrict__ pts, RaySetup *__restrict__ rays,
+             UpdateCounters *__restrict__ ctr)
+{
+  const int ray_id = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = false;
+  RaySetup o;
+  if (ray_id < P.n_points)
+  {
+    Ray r;
+    if (ray_setup(P, pts[ray_id], r))
+    {
+#pragma unroll
+      for (int a = 0; a < 3; a++) { o.p[a] = r.p[a]; o.d[a] = r.d[a]; o.iv[a] = r.iv[a]; }
+      o.distance = r.distance; o.n_steps = r.n_steps; o.flags = (ray_id << 1) | (r.small ? 1 : 0);
+      o.pad0 = o.pad1 = 0u;
+      const double rdist = 1.0 / (double)r.distance;
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+      {
+        o.dq[a] = o.drem[a] = 0u;
+        const unsigned ad = r.d[a] < 0 ? 0u - (unsigned)r.d[a] : (unsigned)r.d[a];
+        if (r.small) divrem_rcp(ad * 32u * (unsigned)P.half_res, (unsigned)r.distance, rdist, o.dq[a], o.drem[a]);
+      }
+      ray_segments(P, r, o.seg);
+      valid = o.seg[1] > o.seg[0] || o.seg[3] > o.seg[2];
+    }
+  }
+  // Written in place, NOT compacted: the march takes rays in scan order, so the ~3,500 rays in flight at
+  // any time belong to a few neighbouring beams and their voxels (keys) stay L2-resident.  A compacted list
+  // filled in atomic order scrambles the beams and made the march 40 % slower (same-box A/B).
+  if (ray_id < P.n_points)
+  {
+    if (!valid)
+    {
+      o.seg[0] = o.seg[1] = o.seg[2] = o.seg[3] = 0;
+      o.flags = ray_id << 1;
+    }
+    int4 *dst = reinterpret_cast<int4 *>(&rays[ray_id]);
+    const int4 *src = reinterpret_cast<const int4 *>(&o);
+    if (valid)
+    {
+#pragma unroll
+      for (int w = 0; w < RAY_WORDS; w++) dst[w] = src[w];
+    }
+    else { dst[2] = src[2]; dst[3] = src[3]; }
+  }
+}
+
 // ATOMIC: the scan's first pass (candidate keys + brick flags + record).  !ATOMIC: regenerate the record
 // only (far part of every ray), used when the record buffer had to grow.
 template <bool ATOMIC>
 __global__ void __launch_bounds__(MARCH_THREADS, MARCH_CTAS)
-march_kernel(const GridDesc g, const UpdateParams P, const ws_pt *__restrict__ pts,
-             UpdateCounters *__restrict__ ctr, Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill,
-             const unsigned cap_chunks)
+march_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__restrict__ rays,
+             UpdateCounters *__restrict__ ctr, Rec *__restrict__ rec,
+             unsigned *__restrict__ chunk_fill, const unsigned cap_chunks)
 {
   __shared__ int4 s_qa[MARCH_WARPS][QCAP], s_qb[MARCH_WARPS][QCAP];   // per-warp queue of surviving march steps
+  __shared__ int4 s_ray[MARCH_WARPS][2][RAY_WORDS];                    // the warp's current and next ray (cp.async)
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   int4 *qa_s = s_qa[wib], *qb_s = s_qb[wib];
-  const int total_warps = gridDim.x * MARCH_WARPS;
+  const unsigned total_warps = gridDim.x * MARCH_WARPS;
+  const unsigned n_work = (unsigned)P.n_points;
 
   MarchCtx cx;
   rec_init(cx.rw, ctr, lane);
   cx.n_cand = 0u;
   cx.err = 0u;
 
-  // rays are fetched RAY_BATCH at a time (again: one same-address atomic per fetch); the next batch is
-  // requested when the current one starts and consumed when it is done
-  int batch = (blockIdx.x * MARCH_WARPS + wib) * RAY_BATCH;
-  unsigned nxt = 0;
-  for (int ray_id = batch; ray_id < P.n_points; )
+  // Work distribution: one ray per fetch from a global counter (same-box A/B of 1/2/4/8 rays per fetch: the
+  // tail of long rays costs more than the atomics), software-pipelined two deep -- while ray k is marched
+  // out of one shared-memory slot, the set-up of ray k+1 is in flight to the other (cp.async) and the index
+  // of ray k+2 is in flight from the counter.
+  unsigned k_cur = blockIdx.x * MARCH_WARPS + wib;
+  unsigned k_nxt = 0;
+  if (lane == 0) k_nxt = atomicAdd(&ctr->ray_counter, 1u);
+  k_nxt = total_warps + __shfl_sync(FULL, k_nxt, 0);
+  int buf = 0;
+  if (lane < RAY_WORDS)
   {
-    if (ray_id == batch && lane == 0) nxt = atomicAdd(&ctr->ray_counter, (unsigned)RAY_BATCH);
+    if (k_cur < n_work)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_ray[wib][0][lane])),
+                   "l"(reinterpret_cast<const int4 *>(&rays[k_cur]) + lane) : "memory");
+    if (k_nxt < n_work)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_ray[wib][1][lane])),
+                   "l"(reinterpret_cast<const int4 *>(&rays[k_nxt]) + lane) : "memory");
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncwarp();
 
-    Ray r;
-    const ws_pt pt = pts[ray_id];
-    if (ray_setup(P, pt, r))
+  while (k_cur < n_work)
+  {
+    unsigned fetched = 0;
+    if (lane == 0) fetched = atom_add_async(&ctr->ray_counter, 1u);
+
+    const int4 *ray_s = s_ray[wib][buf];
+    const int4 w2 = lds_word(ray_s + 2), w3 = lds_word(ray_s + 3);
+    const bool small = (w2.w & 1) != 0;
+#pragma unroll 1
+    for (int sg = 0; sg < 2; sg++)
     {
-      if (r.small) march_ray<ATOMIC, true>(g, P, r, ray_id, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
-      else march_ray<ATOMIC, false>(g, P, r, ray_id, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
+      int start = sg ? w3.z : w3.x;
+      const int end = sg ? w3.w : w3.y;
+      if (!ATOMIC && P.far_len > 1)
+      {
+        const int fs = (P.far_len - 1) / P.half_res;
+        start = start > fs ? start : fs;
+      }
+      if (start >= end) continue;
+      if (small) march_ray<ATOMIC, true>(g, P, ray_s, start, end, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
+      else march_ray<ATOMIC, false>(g, P, ray_s, start, end, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
     }
-    if (++ray_id == batch + RAY_BATCH)
-    {
-      batch = total_warps * RAY_BATCH + (int)__shfl_sync(FULL, nxt, 0);
-      ray_id = batch;
-    }
+
+    // rotate the pipeline.  The empty asm ties the fetched index to a value that is only known once the
+    // march is done: without it the compiler broadcasts (and waits for) the atomic's result right away.
+    asm volatile("" : "+r"(fetched) : "r"(cx.n_cand), "r"(cx.rw.fill));
+    asm volatile("cp.async.wait_all;" ::: "memory");     // ray k+1 has landed in the other slot
+    __syncwarp();                                        // ... and every lane is done reading this one
+    k_cur = k_nxt;
+    k_nxt = total_warps + __shfl_sync(FULL, fetched, 0);
+    if (k_nxt < n_work && lane < RAY_WORDS)
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_ray[wib][buf][lane])),
+                   "l"(reinterpret_cast<const int4 *>(&rays[k_nxt]) + lane) : "memory");
+    buf ^= 1;
   }
 
   rec_finish(cx.rw, lane, chunk_fill, cap_chunks, ctr);
@@ -881,6 +1061,48 @@ static int far_start_len(int res, int dz)
   return fl < 1 ? 1 : (int)(fl > 0x7fffffff ? 0x7fffffff : fl);
 }
 
+// Multi-GPU slabs: the x intervals (mm, map frame) in which a march step can still produce a candidate for a
+// resident brick column -- the resident voxel columns widened by the reach of the interpolation fan
+// (|lowest - proj| <= delta_z and the fan spans 2*delta_z + res more, update_tsdf.cpp:485-493) plus two voxels
+// for the truncating divisions.  Resident columns are cyclically contiguous in ring space (slab + halo), so
+// there are at most two intervals; anything else switches the culling off.
+static void resident_x_intervals(const ws_handle *h, UpdateParams &P)
+{
+  P.n_xiv = 0;
+  const GridDesc &g = h->g;
+  if (g.full) return;
+  const int size = g.size[0];
+  std::vector<char> res_t((size_t)size, 0);
+  for (int t = 0; t < size; t++)
+  {
+    int ring = t + P.ringc[0];
+    if (ring >= size) ring -= size;
+    res_t[(size_t)t] = g.xslot[ring >> 3] >= 0;
+  }
+  const double len_max = 1.7320508 * (double)std::max(g.size[0], std::max(g.size[1], g.size[2])) * h->res + P.tau + h->res;
+  const long long dz_max = (long long)((double)P.dz_per_distance * len_max / WS_MR) + 1;
+  const int margin = (int)((3 * dz_max + h->res) / h->res) + 3;
+  struct Iv { long long lo, hi; };
+  std::vector<Iv> ivs;
+  for (int t = 0; t < size; )
+  {
+    if (!res_t[(size_t)t]) { t++; continue; }
+    int e = t;
+    while (e < size && res_t[(size_t)e]) e++;
+    Iv v;
+    v.lo = ((long long)P.lo[0] + t - margin) * h->res;
+    v.hi = ((long long)P.lo[0] + e + margin) * h->res;
+    if (!ivs.empty() && v.lo <= ivs.back().hi + 4LL * h->res) ivs.back().hi = v.hi;
+    else ivs.push_back(v);
+    t = e;
+  }
+  if (ivs.empty() || ivs.size() > 2) return;          // nothing resident cannot happen; > 2: no culling
+  for (auto &v : ivs)
+    if (v.lo < -(1ll << 30) || v.hi > (1ll << 30)) return;
+  P.n_xiv = (int)ivs.size();
+  for (size_t k = 0; k < ivs.size(); k++) { P.xiv_lo[k] = (int)ivs[k].lo; P.xiv_hi[k] = (int)ivs[k].hi; }
+}
+
 static void ensure_record(ws_handle *h, size_t chunks)
 {
   if (chunks <= h->rec_cap_chunks) return;
@@ -957,6 +1179,7 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
   }
   P.n_points = n;
   P.far_len = far_start_len(h->res, P.dz_per_distance);
+  resident_x_intervals(h, P);
 
   cudaStream_t s = h->stream;
   WS_CUDA_OK(cudaMemsetAsync(h->d_counters, 0, sizeof(UpdateCounters), s));
@@ -965,8 +1188,20 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
     const int march_blocks = h->sm_count * MARCH_CTAS;
     unsigned cap_chunks = (unsigned)h->rec_cap_chunks;
     ws_timer_begin(h, WS_TIMER_MARCH);
-    march_kernel<true><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, d_pts, h->d_counters, h->d_rec,
+    if ((size_t)n > h->rays_cap)
+    {
+      WS_CUDA_OK(cudaStreamSynchronize(s));
+      cudaFree(h->d_rays);
+      h->d_rays = nullptr; h->rays_cap = 0;
+      const size_t want = std::max<size_t>((size_t)n, 1 << 17);
+      WS_CUDA_OK(cudaMalloc(&h->d_rays, want * sizeof(RaySetup)));
+      h->rays_cap = want;
+    }
+    RaySetup *rays = static_cast<RaySetup *>(h->d_rays);
+    setup_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_pts, rays, h->d_counters);
+    march_kernel<true><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_counters, h->d_rec,
                                                               h->d_chunk_fill, cap_chunks);
+    h->launches++;
     ws_timer_end(h);
     ws_timer_begin(h, WS_TIMER_MERGE);
     brick_list_kernel<<<h->sm_count * 4, 256, 0, s>>>(h->g, h->d_brick_list, h->d_counters);
@@ -991,7 +1226,7 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
       ensure_record(h, want);
       cap_chunks = (unsigned)h->rec_cap_chunks;
       rec_reset_kernel<<<1, 1, 0, s>>>(h->d_counters);
-      march_kernel<false><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, d_pts, h->d_counters, h->d_rec,
+      march_kernel<false><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_counters, h->d_rec,
                                                                  h->d_chunk_fill, cap_chunks);
       h->launches += 2;
       launch_replay(h, P);

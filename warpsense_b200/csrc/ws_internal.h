@@ -27,6 +27,9 @@ struct UpdateParams
   int lo[3];           // lowest in-bounds voxel per axis (pos - size/2)
   int ext[3];          // size - 1
   int ringc[3];        // ring coordinate of voxel lo: (offset - size/2) mod size
+  // multi-GPU slabs: x intervals (mm) outside which no march step can reach a resident column; 0 = no culling
+  int n_xiv;
+  int xiv_lo[2], xiv_hi[2];
 };
 
 // one recorded candidate: its key and the voxel address (record) or the pending slot (replay list)
@@ -51,7 +54,8 @@ struct UpdateCounters
   unsigned error;            // bit 0: seq field overflow (too many march/fan steps)
   unsigned rounds;
   unsigned n_parked;         // voxels parked by the merge pass (before any replay round)
-  unsigned pad0[19];
+  unsigned n_work;           // rays the set-up pass put on the work list
+  unsigned pad0[18];
   unsigned ray_counter;      // dynamic ray fetch of the persistent march warps (own 128-byte line)
   unsigned pad1[31];
   unsigned n_chunks;         // record chunks handed out (own 128-byte line)
@@ -93,6 +97,8 @@ struct ws_handle
   // scan points
   ws_pt *d_points = nullptr;      // update_tsdf staging
   size_t points_cap = 0;
+  void *d_rays = nullptr;         // RaySetup[rays_cap]: the work list written by the set-up pass of update_tsdf
+  size_t rays_cap = 0;
   ws_pt *d_reg_points = nullptr;  // registration cloud
   size_t reg_points_cap = 0;
   int reg_n = 0;
