@@ -150,6 +150,23 @@ int ws_reg_solve(ws_handle *h, float it_weight_gradient, float epsilon);/* solve
 int ws_reg_peek(ws_handle *h, int32_t *iterations, int32_t *finished);  /* progress so far (synchronises) */
 int ws_reg_finish(ws_handle *h, float out_transform[16], int32_t *iterations, int32_t *finished);
 
+/* Fused multi-GPU registration: with every rank's mailbox attached, ws_register_cloud on a sharded handle runs
+ * the whole Gauss-Newton loop in ONE persistent kernel per rank and exchanges the 29 sums over NVLink peer
+ * memory inside it (registration.cu "PeerParams"); every rank must call ws_register_cloud with the same
+ * arguments at the same time.  Replaces the per-iteration blocking copies + host solve of
+ * src/warpsense/tsdf_registration.cpp:55-92 and the NCCL all-reduce SURVEY.md 8e would otherwise need.
+ *   ws_peer_export      : 64-byte cudaIpcMemHandle of this rank's mailbox (send it to the other ranks)
+ *   ws_peer_attach_ipc  : handles[world][64] of all ranks in rank order (own entry ignored), other processes
+ *   ws_peer_local_ptr / ws_peer_attach_ptrs : the same for ranks that live in ONE process (raw device
+ *                         pointers; peer access between the devices is enabled here)
+ *   ws_peer_set_timeout : give up (WS_ERR_STATE) when a peer does not deliver within `seconds` (default 5) */
+#define WS_IPC_HANDLE_BYTES 64
+int ws_peer_export(ws_handle *h, uint8_t handle[WS_IPC_HANDLE_BYTES]);
+int ws_peer_attach_ipc(ws_handle *h, const uint8_t *handles, int32_t world);
+void *ws_peer_local_ptr(ws_handle *h);
+int ws_peer_attach_ptrs(ws_handle *h, void *const *mailboxes, const int32_t *devices, int32_t world);
+int ws_peer_set_timeout(ws_handle *h, double seconds);
+
 /* Host-only (no GPU needed): the x-slab of rank `rank` out of `world` for a map of ring side size_x --
  * owned ring-x rows [own_lo, own_hi) and the resident 8-row brick columns (owned + one halo row each
  * side); returns the number of resident columns or WS_ERR_INVALID. */

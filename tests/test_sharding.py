@@ -182,3 +182,102 @@ def test_sharded_handles_match_oracle_on_one_gpu(world, ring_offset):
         assert np.abs(T[:3, :3] - oT[:3, :3]).max() <= 1e-4 and np.abs(T[:3, 3] - oT[:3, 3]).max() <= 0.1
     for t, _ in ranks:
         t.close()
+
+
+# ----------------------------------------------------------------------------- GPU: fused peer exchange
+def _build_sharded_scene(world, device_of_rank, frames=2):
+    res, tau, mw, side = 100, 1000, 640, 96
+    s = ScanStream(32, 256, side, res)
+    om = orc.LocalMap(side, side, side, tau, 0)
+    hm = api.HostLocalMap(side, side, side, tau, 0)
+    ranks = []
+    for r in range(world):
+        t = api.TSDFCuda(api.DeviceMap(hm), tau, mw, res, device=device_of_rank(r), rank=r, world=world)
+        ranks.append((t, api.RegistrationCuda(t)))
+    for k in range(frames):
+        f = s.frame(k)
+        pos, up = fp.convert_pose_to_gpu(f["pose"], res)
+        orc.update_tsdf(om, f["points_map"], pos, up, tau, mw, res)
+        for t, _ in ranks:
+            t.update_tsdf(f["points_map"], pos, up)
+    cloud = s.frame(frames, prior_pose=s.pose(frames - 1))["points_prior"].copy()
+    return s, om, ranks, cloud, res
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_fused_peer_registration_one_process(world, monkeypatch):
+    """register_cloud on slab-sharded handles with the in-kernel mailbox exchange (registration.cu): `world`
+    persistent kernels side by side on ONE GPU (WS_REG_BLOCKS keeps them co-resident), one host thread per
+    rank.  Sums per iteration and the pose must equal the single-map oracle bit for bit."""
+    import threading
+    monkeypatch.setenv("WS_REG_BLOCKS", "24")
+    s, om, ranks, cloud, res = _build_sharded_scene(world, lambda r: 0)
+    iters = 9
+    oT, oit, otr = orc.register_cloud(om, cloud.copy(), np.eye(4, dtype=np.float32), iters, 0.1, 0.0, res, trace=True)
+    ptrs = [reg.peer_local_ptr() for _, reg in ranks]
+    for _, reg in ranks:
+        reg.peer_attach_ptrs(ptrs)
+        reg.peer_set_timeout(4.0)
+    for rep in range(2):                      # twice: the epoch parity of the mailbox slots alternates
+        results, errors = [None] * world, []
+
+        def run(r):
+            try:
+                c = cloud.copy()
+                results[r] = ranks[r][1].register_cloud(c, np.eye(4, dtype=np.float32), iters, 0.1, 0.0, res) + (c,)
+            except Exception as exc:          # noqa: BLE001
+                errors.append((r, repr(exc)))
+
+        ths = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join(timeout=60)
+        assert not errors, errors
+        ocloud = cloud.copy()
+        orc.register_cloud(om, ocloud, np.eye(4, dtype=np.float32), iters, 0.1, 0.0, res)
+        for r in range(world):
+            T, it, c = results[r]
+            assert it == oit
+            assert np.array_equal(ranks[r][1].trace()[:it], otr[:it]), "rank %d: summed sums differ from the oracle" % r
+            assert np.array_equal(T, results[0][0]), "ranks disagree on the transform"
+            assert np.abs(T[:3, :3] - oT[:3, :3]).max() <= 1e-4 and np.abs(T[:3, 3] - oT[:3, 3]).max() <= 0.1
+            assert np.array_equal(c, ocloud), "transformed cloud differs from the oracle"
+    for t, _ in ranks:
+        t.close()
+
+
+@pytest.mark.gpu
+def test_fused_peer_registration_times_out_without_peer(monkeypatch):
+    """A rank whose peer never shows up must return an error, not hang."""
+    monkeypatch.setenv("WS_REG_BLOCKS", "24")
+    s, om, ranks, cloud, res = _build_sharded_scene(2, lambda r: 0, frames=1)
+    ptrs = [reg.peer_local_ptr() for _, reg in ranks]
+    reg0 = ranks[0][1]
+    reg0.peer_attach_ptrs(ptrs)
+    reg0.peer_set_timeout(0.3)
+    with pytest.raises(Exception) as ei:
+        reg0.register_cloud(cloud.copy(), np.eye(4, dtype=np.float32), 4, 0.1, 0.0, res)
+    assert "peer" in str(ei.value)
+    with pytest.raises(Exception):            # sharded map without attached peers
+        ranks[1][1].register_cloud(cloud.copy(), np.eye(4, dtype=np.float32), 4, 0.1, 0.0, res)
+    for t, _ in ranks:
+        t.close()
+
+
+@pytest.mark.gpu
+def test_fused_peer_registration_two_processes():
+    """Two processes, one GPU each, mailboxes exchanged as CUDA IPC handles (tools/mp_peer_check.py)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300),
+           os.path.join(root, "tools", "mp_peer_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "mp peer check ok" in out.stdout

@@ -371,6 +371,31 @@ class RegistrationCuda:
         a = np.ascontiguousarray(sums, dtype=np.int64).reshape(29)
         self._hd.check(self._hd.L.ws_reg_sums_set(self._hd.h, a.ctypes.data_as(C.POINTER(C.c_int64))))
 
+    # -- fused multi-GPU registration: in-kernel exchange over NVLink peer memory (registration.cu) --
+    def peer_export(self):
+        """64-byte IPC handle of this rank's mailbox (bytes); all-gather it and pass the list to peer_attach_ipc."""
+        buf = (C.c_uint8 * 64)()
+        self._hd.check(self._hd.L.ws_peer_export(self._hd.h, buf))
+        return bytes(buf)
+
+    def peer_attach_ipc(self, handles):
+        """handles: the peer_export() of every rank, in rank order (other processes, one GPU each)."""
+        blob = b"".join(handles)
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self._hd.check(self._hd.L.ws_peer_attach_ipc(self._hd.h, arr, len(handles)))
+
+    def peer_local_ptr(self):
+        return int(self._hd.L.ws_peer_local_ptr(self._hd.h) or 0)
+
+    def peer_attach_ptrs(self, ptrs, devices=None):
+        """Ranks that live in ONE process: raw mailbox pointers (peer_local_ptr of every rank, rank order)."""
+        a = (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
+        d = None if devices is None else np.ascontiguousarray(devices, np.int32).ctypes.data_as(_i32p)
+        self._hd.check(self._hd.L.ws_peer_attach_ptrs(self._hd.h, a, d, len(ptrs)))
+
+    def peer_set_timeout(self, seconds):
+        self._hd.check(self._hd.L.ws_peer_set_timeout(self._hd.h, float(seconds)))
+
     def register_cloud_sharded(self, pretransform, max_iterations, it_weight_gradient, epsilon, map_resolution,
                                allreduce, check_every=8):
         """register_cloud over an x-slab sharded map: every rank calls this with the same cloud (staged with

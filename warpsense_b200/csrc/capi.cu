@@ -40,6 +40,25 @@ int guarded(ws_handle *h, F &&f)
   catch (const std::exception &e) { h->last_error = e.what(); return WS_ERR_CUDA; }
 }
 
+void ensure_mailbox(ws_handle *h)
+{
+  if (h->d_mail) return;
+  const size_t bytes = ws_reg_mailbox_bytes(WS_MAX_PEERS);
+  WS_CUDA_OK(cudaMalloc(&h->d_mail, bytes));
+  WS_CUDA_OK(cudaMemset(h->d_mail, 0, bytes));
+  WS_CUDA_OK(cudaDeviceSynchronize());
+}
+
+void detach_peers(ws_handle *h)
+{
+  for (int p = 0; p < WS_MAX_PEERS; p++)
+  {
+    if (h->peer_ipc[p] && h->peer_mail[p]) cudaIpcCloseMemHandle(h->peer_mail[p]);
+    h->peer_mail[p] = nullptr; h->peer_ipc[p] = false;
+  }
+  h->peers_attached = false;
+}
+
 void free_handle(ws_handle *h)
 {
   if (!h) return;
@@ -52,6 +71,7 @@ void free_handle(ws_handle *h)
   cudaFree(h->d_pend_addr); cudaFree(h->d_pend_prev); cudaFree(h->d_pend_key);
   cudaFree(h->d_active[0]); cudaFree(h->d_active[1]);
   cudaFree(h->d_rec); cudaFree(h->d_list); cudaFree(h->d_chunk_fill);
+  detach_peers(h); cudaFree(h->d_mail);
   cudaFree(h->d_acc); cudaFree(h->d_trace); cudaFreeHost(h->h_acc); cudaFree(h->d_reg_partials);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -581,6 +601,8 @@ int ws_register_cloud(ws_handle *h, ws_point *cloud, int64_t n, const float pret
       read_acc(h);
       it_done = (int)h->h_acc->iterations;
       std::memcpy(out_transform, h->h_acc->T, 16 * sizeof(float));
+      if (h->h_acc->finished == 2u)
+        throw std::logic_error("register_cloud: a peer rank did not deliver its Gauss-Newton sums in time");
     }
     else
     {
@@ -615,6 +637,81 @@ int ws_register_cloud(ws_handle *h, ws_point *cloud, int64_t n, const float pret
     if (iterations) *iterations = it_done;
     return WS_OK;
   });
+}
+
+// ---- peer mailboxes of the fused multi-GPU registration (registration.cu) ------------------------
+int ws_peer_export(ws_handle *h, uint8_t handle[WS_IPC_HANDLE_BYTES])
+{
+  static_assert(sizeof(cudaIpcMemHandle_t) == WS_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  return guarded(h, [&]() {
+    if (!handle) throw std::invalid_argument("ws_peer_export: null handle buffer");
+    ensure_mailbox(h);
+    cudaIpcMemHandle_t ipc;
+    WS_CUDA_OK(cudaIpcGetMemHandle(&ipc, h->d_mail));
+    std::memcpy(handle, &ipc, sizeof(ipc));
+    return WS_OK;
+  });
+}
+
+int ws_peer_attach_ipc(ws_handle *h, const uint8_t *handles, int32_t world)
+{
+  return guarded(h, [&]() {
+    if (!handles || world != h->world || world > WS_MAX_PEERS) throw std::invalid_argument("ws_peer_attach_ipc: bad world");
+    ensure_mailbox(h);
+    detach_peers(h);
+    for (int p = 0; p < world; p++)
+    {
+      if (p == h->rank) { h->peer_mail[p] = h->d_mail; continue; }
+      cudaIpcMemHandle_t ipc;
+      std::memcpy(&ipc, handles + (size_t)p * WS_IPC_HANDLE_BYTES, sizeof(ipc));
+      void *ptr = nullptr;
+      WS_CUDA_OK(cudaIpcOpenMemHandle(&ptr, ipc, cudaIpcMemLazyEnablePeerAccess));
+      h->peer_mail[p] = ptr; h->peer_ipc[p] = true;
+    }
+    h->peers_attached = true;
+    return WS_OK;
+  });
+}
+
+void *ws_peer_local_ptr(ws_handle *h)
+{
+  if (!h) return nullptr;
+  void *out = nullptr;
+  guarded(h, [&]() { ensure_mailbox(h); out = h->d_mail; return WS_OK; });
+  return out;
+}
+
+int ws_peer_attach_ptrs(ws_handle *h, void *const *mailboxes, const int32_t *devices, int32_t world)
+{
+  return guarded(h, [&]() {
+    if (!mailboxes || world != h->world || world > WS_MAX_PEERS) throw std::invalid_argument("ws_peer_attach_ptrs: bad world");
+    ensure_mailbox(h);
+    detach_peers(h);
+    for (int p = 0; p < world; p++)
+    {
+      if (p == h->rank) { h->peer_mail[p] = h->d_mail; continue; }
+      if (!mailboxes[p]) throw std::invalid_argument("ws_peer_attach_ptrs: null mailbox");
+      if (devices && devices[p] != h->device)
+      {
+        int can = 0;
+        WS_CUDA_OK(cudaDeviceCanAccessPeer(&can, h->device, devices[p]));
+        if (!can) throw std::runtime_error("ws_peer_attach_ptrs: no peer access between the devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(devices[p], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) WS_CUDA_OK(e);
+        cudaGetLastError();
+      }
+      h->peer_mail[p] = mailboxes[p];
+    }
+    h->peers_attached = true;
+    return WS_OK;
+  });
+}
+
+int ws_peer_set_timeout(ws_handle *h, double seconds)
+{
+  if (!h || !(seconds > 0.0)) return WS_ERR_INVALID;
+  h->peer_timeout_ns = (unsigned long long)(seconds * 1e9);
+  return WS_OK;
 }
 
 int ws_reg_get_trace(ws_handle *h, int64_t *out, int32_t max_iterations)

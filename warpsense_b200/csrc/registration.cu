@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
+#include <cstdlib>
 #include "ws_internal.h"
 
 namespace cg = cooperative_groups;
@@ -332,6 +333,42 @@ struct RegLoopParams
   float epsilon;
 };
 
+// Multi-GPU exchange of the 29 Gauss-Newton sums INSIDE the persistent loop (one all-reduce
+// of 21 + 6 + 2 scalars per iteration).  Every rank owns a mailbox in its own HBM, mapped into every peer
+// (NVLink P2P: cudaIpc* across processes, plain pointers inside one).  After the grid barrier, block 0 of
+// rank r pushes r's totals into slot r of EVERY mailbox as 8-byte words {32 data bits, 32-bit stamp}: an
+// aligned 8-byte store is a single NVLink transaction, so a reader that sees the stamp sees the data (the
+// NCCL "LL" idea) -- no fence, no separate flag, one NVLink write latency per iteration.  All blocks of a
+// rank then poll their LOCAL mailbox, add the slots up (int64: exact, identical on every rank) and run the
+// same solve.  Stamps carry (epoch, iteration); slots alternate with the iteration parity (a rank can be at
+// most one iteration ahead of a peer) and with the epoch parity (... or one register_cloud call ahead).
+#define WS_MAIL_WORDS 64                      // 8-byte words per (parity, sender) slot; 58 are used
+#define WS_MAIL_USED (2 * WS_NSUM)
+struct PeerParams
+{
+  int world, rank;
+  unsigned stamp_base;                        // epoch << 8; stamp of iteration it = stamp_base + it + 1
+  unsigned long long timeout_ns;
+  uint2 *mail[WS_MAX_PEERS];                  // mail[p]: rank p's mailbox [4][world][WS_MAIL_WORDS]
+};
+
+WS_D void st_mail(uint2 *p, uint2 v)
+{
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+WS_D uint2 ld_mail(const uint2 *p)
+{
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+WS_D unsigned long long reg_global_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // one point's contribution for int transform M / centre c (registration.cpp:63-107); all seven voxel
 // loads are issued together
 WS_D void accumulate_cloud_point(const GridDesc &g, const int M[16], const int cx, const int cy, const int cz,
@@ -530,10 +567,13 @@ WS_D void warp_gn_solve(const u64 *s_total, GnState *st, double *s_lu, int *s_pe
 
 __global__ void __launch_bounds__(REG_THREADS)
 reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopParams rp,
-                RegAccum *__restrict__ acc, u64 *__restrict__ partials, u64 *__restrict__ trace, const int trace_cap)
+                RegAccum *__restrict__ acc, u64 *__restrict__ partials, u64 *__restrict__ trace, const int trace_cap,
+                const PeerParams pp)
 {
   cg::grid_group grid = cg::this_grid();
   __shared__ u64 s_w[REG_THREADS / 32][REG_NSLOT];
+  __shared__ unsigned s_half[WS_MAX_PEERS][WS_MAIL_WORDS];
+  __shared__ unsigned s_timeout;
   __shared__ u64 s_total[REG_NSLOT];
   __shared__ GnState s_st;
   __shared__ double s_lu[36], s_inv[36], s_xi[6];
@@ -545,7 +585,7 @@ reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopPa
 
   if (tid < 16) s_st.T[tid] = acc->T[tid];
   if (tid < 4) s_st.prev_err[tid] = 0.f;
-  if (tid == 0) { s_st.alpha = acc->alpha; s_st.finished = 0u; s_st.iterations = 0u; }
+  if (tid == 0) { s_st.alpha = acc->alpha; s_st.finished = 0u; s_st.iterations = 0u; s_timeout = 0u; }
 
   ws_pt my[REG_PTS];
 #pragma unroll
@@ -589,23 +629,73 @@ reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopPa
     __threadfence();
     grid.sync();
 
-    // every block: total over all blocks' rows
+    // total over all blocks' rows: every block (one GPU), block 0 only (several GPUs: the others read it
+    // back from the mailbox together with the peers' totals)
+    if (pp.world == 1 || blockIdx.x == 0)
     {
       const u64 *base = partials + (size_t)(it & 1) * gridDim.x * REG_NSLOT;
       u64 a = 0ull;
       for (int b = warp; b < (int)gridDim.x; b += REG_THREADS / 32) a += __ldcg(&base[(size_t)b * REG_NSLOT + lane]);
       s_w[warp][lane] = a;
-    }
-    __syncthreads();
-    if (tid < REG_NSLOT)
-    {
-      u64 a = 0ull;
+      __syncthreads();
+      if (tid < REG_NSLOT)
+      {
+        u64 a2 = 0ull;
 #pragma unroll
-      for (int w = 0; w < REG_THREADS / 32; w++) a += s_w[w][tid];
-      s_total[tid] = a;
-      if (blockIdx.x == 0 && trace && it < trace_cap && tid < WS_NSUM) trace[(size_t)it * WS_NSUM + tid] = a;
+        for (int w = 0; w < REG_THREADS / 32; w++) a2 += s_w[w][tid];
+        s_total[tid] = a2;
+      }
+      __syncthreads();
     }
-    __syncthreads();
+    if (pp.world > 1)
+    {
+      const unsigned stamp = pp.stamp_base + (unsigned)it + 1u;
+      const size_t parity_off = (size_t)(((pp.stamp_base >> 8) & 1u) * 2u + (unsigned)(it & 1)) * pp.world * WS_MAIL_WORDS;
+      if (blockIdx.x == 0)
+      {
+        // push this rank's totals into slot `rank` of every mailbox (own one included)
+        for (int idx = tid; idx < pp.world * WS_MAIL_USED; idx += REG_THREADS)
+        {
+          const int p = idx / WS_MAIL_USED, w = idx - p * WS_MAIL_USED;
+          const u64 v = s_total[w >> 1];
+          uint2 word;
+          word.x = (w & 1) ? (unsigned)(v >> 32) : (unsigned)v;
+          word.y = stamp;
+          st_mail(pp.mail[p] + parity_off + (size_t)pp.rank * WS_MAIL_WORDS + w, word);
+        }
+      }
+      // every block: wait for all senders' words of this iteration in the LOCAL mailbox
+      const uint2 *mine = pp.mail[pp.rank] + parity_off;
+      const unsigned long long t0 = reg_global_ns();
+      for (int idx = tid; idx < pp.world * WS_MAIL_USED; idx += REG_THREADS)
+      {
+        const int p = idx / WS_MAIL_USED, w = idx - p * WS_MAIL_USED;
+        uint2 word = ld_mail(mine + (size_t)p * WS_MAIL_WORDS + w);
+        unsigned spins = 0;
+        while (word.y != stamp)
+        {
+          if ((++spins & 1023u) == 0u && reg_global_ns() - t0 > pp.timeout_ns) { s_timeout = 1u; break; }
+          word = ld_mail(mine + (size_t)p * WS_MAIL_WORDS + w);
+        }
+        s_half[p][w] = word.x;
+      }
+      __syncthreads();
+      if (tid < REG_NSLOT)
+      {
+        u64 a = 0ull;
+        if (tid < WS_NSUM)
+          for (int p = 0; p < pp.world; p++) a += (u64)s_half[p][2 * tid] | ((u64)s_half[p][2 * tid + 1] << 32);
+        s_total[tid] = a;
+      }
+      __syncthreads();
+      if (s_timeout)          // a peer never delivered: every block of every rank gives up in the same iteration
+      {
+        if (tid == 0) s_st.finished = 2u;
+        __syncthreads();
+        break;
+      }
+    }
+    if (blockIdx.x == 0 && trace && it < trace_cap && tid < WS_NSUM) trace[(size_t)it * WS_NSUM + tid] = s_total[tid];
     if (warp == 0) warp_gn_solve(s_total, &s_st, s_lu, s_perm, s_inv, s_xi, rp.it_weight_gradient, rp.epsilon, lane);
     __syncthreads();
     if (s_st.finished) break;
@@ -702,6 +792,8 @@ void ws_launch_reg_iteration(ws_handle *h, int n, int res, int fused_solve, floa
   h->launches++;
 }
 
+size_t ws_reg_mailbox_bytes(int world) { return (size_t)4 * world * WS_MAIL_WORDS * sizeof(uint2); }
+
 void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float it_weight_gradient, float epsilon)
 {
   if (h->reg_loop_blocks == 0)
@@ -711,6 +803,12 @@ void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float 
     if (per_sm < 1) throw std::runtime_error("reg_loop_kernel does not fit on an SM");
     if (per_sm > 2) per_sm = 2;
     h->reg_loop_blocks = per_sm * h->sm_count;
+    // tests that run several ranks' persistent kernels side by side on ONE GPU need them co-resident
+    if (const char *e = std::getenv("WS_REG_BLOCKS"))
+    {
+      const int v = std::atoi(e);
+      if (v >= 1 && v < h->reg_loop_blocks) h->reg_loop_blocks = v;
+    }
     WS_CUDA_OK(cudaMalloc(&h->d_reg_partials, (size_t)2 * h->reg_loop_blocks * REG_NSLOT * sizeof(u64)));
   }
   RegLoopParams rp;
@@ -719,8 +817,21 @@ void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float 
   rp.max_iterations = max_iterations;
   rp.it_weight_gradient = it_weight_gradient;
   rp.epsilon = epsilon;
+  PeerParams pp{};
+  pp.world = 1; pp.rank = 0;
+  if (h->world > 1)
+  {
+    if (!h->peers_attached) throw std::logic_error("register_cloud on a sharded map needs ws_peer_attach* first");
+    if (max_iterations > 255) throw std::invalid_argument("register_cloud on a sharded map: max_iterations <= 255");
+    pp.world = h->world; pp.rank = h->rank;
+    h->reg_epoch = (h->reg_epoch + 1u) & 0xFFFFFFu;
+    if (h->reg_epoch == 0u) h->reg_epoch = 1u;
+    pp.stamp_base = h->reg_epoch << 8;
+    pp.timeout_ns = h->peer_timeout_ns;
+    for (int p = 0; p < h->world; p++) pp.mail[p] = static_cast<uint2 *>(h->peer_mail[p]);
+  }
   void *args[] = { (void *)&h->g, (void *)&h->d_reg_points, (void *)&rp, (void *)&h->d_acc,
-                   (void *)&h->d_reg_partials, (void *)&h->d_trace, (void *)&h->trace_cap };
+                   (void *)&h->d_reg_partials, (void *)&h->d_trace, (void *)&h->trace_cap, (void *)&pp };
   ws_timer_begin(h, WS_TIMER_REG);
   WS_CUDA_OK(cudaLaunchCooperativeKernel((const void *)reg_loop_kernel, dim3(h->reg_loop_blocks), dim3(REG_THREADS),
                                          args, 0, h->stream));

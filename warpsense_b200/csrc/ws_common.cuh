@@ -16,6 +16,7 @@
 #define WS_WR 64               // WEIGHT_RESOLUTION  (include/warpsense/consts.h:9-10)
 #define WS_BRICK 8
 #define WS_BRICK_VOX 512
+#define WS_MAX_PEERS 16        // ranks one map can be sharded over (one NVSwitch domain: 8)
 #define WS_MAX_XBRICKS 320     // ring-x brick columns a grid may have (2049/8 = 257)
 
 #define WS_HD __host__ __device__ __forceinline__

@@ -128,6 +128,13 @@ struct ws_handle
   RegAccum *h_acc = nullptr;            // pinned
   u64 *d_reg_partials = nullptr;        // [2][reg_loop_blocks][32] per-block sums of the persistent GN loop
   int reg_loop_blocks = 0;
+  // multi-GPU registration: mailboxes for the in-kernel exchange of the Gauss-Newton sums (registration.cu)
+  void *d_mail = nullptr;               // this rank's mailbox (cudaMalloc, exported by cudaIpcGetMemHandle)
+  void *peer_mail[WS_MAX_PEERS] = {};   // every rank's mailbox as mapped into this process (own one included)
+  bool peer_ipc[WS_MAX_PEERS] = {};     // opened with cudaIpcOpenMemHandle (to be closed)
+  bool peers_attached = false;
+  unsigned reg_epoch = 0;
+  unsigned long long peer_timeout_ns = 5000000000ull;
 
   // timing of the dominant kernels (cudaEvents on `stream`)
   bool profile = false;
@@ -174,6 +181,8 @@ void ws_launch_test_reduce(ws_handle *h, const i64 *d_jacobis, const int *d_valu
 #define WS_TIMER_REPLAY 3
 void ws_timer_begin(ws_handle *h, int kind);
 void ws_timer_end(ws_handle *h);
+
+size_t ws_reg_mailbox_bytes(int world);
 
 #define WS_CUDA_OK(expr)                                                                            \
   do {                                                                                              \

@@ -78,6 +78,11 @@ def _signatures():
         "ws_reg_sums_device": (vp, [hp]),
         "ws_reg_sums_get": (C.c_int, [hp, i64p]),
         "ws_reg_sums_set": (C.c_int, [hp, i64p]),
+        "ws_peer_export": (C.c_int, [hp, C.POINTER(C.c_uint8)]),
+        "ws_peer_attach_ipc": (C.c_int, [hp, C.POINTER(C.c_uint8), C.c_int32]),
+        "ws_peer_local_ptr": (vp, [hp]),
+        "ws_peer_attach_ptrs": (C.c_int, [hp, C.POINTER(vp), i32p, C.c_int32]),
+        "ws_peer_set_timeout": (C.c_int, [hp, C.c_double]),
         "ws_slab_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p, C.c_int32]),
         "ws_reg_solve": (C.c_int, [hp, C.c_float, C.c_float]),
         "ws_reg_peek": (C.c_int, [hp, i32p, i32p]),
