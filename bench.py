@@ -12,8 +12,10 @@ registered cloud.
   roofline : update_tsdf kernels (ray march + merge + replay), algorithmic bytes 12*N + 8*T per scan
           (SURVEY.md 8d) over their CUDA-event time, against MEASURED_PEAKS.json's HBM copy bandwidth;
   cpu_baseline : the CPU oracle (a C port of the reference's src/cpu path) on this box's host cores.
-N > 1: the grid is sharded in x-slabs over the ranks (one process per GPU), every rank marches the scan
-into its slab, and the 29 int64 Gauss-Newton sums are all-reduced (NCCL) once per iteration.
+N > 1: the grid is sharded in x-slabs over the ranks (one process per GPU); every rank marches only the ray
+segments that can reach its slab, and the 29 int64 Gauss-Newton sums are exchanged once per iteration INSIDE
+the persistent registration kernel through NVLink peer mailboxes (CUDA IPC); NCCL only carries the timing
+reduction and the barrier.
 """
 import argparse
 import json
@@ -190,7 +192,7 @@ def workload_config(args):
         "tau_mm": TAU, "max_weight": MAX_WEIGHT,
         "l2_policy": "working set larger than L2: every step is a different scan and touches ~21 M voxels "
                      "(12 B key+entry each, ~255 MB) of a 1.6 GB grid+scratch; no explicit flush",
-        "parallelism": "x-slab spatial sharding of the ring, int64[29] all-reduce per GN iteration",
+        "parallelism": "x-slab spatial sharding of the ring; per-rank culling of march steps; int64[29] sums exchanged per GN iteration inside the kernel over NVLink peer memory",
     }
 
 
@@ -237,9 +239,13 @@ def run_native(args):
     hd = tsdf.device_map()
     stream = torch.cuda.Stream()
     tsdf.set_stream(stream.cuda_stream)
-    sums = None
     if world > 1:
-        sums = torch.as_tensor(SumsView(hd.L.ws_reg_sums_device(hd.h)), device="cuda")
+        # fused exchange: every rank maps every rank's mailbox (CUDA IPC over NVLink); the Gauss-Newton sums
+        # then travel inside the persistent registration kernel -- no NCCL call per iteration
+        handles = [None] * world
+        dist.all_gather_object(handles, reg.peer_export())
+        reg.peer_attach_ipc(handles)
+        reg.peer_set_timeout(20.0)
 
     I16 = fp.colmajor16(np.eye(4, dtype=np.float32))
     import ctypes as C
@@ -249,12 +255,8 @@ def run_native(args):
 
     def register(n):
         """20 GN iterations on the cloud already staged with prepare_registration*; returns T (4x4)."""
-        if world == 1:
-            T, _ = reg.register_cloud(None, np.eye(4, dtype=np.float32), GN_ITERS, IT_WEIGHT, EPSILON, res,
-                                      keep_on_device=True)
-            return T
-        T, _ = reg.register_cloud_sharded(np.eye(4, dtype=np.float32), GN_ITERS, IT_WEIGHT, EPSILON, res,
-                                          lambda _r: dist.all_reduce(sums))   # int64 sum: exact, same on every rank
+        T, _ = reg.register_cloud(None, np.eye(4, dtype=np.float32), GN_ITERS, IT_WEIGHT, EPSILON, res,
+                                  keep_on_device=True)
         return T
 
     def step_device(k, dev_cloud):
@@ -334,6 +336,17 @@ def run_native(args):
 
     value = K / (ms_dev / 1000.0)
     e2e_value = K / (ms_e2e / 1000.0)
+    if world > 1:
+        # work counters: sum over the slabs (halo columns count twice); kernel times: slowest rank
+        wk = torch.tensor([counters["n_touched"], counters["n_candidates"], counters["n_touched_bricks"],
+                           counters["n_parked"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(wk)
+        counters = dict(counters)
+        counters["n_touched"], counters["n_candidates"], counters["n_touched_bricks"], counters["n_parked"] = \
+            (int(v) for v in wk.tolist())
+        km = torch.tensor([kern[k][0] for k in ("march", "merge", "reg", "replay")], dtype=torch.float64, device="cuda")
+        dist.all_reduce(km, op=dist.ReduceOp.MAX)
+        kern = {k: (float(v), kern[k][1]) for k, v in zip(("march", "merge", "reg", "replay"), km.tolist())}
 
     if rank == 0:
         # T of this rank's slab; for the roofline at N=1 it is the whole scan's T

@@ -565,6 +565,7 @@ WS_D void warp_gn_solve(const u64 *s_total, GnState *st, double *s_lu, int *s_pe
   }
 }
 
+template <bool MULTI>
 __global__ void __launch_bounds__(REG_THREADS)
 reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopParams rp,
                 RegAccum *__restrict__ acc, u64 *__restrict__ partials, u64 *__restrict__ trace, const int trace_cap,
@@ -631,7 +632,7 @@ reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopPa
 
     // total over all blocks' rows: every block (one GPU), block 0 only (several GPUs: the others read it
     // back from the mailbox together with the peers' totals)
-    if (pp.world == 1 || blockIdx.x == 0)
+    if (!MULTI || blockIdx.x == 0)
     {
       const u64 *base = partials + (size_t)(it & 1) * gridDim.x * REG_NSLOT;
       u64 a = 0ull;
@@ -644,10 +645,13 @@ reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopPa
 #pragma unroll
         for (int w = 0; w < REG_THREADS / 32; w++) a2 += s_w[w][tid];
         s_total[tid] = a2;
+        // (the trace store sits HERE, not after the barrier: there it changed the loop's convergence-barrier
+        // nesting and every grid barrier waited ~10x longer -- 0.25 -> 0.73 ms per 20 iterations on B200)
+        if (!MULTI && blockIdx.x == 0 && trace && it < trace_cap && tid < WS_NSUM) trace[(size_t)it * WS_NSUM + tid] = a2;
       }
       __syncthreads();
     }
-    if (pp.world > 1)
+    if (MULTI)
     {
       const unsigned stamp = pp.stamp_base + (unsigned)it + 1u;
       const size_t parity_off = (size_t)(((pp.stamp_base >> 8) & 1u) * 2u + (unsigned)(it & 1)) * pp.world * WS_MAIL_WORDS;
@@ -686,6 +690,7 @@ reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopPa
         if (tid < WS_NSUM)
           for (int p = 0; p < pp.world; p++) a += (u64)s_half[p][2 * tid] | ((u64)s_half[p][2 * tid + 1] << 32);
         s_total[tid] = a;
+        if (blockIdx.x == 0 && trace && it < trace_cap && tid < WS_NSUM) trace[(size_t)it * WS_NSUM + tid] = a;
       }
       __syncthreads();
       if (s_timeout)          // a peer never delivered: every block of every rank gives up in the same iteration
@@ -695,7 +700,6 @@ reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopPa
         break;
       }
     }
-    if (blockIdx.x == 0 && trace && it < trace_cap && tid < WS_NSUM) trace[(size_t)it * WS_NSUM + tid] = s_total[tid];
     if (warp == 0) warp_gn_solve(s_total, &s_st, s_lu, s_perm, s_inv, s_xi, rp.it_weight_gradient, rp.epsilon, lane);
     __syncthreads();
     if (s_st.finished) break;
@@ -799,7 +803,7 @@ void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float 
   if (h->reg_loop_blocks == 0)
   {
     int per_sm = 0;
-    WS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reg_loop_kernel, REG_THREADS, 0));
+    WS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reg_loop_kernel<true>, REG_THREADS, 0));
     if (per_sm < 1) throw std::runtime_error("reg_loop_kernel does not fit on an SM");
     if (per_sm > 2) per_sm = 2;
     h->reg_loop_blocks = per_sm * h->sm_count;
@@ -833,8 +837,8 @@ void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float 
   void *args[] = { (void *)&h->g, (void *)&h->d_reg_points, (void *)&rp, (void *)&h->d_acc,
                    (void *)&h->d_reg_partials, (void *)&h->d_trace, (void *)&h->trace_cap, (void *)&pp };
   ws_timer_begin(h, WS_TIMER_REG);
-  WS_CUDA_OK(cudaLaunchCooperativeKernel((const void *)reg_loop_kernel, dim3(h->reg_loop_blocks), dim3(REG_THREADS),
-                                         args, 0, h->stream));
+  const void *fn = h->world > 1 ? (const void *)reg_loop_kernel<true> : (const void *)reg_loop_kernel<false>;
+  WS_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(h->reg_loop_blocks), dim3(REG_THREADS), args, 0, h->stream));
   ws_timer_end(h);
   h->launches++;
 }

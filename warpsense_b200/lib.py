@@ -116,6 +116,8 @@ def load(build_if_needed=True):
                            "(the CUDA library is the only compute path; there is no fallback)")
     L = C.CDLL(path)
     for name, (res, args) in _signatures().items():
+        if os.environ.get("WS_LIB_PATH") and not hasattr(L, name):
+            continue               # A/B runs against older builds (tools/gpu_ab.sh) only
         fn = getattr(L, name)      # AttributeError here == ABI/header drift: fail loudly
         fn.restype = res
         fn.argtypes = args
