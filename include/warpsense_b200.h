@@ -125,6 +125,19 @@ int ws_get_update_counters(const ws_handle *h, ws_update_counters *out);
  *                 (centre recomputed every iteration; cloud transformed in place at the end).
  *                 `cloud` may be NULL to register the points given to ws_reg_prepare and leave the
  *                 transformed cloud on the device (ws_reg_points_device). */
+/* ---- scan preprocessing ------------------------------------------------------
+ * ws_preprocess_scan: App::preprocess(cloud, scan_points) (src/warpsense/app.cpp:118-148): the x/y/z floats of
+ *                 a PointCloud2 payload (metres; `point_step_bytes` between points, >= 12) -> drop returns
+ *                 with x, y and z all below 0.3 -> millimetres -> voxel centre (float arithmetic) ->
+ *                 transform_point(., to_int_mat(pose_mm)) -> duplicates removed.  The reference copies its
+ *                 std::unordered_set out in bucket order; here the survivors keep scan order (first
+ *                 occurrence stays): the same set, deterministic.  The result stays on the device
+ *                 (ws_scan_points_device) for ws_update_tsdf_device / ws_reg_prepare_device and is copied
+ *                 to `out_host` (capacity n) when that is not NULL. */
+int ws_preprocess_scan(ws_handle *h, const float *xyz, int64_t n, int32_t point_step_bytes, int32_t on_device,
+                       const float pose_mm[16], int32_t map_resolution, ws_point *out_host, int64_t *n_out);
+const ws_point *ws_scan_points_device(ws_handle *h, int64_t *n);
+
 int ws_reg_prepare(ws_handle *h, const ws_point *points, int64_t n);
 /* same, the cloud already being in device memory (device-to-device copy on the handle's stream) */
 int ws_reg_prepare_device(ws_handle *h, const ws_point *device_points, int64_t n);

@@ -79,6 +79,7 @@ def lib():
         "orc_store_get_value": (C.c_uint32, [vp, C.c_int, C.c_int, C.c_int]),
         "orc_to_int_mat": (None, [f32p, i32p]),
         "orc_transform_points": (None, [vp, C.c_int64, i32p, vp]),
+        "orc_preprocess": (C.c_int64, [vp, C.c_int64, C.c_int, f32p, C.c_int, vp]),
         "orc_to_map": (None, [f32p, C.c_int, i32p]),
         "orc_convert_pose": (None, [f32p, C.c_int, i32p, i32p]),
         "orc_transform_point_cloud": (None, [vp, C.c_int64, f32p]),
@@ -144,6 +145,17 @@ def transform_points(pts, int_mat):
     out = np.zeros_like(pts)
     lib().orc_transform_points(pts.ctypes.data, len(pts), _p(m, C.c_int32), out.ctypes.data)
     return out
+
+
+def preprocess(cloud_xyz_m, pose_mm, map_resolution):
+    """App::preprocess (src/warpsense/app.cpp:118-148): float metres [n, >=3] -> unique int32 mm points in the
+    map frame, in scan order (the reference's std::unordered_set order is implementation defined)."""
+    a = np.ascontiguousarray(cloud_xyz_m, dtype=np.float32)
+    a = a.reshape(-1, 3) if a.ndim == 1 else a
+    out = np.zeros((max(len(a), 1), 3), np.int32)
+    cm = _colmajor(pose_mm)
+    n = lib().orc_preprocess(a.ctypes.data, len(a), a.shape[1], _p(cm, C.c_float), int(map_resolution), out.ctypes.data)
+    return out[:n].copy()
 
 
 def transform_point(p, int_mat):

@@ -402,6 +402,51 @@ void orc_transform_points(const orc_point *in, int64_t n, const int32_t mat[16],
   for (int64_t i = 0; i < n; i++) out[i] = orc_transform_point(in[i], mat);
 }
 
+/* src/warpsense/app.cpp:118-148 (App::preprocess) without ROS: x/y/z floats in metres -> unique int32 mm
+ * points in the map frame.  The reference iterates a std::unordered_set (bucket order, implementation
+ * defined); this restatement emits the SAME SET in scan order (first occurrence stays), which is what the
+ * device path produces.  Returns the number of points written to `out` (capacity n). */
+int64_t orc_preprocess(const float *xyz, int64_t n, int stride_floats, const float pose[16], int map_resolution,
+                       orc_point *out)
+{
+  int32_t im[16];
+  orc_to_int_mat(pose, im);                                                   /* :123 */
+  /* open-addressing set of indices into out[] */
+  int64_t cap = 1024;
+  while (cap < 2 * n) cap <<= 1;
+  int64_t *tab = (int64_t *)malloc((size_t)cap * sizeof(int64_t));
+  for (int64_t i = 0; i < cap; i++) tab[i] = -1;
+  int64_t m = 0;
+  for (int64_t i = 0; i < n; i++)
+  {
+    const float x = xyz[i * stride_floats], y = xyz[i * stride_floats + 1], z = xyz[i * stride_floats + 2];
+    if (x < 0.3 && y < 0.3 && z < 0.3) continue;                              /* :128-131 */
+    const float mm[3] = { x * 1000.f, y * 1000.f, z * 1000.f };               /* :133 */
+    orc_point c;
+    int32_t cc[3];
+    for (int a = 0; a < 3; a++)                                               /* :134-139 */
+      cc[a] = f2i(floorf(mm[a] / (float)map_resolution) * (float)map_resolution + (float)(map_resolution / 2));
+    c.x = cc[0]; c.y = cc[1]; c.z = cc[2];
+    const orc_point p = orc_transform_point(c, im);                           /* :141 */
+    uint64_t h = ((uint64_t)(uint32_t)p.x * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)(uint32_t)p.y * 0xC2B2AE3D27D4EB4Full) ^
+                 ((uint64_t)(uint32_t)p.z * 0x165667B19E3779F9ull);
+    h ^= h >> 29;
+    int64_t s = (int64_t)(h & (uint64_t)(cap - 1));
+    int dup = 0;
+    while (tab[s] >= 0)
+    {
+      const orc_point o = out[tab[s]];
+      if (o.x == p.x && o.y == p.y && o.z == p.z) { dup = 1; break; }
+      s = (s + 1) & (cap - 1);
+    }
+    if (dup) continue;
+    tab[s] = m;
+    out[m++] = p;
+  }
+  free(tab);
+  return m;
+}
+
 /* include/util/util.h:52-56 */
 void orc_to_map(const float pose[16], int map_resolution, int out[3])
 {

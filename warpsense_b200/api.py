@@ -236,6 +236,27 @@ class TSDFCuda:
         hd.check(hd.L.ws_update_tsdf_device(hd.h, C.c_void_p(int(device_ptr)), int(n), sp.ctypes.data_as(_i32p),
                                             u.ctypes.data_as(_i32p)))
 
+    def preprocess_scan(self, cloud_xyz_m, pose_mm, map_resolution, point_step_bytes=None, fetch=True):
+        """App::preprocess (app.cpp:118-148) on the device: float metres [n, >=3] -> unique int32 mm points in
+        the map frame, scan order (first occurrence stays).  The points stay on the device (scan_points_device)
+        and are returned as an array when `fetch`."""
+        a = np.ascontiguousarray(cloud_xyz_m, dtype=np.float32)
+        a = a.reshape(-1, 3) if a.ndim == 1 else a
+        step = int(point_step_bytes or a.shape[1] * 4)
+        n = a.shape[0]
+        out = np.zeros((max(n, 1), 3), np.int32) if fetch else None
+        n_out = C.c_int64()
+        hd = self._hd
+        T = colmajor16(pose_mm)
+        hd.check(hd.L.ws_preprocess_scan(hd.h, a.ctypes.data, n, step, 0, T.ctypes.data_as(C.POINTER(C.c_float)),
+                                         int(map_resolution), out.ctypes.data if fetch else None, C.byref(n_out)))
+        return (out[:n_out.value].copy() if fetch else None), n_out.value
+
+    def scan_points_device(self):
+        n = C.c_int64()
+        ptr = self._hd.L.ws_scan_points_device(self._hd.h, C.byref(n))
+        return ptr, n.value
+
     def avg_map(self):
         return self._avg
 

@@ -66,7 +66,8 @@ void free_handle(ws_handle *h)
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto &t : h->timers) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
   cudaFree(h->g.grid); cudaFree(h->g.keys); cudaFree(h->g.brick_flag); cudaFree(h->g.park_bits);
-  cudaFree(h->d_points); cudaFree(h->d_rays); cudaFree(h->d_reg_points); cudaFree(h->d_brick_list);
+  cudaFree(h->d_points); cudaFree(h->d_rays);
+  cudaFree(h->d_pre_tmp); cudaFree(h->d_pre_slot); cudaFree(h->d_pre_table); cudaFree(h->d_pre_tiles); cudaFree(h->d_pre_xyz); cudaFree(h->d_reg_points); cudaFree(h->d_brick_list);
   cudaFree(h->d_counters); cudaFreeHost(h->h_counters);
   cudaFree(h->d_pend_addr); cudaFree(h->d_pend_prev); cudaFree(h->d_pend_key);
   cudaFree(h->d_active[0]); cudaFree(h->d_active[1]);
@@ -515,6 +516,47 @@ int ws_update_tsdf_device(ws_handle *h, const ws_point *device_points, int64_t n
     ws_launch_update(h, reinterpret_cast<const ws_pt *>(device_points), (int)n, scanner_pos, up);
     return WS_OK;
   });
+}
+
+int ws_preprocess_scan(ws_handle *h, const float *xyz, int64_t n, int32_t point_step_bytes, int32_t on_device,
+                       const float pose_mm[16], int32_t map_resolution, ws_point *out_host, int64_t *n_out)
+{
+  return guarded(h, [&]() {
+    if (n < 0 || (n > 0 && !xyz) || !pose_mm || map_resolution < 2 || point_step_bytes < 12 || (point_step_bytes & 3))
+      throw std::invalid_argument("ws_preprocess_scan: bad argument");
+    if (n > WS_MAX_POINTS) throw std::length_error("ws_preprocess_scan: too many points");
+    ensure_points(&h->d_points, &h->points_cap, (size_t)std::max<int64_t>(n, 1));
+    const int stride = point_step_bytes / 4;
+    const float *d_xyz = xyz;
+    if (!on_device && n > 0)
+    {
+      const size_t floats = (size_t)n * stride;
+      if (floats > h->pre_xyz_cap)
+      {
+        if (h->d_pre_xyz) WS_CUDA_OK(cudaFree(h->d_pre_xyz));
+        h->d_pre_xyz = nullptr; h->pre_xyz_cap = 0;
+        WS_CUDA_OK(cudaMalloc(&h->d_pre_xyz, floats * sizeof(float)));
+        h->pre_xyz_cap = floats;
+      }
+      WS_CUDA_OK(cudaMemcpyAsync(h->d_pre_xyz, xyz, floats * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+      d_xyz = h->d_pre_xyz;
+    }
+    h->scan_n = ws_launch_preprocess(h, d_xyz, n, stride, pose_mm, map_resolution);
+    if (out_host && h->scan_n > 0)
+    {
+      WS_CUDA_OK(cudaMemcpyAsync(out_host, h->d_points, (size_t)h->scan_n * sizeof(ws_pt), cudaMemcpyDeviceToHost, h->stream));
+      WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+    if (n_out) *n_out = h->scan_n;
+    return WS_OK;
+  });
+}
+
+const ws_point *ws_scan_points_device(ws_handle *h, int64_t *n)
+{
+  if (!h) return nullptr;
+  if (n) *n = h->scan_n;
+  return reinterpret_cast<const ws_point *>(h->d_points);
 }
 
 int ws_get_update_counters(const ws_handle *h, ws_update_counters *out)

@@ -3,6 +3,7 @@
 #include <cstddef>
 #include <stdexcept>
 #include <string>
+#include <algorithm>
 #include <unordered_map>
 #include <vector>
 #include "ws_common.cuh"
@@ -99,6 +100,14 @@ struct ws_handle
   size_t points_cap = 0;
   void *d_rays = nullptr;         // RaySetup[rays_cap]: the work list written by the set-up pass of update_tsdf
   size_t rays_cap = 0;
+  // scan preprocessing scratch (preprocess.cu)
+  void *d_pre_tmp = nullptr;      // transformed points, scan order
+  unsigned *d_pre_slot = nullptr; // hash slot of every point
+  unsigned *d_pre_table = nullptr;// hash set: smallest point index per distinct value
+  unsigned *d_pre_tiles = nullptr;// survivors per 1024-point tile (+ the total)
+  float *d_pre_xyz = nullptr;     // staging of a host PointCloud2 payload
+  size_t pre_cap = 0, pre_xyz_cap = 0;
+  int64_t scan_n = 0;             // points the last ws_preprocess_scan left in d_points
   ws_pt *d_reg_points = nullptr;  // registration cloud
   size_t reg_points_cap = 0;
   int reg_n = 0;
@@ -168,6 +177,8 @@ void ws_launch_reg_solve(ws_handle *h, float it_weight_gradient, float epsilon);
 void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float it_weight_gradient, float epsilon);
 void ws_launch_transform_cloud(ws_handle *h, ws_pt *d_pts, int n);
 void ws_host_solve(const i64 H[36], const i64 g[6], int err, int cnt, float alpha, float T[16], double xi_out[6]);
+// preprocess.cu
+int64_t ws_launch_preprocess(ws_handle *h, const float *d_xyz, int64_t n, int stride_floats, const float pose_mm[16], int res);
 // map_ops.cu
 void ws_launch_fill(ws_handle *h, uint32_t entry);
 void ws_launch_upload(ws_handle *h, const uint32_t *d_linear);

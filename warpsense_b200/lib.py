@@ -66,6 +66,8 @@ def _signatures():
         "ws_update_tsdf": (C.c_int, [hp, vp, C.c_int64, i32p, i32p]),
         "ws_update_tsdf_device": (C.c_int, [hp, vp, C.c_int64, i32p, i32p]),
         "ws_get_update_counters": (C.c_int, [hp, C.POINTER(UpdateCounters)]),
+        "ws_preprocess_scan": (C.c_int, [hp, vp, C.c_int64, C.c_int32, C.c_int32, f32p, C.c_int32, vp, i64p]),
+        "ws_scan_points_device": (vp, [hp, i64p]),
         "ws_reg_prepare": (C.c_int, [hp, vp, C.c_int64]),
         "ws_reg_prepare_device": (C.c_int, [hp, vp, C.c_int64]),
         "ws_reg_step": (C.c_int, [hp, f32p, C.c_int32, i64p, i64p, i32p, i32p]),
