@@ -584,3 +584,72 @@ class TSDFRegistration(TSDFMapping):
             T, _ = self.reg_.register_cloud(cloud, pretransform, r.max_iterations, r.it_weight_gradient, r.epsilon,
                                             self.params_.map.resolution, host_solve=host_solve)
         return T
+
+
+class MappingFeed:
+    """The TSDF-facing half of featsense's Mapping::thread_run (src/featsense/mapping.cpp:39-147) without
+    ROS/PCL: F-LOAM/VGICP stay outside -- the caller hands over the cloud already placed in
+    the map frame (metres) and its pose (4x4, metres).
+
+      * the first cloud initialises the map (:66-75);
+      * later clouds are used only after the sensor moved more than `map.update_distance` since the last
+        used pose (:79-81);
+      * while the local map is shifting the clouds are accumulated, and flushed -- concatenated and
+        subsampled at the map resolution -- with the next update (:115-129);
+      * every used pose is offered to the map-shift logic (:140, update_map_shift)."""
+
+    def __init__(self, mapping: TSDFMapping):
+        self.gpu_ = mapping
+        self.initialized_ = False
+        self.last_pose_ = np.eye(4)
+        self.accumulated_ = []
+        self.poses = []                      # what hdf5_global_map_->write_pose would have stored (:137)
+        self.updates = 0
+
+    @staticmethod
+    def subsample(cloud_xyz_m, resolution_m):
+        """mapping.cpp `subsample`: pcl::VoxelGrid with a cubic leaf -- one centroid per occupied leaf."""
+        pts = np.asarray(cloud_xyz_m, dtype=np.float32).reshape(-1, 3)
+        if not len(pts):
+            return pts
+        leaf = np.floor(pts / np.float32(resolution_m)).astype(np.int64)
+        leaf -= leaf.min(axis=0)
+        dims = leaf.max(axis=0) + 1
+        key = (leaf[:, 0] * dims[1] + leaf[:, 1]) * dims[2] + leaf[:, 2]
+        order = np.argsort(key, kind="stable")
+        ks = key[order]
+        first = np.concatenate([[True], ks[1:] != ks[:-1]])
+        idx = np.cumsum(first) - 1
+        n = int(idx[-1]) + 1
+        sums = np.zeros((n, 3), np.float64)
+        np.add.at(sums, idx, pts[order].astype(np.float64))
+        cnt = np.bincount(idx, minlength=n)[:, None]
+        return (sums / cnt).astype(np.float32)
+
+    def push(self, cloud_xyz_m, pose_m):
+        """One (cloud, pose) pair from the odometry front end.  Returns True if the map was updated."""
+        pose = np.asarray(pose_m, dtype=np.float64).reshape(4, 4)
+        res_m = self.gpu_.params_.map.resolution / 1000.0
+        cloud = np.asarray(cloud_xyz_m, dtype=np.float32).reshape(-1, 3)
+        if not self.initialized_:
+            self.last_pose_ = pose.copy()
+            self.gpu_.update_tsdf_from_ros(self.subsample(cloud, res_m), pose)
+            self.initialized_ = True
+            self.updates += 1
+            return True
+        distance = float(np.linalg.norm(self.last_pose_[:3, 3] - pose[:3, 3]))
+        if not distance > self.gpu_.params_.map.update_distance:
+            return False
+        updated = False
+        if self.gpu_.is_shifting():
+            self.accumulated_.append(cloud)
+        else:
+            if self.accumulated_:
+                cloud = self.subsample(np.concatenate([cloud] + self.accumulated_), res_m)
+                self.accumulated_ = []
+            self.gpu_.update_tsdf_from_ros(cloud, pose)
+            self.updates += 1
+            updated = True
+        self.last_pose_ = pose.copy()
+        self.poses.append(pose.copy())
+        return updated
