@@ -38,6 +38,9 @@ GN_ITERS = 20
 IT_WEIGHT = 0.1
 EPSILON = 0.0          # |.| < 0 never holds: exactly GN_ITERS iterations
 TAU, MAX_WEIGHT = 1000, 640
+# DRAM bytes of one update_tsdf on the default workload, from the committed ncu capture (profiles/r01j_*):
+# setup 1.6 + march 221.2 + 538.9 + brick_list 1.1 + merge 353.0 + 380.3 + replay 663.2 + 34.4 MB
+NCU_TRAFFIC_BYTES_PER_SCAN = 2193.7e6
 REF_SUBSAMPLE = 8      # --impl reference: every 8th ray per step (bounded sample)
 
 
@@ -374,7 +377,11 @@ def run_native(args):
             "roofline": {
                 "bound": "hbm", "kernel": "update_tsdf = march_kernel + brick_list/merge_kernel + replay_kernel (per scan)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": NCU_TRAFFIC_BYTES_PER_SCAN if (world == 1 and not args.update_only and args.grid == 512 and args.res == 50
+                                                          and args.beams == 128 and args.cols == 1024) else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of setup + march + brick_list + merge + replay, one "
+                                  "launch each, ncu --set full capture of this workload (profiles/r01j_summary.md)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_scan": upd_bytes,
                 "formula": "12*N + 8*T (SURVEY.md 8d), N=%d points, T=%d touched voxels, C=%d candidates" % (N, T_vox, C_cand),
                 "kernel_ms_per_scan": {"march": march_ms, "merge": merge_ms, "replay": replay_ms, "reg_20_iterations": reg_ms,

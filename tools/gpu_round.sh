@@ -13,6 +13,6 @@ timeout 300 python bench.py --steps 40 --warmup 5 --update-only --no-cpu-baselin
 tail -1 $out/${tag}_bench_update_only.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 200 --csv --log-file $out/${tag}_launches.csv \
    python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-ref-cuda > $out/${tag}_ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'march|merge|resolve|replay|reg_loop|register' -s 30 -c 12 -f -o $out/${tag}_prof \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"setup_kernel|march|merge|brick_list|replay|reg_loop" -s 36 -c 12 -f -o $out/${tag}_prof \
    python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-ref-cuda > $out/${tag}_ncu_full.log 2>&1
 ls -la $out
