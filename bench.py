@@ -268,12 +268,8 @@ def run_native(args):
             pos, up = fp.convert_pose_to_gpu(f["pose"], res)
             tsdf.update_tsdf_device(dev_cloud.data_ptr(), N, pos, up)
             return
-        reg.prepare_registration_device(dev_cloud.data_ptr(), N)
-        T = register(N)
-        pose = (T @ s.pose(k - 1)).astype(np.float32)
-        pos, up = fp.convert_pose_to_gpu(pose, res)
-        ptr, n = reg.points_device()
-        tsdf.update_tsdf_device(ptr, n, pos, up)
+        # one fused call per scan: 20 GN iterations -> pose -> update_tsdf, chained on the device
+        reg.track_scan(None, s.pose(k - 1), GN_ITERS, IT_WEIGHT, EPSILON, res, device_ptr=dev_cloud.data_ptr(), n=N)
 
     def step_host(k, host_cloud):
         f = frames[k]
@@ -281,12 +277,8 @@ def run_native(args):
             pos, up = fp.convert_pose_to_gpu(f["pose"], res)
             tsdf.update_tsdf(host_cloud, pos, up)
             return
-        reg.prepare_registration(host_cloud)             # H2D of the scan (pinned host memory)
-        T = register(N)                                  # D2H of the pose
-        pose = (T @ s.pose(k - 1)).astype(np.float32)
-        pos, up = fp.convert_pose_to_gpu(pose, res)
-        ptr, n = reg.points_device()
-        tsdf.update_tsdf_device(ptr, n, pos, up)         # D2H of the work counters
+        # H2D of the scan, D2H of the transform + pose + work counters, all inside the call
+        reg.track_scan(host_cloud, s.pose(k - 1), GN_ITERS, IT_WEIGHT, EPSILON, res)
 
     key = "points_map" if args.update_only else "points_prior"
     with torch.cuda.stream(stream):
@@ -371,8 +363,8 @@ def run_native(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                     "h2d_bytes_per_step": 12 * N, "d2h_bytes_per_step": 352 + 64,
-                    "note": "scan in pinned host memory -> ws_reg_prepare (H2D) -> 20 GN iterations -> pose D2H -> "
-                            "update_tsdf -> counters D2H"},
+                    "note": "ws_track_scan with the scan in pinned host memory: H2D -> 20 GN iterations -> pose on the "
+                            "device -> update_tsdf -> transform + pose + counters D2H, one host synchronisation"},
             "gpu_launches": launches,
             "roofline": {
                 "bound": "hbm", "kernel": "update_tsdf = march_kernel + brick_list/merge_kernel + replay_kernel (per scan)",

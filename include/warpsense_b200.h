@@ -147,6 +147,16 @@ int ws_register_cloud(ws_handle *h, ws_point *cloud, int64_t n, const float pret
                       int32_t max_iterations, float it_weight_gradient, float epsilon,
                       int32_t map_resolution, int32_t flags, float out_transform[16],
                       int32_t *iterations);
+/* ws_track_scan: the reference's per-scan sequence (App::cloud_callback, src/warpsense/app.cpp:65-112, in the
+ *                 order of BASELINE configs[2]: register_cloud with pretransform = identity against the map
+ *                 of the earlier scans, pose = X * prior_pose, update_tsdf with the registered cloud and
+ *                 convert_pose_to_gpu(pose), tsdf_mapping.cpp:77-85) as one stream of kernels with a single
+ *                 host synchronisation: transform, scanner voxel and up vector stay on the device between
+ *                 the two halves.  Equivalent to ws_register_cloud + ws_update_tsdf_device with the pose
+ *                 product evaluated in float32, accumulating over k = 0..3 in order. */
+int ws_track_scan(ws_handle *h, const ws_point *points, int64_t n, int32_t on_device, const float prior_pose[16],
+                  int32_t max_iterations, float it_weight_gradient, float epsilon, int32_t map_resolution,
+                  float out_transform[16], float out_pose[16], int32_t *iterations);
 /* per-iteration sums of the last ws_register_cloud: 29 int64 per iteration
  * (21 upper-triangle H row-major, 6 g, err, cnt); returns the number of iterations copied */
 int ws_reg_get_trace(ws_handle *h, int64_t *out, int32_t max_iterations);

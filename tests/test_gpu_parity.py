@@ -411,3 +411,46 @@ def test_shift_random_walk_matches_oracle():
     assert sorted(tsdf.chunk_list()) == sorted(om.chunk_list())
     for c in om.chunk_list():
         assert np.array_equal(tsdf.chunk(*c), om.chunk(*c)), "chunk %r" % (c,)
+
+
+# ----------------------------------------------------------------------------- fused per-scan pipeline
+def _compose_f32(X, prior):
+    """pose = X * prior in float32, accumulating over k = 0..3 in order (ws_track_scan's definition)."""
+    X = np.asarray(X, np.float32); prior = np.asarray(prior, np.float32)
+    out = np.zeros((4, 4), np.float32)
+    for r in range(4):
+        for c in range(4):
+            acc = np.float32(X[r, 0] * prior[0, c])
+            for k in range(1, 4):
+                acc = np.float32(acc + np.float32(X[r, k] * prior[k, c]))
+            out[r, c] = acc
+    return out
+
+
+def test_track_scan_matches_register_then_update():
+    """ws_track_scan (registration, pose and update chained on the device, one host sync) against the oracle
+    doing register_cloud -> pose = X * prior -> convert_pose -> update_tsdf step by step."""
+    res = 100
+    s, om, hm, tsdf, tau, mw = _stream_setup(32, 256, 128, res)
+    reg = api.RegistrationCuda(tsdf)
+    f0 = s.frame(0)
+    pos, up = fp.convert_pose_to_gpu(f0["pose"], res)
+    orc.update_tsdf(om, f0["points_map"], pos, up, tau, mw, res)
+    tsdf.update_tsdf(f0["points_map"], pos, up)
+    I = np.eye(4, dtype=np.float32)
+    for k in range(1, 4):
+        prior = s.pose(k - 1)
+        cloud = s.frame(k, prior_pose=prior)["points_prior"]
+        ocloud = cloud.copy()
+        oX, oit = orc.register_cloud(om, ocloud, I, 10, 0.1, 0.0, res)
+        opose = _compose_f32(oX, prior)
+        opos, oup = orc.convert_pose(opose, res)
+        st = orc.update_tsdf(om, ocloud, opos, oup, tau, mw, res)
+        X, pose, it = reg.track_scan(cloud, prior, 10, 0.1, 0.0, res)
+        assert it == oit
+        assert np.array_equal(X, oX), "transform differs from the oracle"
+        assert np.array_equal(pose, opose), "pose product differs"
+        c = tsdf.counters()
+        assert (c["n_candidates"], c["n_touched"], c["n_written"]) == (st["n_candidates"], st["n_touched"], st["n_written"])
+        assert_same_grid(om, tsdf, hm, "frame %d" % k)
+    tsdf.close()

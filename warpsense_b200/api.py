@@ -378,6 +378,27 @@ class RegistrationCuda:
                                         out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(it)))
         return from_colmajor16(out), it.value
 
+    def track_scan(self, points, prior_pose, max_iterations, it_weight_gradient, epsilon, map_resolution,
+                   device_ptr=None, n=None):
+        """One scan through the fused pipeline (ws_track_scan): register against the map (pretransform =
+        identity), pose = X @ prior_pose, update_tsdf with the registered cloud -- one host synchronisation.
+        `points`: int32 [n,3] host array, or None with `device_ptr`/`n`.  Returns (X, pose, iterations)."""
+        hd = self._hd
+        f32p = C.POINTER(C.c_float)
+        P0 = colmajor16(prior_pose)
+        X, pose = np.zeros(16, np.float32), np.zeros(16, np.float32)
+        it = C.c_int32()
+        if points is not None:
+            p = _pts(points)
+            ptr, cnt, dev = p.ctypes.data, len(p), 0
+        else:
+            ptr, cnt, dev = C.c_void_p(int(device_ptr)), int(n), 1
+        hd.check(hd.L.ws_track_scan(hd.h, ptr, cnt, dev, P0.ctypes.data_as(f32p), int(max_iterations),
+                                    float(it_weight_gradient), float(epsilon), int(map_resolution),
+                                    X.ctypes.data_as(f32p), pose.ctypes.data_as(f32p), C.byref(it)))
+        self.curr_n_points = cnt
+        return from_colmajor16(X), from_colmajor16(pose), it.value
+
     # -- multi-GPU (SURVEY.md 8e): one handle per rank, the caller supplies the exchange step --
     def sums_device_ptr(self):
         """Device address of this rank's int64[29] Gauss-Newton sums (what the all-reduce operates on)."""

@@ -72,7 +72,7 @@ void free_handle(ws_handle *h)
   cudaFree(h->d_pend_addr); cudaFree(h->d_pend_prev); cudaFree(h->d_pend_key);
   cudaFree(h->d_active[0]); cudaFree(h->d_active[1]);
   cudaFree(h->d_rec); cudaFree(h->d_list); cudaFree(h->d_chunk_fill);
-  detach_peers(h); cudaFree(h->d_mail);
+  detach_peers(h); cudaFree(h->d_mail); cudaFree(h->d_pose); cudaFreeHost(h->h_pose);
   cudaFree(h->d_acc); cudaFree(h->d_trace); cudaFreeHost(h->h_acc); cudaFree(h->d_reg_partials);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -754,6 +754,44 @@ int ws_peer_set_timeout(ws_handle *h, double seconds)
   if (!h || !(seconds > 0.0)) return WS_ERR_INVALID;
   h->peer_timeout_ns = (unsigned long long)(seconds * 1e9);
   return WS_OK;
+}
+
+// The reference's per-scan sequence (App::cloud_callback, src/warpsense/app.cpp:65-112: register_cloud,
+// pose update, update_tsdf) as ONE stream of kernels with a single host synchronisation at the end: the
+// registration leaves its transform on the device, pose_kernel turns X * prior into the scanner voxel and
+// the up vector there, and update_tsdf's kernels read them from device memory.
+int ws_track_scan(ws_handle *h, const ws_point *points, int64_t n, int32_t on_device, const float prior_pose[16],
+                  int32_t max_iterations, float it_weight_gradient, float epsilon, int32_t map_resolution,
+                  float out_transform[16], float out_pose[16], int32_t *iterations)
+{
+  return guarded(h, [&]() {
+    if (!prior_pose || !out_transform || map_resolution < 1 || max_iterations < 0 || n < 0 || (n > 0 && !points))
+      throw std::invalid_argument("ws_track_scan: bad argument");
+    if (n > WS_MAX_POINTS) throw std::length_error("ws_track_scan: too many points");
+    if (map_resolution != h->res) throw std::invalid_argument("ws_track_scan: map_resolution differs from the map's");
+    ensure_points(&h->d_reg_points, &h->reg_points_cap, (size_t)std::max<int64_t>(n, 1));
+    if (n > 0)
+      WS_CUDA_OK(cudaMemcpyAsync(h->d_reg_points, points, (size_t)n * sizeof(ws_pt),
+                                 on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    h->reg_n = (int)n;
+    h->last_reg_host = false;
+    h->host_trace.clear();
+    const float I16[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    ws_launch_reg_reset(h, I16, 0.f);
+    if (max_iterations > 0) ws_launch_reg_loop(h, (int)n, map_resolution, max_iterations, it_weight_gradient, epsilon);
+    ws_launch_transform_cloud(h, h->d_reg_points, (int)n);
+    ws_launch_pose(h, h->d_acc->T, prior_pose);
+    WS_CUDA_OK(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(RegAccum), cudaMemcpyDeviceToHost, h->stream));
+    h->last_n_points = n;
+    ws_launch_update(h, h->d_reg_points, (int)n, nullptr, nullptr, true);     // synchronises once, at its end
+    if (h->h_acc->finished == 2u)
+      throw std::logic_error("track_scan: a peer rank did not deliver its Gauss-Newton sums in time");
+    std::memcpy(out_transform, h->h_acc->T, 16 * sizeof(float));
+    if (out_pose) std::memcpy(out_pose, static_cast<const PoseDev *>(h->h_pose)->pose, 16 * sizeof(float));
+    h->last_reg_iterations = (int)h->h_acc->iterations;
+    if (iterations) *iterations = h->last_reg_iterations;
+    return WS_OK;
+  });
 }
 
 int ws_reg_get_trace(ws_handle *h, int64_t *out, int32_t max_iterations)

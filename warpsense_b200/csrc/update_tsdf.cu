@@ -30,6 +30,7 @@
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <stdexcept>
 #include <vector>
 #include "ws_internal.h"
@@ -163,12 +164,13 @@ WS_D bool ray_setup(const UpdateParams &P, const ws_pt pt, Ray &r)
 }
 
 // general (wrapping, 64-bit magic) projection of one march step
-WS_D void step_index(const UpdateParams &P, const int d[3], const FastDiv div_dist, int len, int proj[3], int idx[3])
+WS_D void step_index(const UpdateParams &P, const int pos_mm[3], const int d[3], const FastDiv div_dist, int len,
+                     int proj[3], int idx[3])
 {
 #pragma unroll
   for (int a = 0; a < 3; a++)
   {
-    proj[a] = wadd(P.pos_mm[a], fd_sdiv(wmul(d[a], len), div_dist));                             // :452
+    proj[a] = wadd(pos_mm[a], fd_sdiv(wmul(d[a], len), div_dist));                               // :452
     idx[a] = fd_sdiv(proj[a], P.div_res);                                                        // :453
   }
 }
@@ -259,7 +261,7 @@ struct MarchCtx
 // One ray, one warp.  FAST: march_math.cuh (DDA projection, 32-bit magics, int32 fan arithmetic); !FAST: the
 // literal wrapping arithmetic of the oracle.  Both produce identical candidates wherever FAST is allowed.
 template <bool ATOMIC, bool FAST>
-WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const int4 *ray_s, const int start,
+WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const int pos_mm[3], const int4 *ray_s, const int start,
                     const int end, const int lane,
                     int4 *qa_s, int4 *qb_s, MarchCtx &cx, Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill,
                     const unsigned cap_chunks, UpdateCounters *__restrict__ ctr)
@@ -300,7 +302,7 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const int4 *ray_s,
     FastDiv dd = div_dist;
     if (FAST && distance > 1) dd.M = (~0ull) / (u64)(unsigned)distance + 1ull;
     int pj[3], ix[3];
-    step_index(P, dvec, dd, 1 + (start - 1) * P.half_res, pj, ix);
+    step_index(P, pos_mm, dvec, dd, 1 + (start - 1) * P.half_res, pj, ix);
     carry_x = ix[0]; carry_y = ix[1];
   }
 
@@ -316,12 +318,12 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const int4 *ray_s,
 #pragma unroll
         for (int a = 0; a < 3; a++)
         {
-          proj[a] = P.pos_mm[a] + (dvec[a] < 0 ? -(int)dda[a].q : (int)dda[a].q);                // :452
+          proj[a] = pos_mm[a] + (dvec[a] < 0 ? -(int)dda[a].q : (int)dda[a].q);                  // :452
           index[a] = fd32_sdiv(proj[a], P.div_res32);                                            // :453
           dda_advance(dda[a], (unsigned)distance);
         }
       }
-      else step_index(P, dvec, div_dist, 1 + i * P.half_res, proj, index);
+      else step_index(P, pos_mm, dvec, div_dist, 1 + i * P.half_res, proj, index);
 
       int px = __shfl_up_sync(FULL, index[0], 1);
       int py = __shfl_up_sync(FULL, index[1], 1);
@@ -547,9 +549,18 @@ WS_D void ray_segments(const UpdateParams &P, const Ray &r, int seg[4])
 // Set-up pass: one THREAD per ray (the march needs the result warp-uniform; computing it there costs every
 // lane of a warp the same ~600 instructions).  Rays without work on this rank get empty step ranges.
 __global__ void __launch_bounds__(256)
-setup_kernel(const UpdateParams P, const ws_pt *__restrict__ pts, RaySetup *__restrict__ rays,
-             UpdateCounters *__restrict__ ctr)
+setup_kernel(const UpdateParams Pin, const ws_pt *__restrict__ pts, RaySetup *__restrict__ rays,
+             UpdateCounters *__restrict__ ctr, const PoseDev *__restrict__ pose)
 {
+  // the sensor pose comes from the host (kernel parameters) or, in the fused per-scan pipeline, from the
+  // registration that ran just before on the same stream (device memory)
+  UpdateParams P = Pin;
+  if (pose)
+  {
+#pragma unroll
+    for (int a = 0; a < 3; a++) { P.pos_mm[a] = pose->pos_mm[a]; P.up[a] = pose->up[a]; }
+    P.coord_lim = pose->coord_lim;
+  }
   const int ray_id = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = false;
   RaySetup o;
@@ -601,9 +612,12 @@ template <bool ATOMIC>
 __global__ void __launch_bounds__(MARCH_THREADS, MARCH_CTAS)
 march_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__restrict__ rays,
              UpdateCounters *__restrict__ ctr, Rec *__restrict__ rec,
-             unsigned *__restrict__ chunk_fill, const unsigned cap_chunks)
+             unsigned *__restrict__ chunk_fill, const unsigned cap_chunks, const PoseDev *__restrict__ pose)
 {
   __shared__ int4 s_qa[MARCH_WARPS][QCAP], s_qb[MARCH_WARPS][QCAP];   // per-warp queue of surviving march steps
+  int pos_mm[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) pos_mm[a] = pose ? pose->pos_mm[a] : P.pos_mm[a];
   __shared__ int4 s_ray[MARCH_WARPS][2][RAY_WORDS];                    // the warp's current and next ray (cp.async)
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -656,8 +670,8 @@ march_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__restrict_
         start = start > fs ? start : fs;
       }
       if (start >= end) continue;
-      if (small) march_ray<ATOMIC, true>(g, P, ray_s, start, end, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
-      else march_ray<ATOMIC, false>(g, P, ray_s, start, end, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
+      if (small) march_ray<ATOMIC, true>(g, P, pos_mm, ray_s, start, end, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
+      else march_ray<ATOMIC, false>(g, P, pos_mm, ray_s, start, end, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
     }
 
     // rotate the pipeline.  The empty asm ties the fetched index to a value that is only known once the
@@ -1215,8 +1229,76 @@ static void launch_replay(ws_handle *h, const UpdateParams &P)
   h->launches++;
 }
 
-void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3])
+// src/warpsense/tsdf_mapping.cpp:77-85 + include/util/util.h:52-56 on the device: pose = X * prior (float32, the
+// accumulation order of ws_compose_pose_host), scanner voxel = floor(t / res), up = third column of
+// to_int_mat(pose) -- so update_tsdf can follow register_cloud on the stream without the host in between
+__global__ void pose_kernel(const float *__restrict__ X, const float *__restrict__ prior, const int res,
+                            const int coord_lim, PoseDev *__restrict__ out)
 {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float pose[16];
+  for (int c = 0; c < 4; c++)
+    for (int r = 0; r < 4; r++)
+    {
+      float acc = X[0 * 4 + r] * prior[c * 4 + 0];
+      acc = acc + X[1 * 4 + r] * prior[c * 4 + 1];
+      acc = acc + X[2 * 4 + r] * prior[c * 4 + 2];
+      acc = acc + X[3 * 4 + r] * prior[c * 4 + 3];
+      pose[c * 4 + r] = acc;
+    }
+  bool ok = true;
+  for (int a = 0; a < 3; a++)
+  {
+    const int vox = (int)floorf(pose[12 + a] / (float)res);
+    out->pos_mm[a] = (int)((unsigned)vox * (unsigned)res);
+    out->up[a] = (long long)(int)(pose[8 + a] * (float)WS_MR);
+    const long long ap = out->pos_mm[a] < 0 ? -(long long)out->pos_mm[a] : (long long)out->pos_mm[a];
+    if (ap >= (long long)coord_lim) ok = false;
+    out->pos_vox[a] = vox;
+  }
+  out->coord_lim = ok ? coord_lim : 0;
+  for (int i = 0; i < 16; i++) out->pose[i] = pose[i];
+}
+
+void ws_compose_pose_host(const float X[16], const float prior[16], float pose[16])
+{
+  for (int c = 0; c < 4; c++)
+    for (int r = 0; r < 4; r++)
+    {
+      float acc = X[0 * 4 + r] * prior[c * 4 + 0];
+      acc = acc + X[1 * 4 + r] * prior[c * 4 + 1];
+      acc = acc + X[2 * 4 + r] * prior[c * 4 + 2];
+      acc = acc + X[3 * 4 + r] * prior[c * 4 + 3];
+      pose[c * 4 + r] = acc;
+    }
+}
+
+void ws_launch_pose(ws_handle *h, const float *d_X, const float prior[16])
+{
+  if (!h->d_pose)
+  {
+    WS_CUDA_OK(cudaMalloc(&h->d_pose, sizeof(PoseDev) + 16 * sizeof(float)));
+    WS_CUDA_OK(cudaMallocHost(&h->h_pose, sizeof(PoseDev) + 16 * sizeof(float)));
+  }
+  float *d_prior = reinterpret_cast<float *>(reinterpret_cast<char *>(h->d_pose) + sizeof(PoseDev));
+  float *h_prior = reinterpret_cast<float *>(reinterpret_cast<char *>(h->h_pose) + sizeof(PoseDev));
+  std::memcpy(h_prior, prior, 16 * sizeof(float));
+  WS_CUDA_OK(cudaMemcpyAsync(d_prior, h_prior, 16 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  long long lim = (1ll << 31) / h->res - h->tau - (1ll << 17);
+  if (lim < 0 || std::getenv("WS_MARCH_GENERAL")) lim = 0;
+  pose_kernel<<<1, 32, 0, h->stream>>>(d_X, d_prior, h->res, (int)lim, static_cast<PoseDev *>(h->d_pose));
+  h->launches++;
+}
+
+void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos_in[3], const int up_in[3],
+                      bool pose_on_device)
+{
+  // pose_on_device: the scanner pose was left in h->d_pose by ws_launch_pose on this stream; the host copy
+  // (needed only if the candidate record has to be regenerated) is read back with the counters
+  const PoseDev *d_pose = pose_on_device ? static_cast<const PoseDev *>(h->d_pose) : nullptr;
+  const int zero3[3] = { 0, 0, 0 };
+  const int *scanner_pos = pose_on_device ? zero3 : scanner_pos_in;
+  const int *up = pose_on_device ? zero3 : up_in;
   UpdateParams P{};
   P.tau = h->tau;
   P.max_weight = h->max_weight;
@@ -1276,9 +1358,9 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
       h->rays_cap = want;
     }
     RaySetup *rays = static_cast<RaySetup *>(h->d_rays);
-    setup_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_pts, rays, h->d_counters);
+    setup_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_pts, rays, h->d_counters, d_pose);
     march_kernel<true><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_counters, h->d_rec,
-                                                              h->d_chunk_fill, cap_chunks);
+                                                              h->d_chunk_fill, cap_chunks, d_pose);
     h->launches++;
     ws_timer_end(h);
     ws_timer_begin(h, WS_TIMER_MERGE);
@@ -1291,6 +1373,8 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
     launch_replay(h, P);
     ws_timer_end(h);
     WS_CUDA_OK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
+    if (pose_on_device)
+      WS_CUDA_OK(cudaMemcpyAsync(h->h_pose, h->d_pose, sizeof(PoseDev), cudaMemcpyDeviceToHost, s));
     WS_CUDA_OK(cudaStreamSynchronize(s));
     // the record did not fit: grow it, regenerate it from the far part of every ray, settle again
     int guard = 0;
@@ -1305,7 +1389,7 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
       cap_chunks = (unsigned)h->rec_cap_chunks;
       rec_reset_kernel<<<1, 1, 0, s>>>(h->d_counters);
       march_kernel<false><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_counters, h->d_rec,
-                                                                 h->d_chunk_fill, cap_chunks);
+                                                                 h->d_chunk_fill, cap_chunks, d_pose);
       h->launches += 2;
       launch_replay(h, P);
       WS_CUDA_OK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
@@ -1316,6 +1400,8 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
   else
   {
     WS_CUDA_OK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
+    if (pose_on_device)
+      WS_CUDA_OK(cudaMemcpyAsync(h->h_pose, h->d_pose, sizeof(PoseDev), cudaMemcpyDeviceToHost, s));
     WS_CUDA_OK(cudaStreamSynchronize(s));
   }
   WS_CUDA_OK(cudaGetLastError());

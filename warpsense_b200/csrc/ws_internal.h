@@ -33,6 +33,17 @@ struct UpdateParams
   int xiv_lo[2], xiv_hi[2];
 };
 
+// scanner pose handed from the registration to update_tsdf on the device (fused per-scan pipeline)
+struct PoseDev
+{
+  int pos_mm[3];       // scanner voxel * map_resolution
+  int coord_lim;       // UpdateParams::coord_lim after the |pos_mm| check
+  long long up[3];
+  int pos_vox[3];      // scanner voxel (tsdf_mapping.cpp:77-85)
+  int pad;
+  float pose[16];      // X * prior, column-major
+};
+
 // one recorded candidate: its key and the voxel address (record) or the pending slot (replay list)
 struct Rec
 {
@@ -98,6 +109,8 @@ struct ws_handle
   // scan points
   ws_pt *d_points = nullptr;      // update_tsdf staging
   size_t points_cap = 0;
+  void *d_pose = nullptr;         // PoseDev + staged prior pose (fused per-scan pipeline)
+  void *h_pose = nullptr;         // pinned mirror
   void *d_rays = nullptr;         // RaySetup[rays_cap]: the work list written by the set-up pass of update_tsdf
   size_t rays_cap = 0;
   // scan preprocessing scratch (preprocess.cu)
@@ -168,7 +181,10 @@ struct ws_handle
 };
 
 // update_tsdf.cu
-void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3]);
+void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3],
+                      bool pose_on_device = false);
+void ws_launch_pose(ws_handle *h, const float *d_X, const float prior[16]);
+void ws_compose_pose_host(const float X[16], const float prior[16], float pose[16]);
 void ws_update_alloc(ws_handle *h, size_t initial_chunks, size_t max_chunks);
 // registration.cu
 void ws_launch_reg_reset(ws_handle *h, const float T[16], float alpha0);

@@ -73,6 +73,8 @@ def _signatures():
         "ws_reg_step": (C.c_int, [hp, f32p, C.c_int32, i64p, i64p, i32p, i32p]),
         "ws_register_cloud": (C.c_int, [hp, vp, C.c_int64, f32p, C.c_int32, C.c_float, C.c_float,
                                         C.c_int32, C.c_int32, f32p, i32p]),
+        "ws_track_scan": (C.c_int, [hp, vp, C.c_int64, C.c_int32, f32p, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                                    f32p, f32p, i32p]),
         "ws_reg_get_trace": (C.c_int, [hp, i64p, C.c_int32]),
         "ws_reg_points_device": (vp, [hp, i64p]),
         "ws_reg_begin": (C.c_int, [hp, f32p]),
