@@ -575,6 +575,7 @@ reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopPa
   __shared__ u64 s_w[REG_THREADS / 32][REG_NSLOT];
   __shared__ unsigned s_half[WS_MAX_PEERS][WS_MAIL_WORDS];
   __shared__ unsigned s_timeout;
+  __shared__ bool s_last;
   __shared__ u64 s_total[REG_NSLOT];
   __shared__ GnState s_st;
   __shared__ double s_lu[36], s_inv[36], s_xi[6];
@@ -619,6 +620,7 @@ reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopPa
     const i64 mine = warp_transpose_reduce(sum, lane);
     s_w[warp][lane] = (u64)mine;
     __syncthreads();
+#ifdef WS_REG_GRIDSYNC
     u64 *row = partials + ((size_t)(it & 1) * gridDim.x + blockIdx.x) * REG_NSLOT;
     if (tid < REG_NSLOT)
     {
@@ -651,11 +653,53 @@ reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopPa
       }
       __syncthreads();
     }
+    const bool sender = blockIdx.x == 0;
+#else
+    // Grid-wide sum without a grid barrier: every block adds its 29 sums into one of three rotating
+    // accumulators (int64 atomics: exact, order-free) and takes a ticket; whoever holds the last ticket knows
+    // the accumulator is complete.  One GPU: everybody polls the ticket counter and reads the totals.  Several
+    // GPUs: the last block pushes them to the peers and everybody polls the mailbox instead.
+    u64 *tot = partials + (size_t)(it % 3) * REG_NSLOT;
+    unsigned *tickets = reinterpret_cast<unsigned *>(partials + 3 * REG_NSLOT);
+    const unsigned target = (unsigned)(it + 1) * gridDim.x;
+    if (blockIdx.x == 0 && tid < REG_NSLOT) partials[(size_t)((it + 1) % 3) * REG_NSLOT + tid] = 0ull;   // free since it-2
+    if (tid < WS_NSUM)
+    {
+      u64 a = 0ull;
+#pragma unroll
+      for (int w = 0; w < REG_THREADS / 32; w++) a += s_w[w][tid];
+      if (a) atomicAdd(reinterpret_cast<unsigned long long *>(&tot[tid]), (unsigned long long)a);
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0)
+    {
+      const unsigned ticket = atomicAdd(tickets, 1u);
+      s_last = ticket == target - 1u;
+      if (!MULTI)
+      {
+        while (*((volatile unsigned *)tickets) < target) { }
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    const bool sender = s_last;
+    if (!MULTI || sender)
+    {
+      if (tid < REG_NSLOT)
+      {
+        const u64 a2 = tid < WS_NSUM ? __ldcg(&tot[tid]) : 0ull;
+        s_total[tid] = a2;
+        if (!MULTI && blockIdx.x == 0 && trace && it < trace_cap && tid < WS_NSUM) trace[(size_t)it * WS_NSUM + tid] = a2;
+      }
+      __syncthreads();
+    }
+#endif
     if (MULTI)
     {
       const unsigned stamp = pp.stamp_base + (unsigned)it + 1u;
       const size_t parity_off = (size_t)(((pp.stamp_base >> 8) & 1u) * 2u + (unsigned)(it & 1)) * pp.world * WS_MAIL_WORDS;
-      if (blockIdx.x == 0)
+      if (sender)
       {
         // push this rank's totals into slot `rank` of every mailbox (own one included)
         for (int idx = tid; idx < pp.world * WS_MAIL_USED; idx += REG_THREADS)
@@ -813,7 +857,7 @@ void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float 
       const int v = std::atoi(e);
       if (v >= 1 && v < h->reg_loop_blocks) h->reg_loop_blocks = v;
     }
-    WS_CUDA_OK(cudaMalloc(&h->d_reg_partials, (size_t)2 * h->reg_loop_blocks * REG_NSLOT * sizeof(u64)));
+    WS_CUDA_OK(cudaMalloc(&h->d_reg_partials, ((size_t)2 * h->reg_loop_blocks + 4) * REG_NSLOT * sizeof(u64)));
   }
   RegLoopParams rp;
   rp.n = n;
@@ -836,6 +880,9 @@ void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float 
   }
   void *args[] = { (void *)&h->g, (void *)&h->d_reg_points, (void *)&rp, (void *)&h->d_acc,
                    (void *)&h->d_reg_partials, (void *)&h->d_trace, (void *)&h->trace_cap, (void *)&pp };
+#ifndef WS_REG_GRIDSYNC
+  WS_CUDA_OK(cudaMemsetAsync(h->d_reg_partials, 0, (size_t)4 * REG_NSLOT * sizeof(u64), h->stream));   // accumulators + tickets
+#endif
   ws_timer_begin(h, WS_TIMER_REG);
   const void *fn = h->world > 1 ? (const void *)reg_loop_kernel<true> : (const void *)reg_loop_kernel<false>;
   WS_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(h->reg_loop_blocks), dim3(REG_THREADS), args, 0, h->stream));
