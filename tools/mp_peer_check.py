@@ -41,14 +41,24 @@ def main():
             ocloud = cloud.copy()
             oT, oit, otr = orc.register_cloud(om, ocloud, I, 12, 0.1, 0.0, res, trace=True)
             dist.barrier()
-            T, it = reg.register_cloud(cloud, I, 12, 0.1, 0.0, res)
-            assert it == oit, (it, oit)
-            assert np.array_equal(reg.trace()[:it], otr[:it]), "rank %d frame %d: sums differ from the oracle" % (rank, k)
-            assert np.array_equal(cloud, ocloud), "transformed cloud differs"
-            pose = (T @ s.pose(k - 1)).astype(np.float32)
-        pos, up = fp.convert_pose_to_gpu(pose, res)
-        orc.update_tsdf(om, cloud, pos, up, tau, mw, res)
-        tsdf.update_tsdf(cloud, pos, up)
+            if k >= 2:
+                # fused per-scan pipeline on the sharded map: registration -> pose -> update on the device
+                prior = s.pose(k - 1)
+                T, pose, it = reg.track_scan(cloud, prior, 12, 0.1, 0.0, res)
+                assert it == oit and np.array_equal(T, oT), "rank %d frame %d: fused transform differs" % (rank, k)
+                assert np.array_equal(reg.trace()[:it], otr[:it])
+                opos, oup = orc.convert_pose(pose, res)
+                orc.update_tsdf(om, ocloud, opos, oup, tau, mw, res)
+            else:
+                T, it = reg.register_cloud(cloud, I, 12, 0.1, 0.0, res)
+                assert it == oit, (it, oit)
+                assert np.array_equal(reg.trace()[:it], otr[:it]), "rank %d frame %d: sums differ from the oracle" % (rank, k)
+                assert np.array_equal(cloud, ocloud), "transformed cloud differs"
+                pose = (T @ s.pose(k - 1)).astype(np.float32)
+        if k < 2:
+            pos, up = fp.convert_pose_to_gpu(pose, res)
+            orc.update_tsdf(om, cloud, pos, up, tau, mw, res)
+            tsdf.update_tsdf(cloud, pos, up)
         lo, hi, _ = api.slab_layout(int(hm.size[0]), rank, world)
         back = api.HostLocalMap(side, side, side, tau, 0)
         tsdf.avg_map().to_host(api.DeviceMap(back))
