@@ -213,6 +213,25 @@ int ws_store_chunk_list(const ws_handle *h, int32_t *xyz, int64_t cap);
 /* copy one 64^3 chunk (index x*4096 + y*64 + z, hdf5_global_map.cpp:53-57); WS_ERR_INVALID if absent */
 int ws_store_get_chunk(const ws_handle *h, int32_t cx, int32_t cy, int32_t cz, uint32_t *out);
 
+/* ---- global-map file ----------------------------------------------------------------------------
+ * ws_export_hdf5: what HDF5GlobalMap leaves on disk (src/map/hdf5_global_map.cpp): /map/<cx>_<cy>_<cz> = 64^3
+ * uint32 raw entries per stored chunk (:46-57,:120,:170), the /map attributes of write_meta (:208-221) and
+ * /poses/<n>/pose = 7 float32 (x y z qx qy qz qw, already scaled and rounded as write_pose does, :175-200).
+ * Written directly in the HDF5 file format (superblock v0, object headers v1, symbol-table groups,
+ * contiguous little-endian datasets) -- no libhdf5.  Call ws_write_back first to include the local map. */
+typedef struct ws_map_meta
+{
+  int32_t tau;
+  int32_t map_size[3];
+  float max_distance;
+  int32_t map_resolution;
+  int32_t max_weight;
+} ws_map_meta;
+int ws_export_hdf5(ws_handle *h, const char *path, const ws_map_meta *meta, const float *poses7, int64_t n_poses);
+/* the same file from caller-held chunks (host only, no handle): chunk_xyz[n][3], chunk_data[n][64^3] */
+int ws_hdf5_write_chunks(const char *path, const ws_map_meta *meta, const int32_t *chunk_xyz,
+                         const uint32_t *chunk_data, int64_t n_chunks, const float *poses7, int64_t n_poses);
+
 /* ---- timing -------------------------------------------------------------------------------- */
 /* record cudaEvents around the hot kernels on the handle's stream (kind: 0 march, 1 brick list + merge, 2 registration
  * iteration, 3 replay) */

@@ -1,0 +1,94 @@
+"""ws_export_hdf5: the file HDF5GlobalMap leaves behind (src/map/hdf5_global_map.cpp), written
+without libhdf5.  CPU: the header declares the entry point.  GPU (the chunk store lives in a map handle): the
+file parses with tools/h5min.py -- an independent reader of the same format subset -- and holds the stored
+chunks, the write_meta attributes and the poses, bit for bit."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+from warpsense_b200 import api  # noqa: E402
+
+from helpers import make_pair  # noqa: E402
+
+
+def test_header_declares_export():
+    hdr = open(os.path.join(ROOT, "include", "warpsense_b200.h")).read()
+    assert "ws_export_hdf5" in hdr and "ws_map_meta" in hdr
+
+
+@pytest.mark.parametrize("n_chunks,n_poses", [(0, 0), (1, 1), (9, 3), (40, 300), (300, 9)])
+def test_writer_against_independent_reader(tmp_path, n_chunks, n_poses):
+    """Host-only: ws_hdf5_write_chunks -> tools/h5min.py (written from the format specification, checks
+    signatures, sizes, alignment, B-tree key order, heap free list, message counts).  More than 8 links need
+    several symbol-table nodes, more than 256 a two-level B-tree."""
+    import h5min
+    rng = np.random.default_rng(n_chunks * 1000 + n_poses)
+    chunks = {}
+    while len(chunks) < n_chunks:
+        chunks[tuple(int(v) for v in rng.integers(-12, 13, 3))] = rng.integers(0, 2 ** 32, 64 ** 3, dtype=np.uint32) \
+            if len(chunks) < 3 else np.full(64 ** 3, len(chunks), np.uint32)
+    poses = np.round(rng.normal(size=(n_poses, 7)).astype(np.float32) * 1000) / 1000
+    path = str(tmp_path / "m.h5")
+    api.write_map_hdf5(path, chunks, 600, (20, 20, 5), 0.6, 64, 640, poses)
+    f = h5min.File(path)
+    m = f.open("/map")
+    assert {k: v.item() for k, v in m["attrs"].items()} == {
+        "tau": 600, "map_size_x": 20, "map_size_y": 20, "map_size_z": 5, "max_distance": np.float32(0.6),
+        "map_resolution": 64, "max_weight": 640}
+    assert [e["name"] for e in m["links"]] == sorted("%d_%d_%d" % c for c in chunks)
+    for c, want in chunks.items():
+        d = f.open("/map/%d_%d_%d" % c)["data"]
+        assert d.dtype == np.dtype("<u4") and np.array_equal(d, want)
+    assert [e["name"] for e in f.open("/poses")["links"]] == sorted(str(i) for i in range(n_poses))
+    for i in range(n_poses):
+        assert np.array_equal(f.open("/poses/%d/pose" % i)["data"], poses[i])
+    assert sum(1 for _ in f.walk()) == 3 + n_chunks + 2 * n_poses
+    with pytest.raises(h5min.H5Error):                      # the reader does notice damage
+        raw = bytearray(open(path, "rb").read())
+        raw[40:48] = b"\xff" * 8          # end-of-file address
+        open(path, "wb").write(bytes(raw))
+        g = h5min.File(path)
+        list(g.walk())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_poses", [0, 3])
+def test_export_roundtrip(tmp_path, n_poses):
+    import h5min
+    rng = np.random.default_rng(5)
+    res, tau, mw = 64, 600, 640
+    om, hm, tsdf = make_pair((33, 33, 33), tau, mw, res)
+    hm.data[:] = rng.integers(0, 2 ** 32, size=hm.data.shape, dtype=np.uint32)
+    tsdf.avg_map().to_device(api.DeviceMap(hm))
+    for new_pos in ([40, 0, 0], [40, -70, 5], [-30, 10, 90]):     # spread the map over several 64^3 chunks
+        tsdf.shift(new_pos)
+    tsdf.write_back()
+    chunks = tsdf.chunk_list()
+    assert len(chunks) >= 8
+    poses = np.round(rng.normal(size=(n_poses, 7)).astype(np.float32) * 1000) / 1000
+    path = str(tmp_path / "map.h5")
+    tsdf.export_hdf5(path, tau, (20, 20, 5), 0.6, res, mw, poses)
+    f = h5min.File(path)
+    m = f.open("/map")
+    assert {k: v.item() for k, v in m["attrs"].items()} == {
+        "tau": tau, "map_size_x": 20, "map_size_y": 20, "map_size_z": 5, "max_distance": np.float32(0.6),
+        "map_resolution": res, "max_weight": mw}
+    assert m["attrs"]["max_distance"].dtype == np.float32 and m["attrs"]["tau"].dtype == np.int32
+    names = [e["name"] for e in m["links"]]
+    assert sorted(names) == sorted("%d_%d_%d" % tuple(c) for c in chunks)     # tag_from_chunk_pos
+    for c in chunks:
+        d = f.open("/map/%d_%d_%d" % tuple(c))["data"]
+        assert d.dtype == np.dtype("<u4") and d.shape == (64 ** 3,)
+        assert np.array_equal(d, tsdf.chunk(*c).reshape(-1))
+    p = f.open("/poses")
+    assert [e["name"] for e in p["links"]] == sorted(str(i) for i in range(n_poses))
+    for i in range(n_poses):
+        d = f.open("/poses/%d/pose" % i)["data"]
+        assert d.dtype == np.dtype("<f4") and np.array_equal(d, poses[i])
+    assert sum(1 for _ in f.walk()) == 3 + len(chunks) + 2 * n_poses
+    tsdf.close()

@@ -302,6 +302,16 @@ class TSDFCuda:
         rc = hd.L.ws_store_get_chunk(hd.h, int(cx), int(cy), int(cz), out.ctypes.data_as(C.POINTER(C.c_uint32)))
         return out if rc == _lib.WS_OK else None
 
+    def export_hdf5(self, path, tau, map_size, max_distance, map_resolution, max_weight, poses7=None):
+        """HDF5GlobalMap's file (hdf5_global_map.cpp): stored chunks, /map attributes, /poses/<n>/pose.
+        `poses7`: [n,7] float32 rows x y z qx qy qz qw as write_pose rounds them.  write_back() first to
+        include the local map."""
+        meta = _lib.MapMeta(int(tau), (C.c_int32 * 3)(*[int(v) for v in map_size]), float(max_distance),
+                            int(map_resolution), int(max_weight))
+        p = np.zeros((0, 7), np.float32) if poses7 is None else np.ascontiguousarray(poses7, np.float32).reshape(-1, 7)
+        self._hd.check(self._hd.L.ws_export_hdf5(self._hd.h, str(path).encode(), C.byref(meta),
+                                                 p.ctypes.data_as(C.POINTER(C.c_float)), len(p)))
+
     def sync(self):
         self._hd.check(self._hd.L.ws_sync(self._hd.h))
 
@@ -605,6 +615,23 @@ class TSDFRegistration(TSDFMapping):
             T, _ = self.reg_.register_cloud(cloud, pretransform, r.max_iterations, r.it_weight_gradient, r.epsilon,
                                             self.params_.map.resolution, host_solve=host_solve)
         return T
+
+
+def write_map_hdf5(path, chunks, tau, map_size, max_distance, map_resolution, max_weight, poses7=None):
+    """HDF5GlobalMap's file from host data (no GPU): `chunks` maps (cx, cy, cz) -> uint32[64^3]."""
+    L = _lib.load()
+    meta = _lib.MapMeta(int(tau), (C.c_int32 * 3)(*[int(v) for v in map_size]), float(max_distance),
+                        int(map_resolution), int(max_weight))
+    keys = list(chunks.keys())
+    xyz = np.ascontiguousarray(np.array(keys, np.int32).reshape(-1, 3))
+    data = np.ascontiguousarray(np.stack([np.asarray(chunks[k], np.uint32).reshape(64 ** 3) for k in keys])
+                                if keys else np.zeros((0, 64 ** 3), np.uint32))
+    p = np.zeros((0, 7), np.float32) if poses7 is None else np.ascontiguousarray(poses7, np.float32).reshape(-1, 7)
+    rc = L.ws_hdf5_write_chunks(str(path).encode(), C.byref(meta), xyz.ctypes.data_as(_i32p),
+                                data.ctypes.data_as(C.POINTER(C.c_uint32)), len(keys),
+                                p.ctypes.data_as(C.POINTER(C.c_float)), len(p))
+    if rc != _lib.WS_OK:
+        raise _lib.WarpsenseError(rc, "ws_hdf5_write_chunks failed")
 
 
 class MappingFeed:

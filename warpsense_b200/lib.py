@@ -33,6 +33,11 @@ class UpdateCounters(C.Structure):
         return {k: (int(v) if isinstance(v, int) else [int(x) for x in v]) for k, v in d.items()}
 
 
+class MapMeta(C.Structure):
+    _fields_ = [("tau", C.c_int32), ("map_size", C.c_int32 * 3), ("max_distance", C.c_float),
+                ("map_resolution", C.c_int32), ("max_weight", C.c_int32)]
+
+
 class WarpsenseError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("warpsense_b200 error %d: %s" % (code, msg))
@@ -97,6 +102,8 @@ def _signatures():
         "ws_store_num_chunks": (C.c_int64, [hp]),
         "ws_store_chunk_list": (C.c_int, [hp, i32p, C.c_int64]),
         "ws_store_get_chunk": (C.c_int, [hp, C.c_int32, C.c_int32, C.c_int32, u32p]),
+        "ws_export_hdf5": (C.c_int, [hp, C.c_char_p, C.POINTER(MapMeta), f32p, C.c_int64]),
+        "ws_hdf5_write_chunks": (C.c_int, [C.c_char_p, C.POINTER(MapMeta), i32p, u32p, C.c_int64, f32p, C.c_int64]),
         "ws_launch_count": (C.c_int64, [hp]),
         "ws_profile_enable": (C.c_int, [hp, C.c_int32]),
         "ws_profile_reset": (C.c_int, [hp]),
