@@ -16,6 +16,7 @@
 // marshals arguments.  CUDA failures throw std::runtime_error (the reference prints and exit(1)s,
 // include/warpsense/cuda/common.cuh:10-21).
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdint>
@@ -72,6 +73,7 @@ struct TSDFEntry
 struct MapParams
 {
   int resolution = 64;
+  float max_distance = 0.6f;
   int tau = 600;           // int(max_distance * 1000)
   int max_weight = 640;    // max_weight * WEIGHT_RESOLUTION
   float shift = 3.0f;      // metres the sensor must move before the local map is shifted
@@ -80,6 +82,7 @@ struct MapParams
   {
     MapParams p;
     p.resolution = resolution_mm;
+    p.max_distance = max_distance_m;
     p.tau = (int)(max_distance_m * 1000.f);
     p.max_weight = max_weight * WEIGHT_RESOLUTION;
     p.shift = shift_m;
@@ -380,6 +383,55 @@ struct TSDFRegistration : public TSDFMapping
              "register_cloud");
     if (iterations) *iterations = it;
     return out;
+  }
+
+  // App::preprocess (src/warpsense/app.cpp:118-148) on the device: the x/y/z floats of a PointCloud2 payload
+  // (metres, `point_step` bytes apart) -> unique map-frame points, left on the device for track_scan /
+  // ws_update_tsdf_device and copied into `scan_points` as well.
+  void preprocess(const float *xyz, int64_t n, int point_step, const Matrix4f &pose, std::vector<rmagine::Pointi> &scan_points)
+  {
+    scan_points.resize((size_t)std::max<int64_t>(n, 1));
+    int64_t m = 0;
+    std::unique_lock<std::shared_mutex> lock(mutex_);
+    ws_check(tsdf_->device_map(),
+             ws_preprocess_scan(tsdf_->device_map(), xyz, n, point_step, 0, pose.m, params_.map.resolution,
+                                reinterpret_cast<ws_point *>(scan_points.data()), &m), "preprocess");
+    scan_points.resize((size_t)m);
+  }
+
+  // App::cloud_callback's per-scan sequence (app.cpp:65-112) as one stream of kernels and one host
+  // synchronisation: register_cloud(identity) -> pose = X * prior_pose -> update_tsdf(registered cloud, pose).
+  // Returns the new pose; `transform` (optional) receives X.
+  Matrix4f track_scan(const std::vector<rmagine::Pointi> &cloud, const Matrix4f &prior_pose, Matrix4f *transform = nullptr,
+                      int *iterations = nullptr)
+  {
+    Matrix4f X{}, pose{};
+    int32_t it = 0;
+    std::unique_lock<std::shared_mutex> lock(mutex_);
+    ws_check(tsdf_->device_map(),
+             ws_track_scan(tsdf_->device_map(), reinterpret_cast<const ws_point *>(cloud.data()), (int64_t)cloud.size(), 0,
+                           prior_pose.m, params_.registration.max_iterations, params_.registration.it_weight_gradient,
+                           params_.registration.epsilon, params_.map.resolution, X.m, pose.m, &it),
+             "track_scan");
+    if (transform) *transform = X;
+    if (iterations) *iterations = it;
+    return pose;
+  }
+
+  // HDF5GlobalMap::write_back + the file it leaves (hdf5_global_map.cpp:140-221): local map into the chunk
+  // store, then chunks, /map attributes and poses (rows x y z qx qy qz qw) into an HDF5 file.
+  void export_map(const std::string &path, const std::vector<float> &poses7 = {})
+  {
+    std::unique_lock<std::shared_mutex> lock(mutex_);
+    ws_check(tsdf_->device_map(), ws_write_back(tsdf_->device_map()), "write_back");
+    ws_map_meta meta;
+    meta.tau = params_.map.tau;
+    for (int a = 0; a < 3; a++) meta.map_size[a] = params_.map.size[a];
+    meta.max_distance = params_.map.max_distance;
+    meta.map_resolution = params_.map.resolution;
+    meta.max_weight = params_.map.max_weight;
+    ws_check(tsdf_->device_map(),
+             ws_export_hdf5(tsdf_->device_map(), path.c_str(), &meta, poses7.data(), (int64_t)(poses7.size() / 7)), "export_map");
   }
   std::unique_ptr<RegistrationCuda> reg_;
 };

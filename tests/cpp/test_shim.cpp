@@ -1,6 +1,7 @@
 // C++ host-side test of include/warpsense_b200.hpp: the reference's own known-answer test for update_tsdf
 // (test/map.cpp:9-90 == test/cuda.cpp:268-347 under /root/reference, "G1") and a registration round trip,
 // written against the reference's class names.  Needs a CUDA device; built and run by tests/test_cpp_shim.py.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include "warpsense_b200.hpp"
@@ -95,6 +96,34 @@ int main()
     CHECK(local_map->get_pos()[0] == 54);               // floor(3500 / 64)
     const TSDFEntry after = local_map->value(39, 0, 0);
     CHECK(before.raw == after.raw);
+    // App::preprocess on the device: duplicates collapse, the all-below-0.3 return is dropped (app.cpp:128)
+    const float xyz[] = { 1.00f, 2.00f, 0.50f,   1.01f, 2.01f, 0.51f,   0.1f, 0.2f, -0.4f,   -3.0f, 0.5f, 0.2f };
+    std::vector<rmagine::Pointi> pre;
+    gpu.preprocess(xyz, 4, 12, Matrix4f::Identity(), pre);
+    CHECK(pre.size() == 2);
+    CHECK(pre[0].x == 992 && pre[0].y == 2016 && pre[0].z == 480);      // voxel centres at 64 mm, res/2 = 32
+    // the fused per-scan call gives the pose = X * prior
+    std::vector<rmagine::Pointi> cloud2 = scan;
+    Matrix4f X{};
+    int it2 = 0;
+    const Matrix4f newpose = gpu.track_scan(cloud2, pose, &X, &it2);
+    CHECK(it2 == 50);
+    CHECK(std::fabs(newpose(0, 3) - (X(0, 3) + pose(0, 3))) < 1.0f);
+    // global-map file: HDF5 signature and a plausible size (64^3 uint32 per stored chunk)
+    const char *path = "/tmp/ws_shim_map.h5";
+    gpu.export_map(path, { 1.f, 2.f, 3.f, 0.f, 0.f, 0.f, 1.f });
+    FILE *fp = std::fopen(path, "rb");
+    CHECK(fp != nullptr);
+    if (fp)
+    {
+      unsigned char sig[8] = { 0 };
+      CHECK(std::fread(sig, 1, 8, fp) == 8);
+      CHECK(sig[0] == 0x89 && sig[1] == 'H' && sig[2] == 'D' && sig[3] == 'F');
+      std::fseek(fp, 0, SEEK_END);
+      CHECK(std::ftell(fp) > 64L * 64 * 64 * 4);
+      std::fclose(fp);
+      std::remove(path);
+    }
   }
   std::printf("cpp shim ok\n");
   return 0;
