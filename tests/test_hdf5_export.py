@@ -65,7 +65,8 @@ def test_export_roundtrip(tmp_path, n_poses):
     om, hm, tsdf = make_pair((33, 33, 33), tau, mw, res)
     hm.data[:] = rng.integers(0, 2 ** 32, size=hm.data.shape, dtype=np.uint32)
     tsdf.avg_map().to_device(api.DeviceMap(hm))
-    for new_pos in ([40, 0, 0], [40, -70, 5], [-30, 10, 90]):     # spread the map over several 64^3 chunks
+    # spread the map over several 64^3 chunks (one shift moves at most one map size, hdf5_local_map.cpp:63-65)
+    for new_pos in ([30, 0, 0], [30, -30, 5], [40, -60, 30], [10, -70, 60], [-20, -40, 90]):
         tsdf.shift(new_pos)
     tsdf.write_back()
     chunks = tsdf.chunk_list()
