@@ -38,7 +38,7 @@ GN_ITERS = 20
 IT_WEIGHT = 0.1
 EPSILON = 0.0          # |.| < 0 never holds: exactly GN_ITERS iterations
 TAU, MAX_WEIGHT = 1000, 640
-# DRAM bytes of one update_tsdf on the default workload, from the committed ncu capture (profiles/r01j_*):
+# DRAM bytes of one update_tsdf on the default workload, from the committed ncu capture (profiles/r01m_*):
 # setup 1.6 + march 221.2 + 538.9 + brick_list 1.1 + merge 353.0 + 380.3 + replay 663.2 + 34.4 MB
 NCU_TRAFFIC_BYTES_PER_SCAN = 2193.7e6
 REF_SUBSAMPLE = 8      # --impl reference: every 8th ray per step (bounded sample)
@@ -70,54 +70,98 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every few
+    milliseconds from a thread (the timed region of the default run lasts tens of milliseconds -- too short for
+    `nvidia-smi -lms`), nvidia-smi as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.source = None
+
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        try:
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)): "sw_power_cap",
+            }
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(mx)
+                r = int(get_reasons(h))
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.008)
+        finally:
+            nv.nvmlShutdown()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except (ValueError, IndexError):
+                pass
+        return self.gpu
+
+    def _smi_loop(self):
+        proc = subprocess.Popen(["nvidia-smi", "-i", str(self._physical_index()), "--query-gpu=" + self.Q,
+                                 "--format=csv,noheader,nounits", "-lms", "20"],
+                                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in proc.stdout:
+                parts = [p.strip() for p in ln.split(",")]
+                if len(parts) >= 9:
+                    try:
+                        self.sm.append(float(parts[1])); self.mx.append(float(parts[2]))
+                    except ValueError:
+                        continue
+                    for name, val in zip(names, parts[5:9]):
+                        if val.lower().startswith("active"):
+                            self.reasons.add(name)
+                if self.stop_flag.is_set():
+                    break
+        finally:
+            proc.terminate()
+
+    def _run(self):
+        try:
+            self.source = "nvml"
+            self._nvml_loop()
+        except Exception:
+            try:
+                self.source = "nvidia-smi"
+                self._smi_loop()
+            except Exception:
+                self.source = None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        time.sleep(0.02)           # let the first sample land before the timed region begins
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_flag.set()
+        if self.thread:
+            self.thread.join(timeout=3)
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock sampling unavailable"]}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": max(self.mx), "samples": len(self.sm),
+                "reasons": sorted(self.reasons), "source": self.source}
 
 
 def make_frames(args, count):
@@ -372,7 +416,7 @@ def run_native(args):
                 "traffic": NCU_TRAFFIC_BYTES_PER_SCAN if (world == 1 and not args.update_only and args.grid == 512 and args.res == 50
                                                           and args.beams == 128 and args.cols == 1024) else None,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of setup + march + brick_list + merge + replay, one "
-                                  "launch each, ncu --set full capture of this workload (profiles/r01j_summary.md)",
+                                  "launch each, ncu --set full capture of this workload (profiles/r01m_summary.md)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_scan": upd_bytes,
                 "formula": "12*N + 8*T (SURVEY.md 8d), N=%d points, T=%d touched voxels, C=%d candidates" % (N, T_vox, C_cand),
