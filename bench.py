@@ -39,8 +39,8 @@ IT_WEIGHT = 0.1
 EPSILON = 0.0          # |.| < 0 never holds: exactly GN_ITERS iterations
 TAU, MAX_WEIGHT = 1000, 640
 # DRAM bytes of one update_tsdf on the default workload, from the committed ncu capture (profiles/r01m_*):
-# setup 1.6 + march 221.2 + 538.9 + brick_list 1.1 + merge 353.0 + 380.3 + replay 663.2 + 34.4 MB
-NCU_TRAFFIC_BYTES_PER_SCAN = 2193.7e6
+# setup 1.6 + march 221.1 + 543.2 + brick_list 1.1 + merge 353.0 + 379.4 + replay 666.0 + 34.4 MB
+NCU_TRAFFIC_BYTES_PER_SCAN = 2199.8e6
 REF_SUBSAMPLE = 8      # --impl reference: every 8th ray per step (bounded sample)
 
 
