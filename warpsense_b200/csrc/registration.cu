@@ -466,29 +466,44 @@ WS_D void warp_gn_solve(const u64 *s_total, GnState *st, double *s_lu, int *s_pe
     if (c == r) row[c] += damp * 1.0;
   }
   int prow = r;
+  // LU with partial pivoting, one row per lane.  Rows are published to shared memory once per step and every
+  // lane reads the pivot column and the pivot row from there (independent loads) -- the same arithmetic in
+  // the same order as before, without the ~40 dependent warp shuffles per step that made the solve 3.7 us
 #pragma unroll
   for (int k = 0; k < 6; k++)
   {
-    // partial pivoting: first row (lowest index >= k) with the largest |lu[r][k]|
-    double best = (lane < 6 && lane >= k) ? fabs(row[k]) : -1.0;
-    int bidx = lane;
-#pragma unroll
-    for (int o = 4; o >= 1; o >>= 1)
+    if (lane < 6)
     {
-      const double ob = __shfl_xor_sync(FULL, best, o);
-      const int oi = __shfl_xor_sync(FULL, bidx, o);
-      if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
-    }
-    const int piv = __shfl_sync(FULL, bidx, 0);
-    // swap rows k and piv
-    const int src = lane == k ? piv : (lane == piv ? k : lane);
 #pragma unroll
-    for (int c = 0; c < 6; c++) row[c] = __shfl_sync(FULL, row[c], src);
-    prow = __shfl_sync(FULL, prow, src);
-    // eliminate below the pivot
+      for (int c = 0; c < 6; c++) s_lu[lane * 6 + c] = row[c];
+      s_perm[lane] = prow;
+    }
+    __syncwarp();
+    // partial pivoting: first row (lowest index >= k) with the largest |lu[r][k]|
+    int piv = k;
+    double best = fabs(s_lu[k * 6 + k]);
+#pragma unroll
+    for (int rr = 1; rr < 6; rr++)
+    {
+      if (rr > k)
+      {
+        const double v = fabs(s_lu[rr * 6 + k]);
+        if (v > best) { best = v; piv = rr; }
+      }
+    }
+    // swap rows k and piv; the pivot row is the pre-swap row `piv`
+    const int src = lane == k ? piv : (lane == piv ? k : lane);
     double prk[6];
 #pragma unroll
-    for (int c = 0; c < 6; c++) prk[c] = __shfl_sync(FULL, row[c], k);
+    for (int c = 0; c < 6; c++) prk[c] = s_lu[piv * 6 + c];
+    if (lane < 6 && src != lane)
+    {
+#pragma unroll
+      for (int c = 0; c < 6; c++) row[c] = s_lu[src * 6 + c];
+      prow = s_perm[src];
+    }
+    __syncwarp();
+    // eliminate below the pivot
     if (lane < 6 && lane > k)
     {
       row[k] /= prk[k];
@@ -601,6 +616,10 @@ reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopPa
 
   for (int it = 0; it < rp.max_iterations; it++)
   {
+#ifdef WS_REG_TIMING
+    unsigned long long tstamp[4];
+    tstamp[0] = reg_global_ns();
+#endif
     float T[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) T[i] = s_st.T[i];
@@ -620,6 +639,9 @@ reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopPa
     const i64 mine = warp_transpose_reduce(sum, lane);
     s_w[warp][lane] = (u64)mine;
     __syncthreads();
+#ifdef WS_REG_TIMING
+    tstamp[1] = reg_global_ns();
+#endif
 #ifdef WS_REG_GRIDSYNC
     u64 *row = partials + ((size_t)(it & 1) * gridDim.x + blockIdx.x) * REG_NSLOT;
     if (tid < REG_NSLOT)
@@ -744,8 +766,16 @@ reg_loop_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const RegLoopPa
         break;
       }
     }
+#ifdef WS_REG_TIMING
+    tstamp[2] = reg_global_ns();
+#endif
     if (warp == 0) warp_gn_solve(s_total, &s_st, s_lu, s_perm, s_inv, s_xi, rp.it_weight_gradient, rp.epsilon, lane);
     __syncthreads();
+#ifdef WS_REG_TIMING
+    tstamp[3] = reg_global_ns();
+    if (blockIdx.x == 0 && tid == 0 && trace && it < trace_cap)
+      for (int q = 0; q < 4; q++) trace[(size_t)it * WS_NSUM + q] = tstamp[q];
+#endif
     if (s_st.finished) break;
   }
 
