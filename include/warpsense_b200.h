@@ -196,6 +196,14 @@ int ws_peer_set_timeout(ws_handle *h, double seconds);
 int ws_slab_layout(int32_t size_x, int32_t rank, int32_t world, int32_t *own_lo, int32_t *own_hi,
                    int32_t *resident_cols, int32_t cap);
 
+/* which ring-x brick columns (8 rows each) a handle owns / keeps resident: contiguous slabs by default, stripes
+ * of WS_STRIPE_COLS columns dealt round-robin to the ranks when that environment variable is set (the same
+ * value on every rank).  Returns the number of columns. */
+int ws_shard_columns(const ws_handle *h, uint8_t *owned, uint8_t *resident, int32_t cap);
+/* the same without a handle (host only): stripe_cols <= 0 gives the slabs of ws_slab_layout */
+int ws_shard_layout(int32_t size_x, int32_t rank, int32_t world, int32_t stripe_cols, uint8_t *owned, uint8_t *resident,
+                    int32_t cap);
+
 /* test hook for the reduction shape (test/cuda.cpp:416-532): sums of n Jacobians with values */
 int ws_test_reduce(ws_handle *h, const int64_t *jacobis6, const int32_t *values, int64_t n,
                    int64_t H[36], int64_t g[6], int32_t *err, int32_t *cnt);

@@ -2,6 +2,7 @@
 (about 6 s of single-threaded CPU work), then size-independent properties on the following scans --
 results independent of the number of slabs the map is sharded into, registration sums equal to the oracle's on
 the device-built map, counter identities, and run-to-run determinism."""
+import os
 import zlib
 
 import numpy as np
@@ -65,10 +66,15 @@ def test_full_size_properties_sharding_and_determinism(stream):
         pos_ = np.zeros(3, np.int32)
         data_ = None
 
-    def run(world):
+    def run(world, stripe=0):
         """three scans through `world` slab-sharded handles on this GPU; returns per-scan counters, the grids'
         owned slabs stitched together (crc) and the registration traces"""
-        hs = [api.TSDFCuda(_View(), TAU, MW, RES, rank=r, world=world, upload=False) for r in range(world)]
+        if stripe:
+            os.environ["WS_STRIPE_COLS"] = str(stripe)
+        try:
+            hs = [api.TSDFCuda(_View(), TAU, MW, RES, rank=r, world=world, upload=False) for r in range(world)]
+        finally:
+            os.environ.pop("WS_STRIPE_COLS", None)
         counters = []
         for k in range(3):
             f = s.frame(k)
@@ -79,12 +85,13 @@ def test_full_size_properties_sharding_and_determinism(stream):
                 cs.append(t.counters())
             counters.append(cs)
         row = size[1] * size[2]
-        crc = 0
+        whole = np.zeros((size[0], row), np.uint32)
         back = api.HostLocalMap(*size, TAU, 0)
         for r, t in enumerate(hs):
-            lo, hi, _ = api.slab_layout(size[0], r, world)
+            rows = t.owned_rows()
             t.avg_map().to_host(api.DeviceMap(back))
-            crc = zlib.crc32(back.data[lo * row:hi * row].view(np.uint8), crc)
+            whole[rows] = back.data.reshape(-1, row)[rows]
+        crc = zlib.crc32(whole.view(np.uint8))
         # registration sums of the slabs add up (host-side sum stands in for the exchange)
         cloud = s.frame(3, prior_pose=s.pose(2))["points_prior"]
         regs = [api.RegistrationCuda(t) for t in hs]
@@ -108,6 +115,8 @@ def test_full_size_properties_sharding_and_determinism(stream):
     c2, crc2, sums2 = run(2)
     assert crc2 == crc1, "the map depends on the number of slabs"
     assert np.array_equal(sums2, sums1), "registration sums depend on the number of slabs"
+    c3, crc3, sums3 = run(3, stripe=6)                      # round-robin stripes of 6 brick columns
+    assert crc3 == crc1 and np.array_equal(sums3, sums1), "the result depends on the partition (stripes)"
     for k in range(3):
         one = c1[k][0]
         assert one["n_written"] <= one["n_touched"] <= one["n_candidates"]

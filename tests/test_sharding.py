@@ -35,6 +35,25 @@ def test_slab_layout_is_a_partition_with_halos(size_x, world):
     assert (owned == 1).all(), "every ring-x row is owned by exactly one rank"
 
 
+@pytest.mark.parametrize("size_x,world,stripe", [(97, 2, 2), (97, 3, 1), (513, 2, 8), (513, 4, 4), (513, 8, 4), (513, 8, 8),
+                                                 (2049, 8, 16), (129, 3, 0), (65, 8, 1)])
+def test_stripe_layout_is_a_partition_with_halos(size_x, world, stripe):
+    """Round-robin stripes: every brick column has exactly one owner, and every rank keeps resident the
+    columns that hold the rows just outside each of its stripes (registration reads x +- 1)."""
+    nbx = (size_x + 7) // 8
+    owners = np.zeros(nbx, np.int32)
+    for r in range(world):
+        own, res = api.shard_layout(size_x, r, world, stripe)
+        owners += own
+        assert own.any() and (res | ~own).all()
+        for c in np.nonzero(own)[0]:
+            lo_row, hi_row = c * 8, min(c * 8 + 8, size_x) - 1
+            assert res[((lo_row - 1) % size_x) // 8] and res[((hi_row + 1) % size_x) // 8]
+        if stripe and nbx // stripe >= world:
+            assert all(((c // stripe) % world == r) == bool(own[c]) for c in range(nbx))
+    assert (owners == 1).all()
+
+
 def test_slab_layout_rejects_more_ranks_than_columns():
     with pytest.raises(ValueError):
         api.slab_layout(17, 0, 4)      # 3 brick columns, 4 ranks: rank 0 gets none
@@ -117,8 +136,12 @@ def _slab_rows(hm_size, lo, hi):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,ring_offset", [(2, None), (3, None), (4, (30, 5, 60)), (2, (93, 0, 11))])
-def test_sharded_handles_match_oracle_on_one_gpu(world, ring_offset):
+@pytest.mark.parametrize("world,ring_offset,stripe", [(2, None, 0), (3, None, 0), (4, (30, 5, 60), 0), (2, (93, 0, 11), 0),
+                                                      (2, None, 2), (3, (30, 5, 60), 1), (4, None, 1), (2, (93, 0, 11), 3)])
+def test_sharded_handles_match_oracle_on_one_gpu(world, ring_offset, stripe, monkeypatch):
+    """stripe = 0: contiguous x slabs; stripe = k: stripes of k brick columns dealt round-robin (WS_STRIPE_COLS)."""
+    if stripe:
+        monkeypatch.setenv("WS_STRIPE_COLS", str(stripe))
     res, tau, mw, side = 100, 1000, 640, 96
     s = ScanStream(32, 256, side, res)
     om = orc.LocalMap(side, side, side, tau, 0)
@@ -145,12 +168,16 @@ def test_sharded_handles_match_oracle_on_one_gpu(world, ring_offset):
             touched += c["n_touched"]
         assert touched >= st["n_touched"]                        # halo columns are updated twice
         assert cands >= st["n_candidates"]
+    covered = np.zeros(int(hm.size[0]), np.int32)
+    row = int(hm.size[1]) * int(hm.size[2])
     for r, (t, _) in enumerate(ranks):
-        lo, hi, _ = api.slab_layout(int(hm.size[0]), r, world)
+        rows = t.owned_rows()
+        covered += rows
         back = api.HostLocalMap(side, side, side, tau, 0)
         t.avg_map().to_host(api.DeviceMap(back))
-        sl = _slab_rows(hm.size, lo, hi)
-        assert np.array_equal(back.data[sl], om.data[sl]), "rank %d slab differs from the oracle" % r
+        got = back.data.reshape(-1, row)[rows]
+        assert np.array_equal(got, om.data.reshape(-1, row)[rows]), "rank %d: owned rows differ from the oracle" % r
+    assert (covered == 1).all(), "the owned rows of the ranks are not a partition of the ring"
     # ---- registration: host-side sum of the 29 int64 stands in for ncclAllReduce ----
     cloud = s.frame(3, prior_pose=s.pose(2))["points_prior"].copy()
     oT, oit, otr = orc.register_cloud(om, cloud.copy(), np.eye(4, dtype=np.float32), 8, 0.1, 0.0, res, trace=True)

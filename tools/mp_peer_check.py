@@ -59,11 +59,11 @@ def main():
             pos, up = fp.convert_pose_to_gpu(pose, res)
             orc.update_tsdf(om, cloud, pos, up, tau, mw, res)
             tsdf.update_tsdf(cloud, pos, up)
-        lo, hi, _ = api.slab_layout(int(hm.size[0]), rank, world)
+        rows = tsdf.owned_rows()
         back = api.HostLocalMap(side, side, side, tau, 0)
         tsdf.avg_map().to_host(api.DeviceMap(back))
         row = int(hm.size[1]) * int(hm.size[2])
-        assert np.array_equal(back.data[lo * row:hi * row], om.data[lo * row:hi * row]), "rank %d slab differs" % rank
+        assert np.array_equal(back.data.reshape(-1, row)[rows], om.data.reshape(-1, row)[rows]), "rank %d: owned rows differ" % rank
     dist.barrier()
     tsdf.close()
     if rank == 0:

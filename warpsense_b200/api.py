@@ -129,6 +129,16 @@ def slab_layout(size_x, rank, world):
     return lo.value, hi.value, [int(c) for c in cols[:n]]
 
 
+def shard_layout(size_x, rank, world, stripe_cols=0):
+    """Host-only: (owned, resident) boolean arrays over the ring-x brick columns (ws_shard_layout)."""
+    L = _lib.load()
+    own, res = (C.c_uint8 * 512)(), (C.c_uint8 * 512)()
+    nbx = L.ws_shard_layout(int(size_x), int(rank), int(world), int(stripe_cols), own, res, 512)
+    if nbx < 0:
+        raise _lib.WarpsenseError(nbx, "ws_shard_layout")
+    return np.frombuffer(own, np.uint8, nbx).astype(bool), np.frombuffer(res, np.uint8, nbx).astype(bool)
+
+
 class _Handle:
     """Owns one ws_handle (RAII like the reference's device wrappers; copy is not supported)."""
 
@@ -256,6 +266,15 @@ class TSDFCuda:
         n = C.c_int64()
         ptr = self._hd.L.ws_scan_points_device(self._hd.h, C.byref(n))
         return ptr, n.value
+
+    def owned_rows(self):
+        """Boolean mask over the ring-x rows this handle owns (contiguous slab or round-robin stripes)."""
+        hd = self._hd
+        own = (C.c_uint8 * 512)()
+        nbx = hd.check(hd.L.ws_shard_columns(hd.h, own, None, 512))
+        size_x = int(self._avg.params()[0][0])
+        rows = np.repeat(np.frombuffer(own, np.uint8, nbx).astype(bool), 8)[:size_x]
+        return rows
 
     def avg_map(self):
         return self._avg

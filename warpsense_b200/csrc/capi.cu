@@ -88,26 +88,52 @@ void ensure_points(ws_pt **buf, size_t *cap, size_t n)
   *cap = want;
 }
 
-// Host-only: which ring-x rows rank `rank` of `world` owns and which brick columns it keeps resident
-// (contiguous slabs in ring coordinates + one halo row each side).
-bool slab_layout(int size_x, int rank, int world, int *own_lo, int *own_hi, std::vector<int> &cols)
+// Host-only: which ring-x brick columns rank `rank` of `world` owns and which it keeps resident.
+//   stripe_cols <= 0 : contiguous slabs in ring coordinates;
+//   stripe_cols  > 0 : stripes of `stripe_cols` columns dealt round-robin to the ranks -- every rank then
+//                      holds a part of every ray whatever the sensor position (balanced march), at the price
+//                      of one halo column on each side of every stripe.
+// Resident = owned columns + the columns holding the rows just outside (the registration stencil reads x+-1).
+bool shard_layout(int size_x, int rank, int world, int stripe_cols, std::vector<char> &owned, std::vector<int> &cols)
 {
   const int nbx = (size_x + WS_BRICK - 1) / WS_BRICK;
-  const int c_lo = (int)((i64)nbx * rank / world), c_hi = (int)((i64)nbx * (rank + 1) / world);
-  if (c_hi <= c_lo) return false;
-  *own_lo = c_lo * WS_BRICK;
-  *own_hi = std::min(c_hi * WS_BRICK, size_x);
-  cols.clear();
-  if (world == 1) for (int c = 0; c < nbx; c++) cols.push_back(c);
+  owned.assign((size_t)nbx, 0);
+  if (stripe_cols > 0 && nbx / stripe_cols >= world)
+  {
+    for (int c = 0; c < nbx; c++) owned[(size_t)c] = ((c / stripe_cols) % world) == rank;
+  }
   else
   {
-    const int below = (*own_lo - 1 + size_x) % size_x, above = *own_hi % size_x;
-    for (int c = c_lo; c < c_hi; c++) cols.push_back(c);
-    cols.push_back(below / WS_BRICK);
-    cols.push_back(above / WS_BRICK);
-    std::sort(cols.begin(), cols.end());
-    cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+    const int c_lo = (int)((i64)nbx * rank / world), c_hi = (int)((i64)nbx * (rank + 1) / world);
+    if (c_hi <= c_lo) return false;
+    for (int c = c_lo; c < c_hi; c++) owned[(size_t)c] = 1;
   }
+  cols.clear();
+  std::vector<char> res((size_t)nbx, 0);
+  for (int c = 0; c < nbx; c++)
+  {
+    if (!owned[(size_t)c]) continue;
+    res[(size_t)c] = 1;
+    if (world > 1)
+    {
+      const int lo_row = c * WS_BRICK, hi_row = std::min((c + 1) * WS_BRICK, size_x) - 1;
+      res[(size_t)(((lo_row - 1 + size_x) % size_x) / WS_BRICK)] = 1;
+      res[(size_t)(((hi_row + 1) % size_x) / WS_BRICK)] = 1;
+    }
+  }
+  for (int c = 0; c < nbx; c++) if (res[(size_t)c]) cols.push_back(c);
+  return !cols.empty();
+}
+
+// contiguous slabs: the owned rows as a range (ws_slab_layout)
+bool slab_layout(int size_x, int rank, int world, int *own_lo, int *own_hi, std::vector<int> &cols)
+{
+  std::vector<char> owned;
+  if (!shard_layout(size_x, rank, world, 0, owned, cols)) return false;
+  int lo = -1, hi = -1;
+  for (int c = 0; c < (int)owned.size(); c++) if (owned[(size_t)c]) { if (lo < 0) lo = c; hi = c; }
+  *own_lo = lo * WS_BRICK;
+  *own_hi = std::min((hi + 1) * WS_BRICK, size_x);
   return true;
 }
 
@@ -140,8 +166,12 @@ int create_impl(const int32_t size[3], int tau, int max_weight, int res, int dev
     // x-slab residency: this rank owns ring-x brick columns [c_lo, c_hi) plus the columns holding the
     // rows just outside (the registration stencil reads x+-1)
     std::vector<int> cols;
-    if (!slab_layout(g.size[0], rank, world, &g.own_lo, &g.own_hi, cols))
+    std::vector<char> owned;
+    int stripe_cols = 0;
+    if (const char *env = std::getenv("WS_STRIPE_COLS")) stripe_cols = std::atoi(env);
+    if (!shard_layout(g.size[0], rank, world, stripe_cols, owned, cols))
       throw std::invalid_argument("more ranks than ring-x brick columns");
+    for (int c = 0; c < WS_MAX_XBRICKS; c++) g.xown[c] = c < (int)owned.size() ? (unsigned char)owned[(size_t)c] : 0;
     g.full = (world == 1) ? 1 : 0;
     for (int c = 0; c < WS_MAX_XBRICKS; c++) g.xslot[c] = -1;
     for (size_t s = 0; s < cols.size(); s++) g.xslot[cols[s]] = (short)s;
@@ -877,6 +907,35 @@ int ws_slab_layout(int32_t size_x, int32_t rank, int32_t world, int32_t *own_lo,
   if (resident_cols)
     for (size_t i = 0; i < cols.size() && (int)i < cap; i++) resident_cols[i] = cols[i];
   return (int)cols.size();
+}
+
+int ws_shard_layout(int32_t size_x, int32_t rank, int32_t world, int32_t stripe_cols, uint8_t *owned, uint8_t *resident, int32_t cap)
+{
+  if (size_x < 1 || world < 1 || rank < 0 || rank >= world) return WS_ERR_INVALID;
+  std::vector<char> own;
+  std::vector<int> cols;
+  if (!shard_layout(size_x, rank, world, stripe_cols, own, cols)) return WS_ERR_INVALID;
+  const int nbx = (int)own.size();
+  for (int c = 0; c < nbx && c < cap; c++)
+  {
+    if (owned) owned[c] = (uint8_t)own[(size_t)c];
+    if (resident) resident[c] = 0;
+  }
+  if (resident)
+    for (int c : cols) if (c < cap) resident[c] = 1;
+  return nbx;
+}
+
+int ws_shard_columns(const ws_handle *h, uint8_t *owned, uint8_t *resident, int32_t cap)
+{
+  if (!h) return WS_ERR_INVALID;
+  const int nbx = h->g.nb[0];
+  for (int c = 0; c < nbx && c < cap; c++)
+  {
+    if (owned) owned[c] = h->g.xown[c];
+    if (resident) resident[c] = h->g.xslot[c] >= 0;
+  }
+  return nbx;
 }
 
 int ws_reg_solve(ws_handle *h, float it_weight_gradient, float epsilon)

@@ -269,7 +269,7 @@ reg_accum_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const int n, c
     dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy; dz = dz < 0 ? -dz : dz;
     if (dx > g.half[0] || dy > g.half[1] || dz > g.half[2]) continue;
     const int rx = ring_coord(bx, g.pos[0], g.offset[0], g.size[0]);
-    if (rx < g.own_lo || rx >= g.own_hi) continue;       // another rank sums this point
+    if (!g.xown[rx >> 3]) continue;                      // another rank sums this point
     const int ry = ring_coord(by, g.pos[1], g.offset[1], g.size[1]);
     const int rz = ring_coord(bz, g.pos[2], g.offset[2], g.size[2]);
     const uint32_t cur = g.grid[brick_of(g, rx, ry, rz) * WS_BRICK_VOX + brick_local(rx, ry, rz)];
@@ -382,7 +382,7 @@ WS_D void accumulate_cloud_point(const GridDesc &g, const int M[16], const int c
   dx = dx < 0 ? -dx : dx; dy = dy < 0 ? -dy : dy; dz = dz < 0 ? -dz : dz;
   if (dx > g.half[0] || dy > g.half[1] || dz > g.half[2]) return;                        // :68 throws
   const int rx = ring_coord(bx, g.pos[0], g.offset[0], g.size[0]);
-  if (rx < g.own_lo || rx >= g.own_hi) return;             // another rank sums this point
+  if (!g.xown[rx >> 3]) return;                            // another rank sums this point
   const int ry = ring_coord(by, g.pos[1], g.offset[1], g.size[1]);
   const int rz = ring_coord(bz, g.pos[2], g.offset[2], g.size[2]);
   const bool inner = !(dx > g.half[0] - 1 || dy > g.half[1] - 1 || dz > g.half[2] - 1);  // :76-81 throw otherwise

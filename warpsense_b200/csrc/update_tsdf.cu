@@ -89,15 +89,16 @@ struct Ray
 };
 
 // What the set-up pass leaves per ray for the march warps: six 16-byte words, staged in shared memory
-#define RAY_WORDS 6
+#define RAY_WORDS 8
+#define RAY_SEGS WS_MAX_XIV
 struct __align__(16) RaySetup
 {
   int p[3], distance;  // word 0
   int d[3], n_steps;   // word 1
   int iv[3], flags;    // word 2: bit 0 = small (fast path), bits 1.. = ray index
-  int seg[4];          // word 3: march-step ranges [seg[0], seg[1]) and [seg[2], seg[3]) this rank has to process
-  unsigned dq[3], pad0;    // word 4: DDA increments of 32 march steps per axis (fast path), quotient ...
-  unsigned drem[3], pad1;  // word 5: ... and remainder of |d| * 32 * h / distance
+  unsigned dq[3], pad0;    // word 3: DDA increments of 32 march steps per axis (fast path), quotient ...
+  unsigned drem[3], pad1;  // word 4: ... and remainder of |d| * 32 * h / distance
+  int seg[2 * RAY_SEGS];   // words 5-7: march-step ranges [seg[2k], seg[2k+1]) this rank has to process
 };
 static_assert(sizeof(RaySetup) == 16 * RAY_WORDS, "RaySetup layout");
 
@@ -284,7 +285,7 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const int pos_mm[3
   {
     const double rdist = 1.0 / (double)distance;
     const unsigned len0 = 1u + (unsigned)(start + lane) * (unsigned)P.half_res;
-    const int4 w4 = lds_word(ray_s + 4), w5 = lds_word(ray_s + 5);
+    const int4 w4 = lds_word(ray_s + 3), w5 = lds_word(ray_s + 4);
     const unsigned dq[3] = { (unsigned)w4.x, (unsigned)w4.y, (unsigned)w4.z };
     const unsigned dr[3] = { (unsigned)w5.x, (unsigned)w5.y, (unsigned)w5.z };
 #pragma unroll
@@ -509,14 +510,17 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const int pos_mm[3
 // coordinate is monotone in the step index, so every resident x interval (already widened by the fan's
 // reach, UpdateParams::xiv_*) maps to one contiguous step range.  Conservative by two steps either side;
 // the exact per-candidate residency test stays in the march.
-WS_D void ray_segments(const UpdateParams &P, const Ray &r, int seg[4])
+WS_D void ray_segments(const UpdateParams &P, const Ray &r, int seg[2 * RAY_SEGS])
 {
-  seg[0] = 0; seg[1] = r.n_steps; seg[2] = 0; seg[3] = 0;
-  if (P.n_xiv <= 0) return;                          // everything resident
-  seg[1] = 0;
+#pragma unroll
+  for (int k = 0; k < 2 * RAY_SEGS; k++) seg[k] = 0;
+  if (P.n_xiv <= 0) { seg[1] = r.n_steps; return; }     // everything resident
+  // the intervals are sorted by x; the ray's x is monotone in the step index, so walking them in the
+  // direction of travel yields step ranges in ascending order: overlapping neighbours are merged
   int n = 0;
-  for (int k = 0; k < P.n_xiv && n < 2; k++)
+  for (int kk = 0; kk < P.n_xiv; kk++)
   {
+    const int k = r.d[0] >= 0 ? kk : P.n_xiv - 1 - kk;
     const double x0 = (double)P.xiv_lo[k] - (double)P.pos_mm[0], x1 = (double)P.xiv_hi[k] - (double)P.pos_mm[0];
     int i0 = 0, i1 = r.n_steps;
     if (r.d[0] == 0)
@@ -535,10 +539,10 @@ WS_D void ray_segments(const UpdateParams &P, const Ray &r, int seg[4])
       i1 = f1 > (double)r.n_steps ? r.n_steps : (int)f1;
     }
     if (i0 >= i1) continue;
-    if (n == 1 && i0 <= seg[1] && i1 >= seg[0])      // touches the first range: merge
+    if (n > 0 && i0 <= seg[2 * n - 1])               // touches the previous range: extend it
     {
-      seg[0] = i0 < seg[0] ? i0 : seg[0];
-      seg[1] = i1 > seg[1] ? i1 : seg[1];
+      if (i1 > seg[2 * n - 1]) seg[2 * n - 1] = i1;
+      if (i0 < seg[2 * n - 2]) seg[2 * n - 2] = i0;
       continue;
     }
     seg[2 * n] = i0; seg[2 * n + 1] = i1;
@@ -582,7 +586,7 @@ setup_kernel(const UpdateParams Pin, const ws_pt *__restrict__ pts, RaySetup *__
         if (r.small) divrem_rcp(ad * 32u * (unsigned)P.half_res, (unsigned)r.distance, rdist, o.dq[a], o.drem[a]);
       }
       ray_segments(P, r, o.seg);
-      valid = o.seg[1] > o.seg[0] || o.seg[3] > o.seg[2];
+      valid = o.seg[1] > o.seg[0];                      // ranges are packed from slot 0
     }
   }
   // Written in place, NOT compacted: the march takes rays in scan order, so the ~3,500 rays in flight at
@@ -592,7 +596,8 @@ setup_kernel(const UpdateParams Pin, const ws_pt *__restrict__ pts, RaySetup *__
   {
     if (!valid)
     {
-      o.seg[0] = o.seg[1] = o.seg[2] = o.seg[3] = 0;
+#pragma unroll
+      for (int k = 0; k < 2 * RAY_SEGS; k++) o.seg[k] = 0;
       o.flags = ray_id << 1;
     }
     int4 *dst = reinterpret_cast<int4 *>(&rays[ray_id]);
@@ -602,7 +607,7 @@ setup_kernel(const UpdateParams Pin, const ws_pt *__restrict__ pts, RaySetup *__
 #pragma unroll
       for (int w = 0; w < RAY_WORDS; w++) dst[w] = src[w];
     }
-    else { dst[2] = src[2]; dst[3] = src[3]; }
+    else { dst[2] = src[2]; dst[5] = src[5]; }
   }
 }
 
@@ -657,13 +662,16 @@ march_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__restrict_
     if (lane == 0) fetched = atom_add_async(&ctr->ray_counter, 1u);
 
     const int4 *ray_s = s_ray[wib][buf];
-    const int4 w2 = lds_word(ray_s + 2), w3 = lds_word(ray_s + 3);
+    const int4 w2 = lds_word(ray_s + 2);
     const bool small = (w2.w & 1) != 0;
 #pragma unroll 1
-    for (int sg = 0; sg < 2; sg++)
+    for (int sg = 0; sg < RAY_SEGS; sg++)
     {
-      int start = sg ? w3.z : w3.x;
-      const int end = sg ? w3.w : w3.y;
+      // two ranges per staged word; an empty range ends the list
+      const int4 ws = lds_word(ray_s + 5 + (sg >> 1));
+      int start = (sg & 1) ? ws.z : ws.x;
+      const int end = (sg & 1) ? ws.w : ws.y;
+      if (start >= end) break;
       if (!ATOMIC && P.far_len > 1)
       {
         const int fs = (P.far_len - 1) / P.half_res;
@@ -1157,7 +1165,8 @@ static int far_start_len(int res, int dz)
 // resident brick column -- the resident voxel columns widened by the reach of the interpolation fan
 // (|lowest - proj| <= delta_z and the fan spans 2*delta_z + res more, update_tsdf.cpp:485-493) plus two voxels
 // for the truncating divisions.  Resident columns are cyclically contiguous in ring space (slab + halo), so
-// there are at most two intervals; anything else switches the culling off.
+// there are at most two intervals for a slab; round-robin stripes give one per stripe (up to WS_MAX_XIV, beyond
+// that the culling is switched off).
 static void resident_x_intervals(const ws_handle *h, UpdateParams &P)
 {
   P.n_xiv = 0;
@@ -1188,7 +1197,7 @@ static void resident_x_intervals(const ws_handle *h, UpdateParams &P)
     else ivs.push_back(v);
     t = e;
   }
-  if (ivs.empty() || ivs.size() > 2) return;          // nothing resident cannot happen; > 2: no culling
+  if (ivs.empty() || ivs.size() > WS_MAX_XIV) return;  // nothing resident cannot happen; too many: no culling
   for (auto &v : ivs)
     if (v.lo < -(1ll << 30) || v.hi > (1ll << 30)) return;
   P.n_xiv = (int)ivs.size();

@@ -84,14 +84,13 @@ struct GridDesc
   int offset[3];    // ring offset of the centre (hdf5_local_map.h:59-70)
   int nb[3];        // bricks per axis = ceil(size / 8)
   int full;         // 1: every ring-x brick column is resident and slot == column
-  int own_lo;       // ring-x voxel range [own_lo, own_hi) this rank owns for the registration sum
-  int own_hi;
   i64 n_bricks;     // resident bricks
   uint32_t *grid;   // n_bricks * 512 TSDF entries  {int16 value | int16 weight << 16}
   u64 *keys;        // n_bricks * 512 candidate keys (all-ones when idle)
   unsigned *brick_flag;  // per resident brick: touched by the current scan
   unsigned *park_bits;   // 1 bit per voxel: parked by the current scan's merge pass (valid for touched bricks)
   short xslot[WS_MAX_XBRICKS];  // ring-x brick column -> resident slot, -1 if not resident
+  unsigned char xown[WS_MAX_XBRICKS];   // 1: this rank owns the column (sums its points in the registration)
 };
 
 WS_HD bool grid_in_bounds(const GridDesc &g, int x, int y, int z)

@@ -9,6 +9,8 @@
 #include "ws_common.cuh"
 #include "march_math.cuh"
 
+#define WS_MAX_XIV 6         // resident x intervals of a rank == march-step ranges per ray
+
 struct UpdateParams
 {
   int tau, max_weight, res, weight_epsilon, dz_per_distance;
@@ -30,7 +32,7 @@ struct UpdateParams
   int ringc[3];        // ring coordinate of voxel lo: (offset - size/2) mod size
   // multi-GPU slabs: x intervals (mm) outside which no march step can reach a resident column; 0 = no culling
   int n_xiv;
-  int xiv_lo[2], xiv_hi[2];
+  int xiv_lo[WS_MAX_XIV], xiv_hi[WS_MAX_XIV];
 };
 
 // scanner pose handed from the registration to update_tsdf on the device (fused per-scan pipeline)

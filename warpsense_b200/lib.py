@@ -93,6 +93,8 @@ def _signatures():
         "ws_peer_attach_ptrs": (C.c_int, [hp, C.POINTER(vp), i32p, C.c_int32]),
         "ws_peer_set_timeout": (C.c_int, [hp, C.c_double]),
         "ws_slab_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, i32p, i32p, i32p, C.c_int32]),
+        "ws_shard_layout": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_int32]),
+        "ws_shard_columns": (C.c_int, [hp, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8), C.c_int32]),
         "ws_reg_solve": (C.c_int, [hp, C.c_float, C.c_float]),
         "ws_reg_peek": (C.c_int, [hp, i32p, i32p]),
         "ws_reg_finish": (C.c_int, [hp, f32p, i32p, i32p]),
