@@ -65,7 +65,7 @@ void free_handle(ws_handle *h)
   DeviceGuard dg(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto &t : h->timers) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
-  cudaFree(h->g.grid); cudaFree(h->g.keys); cudaFree(h->g.brick_flag); cudaFree(h->g.park_bits);
+  cudaFree(h->g.grid); cudaFree(h->g.keys); cudaFree(h->g.brick_flag); cudaFree(h->g.park_bits); cudaFree(h->g.brick_slot_base);
   cudaFree(h->d_points); cudaFree(h->d_rays);
   cudaFree(h->d_pre_tmp); cudaFree(h->d_pre_slot); cudaFree(h->d_pre_table); cudaFree(h->d_pre_tiles); cudaFree(h->d_pre_xyz); cudaFree(h->d_reg_points); cudaFree(h->d_brick_list);
   cudaFree(h->d_counters); cudaFreeHost(h->h_counters);
@@ -184,6 +184,7 @@ int create_impl(const int32_t size[3], int tau, int max_weight, int res, int dev
     WS_CUDA_OK(cudaMalloc(&g.grid, n_vox * sizeof(uint32_t)));
     WS_CUDA_OK(cudaMalloc(&g.keys, n_vox * sizeof(u64)));
     WS_CUDA_OK(cudaMalloc(&g.brick_flag, (size_t)g.n_bricks * sizeof(unsigned)));
+    WS_CUDA_OK(cudaMalloc(&g.brick_slot_base, (size_t)g.n_bricks * sizeof(unsigned)));
     WS_CUDA_OK(cudaMalloc(&g.park_bits, n_vox / 8));
     WS_CUDA_OK(cudaMemsetAsync(g.park_bits, 0, n_vox / 8, h->stream));
     WS_CUDA_OK(cudaMalloc(&h->d_brick_list, (size_t)g.n_bricks * sizeof(unsigned)));

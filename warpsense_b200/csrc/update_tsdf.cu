@@ -888,6 +888,7 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
       for (int w = 0; w < 8; w++)
         for (int q = 0; q < 2; q++) { const unsigned c = s_cnt[w][q]; s_cnt[w][q] = tot; tot += c; }
       s_base = tot ? atomicAdd(&ctr->n_pending, tot) : 0u;
+      g.brick_slot_base[base >> 9] = s_base;
     }
     __syncthreads();
     u64 nk[2] = { WS_KEY_EMPTY, WS_KEY_EMPTY };
@@ -902,7 +903,9 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
           pend_addr[slot] = (u64)(base + 2u * (unsigned)tid + (unsigned)j) | (entry_weight(e2[j]) > 0 ? PEND_SEEN_FLAG : 0ull);
           pend_prev[slot] = k2[j];
           pend_key[slot] = WS_KEY_EMPTY;
-          nk[j] = WS_KEY_PENDING_TAG | (u64)slot;
+          // what the replay needs from a parked voxel in ONE load: its slot (per-brick base + rank) and the
+          // order of the parked winner (candidates that come later in the reference's order are offered)
+          nk[j] = WS_KEY_PENDING_TAG | ((u64)(slot - s_base) << WS_SEQ_BITS) | key_seq(k2[j]);
         }
         else atomicAdd(&ctr->pending_overflow, 1u);
       }
@@ -1018,18 +1021,18 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
       ok[u] = ok[u] && ((pw[u] >> park_bit(rr[u].ref)) & 1u);
       kv[u] = ok[u] ? __ldcg(&g.keys[rr[u].ref]) : WS_KEY_EMPTY;
     }
-    u64 thr[4];
+    unsigned sb[4];
 #pragma unroll
     for (int u = 0; u < 4; u++)
     {
       ok[u] = ok[u] && key_is_pending(kv[u]);
-      thr[u] = ok[u] ? pend_prev[(unsigned)(kv[u] & 0xFFFFFFFFull)] : 0ull;
+      sb[u] = ok[u] ? __ldcg(&g.brick_slot_base[rr[u].ref >> 9]) : 0u;        // 1 MB table, L2 resident
     }
 #pragma unroll
     for (int u = 0; u < 4; u++)
     {
-      const unsigned slot = (unsigned)(kv[u] & 0xFFFFFFFFull);
-      const bool hit = ok[u] && key_seq(rr[u].key) > key_seq(thr[u]);
+      const unsigned slot = sb[u] + (unsigned)((kv[u] >> WS_SEQ_BITS) & 0x1FFull);
+      const bool hit = ok[u] && key_seq(rr[u].key) > (kv[u] & WS_SEQ_MAX);
       if (hit) atomicMin(&pend_key[slot], rr[u].key);
       Rec e; e.key = rr[u].key; e.ref = (u64)slot;
       list_append(lw, hit, e, lane, list, &ctr->n_list);

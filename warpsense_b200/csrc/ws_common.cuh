@@ -89,6 +89,7 @@ struct GridDesc
   u64 *keys;        // n_bricks * 512 candidate keys (all-ones when idle)
   unsigned *brick_flag;  // per resident brick: touched by the current scan
   unsigned *park_bits;   // 1 bit per voxel: parked by the current scan's merge pass (valid for touched bricks)
+  unsigned *brick_slot_base;   // per resident brick: first pending slot of the voxels it parked in the current scan
   short xslot[WS_MAX_XBRICKS];  // ring-x brick column -> resident slot, -1 if not resident
   unsigned char xown[WS_MAX_XBRICKS];   // 1: this rank owns the column (sums its points in the registration)
 };
@@ -125,7 +126,8 @@ WS_HD i64 brick_of(const GridDesc &g, int rx, int ry, int rz)
 // ---------------------------------------------------------------------------------------------
 // Candidate key (one 64-bit atomicMin per candidate reproduces the reference's sequential
 // collision rule, update_tsdf.cpp:508-512 -- derivation in DESIGN.md "Collision rule"):
-//   [63:62] tag      00 candidate, 10 PENDING(slot), 11..1 EMPTY
+//   [63:62] tag      00 candidate, 10 PENDING (parked: [53:45] rank in the brick's slots, [44:0] seq of the parked
+//                    winner), 11..1 EMPTY
 //   [61:47] |value|  (<= tau <= 32767)
 //   [46]    1 = interpolated candidate (negative weight)
 //   [45:1]  order    seq for real candidates, SEQ_MAX - seq for interpolated ones
