@@ -38,9 +38,9 @@ GN_ITERS = 20
 IT_WEIGHT = 0.1
 EPSILON = 0.0          # |.| < 0 never holds: exactly GN_ITERS iterations
 TAU, MAX_WEIGHT = 1000, 640
-# DRAM bytes of one update_tsdf on the default workload, from the committed ncu capture (profiles/r01m_*):
-# setup 1.6 + march 221.1 + 543.2 + brick_list 1.1 + merge 353.0 + 379.4 + replay 666.0 + 34.4 MB
-NCU_TRAFFIC_BYTES_PER_SCAN = 2199.8e6
+# DRAM bytes of one update_tsdf on the default workload, from the committed ncu capture (profiles/r01p_*):
+# setup 1.6 + 12.5 + march 224.9 + 541.9 + brick_list 1.1 + merge 353.2 + 380.3 + replay 623.9 + 35.5 MB
+NCU_TRAFFIC_BYTES_PER_SCAN = 2174.9e6
 REF_SUBSAMPLE = 8      # --impl reference: every 8th ray per step (bounded sample)
 
 
@@ -416,7 +416,7 @@ def run_native(args):
                 "traffic": NCU_TRAFFIC_BYTES_PER_SCAN if (world == 1 and not args.update_only and args.grid == 512 and args.res == 50
                                                           and args.beams == 128 and args.cols == 1024) else None,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of setup + march + brick_list + merge + replay, one "
-                                  "launch each, ncu --set full capture of this workload (profiles/r01m_summary.md)",
+                                  "launch each, ncu --set full capture of this workload (profiles/r01p_summary.md)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_scan": upd_bytes,
                 "formula": "12*N + 8*T (SURVEY.md 8d), N=%d points, T=%d touched voxels, C=%d candidates" % (N, T_vox, C_cand),

@@ -604,8 +604,10 @@ setup_kernel(const UpdateParams Pin, const ws_pt *__restrict__ pts, RaySetup *__
     const int4 *src = reinterpret_cast<const int4 *>(&o);
     if (valid)
     {
+      // a fully resident map has one step range per ray: the last two words (ranges 2..5) are not needed
 #pragma unroll
-      for (int w = 0; w < RAY_WORDS; w++) dst[w] = src[w];
+      for (int w = 0; w < RAY_WORDS; w++)
+        if (w < 6 || P.n_xiv > 0) dst[w] = src[w];
     }
     else { dst[2] = src[2]; dst[5] = src[5]; }
   }
@@ -664,8 +666,9 @@ march_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__restrict_
     const int4 *ray_s = s_ray[wib][buf];
     const int4 w2 = lds_word(ray_s + 2);
     const bool small = (w2.w & 1) != 0;
+    const int n_segs = P.n_xiv > 0 ? RAY_SEGS : 1;
 #pragma unroll 1
-    for (int sg = 0; sg < RAY_SEGS; sg++)
+    for (int sg = 0; sg < n_segs; sg++)
     {
       // two ranges per staged word; an empty range ends the list
       const int4 ws = lds_word(ray_s + 5 + (sg >> 1));
