@@ -295,7 +295,7 @@ def test_fused_peer_registration_times_out_without_peer(monkeypatch):
 
 @pytest.mark.gpu
 def test_fused_peer_registration_two_processes():
-    """Two processes, one GPU each, mailboxes exchanged as CUDA IPC handles (tools/mp_peer_check.py)."""
+    """Two processes, one GPU each, mailboxes exchanged as CUDA IPC handles (tests/mp_peer_check.py)."""
     import subprocess
     import sys
     import torch
@@ -304,7 +304,7 @@ def test_fused_peer_registration_two_processes():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + os.getpid() % 300),
-           os.path.join(root, "tools", "mp_peer_check.py")]
+           os.path.join(root, "tests", "mp_peer_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "mp peer check ok" in out.stdout

@@ -3,7 +3,7 @@
 tag=$1; N=${2:-2}
 out=gpurun_out; mkdir -p $out
 nvidia-smi -L | head -8
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tools/mp_peer_check.py > $out/${tag}_mpcheck.log 2>&1; echo "mp check exit $?"; tail -3 $out/${tag}_mpcheck.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 tests/mp_peer_check.py > $out/${tag}_mpcheck.log 2>&1; echo "mp check exit $?"; tail -3 $out/${tag}_mpcheck.log
 timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-ref-cuda > $out/${tag}_bench_n1.json 2> $out/${tag}_bench_n1.err
 n=2
 while [ $n -le $N ]; do
