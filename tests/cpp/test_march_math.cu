@@ -144,6 +144,50 @@ int main()
       }
     }
   }
+  // 5. multi-GPU culling: every march step whose x lies in a resident interval is inside one of the step ranges
+  long long culled_rays = 0, covered_steps = 0, skipped_steps = 0;
+  for (int t = 0; t < 20000; t++)
+  {
+    const int res = (int[]){ 20, 50, 64, 100 }[t % 4], h = res / 2, tau = 1000;
+    int n_xiv = 1 + (int)uni(0, 5);
+    int lo[6], hi[6];
+    long long x = uni(-30000, -20000);
+    for (int k = 0; k < n_xiv; k++)
+    {
+      lo[k] = (int)x; x += uni(1, 6000); hi[k] = (int)x; x += uni(5 * res, 9000);     // sorted, disjoint
+    }
+    const int pos_x = (int)uni(-26000, 26000);
+    int dx = (int)uni(-26000, 26000);
+    if (t % 17 == 0) dx = 0;
+    const int dy = (int)uni(-20000, 20000);
+    const int dist = norm_i32(dx, dy, 0);
+    if (dist == 0) continue;
+    const int n_steps = (dist + tau - 1) / h + 1;
+    int seg[12];
+    ray_step_ranges<6>(n_xiv, lo, hi, pos_x, h, dx, dist, n_steps, seg);
+    culled_rays++;
+    int prev_end = -1;
+    for (int k = 0; k < 6; k++)
+    {
+      if (seg[2 * k + 1] <= seg[2 * k]) { for (int q = k; q < 6; q++) CHECK(seg[2 * q] == 0 && seg[2 * q + 1] == 0, "ranges not packed"); break; }
+      CHECK(seg[2 * k] >= 0 && seg[2 * k + 1] <= n_steps && seg[2 * k] > prev_end, "ranges not ascending / disjoint");
+      prev_end = seg[2 * k + 1];
+    }
+    for (int i = 0; i < n_steps; i++)
+    {
+      const int len = 1 + i * h;
+      const long long px = pos_x + ((long long)dx * len) / dist;
+      bool need = false;
+      for (int k = 0; k < n_xiv; k++) if (px >= lo[k] && px < hi[k]) need = true;
+      bool have = false;
+      for (int k = 0; k < 6; k++) if (i >= seg[2 * k] && i < seg[2 * k + 1]) have = true;
+      CHECK(!need || have, "step %d (x %lld) of a ray with dx %d is resident but not in a range", i, px, dx);
+      if (have) covered_steps++; else skipped_steps++;
+    }
+  }
+  printf("culling: %lld rays, %lld steps kept, %lld skipped\n", culled_rays, covered_steps, skipped_steps);
+  CHECK(culled_rays > 10000 && skipped_steps > covered_steps / 4, "culling coverage too small");
+
   printf("rays %lld steps %lld\n", rays, steps);
   CHECK(rays > 1000 && steps > 1000000, "coverage too small");
   if (failures) { printf("march math: %d FAILURES\n", failures); return 1; }

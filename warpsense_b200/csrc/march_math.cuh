@@ -107,3 +107,49 @@ WS_HD bool ray_is_small(const int d[3], const int p[3], int distance, int tau, i
   const i64 L = (i64)distance + tau + 32ll * half_res + 1;
   return coord_lim > 0 && c < (unsigned)coord_lim && (i64)m * L < (1ll << 31) && (i64)dz * L < (1ll << 30);
 }
+
+// Multi-GPU culling: the march-step ranges [seg[2k], seg[2k+1]) of a ray that can put a candidate into one of
+// the x intervals [xiv_lo[k], xiv_hi[k]) (mm, map frame; sorted, disjoint, already widened by the reach of the
+// interpolation fan).  The ray's x coordinate pos_x + (dx * len) / distance is monotone in the step index
+// (len = 1 + i * h), so every interval maps to one contiguous range; ranges are conservative by two steps on
+// either side, emitted in ascending order, overlapping neighbours merged, packed from slot 0, the rest zero.
+// n_xiv <= 0 means "everything resident": one range [0, n_steps).
+template <int MAXSEG>
+WS_HD void ray_step_ranges(int n_xiv, const int *xiv_lo, const int *xiv_hi, int pos_x, int half_res, int dx,
+                           int distance, int n_steps, int seg[2 * MAXSEG])
+{
+#pragma unroll
+  for (int k = 0; k < 2 * MAXSEG; k++) seg[k] = 0;
+  if (n_xiv <= 0) { seg[1] = n_steps; return; }
+  int n = 0;
+  for (int kk = 0; kk < n_xiv && n < MAXSEG; kk++)
+  {
+    const int k = dx >= 0 ? kk : n_xiv - 1 - kk;        // walk the intervals in the ray's direction of travel
+    const double x0 = (double)xiv_lo[k] - (double)pos_x, x1 = (double)xiv_hi[k] - (double)pos_x;
+    int i0 = 0, i1 = n_steps;
+    if (dx == 0)
+    {
+      if (!(x0 <= 0.0 && 0.0 < x1)) continue;
+    }
+    else
+    {
+      const double s = (double)distance / (double)dx;
+      double l0 = x0 * s, l1 = x1 * s;                   // lengths at which the ray crosses the interval ends
+      if (l0 > l1) { const double t = l0; l0 = l1; l1 = t; }
+      const double h = (double)half_res;
+      const double f0 = floor((l0 - 1.0) / h) - 2.0, f1 = ceil((l1 - 1.0) / h) + 3.0;
+      if (f1 <= 0.0 || f0 >= (double)n_steps) continue;
+      i0 = f0 < 0.0 ? 0 : (int)f0;
+      i1 = f1 > (double)n_steps ? n_steps : (int)f1;
+    }
+    if (i0 >= i1) continue;
+    if (n > 0 && i0 <= seg[2 * n - 1])                  // touches the previous range: extend it
+    {
+      if (i1 > seg[2 * n - 1]) seg[2 * n - 1] = i1;
+      if (i0 < seg[2 * n - 2]) seg[2 * n - 2] = i0;
+      continue;
+    }
+    seg[2 * n] = i0; seg[2 * n + 1] = i1;
+    n++;
+  }
+}

@@ -506,48 +506,11 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const int pos_mm[3
   }
 }
 
-// March steps of a ray whose candidates can land in a resident x column (multi-GPU slabs): the ray's x
-// coordinate is monotone in the step index, so every resident x interval (already widened by the fan's
-// reach, UpdateParams::xiv_*) maps to one contiguous step range.  Conservative by two steps either side;
-// the exact per-candidate residency test stays in the march.
+// March steps of a ray whose candidates can land in a resident x column (multi-GPU slabs / stripes): see
+// ray_step_ranges in march_math.cuh (host-tested).  The exact per-candidate residency test stays in the march.
 WS_D void ray_segments(const UpdateParams &P, const Ray &r, int seg[2 * RAY_SEGS])
 {
-#pragma unroll
-  for (int k = 0; k < 2 * RAY_SEGS; k++) seg[k] = 0;
-  if (P.n_xiv <= 0) { seg[1] = r.n_steps; return; }     // everything resident
-  // the intervals are sorted by x; the ray's x is monotone in the step index, so walking them in the
-  // direction of travel yields step ranges in ascending order: overlapping neighbours are merged
-  int n = 0;
-  for (int kk = 0; kk < P.n_xiv; kk++)
-  {
-    const int k = r.d[0] >= 0 ? kk : P.n_xiv - 1 - kk;
-    const double x0 = (double)P.xiv_lo[k] - (double)P.pos_mm[0], x1 = (double)P.xiv_hi[k] - (double)P.pos_mm[0];
-    int i0 = 0, i1 = r.n_steps;
-    if (r.d[0] == 0)
-    {
-      if (!(x0 <= 0.0 && 0.0 < x1)) continue;
-    }
-    else
-    {
-      const double s = (double)r.distance / (double)r.d[0];
-      double l0 = x0 * s, l1 = x1 * s;               // lengths at which the ray crosses the interval ends
-      if (l0 > l1) { const double t = l0; l0 = l1; l1 = t; }
-      const double h = (double)P.half_res;
-      const double f0 = floor((l0 - 1.0) / h) - 2.0, f1 = ceil((l1 - 1.0) / h) + 3.0;
-      if (f1 <= 0.0 || f0 >= (double)r.n_steps) continue;
-      i0 = f0 < 0.0 ? 0 : (int)f0;
-      i1 = f1 > (double)r.n_steps ? r.n_steps : (int)f1;
-    }
-    if (i0 >= i1) continue;
-    if (n > 0 && i0 <= seg[2 * n - 1])               // touches the previous range: extend it
-    {
-      if (i1 > seg[2 * n - 1]) seg[2 * n - 1] = i1;
-      if (i0 < seg[2 * n - 2]) seg[2 * n - 2] = i0;
-      continue;
-    }
-    seg[2 * n] = i0; seg[2 * n + 1] = i1;
-    n++;
-  }
+  ray_step_ranges<RAY_SEGS>(P.n_xiv, P.xiv_lo, P.xiv_hi, P.pos_mm[0], P.half_res, r.d[0], r.distance, r.n_steps, seg);
 }
 
 // Set-up pass: one THREAD per ray (the march needs the result warp-uniform; computing it there costs every
