@@ -186,6 +186,11 @@ def run_reference(args):
     s, frames = make_frames(args, K + W)
     side, res = args.grid, args.res
     om = orc.LocalMap(side, side, side, TAU, 0)
+    # all the host threads this process may use (torchrun sets OMP_NUM_THREADS=1 for its workers)
+    try:
+        orc.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        orc.set_num_threads(os.cpu_count() or 1)
     cores = orc.num_threads()
     pos, up = fp.convert_pose_to_gpu(frames[0]["pose"], res)
     orc.update_tsdf(om, frames[0]["points_map"][::REF_SUBSAMPLE], pos, up, TAU, MAX_WEIGHT, res)
@@ -495,6 +500,10 @@ def cpu_baseline(args, frames, s):
     from warpsense_b200 import fixedpoint as fp
     side, res = args.grid, args.res
     om = orc.LocalMap(side, side, side, TAU, 0)
+    try:
+        orc.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        orc.set_num_threads(os.cpu_count() or 1)
     pos, up = fp.convert_pose_to_gpu(frames[0]["pose"], res)
     t0 = time.perf_counter()
     st = orc.update_tsdf(om, frames[0]["points_map"], pos, up, TAU, MAX_WEIGHT, res)
