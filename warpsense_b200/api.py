@@ -411,22 +411,27 @@ class RegistrationCuda:
                    device_ptr=None, n=None):
         """One scan through the fused pipeline (ws_track_scan): register against the map (pretransform =
         identity), pose = X @ prior_pose, update_tsdf with the registered cloud -- one host synchronisation.
-        `points`: int32 [n,3] host array, or None with `device_ptr`/`n`.  Returns (X, pose, iterations)."""
+        `points`: int32 [n,3] host array, or None with `device_ptr`/`n`.  `prior_pose`: 4x4, or a float32[16]
+        already in the column-major ABI layout (colmajor16).  Returns (X, pose, iterations)."""
         hd = self._hd
         f32p = C.POINTER(C.c_float)
-        P0 = colmajor16(prior_pose)
-        X, pose = np.zeros(16, np.float32), np.zeros(16, np.float32)
-        it = C.c_int32()
+        pp = prior_pose
+        if not (isinstance(pp, np.ndarray) and pp.dtype == np.float32 and pp.shape == (16,) and pp.flags.c_contiguous):
+            pp = colmajor16(prior_pose)
+        buf = getattr(self, "_track_buf", None)
+        if buf is None:                              # marshalling buffers, reused from call to call
+            buf = self._track_buf = (np.zeros(16, np.float32), np.zeros(16, np.float32), C.c_int32())
+            self._track_ptrs = (buf[0].ctypes.data_as(f32p), buf[1].ctypes.data_as(f32p), C.byref(buf[2]))
         if points is not None:
             p = _pts(points)
             ptr, cnt, dev = p.ctypes.data, len(p), 0
         else:
             ptr, cnt, dev = C.c_void_p(int(device_ptr)), int(n), 1
-        hd.check(hd.L.ws_track_scan(hd.h, ptr, cnt, dev, P0.ctypes.data_as(f32p), int(max_iterations),
+        hd.check(hd.L.ws_track_scan(hd.h, ptr, cnt, dev, pp.ctypes.data_as(f32p), int(max_iterations),
                                     float(it_weight_gradient), float(epsilon), int(map_resolution),
-                                    X.ctypes.data_as(f32p), pose.ctypes.data_as(f32p), C.byref(it)))
+                                    self._track_ptrs[0], self._track_ptrs[1], self._track_ptrs[2]))
         self.curr_n_points = cnt
-        return from_colmajor16(X), from_colmajor16(pose), it.value
+        return from_colmajor16(buf[0]), from_colmajor16(buf[1]), buf[2].value
 
     # -- multi-GPU (SURVEY.md 8e): one handle per rank, the caller supplies the exchange step --
     def sums_device_ptr(self):
