@@ -5,21 +5,28 @@
 // (src/cpu/update_tsdf.cpp:397-564), which is the parity target.
 //
 // Pipeline per scan (one stream, one host synchronisation at the end to fetch the work counters):
-//   1. march_kernel<true>   persistent warps, one ray per warp at a time (rays are fetched from a global
-//                           counter).  Lanes stride over the res/2 march steps; the steps that survive the
-//                           reference's "same (x,y) column as the previous step" filter (:455-458) are
-//                           compacted through a per-warp shared-memory queue so the expensive part (value,
-//                           weight, fan of interpolated voxels, addressing) runs with full lanes.  Every
-//                           candidate (voxel, value, real|interpolated, order) is ONE 64-bit atomicMin
-//                           (RED, no return) on the voxel's key -- see ws_common.cuh / DESIGN.md for why
-//                           min over (|value|, interpolated, order) reproduces the sequential rule at
-//                           :508-512 -- plus a plain store that flags the voxel's 8x8x8 brick.
-//                           Far-field candidates (the only ones that can meet an interpolated winner)
-//                           are also appended to a record list in 64-entry chunks owned by the warp.
+//   0. setup_kernel         one THREAD per ray: direction, distance, interpolation vector, DDA increments,
+//                           fast-path flag and -- on a sharded map -- the march-step ranges that can reach this
+//                           rank's columns; 128-byte RaySetup per ray, in scan order.
+//   1. march_kernel<true>   persistent warps, one ray per warp at a time (indices from a global counter, the
+//                           next ray's RaySetup staged to shared memory by cp.async while this one is
+//                           marched).  Lanes stride over the res/2 march steps (exact DDA, 32-bit magics:
+//                           march_math.cuh); the steps that survive the reference's "same (x,y) column as
+//                           the previous step" filter (:455-458) are compacted through a per-warp
+//                           shared-memory queue so the expensive part (value, fan of interpolated voxels,
+//                           addressing) runs with full lanes.  Every candidate (voxel, value,
+//                           real|interpolated, order) is ONE 64-bit atomicMin (RED, no return) on the
+//                           voxel's key -- see ws_common.cuh / DESIGN.md for why min over (|value|,
+//                           interpolated, order) reproduces the sequential rule at :508-512 -- plus a plain
+//                           store that flags the voxel's 8x8x8 brick.  Far-field candidates (the only ones
+//                           that can meet an interpolated winner) are also appended to a record list in
+//                           64-entry chunks owned by the warp.
 //   2. brick_list_kernel    touched-brick flags -> compact list (and flags reset for the next scan).
-//   3. merge_kernel         streams the touched bricks (4 KB keys + 2 KB entries each), folds final
+//   3. merge_kernel         moves the touched bricks (4 KB keys + 2 KB entries each) through shared memory
+//                           with TMA bulk copies (cp.async.bulk + mbarrier, three stages per CTA), folds final
 //                           winners into the grid (:542-560), resets the keys, and parks the voxels whose
-//                           winner is an interpolated candidate below tau ("pending").
+//                           winner is an interpolated candidate below tau ("pending"): their key word then
+//                           carries the slot rank within the brick and the order of the parked winner.
 //   4. replay_kernel        cooperative (grid-synchronised).  Round 1 streams the record list once and
 //                           keeps, per pending voxel, the minimum key among the candidates that follow the
 //                           parked winner in the reference's order; those candidates are also compacted
@@ -27,6 +34,8 @@
 //                           device until every pending voxel has its final winner.
 // If the record list overflows its buffer the host grows it and regenerates it with march_kernel<false>
 // (far part of every ray, no atomics) before running replay_kernel again.
+// The scanner pose arrives as kernel parameters or, in the fused per-scan pipeline (ws_track_scan), from
+// device memory written by pose_kernel right after the registration.
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cstdlib>
