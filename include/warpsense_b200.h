@@ -133,7 +133,12 @@ int ws_get_update_counters(const ws_handle *h, ws_update_counters *out);
  *                 std::unordered_set out in bucket order; here the survivors keep scan order (first
  *                 occurrence stays): the same set, deterministic.  The result stays on the device
  *                 (ws_scan_points_device) for ws_update_tsdf_device / ws_reg_prepare_device and is copied
- *                 to `out_host` (capacity n) when that is not NULL. */
+ *                 to `out_host` (capacity n) when that is not NULL.
+ *                 `on_device`: bit 0 = xyz is a device pointer; WS_PREPROCESS_CPU_NODE selects the CPU node's
+ *                 variant instead (src/cpu/fastsense.cpp:143-163: duplicates are detected by the voxel of the
+ *                 untransformed millimetre point and the point itself is transformed, in scan order -- which
+ *                 is exactly the order produced here). */
+#define WS_PREPROCESS_CPU_NODE 2
 int ws_preprocess_scan(ws_handle *h, const float *xyz, int64_t n, int32_t point_step_bytes, int32_t on_device,
                        const float pose_mm[16], int32_t map_resolution, ws_point *out_host, int64_t *n_out);
 const ws_point *ws_scan_points_device(ws_handle *h, int64_t *n);

@@ -80,6 +80,7 @@ def lib():
         "orc_to_int_mat": (None, [f32p, i32p]),
         "orc_transform_points": (None, [vp, C.c_int64, i32p, vp]),
         "orc_preprocess": (C.c_int64, [vp, C.c_int64, C.c_int, f32p, C.c_int, vp]),
+        "orc_preprocess_cpu_node": (C.c_int64, [vp, C.c_int64, C.c_int, f32p, C.c_int, vp]),
         "orc_to_map": (None, [f32p, C.c_int, i32p]),
         "orc_convert_pose": (None, [f32p, C.c_int, i32p, i32p]),
         "orc_transform_point_cloud": (None, [vp, C.c_int64, f32p]),
@@ -147,14 +148,16 @@ def transform_points(pts, int_mat):
     return out
 
 
-def preprocess(cloud_xyz_m, pose_mm, map_resolution):
+def preprocess(cloud_xyz_m, pose_mm, map_resolution, cpu_node=False):
     """App::preprocess (src/warpsense/app.cpp:118-148): float metres [n, >=3] -> unique int32 mm points in the
-    map frame, in scan order (the reference's std::unordered_set order is implementation defined)."""
+    map frame, in scan order (the reference's std::unordered_set order is implementation defined).
+    cpu_node=True: the CPU node's variant (src/cpu/fastsense.cpp:143-163), whose own order is scan order."""
     a = np.ascontiguousarray(cloud_xyz_m, dtype=np.float32)
     a = a.reshape(-1, 3) if a.ndim == 1 else a
     out = np.zeros((max(len(a), 1), 3), np.int32)
     cm = _colmajor(pose_mm)
-    n = lib().orc_preprocess(a.ctypes.data, len(a), a.shape[1], _p(cm, C.c_float), int(map_resolution), out.ctypes.data)
+    fn = lib().orc_preprocess_cpu_node if cpu_node else lib().orc_preprocess
+    n = fn(a.ctypes.data, len(a), a.shape[1], _p(cm, C.c_float), int(map_resolution), out.ctypes.data)
     return out[:n].copy()
 
 

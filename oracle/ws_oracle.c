@@ -447,6 +447,46 @@ int64_t orc_preprocess(const float *xyz, int64_t n, int stride_floats, const flo
   return m;
 }
 
+/* src/cpu/fastsense.cpp:143-163 (the CPU node's cloud callback): metres -> (int)(v * 1000), duplicates detected
+ * by the voxel of that point (`point / MAP_RESOLUTION`, truncating), the point itself transformed and pushed in
+ * scan order -- the reference's own order here. */
+int64_t orc_preprocess_cpu_node(const float *xyz, int64_t n, int stride_floats, const float pose[16], int map_resolution,
+                                orc_point *out)
+{
+  int32_t im[16];
+  orc_to_int_mat(pose, im);                                                   /* :146 */
+  int64_t cap = 1024;
+  while (cap < 2 * n) cap <<= 1;
+  int64_t *tab = (int64_t *)malloc((size_t)cap * sizeof(int64_t));
+  orc_point *keys = (orc_point *)malloc((size_t)(n > 0 ? n : 1) * sizeof(orc_point));
+  for (int64_t i = 0; i < cap; i++) tab[i] = -1;
+  int64_t m = 0;
+  for (int64_t i = 0; i < n; i++)
+  {
+    const float x = xyz[i * stride_floats], y = xyz[i * stride_floats + 1], z = xyz[i * stride_floats + 2];
+    if (x < 0.3 && y < 0.3 && z < 0.3) continue;                              /* :152-155 */
+    orc_point pt = { f2i(x * 1000), f2i(y * 1000), f2i(z * 1000) };           /* :156-159 */
+    const orc_point k = { pt.x / map_resolution, pt.y / map_resolution, pt.z / map_resolution };   /* :160 */
+    uint64_t h = ((uint64_t)(uint32_t)k.x * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)(uint32_t)k.y * 0xC2B2AE3D27D4EB4Full) ^
+                 ((uint64_t)(uint32_t)k.z * 0x165667B19E3779F9ull);
+    h ^= h >> 29;
+    int64_t s = (int64_t)(h & (uint64_t)(cap - 1));
+    int dup = 0;
+    while (tab[s] >= 0)
+    {
+      const orc_point o = keys[tab[s]];
+      if (o.x == k.x && o.y == k.y && o.z == k.z) { dup = 1; break; }
+      s = (s + 1) & (cap - 1);
+    }
+    if (dup) continue;
+    tab[s] = m;
+    keys[m] = k;
+    out[m++] = orc_transform_point(pt, im);                                   /* :162 */
+  }
+  free(tab); free(keys);
+  return m;
+}
+
 /* include/util/util.h:52-56 */
 void orc_to_map(const float pose[16], int map_resolution, int out[3])
 {

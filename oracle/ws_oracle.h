@@ -81,6 +81,8 @@ void orc_to_int_mat(const float m_colmajor[16], int32_t out_colmajor[16]);      
 orc_point orc_transform_point(orc_point p, const int32_t mat_colmajor[16]);            /* util.h:13-18  */
 int64_t orc_preprocess(const float *xyz, int64_t n, int stride_floats, const float pose_colmajor[16],
                        int map_resolution, orc_point *out);                                 /* app.cpp:118-148 */
+int64_t orc_preprocess_cpu_node(const float *xyz, int64_t n, int stride_floats, const float pose_colmajor[16],
+                                int map_resolution, orc_point *out);                        /* fastsense.cpp:143-163 */
 void orc_transform_points(const orc_point *in, int64_t n, const int32_t mat_colmajor[16], orc_point *out);
 void orc_to_map(const float pose_colmajor[16], int map_resolution, int out[3]);        /* util.h:52-56  */
 void orc_convert_pose(const float pose_colmajor[16], int map_resolution,

@@ -69,6 +69,26 @@ def test_oracle_preprocess_matches_literal_formulas():
         assert [tuple(p) for p in got.tolist()] == want
 
 
+def test_oracle_cpu_node_preprocess_matches_literal_formulas():
+    """src/cpu/fastsense.cpp:143-163: key = voxel of the untransformed mm point, value = transform_point(point)."""
+    res = 64
+    cloud = _cloud(1200, 9)
+    pose = _pose(-20.0, [500.0, 20.5, -77.0])
+    M = orc.to_int_mat(pose)
+    seen, want = set(), []
+    for x, y, z in cloud:
+        if x < 0.3 and y < 0.3 and z < 0.3:
+            continue
+        pt = [int(np.float32(v) * np.float32(1000)) for v in (x, y, z)]
+        key = tuple(int(c / res) for c in pt)                  # C++ integer division truncates toward zero
+        if key in seen:
+            continue
+        seen.add(key)
+        want.append(tuple(int(v) for v in orc.transform_point(np.array(pt, np.int32), M)))
+    got = orc.preprocess(cloud, pose, res, cpu_node=True)
+    assert [tuple(p) for p in got.tolist()] == want
+
+
 def test_oracle_preprocess_strided_and_empty():
     cloud = _cloud(300, 4)
     wide = np.zeros((300, 6), np.float32)      # PointCloud2 with extra fields (point_step 24)
@@ -95,6 +115,9 @@ def test_preprocess_scan_device_matches_oracle(n, res):
     assert np.array_equal(got2, want)
     got3, m3 = tsdf.preprocess_scan(np.zeros((0, 3), np.float32), pose, res)
     assert m3 == 0
+    want4 = orc.preprocess(cloud, pose, res, cpu_node=True)          # the CPU node's variant, its own order
+    got4, m4 = tsdf.preprocess_scan(cloud, pose, res, cpu_node=True)
+    assert m4 == len(want4) and np.array_equal(got4, want4)
     tsdf.close()
 
 

@@ -246,10 +246,10 @@ class TSDFCuda:
         hd.check(hd.L.ws_update_tsdf_device(hd.h, C.c_void_p(int(device_ptr)), int(n), sp.ctypes.data_as(_i32p),
                                             u.ctypes.data_as(_i32p)))
 
-    def preprocess_scan(self, cloud_xyz_m, pose_mm, map_resolution, point_step_bytes=None, fetch=True):
+    def preprocess_scan(self, cloud_xyz_m, pose_mm, map_resolution, point_step_bytes=None, fetch=True, cpu_node=False):
         """App::preprocess (app.cpp:118-148) on the device: float metres [n, >=3] -> unique int32 mm points in
         the map frame, scan order (first occurrence stays).  The points stay on the device (scan_points_device)
-        and are returned as an array when `fetch`."""
+        and are returned as an array when `fetch`.  cpu_node=True: the CPU node's variant (fastsense.cpp:143-163)."""
         a = np.ascontiguousarray(cloud_xyz_m, dtype=np.float32)
         a = a.reshape(-1, 3) if a.ndim == 1 else a
         step = int(point_step_bytes or a.shape[1] * 4)
@@ -258,7 +258,7 @@ class TSDFCuda:
         n_out = C.c_int64()
         hd = self._hd
         T = colmajor16(pose_mm)
-        hd.check(hd.L.ws_preprocess_scan(hd.h, a.ctypes.data, n, step, 0, T.ctypes.data_as(C.POINTER(C.c_float)),
+        hd.check(hd.L.ws_preprocess_scan(hd.h, a.ctypes.data, n, step, 2 if cpu_node else 0, T.ctypes.data_as(C.POINTER(C.c_float)),
                                          int(map_resolution), out.ctypes.data if fetch else None, C.byref(n_out)))
         return (out[:n_out.value].copy() if fetch else None), n_out.value
 

@@ -67,7 +67,7 @@ void free_handle(ws_handle *h)
   for (auto &t : h->timers) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
   cudaFree(h->g.grid); cudaFree(h->g.keys); cudaFree(h->g.brick_flag); cudaFree(h->g.park_bits); cudaFree(h->g.brick_slot_base);
   cudaFree(h->d_points); cudaFree(h->d_rays);
-  cudaFree(h->d_pre_tmp); cudaFree(h->d_pre_slot); cudaFree(h->d_pre_table); cudaFree(h->d_pre_tiles); cudaFree(h->d_pre_xyz); cudaFree(h->d_reg_points); cudaFree(h->d_brick_list);
+  cudaFree(h->d_pre_tmp); cudaFree(h->d_pre_val); cudaFree(h->d_pre_slot); cudaFree(h->d_pre_table); cudaFree(h->d_pre_tiles); cudaFree(h->d_pre_xyz); cudaFree(h->d_reg_points); cudaFree(h->d_brick_list);
   cudaFree(h->d_counters); cudaFreeHost(h->h_counters);
   cudaFree(h->d_pend_addr); cudaFree(h->d_pend_prev); cudaFree(h->d_pend_key);
   cudaFree(h->d_active[0]); cudaFree(h->d_active[1]);
@@ -552,6 +552,8 @@ int ws_update_tsdf_device(ws_handle *h, const ws_point *device_points, int64_t n
 int ws_preprocess_scan(ws_handle *h, const float *xyz, int64_t n, int32_t point_step_bytes, int32_t on_device,
                        const float pose_mm[16], int32_t map_resolution, ws_point *out_host, int64_t *n_out)
 {
+  const int mode = (on_device & WS_PREPROCESS_CPU_NODE) ? 1 : 0;
+  on_device &= 1;
   return guarded(h, [&]() {
     if (n < 0 || (n > 0 && !xyz) || !pose_mm || map_resolution < 2 || point_step_bytes < 12 || (point_step_bytes & 3))
       throw std::invalid_argument("ws_preprocess_scan: bad argument");
@@ -572,7 +574,7 @@ int ws_preprocess_scan(ws_handle *h, const float *xyz, int64_t n, int32_t point_
       WS_CUDA_OK(cudaMemcpyAsync(h->d_pre_xyz, xyz, floats * sizeof(float), cudaMemcpyHostToDevice, h->stream));
       d_xyz = h->d_pre_xyz;
     }
-    h->scan_n = ws_launch_preprocess(h, d_xyz, n, stride, pose_mm, map_resolution);
+    h->scan_n = ws_launch_preprocess(h, d_xyz, n, stride, pose_mm, map_resolution, mode);
     if (out_host && h->scan_n > 0)
     {
       WS_CUDA_OK(cudaMemcpyAsync(out_host, h->d_points, (size_t)h->scan_n * sizeof(ws_pt), cudaMemcpyDeviceToHost, h->stream));

@@ -27,20 +27,31 @@ struct PreParams
   int n;
   int stride_floats;  // floats between consecutive points (PointCloud2 point_step / 4)
   unsigned mask;      // table size - 1
+  int mode;           // 0: App::preprocess (src/warpsense/app.cpp:118-148), 1: the CPU node (src/cpu/fastsense.cpp:143-163)
 };
 
 WS_D int pre_div_mr(int x) { return (x + ((x >> 31) & (WS_MR - 1))) >> WS_MR_SHIFT; }
 
-WS_D bool pre_point(const PreParams &P, const float *__restrict__ xyz, int i, ws_pt &out)
+// one return -> (key the duplicates are detected by, point handed on).  Mode 0: both are the transformed voxel
+// centre.  Mode 1 (fastsense.cpp:149-163): the key is the voxel of the untransformed millimetre point
+// (`point / MAP_RESOLUTION`, truncating), the point handed on is transform_point(point) itself.
+WS_D bool pre_point(const PreParams &P, const float *__restrict__ xyz, int i, ws_pt &key, ws_pt &out)
 {
   const float x = xyz[(size_t)i * P.stride_floats], y = xyz[(size_t)i * P.stride_floats + 1],
               z = xyz[(size_t)i * P.stride_floats + 2];
-  if (x < 0.3 && y < 0.3 && z < 0.3) return false;                       // app.cpp:128-131 (double compare)
-  const float mm[3] = { x * 1000.f, y * 1000.f, z * 1000.f };             // :133
+  if (x < 0.3 && y < 0.3 && z < 0.3) return false;                       // app.cpp:128-131 / fastsense.cpp:152-155
   int c[3];
+  if (P.mode == 0)
+  {
+    const float mm[3] = { x * 1000.f, y * 1000.f, z * 1000.f };           // app.cpp:133
 #pragma unroll
-  for (int a = 0; a < 3; a++)                                             // :134-139: float / int -> float
-    c[a] = (int)(floorf(mm[a] / (float)P.res) * (float)P.res + (float)(P.res / 2));
+    for (int a = 0; a < 3; a++)                                           // :134-139: float / int -> float
+      c[a] = (int)(floorf(mm[a] / (float)P.res) * (float)P.res + (float)(P.res / 2));
+  }
+  else
+  {
+    c[0] = (int)(x * 1000); c[1] = (int)(y * 1000); c[2] = (int)(z * 1000);   // fastsense.cpp:156-159 (float * int)
+  }
   int q[3];
 #pragma unroll
   for (int r = 0; r < 3; r++)                                             // util.h:13-18
@@ -50,6 +61,8 @@ WS_D bool pre_point(const PreParams &P, const float *__restrict__ xyz, int i, ws
     q[r] = pre_div_mr((int)acc);
   }
   out.x = q[0]; out.y = q[1]; out.z = q[2];
+  if (P.mode == 0) key = out;
+  else { key.x = c[0] / P.res; key.y = c[1] / P.res; key.z = c[2] / P.res; }   // fastsense.cpp:160 (Eigen int division)
   return true;
 }
 
@@ -62,14 +75,15 @@ WS_D unsigned pre_hash(const ws_pt p)
 }
 
 __global__ void __launch_bounds__(256)
-insert_kernel(const PreParams P, const float *__restrict__ xyz, ws_pt *__restrict__ tmp, unsigned *__restrict__ slot_of,
-              unsigned *__restrict__ table)
+insert_kernel(const PreParams P, const float *__restrict__ xyz, ws_pt *__restrict__ tmp, ws_pt *__restrict__ vals,
+              unsigned *__restrict__ slot_of, unsigned *__restrict__ table)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n) return;
-  ws_pt p;
-  if (!pre_point(P, xyz, i, p)) { slot_of[i] = PRE_EMPTY; return; }
+  ws_pt p, v;
+  if (!pre_point(P, xyz, i, p, v)) { slot_of[i] = PRE_EMPTY; return; }
   tmp[i] = p;
+  vals[i] = v;
   __threadfence();                       // the point must be readable by whoever finds index i in a slot
   unsigned h = pre_hash(p) & P.mask;
   for (;;)
@@ -156,7 +170,8 @@ scatter_kernel(const int n, const int n_tiles, const ws_pt *__restrict__ tmp, co
 }  // namespace
 
 // out: h->d_points (the update_tsdf staging buffer); returns the number of surviving points
-int64_t ws_launch_preprocess(ws_handle *h, const float *d_xyz, int64_t n, int stride_floats, const float pose_mm[16], int res)
+int64_t ws_launch_preprocess(ws_handle *h, const float *d_xyz, int64_t n, int stride_floats, const float pose_mm[16], int res,
+                             int mode)
 {
   if (n <= 0) return 0;
   cudaStream_t s = h->stream;
@@ -167,12 +182,13 @@ int64_t ws_launch_preprocess(ws_handle *h, const float *d_xyz, int64_t n, int st
   if ((size_t)n > h->pre_cap)
   {
     WS_CUDA_OK(cudaStreamSynchronize(s));
-    cudaFree(h->d_pre_tmp); cudaFree(h->d_pre_slot); cudaFree(h->d_pre_table); cudaFree(h->d_pre_tiles);
-    h->d_pre_tmp = nullptr; h->d_pre_slot = nullptr; h->d_pre_table = nullptr; h->d_pre_tiles = nullptr; h->pre_cap = 0;
+    cudaFree(h->d_pre_tmp); cudaFree(h->d_pre_val); cudaFree(h->d_pre_slot); cudaFree(h->d_pre_table); cudaFree(h->d_pre_tiles);
+    h->d_pre_val = nullptr; h->d_pre_tmp = nullptr; h->d_pre_slot = nullptr; h->d_pre_table = nullptr; h->d_pre_tiles = nullptr; h->pre_cap = 0;
     const size_t want = std::max<size_t>((size_t)n, 1 << 17);
     size_t wtab = 1024;
     while (wtab < want * 2) wtab <<= 1;
     WS_CUDA_OK(cudaMalloc(&h->d_pre_tmp, want * sizeof(ws_pt)));
+    WS_CUDA_OK(cudaMalloc(&h->d_pre_val, want * sizeof(ws_pt)));
     WS_CUDA_OK(cudaMalloc(&h->d_pre_slot, want * sizeof(unsigned)));
     WS_CUDA_OK(cudaMalloc(&h->d_pre_table, wtab * sizeof(unsigned)));
     WS_CUDA_OK(cudaMalloc(&h->d_pre_tiles, ((want + PRE_TILE - 1) / PRE_TILE + 1) * sizeof(unsigned)));
@@ -180,13 +196,14 @@ int64_t ws_launch_preprocess(ws_handle *h, const float *d_xyz, int64_t n, int st
   }
   PreParams P;
   for (int i = 0; i < 16; i++) P.M[i] = (int)(pose_mm[i] * (float)WS_MR);    // util.h:8-11
-  P.res = res; P.n = (int)n; P.stride_floats = stride_floats; P.mask = (unsigned)(tab - 1);
+  P.res = res; P.n = (int)n; P.stride_floats = stride_floats; P.mask = (unsigned)(tab - 1); P.mode = mode;
   ws_pt *tmp = static_cast<ws_pt *>(h->d_pre_tmp);
+  ws_pt *vals = static_cast<ws_pt *>(h->d_pre_val);
   unsigned *n_out = h->d_pre_tiles + n_tiles;
   WS_CUDA_OK(cudaMemsetAsync(h->d_pre_table, 0xFF, tab * sizeof(unsigned), s));
-  insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(P, d_xyz, tmp, h->d_pre_slot, h->d_pre_table);
+  insert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(P, d_xyz, tmp, vals, h->d_pre_slot, h->d_pre_table);
   count_kernel<<<n_tiles, 256, 0, s>>>((int)n, h->d_pre_slot, h->d_pre_table, h->d_pre_tiles);
-  scatter_kernel<<<n_tiles, 256, 0, s>>>((int)n, n_tiles, tmp, h->d_pre_slot, h->d_pre_table, h->d_pre_tiles,
+  scatter_kernel<<<n_tiles, 256, 0, s>>>((int)n, n_tiles, vals, h->d_pre_slot, h->d_pre_table, h->d_pre_tiles,
                                         h->d_points, n_out);
   h->launches += 3;
   unsigned host_n = 0;

@@ -116,7 +116,8 @@ struct ws_handle
   void *d_rays = nullptr;         // RaySetup[rays_cap]: the work list written by the set-up pass of update_tsdf
   size_t rays_cap = 0;
   // scan preprocessing scratch (preprocess.cu)
-  void *d_pre_tmp = nullptr;      // transformed points, scan order
+  void *d_pre_tmp = nullptr;      // duplicate-detection keys, scan order
+  void *d_pre_val = nullptr;      // points handed on, scan order
   unsigned *d_pre_slot = nullptr; // hash slot of every point
   unsigned *d_pre_table = nullptr;// hash set: smallest point index per distinct value
   unsigned *d_pre_tiles = nullptr;// survivors per 1024-point tile (+ the total)
@@ -196,7 +197,8 @@ void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float 
 void ws_launch_transform_cloud(ws_handle *h, ws_pt *d_pts, int n);
 void ws_host_solve(const i64 H[36], const i64 g[6], int err, int cnt, float alpha, float T[16], double xi_out[6]);
 // preprocess.cu
-int64_t ws_launch_preprocess(ws_handle *h, const float *d_xyz, int64_t n, int stride_floats, const float pose_mm[16], int res);
+int64_t ws_launch_preprocess(ws_handle *h, const float *d_xyz, int64_t n, int stride_floats, const float pose_mm[16], int res,
+                             int mode);
 // map_ops.cu
 void ws_launch_fill(ws_handle *h, uint32_t entry);
 void ws_launch_upload(ws_handle *h, const uint32_t *d_linear);
