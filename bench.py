@@ -315,10 +315,10 @@ def run_native(args):
         f = frames[k]
         if args.update_only:
             pos, up = fp.convert_pose_to_gpu(f["pose"], res)
-            tsdf.update_tsdf_device(dev_cloud.data_ptr(), N, pos, up)
+            tsdf.update_tsdf_device(dev_cloud.data_ptr(), counts[k], pos, up)
             return
         # one fused call per scan: 20 GN iterations -> pose -> update_tsdf, chained on the device
-        reg.track_scan(None, priors[k], GN_ITERS, IT_WEIGHT, EPSILON, res, device_ptr=dev_ptrs[k], n=N)
+        reg.track_scan(None, priors[k], GN_ITERS, IT_WEIGHT, EPSILON, res, device_ptr=dev_ptrs[k], n=counts[k])
 
     def step_host(k, host_cloud):
         f = frames[k]
@@ -341,6 +341,7 @@ def run_native(args):
         # step inputs prepared outside the timed region: the odometry prior of every scan in the ABI layout
         priors = [None] + [fp.colmajor16(s.pose(k - 1)) for k in range(1, K + W + 1)]
         dev_ptrs = [None] + [c.data_ptr() for c in dev_clouds[1:]]
+        counts = [0] + [int(c.shape[0]) for c in dev_clouds[1:]]
 
         def barrier():
             stream.synchronize()

@@ -91,7 +91,11 @@ def raycast(scene, origin, dirs):
 
 
 def frame_pose(frame, step_m=0.10, yaw_deg=0.5):
-    """Ground-truth sensor pose of a frame: 4x4 float32, translation in millimetres."""
+    """Ground-truth sensor pose of a frame: 4x4 float32, translation in millimetres.  The 100-frame trajectory
+     is walked back and forth for longer runs, so the sensor never leaves the room."""
+    frame = frame % 200
+    if frame > 100:
+        frame = 200 - frame
     T = np.eye(4, dtype=np.float64)
     T[:3, :3] = _rotz(math.radians(yaw_deg * frame))
     T[0, 3] = step_m * frame * 1000.0
