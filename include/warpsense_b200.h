@@ -95,6 +95,12 @@ int ws_map_get_params(const ws_handle *h, int32_t size[3], int32_t offset[3], in
  * HDF5GlobalMap(name, initial_value, initial_weight) + HDF5LocalMap ctor fill
  * (hdf5_global_map.cpp:24-27, hdf5_local_map.cpp:15-19) */
 int ws_map_fill(ws_handle *h, int32_t value, int32_t weight);
+/* Order-free 64-bit checksum of the stored entries of ring-x rows [x_lo, x_hi) (storage coordinates,
+ * include/map/hdf5_local_map.h:140-151), computed on the device; owned_only != 0 restricts a sharded handle to
+ * the rows it owns (halo columns excluded).  Equal map contents give equal checksums whatever the sharding:
+ * the multi-GPU result check of bench.py and tests (no reference counterpart: the reference is single-GPU). */
+int ws_map_checksum(ws_handle *h, int32_t x_lo, int32_t x_hi, int32_t owned_only, uint64_t *out);
+
 /* single-voxel access in map (voxel) coordinates: DeviceMap::value_unchecked + in_bounds
  * (include/warpsense/cuda/device_map.h:94-150); returns WS_ERR_INVALID when out of bounds */
 int ws_map_get_voxel(ws_handle *h, int32_t x, int32_t y, int32_t z, uint32_t *entry);

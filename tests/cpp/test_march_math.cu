@@ -35,6 +35,7 @@ int main()
       if (n < (1ll << 31))
       {
         CHECK(fd32_sdiv((int)n, f) == (int)(n / d), "sdiv %lld / %u", n, d);
+        if (d >= 3) CHECK(fd32_sdiv_s((int)n, f) == (int)(n / d) && fd32_sdiv_s((int)-n, f) == (int)((-n) / (long long)d), "sdiv_s %lld / %u", n, d);
         CHECK(fd32_sdiv((int)-n, f) == (int)((-n) / (long long)d), "sdiv -%lld / %u", n, d);
       }
     }

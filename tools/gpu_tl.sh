@@ -1,0 +1,16 @@
+#!/bin/bash
+# parity tests + short bench + per-kernel list.  Usage: bash tools/gpu_tl.sh <tag>
+tag=${1:-r02x}
+out=gpurun_out; mkdir -p $out
+timeout 1200 python -m pytest tests -m gpu -x -q > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log
+tail -8 $out/${tag}_pytest.log
+timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-ref-cuda > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench exit $?"
+python - <<PY
+import json
+d=json.loads(open("$out/${tag}_bench.json").read().strip().splitlines()[-1])
+k=d["roofline"]["kernel_ms_per_scan"]
+print("value %.1f e2e %.1f march %.3f merge %.3f replay %.3f reg %.3f step %.3f" % (d["value"], d["e2e"]["value"], k["march"], k["merge"], k["replay"], k["reg_20_iterations"], k["step_total"]))
+print(d["work"])
+PY
+tail -3 $out/${tag}_bench.err
+bash tools/gpu_list.sh $tag 2>&1 | head -14

@@ -276,6 +276,16 @@ class TSDFCuda:
         rows = np.repeat(np.frombuffer(own, np.uint8, nbx).astype(bool), 8)[:size_x]
         return rows
 
+    def checksum(self, x_lo=0, x_hi=None, owned_only=False):
+        """Order-free 64-bit checksum of the entries of ring-x rows [x_lo, x_hi), computed on the device
+        (equal for any sharding of equal map contents)."""
+        hd = self._hd
+        if x_hi is None:
+            x_hi = int(hd.size[0])
+        out = C.c_uint64()
+        hd.check(hd.L.ws_map_checksum(hd.h, int(x_lo), int(x_hi), 1 if owned_only else 0, C.byref(out)))
+        return int(out.value)
+
     def avg_map(self):
         return self._avg
 

@@ -65,8 +65,8 @@ void free_handle(ws_handle *h)
   DeviceGuard dg(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto &t : h->timers) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
-  cudaFree(h->g.grid); cudaFree(h->g.keys); cudaFree(h->g.brick_flag); cudaFree(h->g.park_bits); cudaFree(h->g.brick_slot_base);
-  cudaFree(h->d_points); cudaFree(h->d_rays);
+  cudaFree(h->g.grid); cudaFree(h->g.keys); cudaFree(h->g.brick_flag); cudaFree(h->g.brick_flag2); cudaFree(h->g.vstate); cudaFree(h->g.brick_slot_base);
+  cudaFree(h->d_points); cudaFree(h->d_rays); cudaFree(h->d_grp_info); cudaFree(h->d_item_off); cudaFree(h->d_gen_list);
   cudaFree(h->d_pre_tmp); cudaFree(h->d_pre_val); cudaFree(h->d_pre_slot); cudaFree(h->d_pre_table); cudaFree(h->d_pre_tiles); cudaFree(h->d_pre_xyz); cudaFree(h->d_reg_points); cudaFree(h->d_brick_list);
   cudaFree(h->d_counters); cudaFreeHost(h->h_counters);
   cudaFree(h->d_pend_addr); cudaFree(h->d_pend_prev); cudaFree(h->d_pend_key);
@@ -185,9 +185,12 @@ int create_impl(const int32_t size[3], int tau, int max_weight, int res, int dev
     WS_CUDA_OK(cudaMalloc(&g.keys, n_vox * sizeof(u64)));
     WS_CUDA_OK(cudaMalloc(&g.brick_flag, (size_t)g.n_bricks * sizeof(unsigned)));
     WS_CUDA_OK(cudaMalloc(&g.brick_slot_base, (size_t)g.n_bricks * sizeof(unsigned)));
-    WS_CUDA_OK(cudaMalloc(&g.park_bits, n_vox / 8));
-    WS_CUDA_OK(cudaMemsetAsync(g.park_bits, 0, n_vox / 8, h->stream));
-    WS_CUDA_OK(cudaMalloc(&h->d_brick_list, (size_t)g.n_bricks * sizeof(unsigned)));
+    WS_CUDA_OK(cudaMemsetAsync(g.brick_slot_base, 0xFF, (size_t)g.n_bricks * sizeof(unsigned), h->stream));
+    WS_CUDA_OK(cudaMalloc(&g.brick_flag2, (size_t)g.n_bricks * sizeof(unsigned)));
+    WS_CUDA_OK(cudaMemsetAsync(g.brick_flag2, 0, (size_t)g.n_bricks * sizeof(unsigned), h->stream));
+    WS_CUDA_OK(cudaMalloc(&g.vstate, n_vox / 2));
+    WS_CUDA_OK(cudaMemsetAsync(g.vstate, 0, n_vox / 2, h->stream));
+    WS_CUDA_OK(cudaMalloc(&h->d_brick_list, 2 * (size_t)g.n_bricks * sizeof(unsigned)));
     WS_CUDA_OK(cudaMalloc(&h->d_counters, sizeof(UpdateCounters)));
     WS_CUDA_OK(cudaMallocHost(&h->h_counters, sizeof(UpdateCounters)));
     std::memset(h->h_counters, 0, sizeof(UpdateCounters));
@@ -495,6 +498,23 @@ static i64 voxel_addr(ws_handle *h, int x, int y, int z)
   const i64 b = brick_of(g, rx, ry, rz);
   if (b < 0) throw std::invalid_argument("voxel not resident on this rank");
   return b * WS_BRICK_VOX + brick_local(rx, ry, rz);
+}
+
+int ws_map_checksum(ws_handle *h, int32_t x_lo, int32_t x_hi, int32_t owned_only, uint64_t *out)
+{
+  return guarded(h, [&]() {
+    if (!out) throw std::invalid_argument("ws_map_checksum: null argument");
+    u64 *scratch = nullptr;
+    WS_CUDA_OK(cudaMalloc(&scratch, sizeof(u64)));
+    ws_launch_checksum(h, x_lo, x_hi, owned_only, scratch);
+    u64 v = 0;
+    cudaError_t e = cudaMemcpyAsync(&v, scratch, sizeof(u64), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(scratch);
+    WS_CUDA_OK(e);
+    *out = v;
+    return WS_OK;
+  });
 }
 
 int ws_map_get_voxel(ws_handle *h, int32_t x, int32_t y, int32_t z, uint32_t *entry)

@@ -47,6 +47,18 @@ WS_HD int fd32_sdiv(int n, const FastDiv32 f)
   return n < 0 ? -q : q;
 }
 
+// the same with the SIGNED high product: floor(n * M / 2^32) is the floored quotient, one below the truncated one
+// for every negative n (multiples of d included: M > 2^32 / d), so adding n's sign bit gives C's `/`.
+// Three instructions (IMAD.HI, SHF, IADD3 -- the add folds into a following subtraction).  Needs M < 2^31: d >= 3.
+WS_HD int fd32_sdiv_s(int n, const FastDiv32 f)
+{
+#ifdef __CUDA_ARCH__
+  return __mulhi(n, (int)f.M) + (int)((unsigned)n >> 31);
+#else
+  return (int)(((i64)n * (i64)f.M) >> 32) + (int)((unsigned)n >> 31);
+#endif
+}
+
 // floor(n / dist) and the remainder from a double-precision reciprocal: the estimate is within +-1
 // for n < 2^46 (relative error of fl(n * fl(1/dist)) <= 2^-52), one correction step makes it exact.
 WS_HD void divrem_rcp(unsigned n, unsigned dist, double rdist, unsigned &q, unsigned &rem)

@@ -57,6 +57,7 @@ namespace cg = cooperative_groups;
 #endif
 #define MARCH_THREADS (MARCH_WARPS * 32)
 #define QCAP 64
+#define LS_BLOCK 64          // march steps per work item of the lockstep march
 #ifndef RAY_BATCH
 #define RAY_BATCH 1          // same-box A/B on B200: 1 -> 0.77 ms, 2 -> 0.79, 4 -> 0.91, 8 -> 1.07 (tail of long rays)
 #endif
@@ -105,7 +106,7 @@ struct __align__(16) RaySetup
   int p[3], distance;  // word 0
   int d[3], n_steps;   // word 1
   int iv[3], flags;    // word 2: bit 0 = small (fast path), bits 1.. = ray index
-  unsigned dq[3], pad0;    // word 3: DDA increments of 32 march steps per axis (fast path), quotient ...
+  unsigned dq[3], pad0;    // word 3: DDA increments of ONE march step per axis (fast path), quotient ...; pad0 = first step of the surface phase
   unsigned drem[3], pad1;  // word 4: ... and remainder of |d| * 32 * h / distance
   int seg[2 * RAY_SEGS];   // words 5-7: march-step ranges [seg[2k], seg[2k+1]) this rank has to process
 };
@@ -526,6 +527,7 @@ WS_D void ray_segments(const UpdateParams &P, const Ray &r, int seg[2 * RAY_SEGS
 // lane of a warp the same ~600 instructions).  Rays without work on this rank get empty step ranges.
 __global__ void __launch_bounds__(256)
 setup_kernel(const UpdateParams Pin, const ws_pt *__restrict__ pts, RaySetup *__restrict__ rays,
+             uint2 *__restrict__ grp_info, const unsigned grp_stride, unsigned *__restrict__ gen_list,
              UpdateCounters *__restrict__ ctr, const PoseDev *__restrict__ pose)
 {
   // the sensor pose comes from the host (kernel parameters) or, in the fused per-scan pipeline, from the
@@ -548,17 +550,25 @@ setup_kernel(const UpdateParams Pin, const ws_pt *__restrict__ pts, RaySetup *__
 #pragma unroll
       for (int a = 0; a < 3; a++) { o.p[a] = r.p[a]; o.d[a] = r.d[a]; o.iv[a] = r.iv[a]; }
       o.distance = r.distance; o.n_steps = r.n_steps; o.flags = (ray_id << 1) | (r.small ? 1 : 0);
-      o.pad0 = o.pad1 = 0u;
+      o.pad1 = 0u;
       const double rdist = 1.0 / (double)r.distance;
 #pragma unroll
       for (int a = 0; a < 3; a++)
       {
         o.dq[a] = o.drem[a] = 0u;
         const unsigned ad = r.d[a] < 0 ? 0u - (unsigned)r.d[a] : (unsigned)r.d[a];
-        if (r.small) divrem_rcp(ad * 32u * (unsigned)P.half_res, (unsigned)r.distance, rdist, o.dq[a], o.drem[a]);
+        if (r.small) divrem_rcp(ad * (unsigned)P.half_res, (unsigned)r.distance, rdist, o.dq[a], o.drem[a]);
       }
       ray_segments(P, r, o.seg);
       valid = o.seg[1] > o.seg[0];                      // ranges are packed from slot 0
+      // first march step of the surface phase: len <= distance - tau - 3 * res - 4 keeps the centre of the
+      // marched voxel (at most 1.5 * res * sqrt(3) + sqrt(3) from the ray point, truncation included) farther
+      // than tau from the hit, so min(norm, tau) == tau (update_tsdf.cpp:466-468)
+      {
+        const long long lim = (long long)r.distance - P.tau - 3ll * P.res - 4ll;
+        o.pad0 = lim < 1 ? 0u : (unsigned)((lim - 1) / P.half_res + 1);
+        if (o.pad0 > (unsigned)r.n_steps) o.pad0 = (unsigned)r.n_steps;
+      }
     }
   }
   // Written in place, NOT compacted: the march takes rays in scan order, so the ~3,500 rays in flight at
@@ -583,61 +593,74 @@ setup_kernel(const UpdateParams Pin, const ws_pt *__restrict__ pts, RaySetup *__
     }
     else { dst[2] = src[2]; dst[5] = src[5]; }
   }
+  // The lockstep march's work items, per phase: the step blocks in which any of the group's (= this warp's)
+  // fast-path rays has work.  A ray's steps split at `split` (word 3, pad0): before it the marched voxel is
+  // farther than tau from the hit whatever the rounding (free-space phase: value == tau), from it on the
+  // surface phase computes the value.  Rays outside the fast path go on a list for march_kernel.
+  const bool small = valid && (o.flags & 1);
+  int lo_s = 0x7fffffff, hi_s = 0, lo_f = 0x7fffffff, hi_f = 0;
+  if (small)
+  {
+    const int split = (int)o.pad0;
+#pragma unroll
+    for (int k = 0; k < RAY_SEGS; k++)
+    {
+      const int a = o.seg[2 * k], b = o.seg[2 * k + 1];
+      if (b <= a) continue;
+      const int as = a > split ? a : split, bf = b < split ? b : split;
+      if (b > as) { lo_s = lo_s < as ? lo_s : as; hi_s = b; }
+      if (bf > a) { lo_f = lo_f < a ? lo_f : a; hi_f = bf; }
+    }
+  }
+  lo_s = __reduce_min_sync(FULL, lo_s); hi_s = __reduce_max_sync(FULL, hi_s);
+  lo_f = __reduce_min_sync(FULL, lo_f); hi_f = __reduce_max_sync(FULL, hi_f);
+  if ((threadIdx.x & 31) == 0 && ray_id < P.n_points)
+  {
+    unsigned b_lo = hi_s > lo_s ? (unsigned)lo_s / LS_BLOCK : 0u;
+    unsigned nb = hi_s > lo_s ? ((unsigned)hi_s + LS_BLOCK - 1u) / LS_BLOCK - b_lo : 0u;
+    grp_info[ray_id >> 5] = make_uint2(b_lo, nb);
+    b_lo = hi_f > lo_f ? (unsigned)lo_f / LS_BLOCK : 0u;
+    nb = hi_f > lo_f ? ((unsigned)hi_f + LS_BLOCK - 1u) / LS_BLOCK - b_lo : 0u;
+    grp_info[grp_stride + (ray_id >> 5)] = make_uint2(b_lo, nb);
+  }
+  if (valid && !small) gen_list[atomicAdd(&ctr->n_general, 1u)] = (unsigned)ray_id;
 }
 
+// The literal-arithmetic march for the rays the set-up pass found outside the bounds of the 32-bit fast path
+// (gen_list; none on a sane scan -- the kernel then returns at once): one ray per warp, lanes stride over
+// the march steps, survivors of the column filter compacted through a per-warp shared-memory queue.
 // ATOMIC: the scan's first pass (candidate keys + brick flags + record).  !ATOMIC: regenerate the record
 // only (far part of every ray), used when the record buffer had to grow.
 template <bool ATOMIC>
 __global__ void __launch_bounds__(MARCH_THREADS, MARCH_CTAS)
 march_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__restrict__ rays,
+             const unsigned *__restrict__ gen_list,
              UpdateCounters *__restrict__ ctr, Rec *__restrict__ rec,
              unsigned *__restrict__ chunk_fill, const unsigned cap_chunks, const PoseDev *__restrict__ pose)
 {
+  const unsigned n_work = __ldcg(&ctr->n_general);
+  if (n_work == 0u) return;
   __shared__ int4 s_qa[MARCH_WARPS][QCAP], s_qb[MARCH_WARPS][QCAP];   // per-warp queue of surviving march steps
   int pos_mm[3];
 #pragma unroll
   for (int a = 0; a < 3; a++) pos_mm[a] = pose ? pose->pos_mm[a] : P.pos_mm[a];
-  __shared__ int4 s_ray[MARCH_WARPS][2][RAY_WORDS];                    // the warp's current and next ray (cp.async)
+  __shared__ int4 s_ray[MARCH_WARPS][RAY_WORDS];                       // the warp's current ray
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   int4 *qa_s = s_qa[wib], *qb_s = s_qb[wib];
   const unsigned total_warps = gridDim.x * MARCH_WARPS;
-  const unsigned n_work = (unsigned)P.n_points;
 
   MarchCtx cx;
   rec_init(cx.rw, ctr, lane);
   cx.n_cand = 0u;
   cx.err = 0u;
 
-  // Work distribution: one ray per fetch from a global counter (same-box A/B of 1/2/4/8 rays per fetch: the
-  // tail of long rays costs more than the atomics), software-pipelined two deep -- while ray k is marched
-  // out of one shared-memory slot, the set-up of ray k+1 is in flight to the other (cp.async) and the index
-  // of ray k+2 is in flight from the counter.
   unsigned k_cur = blockIdx.x * MARCH_WARPS + wib;
-  unsigned k_nxt = 0;
-  if (lane == 0) k_nxt = atomicAdd(&ctr->ray_counter, 1u);
-  k_nxt = total_warps + __shfl_sync(FULL, k_nxt, 0);
-  int buf = 0;
-  if (lane < RAY_WORDS)
-  {
-    if (k_cur < n_work)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_ray[wib][0][lane])),
-                   "l"(reinterpret_cast<const int4 *>(&rays[k_cur]) + lane) : "memory");
-    if (k_nxt < n_work)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_ray[wib][1][lane])),
-                   "l"(reinterpret_cast<const int4 *>(&rays[k_nxt]) + lane) : "memory");
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncwarp();
-
   while (k_cur < n_work)
   {
-    unsigned fetched = 0;
-    if (lane == 0) fetched = atom_add_async(&ctr->ray_counter, 1u);
-
-    const int4 *ray_s = s_ray[wib][buf];
-    const int4 w2 = lds_word(ray_s + 2);
-    const bool small = (w2.w & 1) != 0;
+    if (lane < RAY_WORDS) s_ray[wib][lane] = reinterpret_cast<const int4 *>(&rays[gen_list[k_cur]])[lane];
+    __syncwarp();
+    const int4 *ray_s = s_ray[wib];
     const int n_segs = P.n_xiv > 0 ? RAY_SEGS : 1;
 #pragma unroll 1
     for (int sg = 0; sg < n_segs; sg++)
@@ -653,21 +676,12 @@ march_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__restrict_
         start = start > fs ? start : fs;
       }
       if (start >= end) continue;
-      if (small) march_ray<ATOMIC, true>(g, P, pos_mm, ray_s, start, end, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
-      else march_ray<ATOMIC, false>(g, P, pos_mm, ray_s, start, end, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
+      march_ray<ATOMIC, false>(g, P, pos_mm, ray_s, start, end, lane, qa_s, qb_s, cx, rec, chunk_fill, cap_chunks, ctr);
     }
-
-    // rotate the pipeline.  The empty asm ties the fetched index to a value that is only known once the
-    // march is done: without it the compiler broadcasts (and waits for) the atomic's result right away.
-    asm volatile("" : "+r"(fetched) : "r"(cx.n_cand), "r"(cx.rw.fill));
-    asm volatile("cp.async.wait_all;" ::: "memory");     // ray k+1 has landed in the other slot
-    __syncwarp();                                        // ... and every lane is done reading this one
-    k_cur = k_nxt;
-    k_nxt = total_warps + __shfl_sync(FULL, fetched, 0);
-    if (k_nxt < n_work && lane < RAY_WORDS)
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(&s_ray[wib][buf][lane])),
-                   "l"(reinterpret_cast<const int4 *>(&rays[k_nxt]) + lane) : "memory");
-    buf ^= 1;
+    __syncwarp();
+    unsigned nxt = 0;
+    if (lane == 0) nxt = atomicAdd(&ctr->gen_counter, 1u);
+    k_cur = total_warps + __shfl_sync(FULL, nxt, 0);
   }
 
   rec_finish(cx.rw, lane, chunk_fill, cap_chunks, ctr);
@@ -681,25 +695,538 @@ march_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__restrict_
   if (cx.err) atomicOr(&ctr->error, cx.err);
 }
 
-// touched-brick flags -> compact list; flags are reset for the next scan
+// replay list writer: a warp reserves WS_LIST_SPAN entries at a time (one same-address atomic per span) and
+// pads what it does not use with entries whose slot is LIST_NONE
+#define WS_LIST_SPAN 128
+#define LIST_NONE 0xFFFFFFFFFFFFFFFFull
+struct ListWriter
+{
+  unsigned base, used;
+};
+
+WS_D void list_pad(ListWriter &w, const int lane, Rec *__restrict__ list, const unsigned cap)
+{
+  for (unsigned t = w.used + (unsigned)lane; t < WS_LIST_SPAN; t += 32u)
+  {
+    Rec e; e.key = 0ull; e.ref = LIST_NONE;
+    if (w.base + t < cap) list[w.base + t] = e;
+  }
+  w.used = WS_LIST_SPAN;
+}
+
+WS_D void list_append(ListWriter &w, const bool want, const Rec e, const int lane, Rec *__restrict__ list, const unsigned cap,
+                      UpdateCounters *__restrict__ ctr)
+{
+  const unsigned m = __ballot_sync(FULL, want);
+  if (m == 0u) return;
+  const unsigned n = (unsigned)__popc(m);
+  if (w.used + n > WS_LIST_SPAN)
+  {
+    if (w.used < WS_LIST_SPAN) list_pad(w, lane, list, cap);
+    unsigned b = 0;
+    if (lane == 0)
+    {
+      b = atomicAdd(&ctr->n_list, (unsigned)WS_LIST_SPAN);
+      if (b + WS_LIST_SPAN > cap) atomicOr(&ctr->error, 2u);
+    }
+    w.base = __shfl_sync(FULL, b, 0);
+    w.used = 0;
+  }
+  const unsigned at = w.base + w.used + (unsigned)__popc(m & ((1u << lane) - 1u));
+  if (want && at < cap) list[at] = e;
+  w.used += n;
+}
+
+// ---- lockstep march --------------------------------------------------------------------------------
+// One RAY per LANE: the 32 lanes of a warp walk 32 consecutive rays of the scan in lockstep, march step i of
+// all of them in the same loop turn.  What depends on the step alone (len, delta_z, the shape of the
+// interpolation fan, near/far) is warp-uniform; the DDA, the "same (x,y) column" filter
+// (update_tsdf.cpp:455-458) and the brick flag are private to the lane -- no shuffles, no queue.  A work item
+// is (group of 32 rays, block of LS_BLOCK march steps), handed out by a global counter, group-major.
+//
+// Two phases (two launches), split per ray at RaySetup::pad0:
+//   SURF   the last ~2 * tau of every ray: the value of the marched voxel is computed (:466-472), every
+//          candidate is a 64-bit atomicMin on the voxel's key, far-field candidates are recorded -- the
+//          order-dependent machinery (merge, parked voxels, replay) works on these candidates alone;
+//   FREE   everything before: value == tau by construction, so a candidate is just "a real / an interpolated
+//          free-space candidate arrived" -- one bit OR-ed into the voxel's 4-bit state (L2 resident), no key,
+//          no record, no DRAM traffic.  Free-space candidates lose against any candidate of the surface phase
+//          (|value| < tau); the only thing the order of processing still decides is whether one of them
+//          FOLLOWS the interpolated winner of a parked voxel, so this phase runs after the surface merge has
+//          parked those voxels and offers such a candidate to the replay on the spot.
+// Voxel addresses come from three per-axis tables in shared memory (ring wrap, residency, bricking).
+// Rays outside the bounds of the 32-bit arithmetic (march_math.cuh) are left to march_kernel.
+#ifndef LS_CTAS
+#define LS_CTAS 3
+#endif
+#define TAB_INVALID 0xFFFFFFFFu
+
+WS_D u64 step_bits(int a, int b)   // bits [a, b) of a 64-bit mask, 0 <= a < b <= 64
+{
+  const u64 hi = b >= 64 ? ~0ull : ((1ull << b) - 1ull);
+  return hi & ~((1ull << a) - 1ull);
+}
+
+struct LsShared        // per CTA: address tables; per warp: ray table and queue of surviving march steps
+{
+  const unsigned *tx, *ty, *tz;     // voxel - lo (0 .. size-1) -> address parts, see the table set-up in the kernel
+  int4 *ray;                        // [32][2] per lane of the group: {hit point, distance}, {interpolation vector, -}
+  int4 *queue;                      // [QCAP] {proj x, y, z, march step << 5 | lane}
+};
+
+struct LsOut           // where the free-space phase offers candidates that land on parked voxels
+{
+  u64 *pend_key;
+  Rec *list;
+  unsigned pending_cap, list_cap;
+};
+
+#define NO_PARK 0xFFFFFFFFu     // brick_slot_base of a brick without parked voxels
+
+struct LsWarp          // a warp's running state across work items
+{
+  RecWriter rw;
+  ListWriter lw;
+  unsigned n_cand, err;
+  unsigned last_brick;
+  // FREE: the lane's last candidate, whose old voxel state (returned by its atomic) has not been looked at yet
+  bool pd_valid;
+  unsigned pd_old, pd_info;      // info: state shift [4:0], interpolated [5], fan step [11:6], march step [26:12], lane of the ray [31:27]
+  u64 pd_addr;
+};
+
+// FREE phase, rare: a free-space candidate (|value| == tau) landed on a parked voxel.  What the replay's first
+// round does for a recorded candidate: offer it to the voxel if it follows the parked winner in the
+// reference's order, and keep it for the later rounds.  Warp-collective (list_append).
+WS_D void offer_parked(const GridDesc &g, const UpdateParams &P, const LsOut &out, LsWarp &W,
+                                          const bool chk, const unsigned ray_base, const int lane,
+                                          UpdateCounters *__restrict__ ctr)
+{
+  unsigned slot = 0u;
+  bool hit = false;
+  u64 key = 0ull;
+  if (chk)
+  {
+    const unsigned info = W.pd_info;
+    const unsigned step = (info >> 6) & 63u, i = (info >> 12) & 0x7FFFu, ray = ray_base + (info >> 27);
+    const u64 seq2 = make_seq(ray, i, step) << 1;
+    key = (info & 32u) ? (((u64)(unsigned)P.tau << 47) | (1ull << 46) | (((1ull << 46) - 2ull) - seq2))
+                       : (((u64)(unsigned)P.tau << 47) | seq2);
+    const u64 kv = __ldcg(&g.keys[W.pd_addr]);
+    if (key_is_pending(kv))
+    {
+      slot = __ldcg(&g.brick_slot_base[W.pd_addr >> 9]) + (unsigned)((kv >> WS_SEQ_BITS) & 0x1FFull);
+      hit = slot < out.pending_cap && key_seq(key) > (kv & WS_SEQ_MAX);
+      if (hit) atomicMin(&out.pend_key[slot], key);
+    }
+  }
+  Rec e; e.key = key; e.ref = (u64)slot;
+  list_append(W.lw, hit, e, lane, out.list, out.list_cap, ctr);
+  W.pd_valid = false;
+}
+
+// The heavy part: `take` queued march steps, one per lane, of any of the group's rays.
+// WIDE: voxel addresses need more than 32 bits (the x table then holds address / 64)
+template <bool SURF, bool ATOMIC, bool WIDE>
+WS_D void march_drain(const GridDesc &g, const UpdateParams &P, const LsShared &sh, const int qh, const int take,
+                      const unsigned ray_base, const int lane, LsWarp &W, Rec *__restrict__ rec,
+                      unsigned *__restrict__ chunk_fill, const unsigned cap_chunks, UpdateCounters *__restrict__ ctr,
+                      const LsOut &out)
+{
+  bool have = lane < take;
+  const int4 q = sh.queue[(qh + lane) & (QCAP - 1)];
+  const int rl = q.w & 31, i = q.w >> 5;
+  const int4 r1 = sh.ray[2 * rl + 1];
+  const int riv[3] = { r1.x, r1.y, r1.z };
+  const int nlo[3] = { -P.lo[0], -P.lo[1], -P.lo[2] };
+#define LS_VOX(x, a) ((unsigned)(fd32_sdiv_s((x), P.div_res32) + nlo[a]))
+  const int len = 1 + i * P.half_res;
+
+  u64 key_real0 = 0ull, key_int0 = 0ull;
+  if (SURF)
+  {
+    // ---- value of the marched voxel (:466-472) -------------------------------------------------
+    const int4 r0 = sh.ray[2 * rl];
+    const int mx = fd32_sdiv_s(q.x, P.div_res32), my = fd32_sdiv_s(q.y, P.div_res32), mz = fd32_sdiv_s(q.z, P.div_res32);
+    const int ex = wsub(r0.x, wadd(wmul(mx, P.res), P.half_res));
+    const int ey = wsub(r0.y, wadd(wmul(my, P.res), P.half_res));
+    const int ez = wsub(r0.z, wadd(wmul(mz, P.res), P.half_res));
+    const int vsq = wadd(wadd(wmul(ex, ex), wmul(ey, ey)), wmul(ez, ez));
+    int value = P.tau;
+    if (__any_sync(FULL, have && (unsigned)vsq < (unsigned)P.tau_sq))
+    {
+      const int root = isqrt31(vsq < 0 ? 0 : vsq);
+      if ((unsigned)vsq < (unsigned)P.tau_sq) value = root < P.tau ? root : P.tau;
+    }
+    if (len > r0.w) value = -value;
+    if (value <= P.zero_weight_max) have = false;        // weight == 0 (:475-483)
+    const unsigned ray = ray_base + (unsigned)rl;
+    const unsigned av = (unsigned)(value < 0 ? -value : value);
+    const unsigned klo = (ray << 22) | ((unsigned)i << (WS_SEQ_STEP_BITS + 1)) | (value < 0 ? 1u : 0u);
+    key_real0 = ((u64)((av << 15) | (ray >> 10)) << 32) | (u64)klo;
+    // interpolated: order field = SEQ_MAX - seq, i.e. (2^46 - 2) - (seq << 1) in place
+    key_int0 = ((u64)av << 47) | (1ull << 46) | (((1ull << 46) - 2ull) - (((u64)(ray >> 10) << 32) | (u64)(klo & ~1u))) | (u64)(klo & 1u);
+  }
+
+  // ---- the fan of interpolated voxels around the step (:485-506) -----------------------------------
+  const int delta_z = div_mr32(wmul(P.dz_per_distance, len));                                 // :485
+  const int iter_steps = (int)fd32_udiv((unsigned)(delta_z * 2), P.div_res32) + 1;           // :486
+  const int mid = (int)fd32_udiv((unsigned)delta_z, P.div_res32);                            // :487
+  if (have && iter_steps > (1 << WS_SEQ_STEP_BITS)) W.err |= 1u;
+  const int low_x = q.x - div_mr32(delta_z * riv[0]);                                        // :488
+  const int low_y = q.y - div_mr32(delta_z * riv[1]);
+  const int low_z = q.z - div_mr32(delta_z * riv[2]);
+  const bool far = len >= P.far_len;
+  const int max_steps = __reduce_max_sync(FULL, have ? iter_steps : 0);
+
+#pragma unroll 1
+  for (int step = 0; step < max_steps; ++step)                                               // :491
+  {
+    int fx = 0, fy = 0, fz = 0;
+    if (step > 0)
+    {
+      const int sr = wmul(step, P.res);
+      fx = div_mr32(sr * riv[0]); fy = div_mr32(sr * riv[1]); fz = div_mr32(sr * riv[2]);
+    }
+    const unsigned tx = LS_VOX(low_x + fx, 0), ty = LS_VOX(low_y + fy, 1), tz = LS_VOX(low_z + fz, 2);   // :493
+    bool valid = have && step < iter_steps &&
+                 !(tx > (unsigned)P.ext[0] || ty > (unsigned)P.ext[1] || tz > (unsigned)P.ext[2]);       // :495-498
+    unsigned ax = TAB_INVALID;
+    if (valid) ax = sh.tx[tx];
+    valid = ax != TAB_INVALID;                       // else: out of bounds, or the column lives on another rank
+    u64 key = 0ull, addr = 0ull;
+    if (!SURF)
+    {
+      // ---- free-space candidate: OR its bit into the voxel's state.  The atomic returns the old state;
+      // whether it shows a PARKED voxel is looked at one candidate later (pd_*), when the answer has long
+      // arrived -- the loop never waits for memory.
+      const bool chk = W.pd_valid && ((W.pd_old >> (W.pd_info & 31u)) & VS_PARKED) != 0u;
+      if (__any_sync(FULL, chk)) offer_parked(g, P, out, W, chk, ray_base, lane, ctr);
+      if (valid)
+      {
+        W.n_cand++;
+        unsigned brick;
+        if (WIDE) { addr = ((u64)ax << 6) + (u64)(sh.ty[ty] + sh.tz[tz]); brick = (unsigned)(addr >> 9); }
+        else { const unsigned a32 = ax + sh.ty[ty] + sh.tz[tz]; addr = (u64)a32; brick = a32 >> 9; }
+        if (brick != W.last_brick) { g.brick_flag2[brick] = 1u; W.last_brick = brick; }
+        const unsigned shft = vstate_shift(addr);
+        W.pd_old = atomicOr(g.vstate + vstate_word(addr), (step == mid ? VS_FREE_REAL : VS_FREE_INT) << shft);
+        W.pd_addr = addr;
+        W.pd_info = shft | ((unsigned)(step == mid ? 0 : 1) << 5) | ((unsigned)step << 6) | ((unsigned)i << 12) | ((unsigned)rl << 27);
+        W.pd_valid = true;
+      }
+      continue;
+    }
+    if (valid)
+    {
+      W.n_cand++;
+      unsigned brick;
+      if (WIDE) { addr = ((u64)ax << 6) + (u64)(sh.ty[ty] + sh.tz[tz]); brick = (unsigned)(addr >> 9); }
+      else { const unsigned a32 = ax + sh.ty[ty] + sh.tz[tz]; addr = (u64)a32; brick = a32 >> 9; }
+      const u64 s2 = (u64)(unsigned)step << 1;
+      key = step == mid ? key_real0 + s2 : key_int0 - s2;                                    // :503-506
+      if (ATOMIC)
+      {
+        atomicMin(&g.keys[addr], key);                                                       // :508-512
+        if (brick != W.last_brick) { g.brick_flag[brick] = 1u; W.last_brick = brick; }
+      }
+    }
+    rec_append(W.rw, valid && far, key, addr, lane, rec, chunk_fill, cap_chunks, ctr);     // warp-collective
+  }
+#undef LS_VOX
+}
+
+// One work item: LS_BLOCK march steps of a group of 32 rays.  Step phase in lockstep (one ray per lane),
+// survivors of the column filter queued, heavy part on full batches of 32.
+template <bool SURF, bool ATOMIC, bool WIDE>
+WS_D void march_block(const GridDesc &g, const UpdateParams &P, const int pos_mm[3], const LsShared &sh,
+                      const RaySetup *__restrict__ rays, const unsigned ray_base, const int s0, const int lane, LsWarp &W,
+                      Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill, const unsigned cap_chunks,
+                      UpdateCounters *__restrict__ ctr, const LsOut &out)
+{
+  // ---- this lane's ray ------------------------------------------------------------------------
+  const unsigned ray = ray_base + (unsigned)lane;
+  const bool in_scan = ray < (unsigned)P.n_points;
+  const int4 *rw4 = reinterpret_cast<const int4 *>(rays + (in_scan ? ray : 0u));
+  const int4 w2 = __ldg(rw4 + 2), w3 = __ldg(rw4 + 3);
+  const bool ok = in_scan && (w2.w & 1);            // fast-path rays only
+  u64 mask = 0ull;                                  // march steps of this block the lane has to process
+  if (ok)
+  {
+    const int n_segs = P.n_xiv > 0 ? RAY_SEGS : 1;
+    const int split = w3.w;
+    int lo_lim = SURF ? split : 0;
+    const int hi_lim = SURF ? 0x7fffffff : split;
+    if (!ATOMIC && P.far_len > 1) { const int fs = (P.far_len - 1) / P.half_res; lo_lim = lo_lim > fs ? lo_lim : fs; }
+    lo_lim = lo_lim > s0 ? lo_lim : s0;
+    const int hi_blk = hi_lim < s0 + LS_BLOCK ? hi_lim : s0 + LS_BLOCK;
+#pragma unroll 1
+    for (int sg = 0; sg < n_segs; sg += 2)
+    {
+      const int4 ws = __ldg(rw4 + 5 + (sg >> 1));
+      if (ws.x >= ws.y) break;
+      int a = (ws.x > lo_lim ? ws.x : lo_lim) - s0, b = (ws.y < hi_blk ? ws.y : hi_blk) - s0;
+      if (a < b) mask |= step_bits(a, b);
+      if (n_segs == 1 || ws.z >= ws.w) break;
+      a = (ws.z > lo_lim ? ws.z : lo_lim) - s0; b = (ws.w < hi_blk ? ws.w : hi_blk) - s0;
+      if (a < b) mask |= step_bits(a, b);
+    }
+  }
+  const int f = __reduce_min_sync(FULL, mask ? __ffsll((long long)mask) - 1 : LS_BLOCK);
+  const int l = __reduce_max_sync(FULL, mask ? 63 - __clzll((long long)mask) : -1);
+  if (l < 0) return;
+  const int i0 = s0 + f, i1 = s0 + l;
+
+  const int4 w0 = __ldg(rw4 + 0), w1 = __ldg(rw4 + 1), w4 = __ldg(rw4 + 4);
+  const int distance = ok ? w0.w : 1;
+  if (ok && w1.w > (1 << WS_SEQ_MARCH_BITS)) W.err |= 1u;
+  __syncwarp();                                      // the previous item's heavy part is done with the tables
+  sh.ray[2 * lane] = w0;
+  sh.ray[2 * lane + 1] = w2;
+  __syncwarp();
+
+  // ---- DDA (march_math.cuh), one step per turn: proj = pos + sgn * floor(|d| * len / distance) ----------
+  int proj[3], sdq[3], sgn[3];
+  unsigned rem[3], drem[3];
+  {
+    const int ii = i0 > 0 ? i0 - 1 : 0;
+    const unsigned len_i = 1u + (unsigned)ii * (unsigned)P.half_res;
+    const double rdist = 1.0 / (double)distance;
+    const int dv[3] = { w1.x, w1.y, w1.z };
+    const unsigned dq1[3] = { (unsigned)w3.x, (unsigned)w3.y, (unsigned)w3.z };
+    drem[0] = (unsigned)w4.x; drem[1] = (unsigned)w4.y; drem[2] = (unsigned)w4.z;
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+    {
+      const unsigned ad = dv[a] < 0 ? 0u - (unsigned)dv[a] : (unsigned)dv[a];
+      unsigned q;
+      divrem_rcp(ad * len_i, (unsigned)distance, rdist, q, rem[a]);
+      sgn[a] = dv[a] < 0 ? -1 : 1;
+      proj[a] = pos_mm[a] + sgn[a] * (int)q;
+      sdq[a] = sgn[a] * (int)dq1[a];
+    }
+  }
+#define LS_ADVANCE()                                                                   \
+  _Pragma("unroll") for (int a = 0; a < 3; a++)                                        \
+  {                                                                                    \
+    proj[a] += sdq[a];                                                                 \
+    rem[a] += drem[a];                                                                 \
+    if (rem[a] >= (unsigned)distance) { rem[a] -= (unsigned)distance; proj[a] += sgn[a]; } \
+  }
+  // voxel - lo per axis (the in-bounds test is then one unsigned compare, :460-463)
+  const int nlo[3] = { -P.lo[0], -P.lo[1], -P.lo[2] };
+#define LS_VOX(x, a) ((unsigned)(fd32_sdiv_s((x), P.div_res32) + nlo[a]))
+  unsigned px = 0x80000000u, py = 0x80000000u;       // no previous step (update_tsdf.cpp:448)
+  if (i0 > 0)
+  {
+    px = LS_VOX(proj[0], 0);
+    py = LS_VOX(proj[1], 1);
+    LS_ADVANCE();
+  }
+
+  const unsigned lt = (1u << lane) - 1u;
+  int qn = 0, qh = 0;                                // queue fill / head (warp-uniform)
+  for (int i = i0; i <= i1; ++i)
+  {
+    const int cx = proj[0], cy = proj[1], cz = proj[2];                                         // :452
+    LS_ADVANCE();
+    const unsigned ix = LS_VOX(cx, 0), iy = LS_VOX(cy, 1), iz = LS_VOX(cz, 2);                  // :453 (- lo)
+    bool act = ((mask >> (i - s0)) & 1ull) != 0ull;
+    if (ix == px && iy == py) act = false;                                                      // :455-458
+    px = ix; py = iy;
+    if (ix > (unsigned)P.ext[0] || iy > (unsigned)P.ext[1] || iz > (unsigned)P.ext[2]) act = false;   // :460-463
+    const unsigned m = __ballot_sync(FULL, act);
+    if (m == 0u) continue;
+    if (act) sh.queue[(qh + qn + __popc(m & lt)) & (QCAP - 1)] = make_int4(cx, cy, cz, (i << 5) | lane);
+    qn += __popc(m);
+    __syncwarp();
+    if (qn >= 32)
+    {
+      march_drain<SURF, ATOMIC, WIDE>(g, P, sh, qh, 32, ray_base, lane, W, rec, chunk_fill, cap_chunks, ctr, out);
+      qh = (qh + 32) & (QCAP - 1);
+      qn -= 32;
+      __syncwarp();
+    }
+  }
+  if (qn > 0) march_drain<SURF, ATOMIC, WIDE>(g, P, sh, qh, qn, ray_base, lane, W, rec, chunk_fill, cap_chunks, ctr, out);
+  if (!SURF)
+  {
+    // the last candidates' old states, before the ray table changes
+    const bool chk = W.pd_valid && ((W.pd_old >> (W.pd_info & 31u)) & VS_PARKED) != 0u;
+    if (__any_sync(FULL, chk)) offer_parked(g, P, out, W, chk, ray_base, lane, ctr);
+    W.pd_valid = false;
+  }
+#undef LS_ADVANCE
+#undef LS_VOX
+}
+
+template <bool SURF, bool ATOMIC, bool WIDE>
+__global__ void __launch_bounds__(MARCH_THREADS, LS_CTAS)
+march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__restrict__ rays,
+                      const uint2 *__restrict__ grp_info, const unsigned *__restrict__ item_off, const unsigned n_groups,
+                      UpdateCounters *__restrict__ ctr, Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill,
+                      const unsigned cap_chunks, const PoseDev *__restrict__ pose, const LsOut out)
+{
+  extern __shared__ unsigned s_tab[];               // size[0] + size[1] + size[2] address parts
+  __shared__ int4 s_ray[MARCH_WARPS][64];
+  __shared__ int4 s_queue[MARCH_WARPS][QCAP];
+  const unsigned n_items = __ldcg(&ctr->n_items[SURF ? 0 : 1]);
+  if (n_items == 0u) return;
+  if (!SURF && __ldcg(&ctr->rec_overflow) != 0u && __ldcg(&ctr->pending_overflow) == 0u) return;   // redone after the regrow
+  const int lane = threadIdx.x & 31;
+  const int wib = threadIdx.x >> 5;
+  LsShared sh;
+  sh.tx = s_tab; sh.ty = s_tab + g.size[0]; sh.tz = sh.ty + g.size[1];
+  sh.ray = s_ray[wib]; sh.queue = s_queue[wib];
+  for (int t = threadIdx.x; t < g.size[0] + g.size[1] + g.size[2]; t += blockDim.x)
+  {
+    // ring coordinate (hdf5_local_map.h:140-151) of voxel lo + t, then its share of the bricked address:
+    // address = x part (<< 6 if WIDE) + y part + z part
+    unsigned v;
+    if (t < g.size[0])
+    {
+      int r = t + P.ringc[0]; r -= r >= g.size[0] ? g.size[0] : 0;
+      const int slot = g.full ? (r >> 3) : (int)g.xslot[r >> 3];
+      v = slot < 0 ? TAB_INVALID : (unsigned)slot * (unsigned)(g.nb[1] * g.nb[2]) * 8u + (unsigned)(r & 7);
+      if (!WIDE && slot >= 0) v <<= 6;
+    }
+    else if (t < g.size[0] + g.size[1])
+    {
+      int r = t - g.size[0] + P.ringc[1]; r -= r >= g.size[1] ? g.size[1] : 0;
+      v = (unsigned)(r >> 3) * (unsigned)g.nb[2] * WS_BRICK_VOX + (unsigned)((r & 7) << 3);
+    }
+    else
+    {
+      int r = t - g.size[0] - g.size[1] + P.ringc[2]; r -= r >= g.size[2] ? g.size[2] : 0;
+      v = (unsigned)(r >> 3) * WS_BRICK_VOX + (unsigned)(r & 7);
+    }
+    s_tab[t] = v;
+  }
+  __syncthreads();
+
+  int pos_mm[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) pos_mm[a] = pose ? pose->pos_mm[a] : P.pos_mm[a];
+  const unsigned total_warps = gridDim.x * MARCH_WARPS;
+  const uint2 *ginfo = grp_info + (SURF ? 0u : n_groups);
+  const unsigned *ioff = item_off + (SURF ? 0u : n_groups + 1u);
+  unsigned *counter = &ctr->item_counter[SURF ? 0 : 1];
+
+  LsWarp W;
+  if (SURF) rec_init(W.rw, ctr, lane);
+  W.lw.base = 0u; W.lw.used = WS_LIST_SPAN;
+  W.n_cand = 0u; W.err = 0u; W.last_brick = 0xFFFFFFFFu;
+  W.pd_valid = false; W.pd_old = 0u; W.pd_info = 0u; W.pd_addr = 0ull;
+
+  // items: the first one by warp index, the others from a global counter, fetched one item ahead
+  unsigned k_cur = blockIdx.x * MARCH_WARPS + wib;
+  unsigned k_nxt = 0;
+  if (lane == 0) k_nxt = atomicAdd(counter, 1u);
+  k_nxt = total_warps + __shfl_sync(FULL, k_nxt, 0);
+  while (k_cur < n_items)
+  {
+    unsigned fetched = 0;
+    if (lane == 0) fetched = atom_add_async(counter, 1u);
+    // item -> (group, block): the last group whose first item is <= k_cur
+    unsigned lo = 0u, hi = n_groups;
+    while (hi - lo > 1u)
+    {
+      const unsigned m = (lo + hi) >> 1;
+      if (__ldg(&ioff[m]) <= k_cur) lo = m; else hi = m;
+    }
+    const uint2 gi = __ldg(&ginfo[lo]);
+    const int blk = (int)(gi.x + (k_cur - __ldg(&ioff[lo])));
+    march_block<SURF, ATOMIC, WIDE>(g, P, pos_mm, sh, rays, lo * 32u, blk * LS_BLOCK, lane, W, rec, chunk_fill, cap_chunks, ctr, out);
+    asm volatile("" : "+r"(fetched) : "r"(W.n_cand), "r"(W.lw.used));   // keep the fetch in flight behind the march
+    k_cur = k_nxt;
+    k_nxt = total_warps + __shfl_sync(FULL, fetched, 0);
+  }
+
+  if (SURF) rec_finish(W.rw, lane, chunk_fill, cap_chunks, ctr);
+  else if (W.lw.used < WS_LIST_SPAN) list_pad(W.lw, lane, out.list, out.list_cap);
+  if (ATOMIC)
+  {
+    unsigned long long nc = W.n_cand;
+    for (int o = 16; o > 0; o >>= 1) nc += __shfl_down_sync(FULL, nc, o);
+    if (lane == 0 && nc) atomicAdd(&ctr->n_candidates, nc);
+  }
+  if (W.err) atomicOr(&ctr->error, W.err);
+}
+
+// exclusive prefix sums of the groups' block counts, per phase -> item_off[phase][0 .. n_groups], n_items[phase]
+// (one CTA)
+__global__ void __launch_bounds__(1024)
+item_scan_kernel(const uint2 *__restrict__ grp_info, const unsigned n_groups, unsigned *__restrict__ item_off,
+                 UpdateCounters *__restrict__ ctr)
+{
+  __shared__ unsigned s_warp[32];
+  __shared__ unsigned s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int phase = 0; phase < 2; phase++)
+  {
+    const uint2 *gi = grp_info + (size_t)phase * n_groups;
+    unsigned *io = item_off + (size_t)phase * (n_groups + 1u);
+    __syncthreads();
+    if (tid == 0) s_carry = 0u;
+    __syncthreads();
+    for (unsigned base = 0; base < n_groups; base += 1024u)
+    {
+      const unsigned gidx = base + (unsigned)tid;
+      const unsigned v = gidx < n_groups ? gi[gidx].y : 0u;
+      unsigned x = v;
+      for (int o = 1; o < 32; o <<= 1)
+      {
+        const unsigned y = __shfl_up_sync(FULL, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) s_warp[warp] = x;
+      __syncthreads();
+      if (warp == 0)
+      {
+        unsigned w = s_warp[lane];
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          const unsigned y = __shfl_up_sync(FULL, w, o);
+          if (lane >= o) w += y;
+        }
+        s_warp[lane] = w;
+      }
+      __syncthreads();
+      const unsigned incl = s_carry + x + (warp > 0 ? s_warp[warp - 1] : 0u);
+      if (gidx < n_groups) io[gidx] = incl - v;
+      __syncthreads();
+      if (tid == 1023) s_carry = incl;
+      __syncthreads();
+    }
+    if (tid == 0) { io[n_groups] = s_carry; ctr->n_items[phase] = s_carry; }
+  }
+}
+
+// touched-brick flags -> compact list; flags are reset for the next scan.  SURF: the bricks of the surface
+// phase (they are also marked as touched at all); !SURF: every brick the scan touched.
+template <bool SURF>
 __global__ void __launch_bounds__(256)
 brick_list_kernel(const GridDesc g, unsigned *__restrict__ brick_list, UpdateCounters *__restrict__ ctr)
 {
+  if (!SURF && ctr->rec_overflow != 0u && ctr->pending_overflow == 0u) return;     // redone after the regrow
   const int lane = threadIdx.x & 31;
   const i64 stride = (i64)gridDim.x * blockDim.x;
   const i64 n_round = (g.n_bricks + 31) & ~31ll;
+  unsigned *flag = SURF ? g.brick_flag : g.brick_flag2;
+  unsigned *count = SURF ? &ctr->n_surf_bricks : &ctr->n_touched_bricks;
   for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < n_round; b += stride)
   {
-    const bool set = b < g.n_bricks && g.brick_flag[b] != 0u;
+    const bool set = b < g.n_bricks && flag[b] != 0u;
     const unsigned m = __ballot_sync(FULL, set);
     if (m == 0u) continue;
     unsigned first = 0;
-    if (lane == 0) first = atomicAdd(&ctr->n_touched_bricks, (unsigned)__popc(m));
+    if (lane == 0) first = atomicAdd(count, (unsigned)__popc(m));
     first = __shfl_sync(FULL, first, 0);
     if (set)
     {
       brick_list[first + (unsigned)__popc(m & ((1u << lane) - 1u))] = (unsigned)b;
-      g.brick_flag[b] = 0u;
+      flag[b] = 0u;
+      if (SURF) g.brick_flag2[b] = 1u;
     }
   }
 }
@@ -753,11 +1280,11 @@ WS_D void mbar_wait(u64 *bar, unsigned parity)
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
+      "WAIT_LOOP_%=:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra.uni WAIT_DONE;\n"
-      "bra.uni WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
+      "@p bra.uni WAIT_DONE_%=;\n"
+      "bra.uni WAIT_LOOP_%=;\n"
+      "WAIT_DONE_%=:\n"
       "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 WS_D void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, u64 *bar)
@@ -781,7 +1308,8 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
   __shared__ __align__(8) u64 s_bar[MERGE_STAGES];
   __shared__ unsigned s_cnt[8][2];
   __shared__ unsigned s_base;
-  const unsigned n_tb = ctr->n_touched_bricks;
+  __shared__ __align__(128) unsigned char s_state[MERGE_STAGES][WS_BRICK_VOX / 2];
+  const unsigned n_tb = ctr->n_surf_bricks;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned touched = 0, written = 0;
 
@@ -830,15 +1358,22 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
     const u64 k2[2] = { kk.x, kk.y };
     uint32_t e2[2] = { ee.x, ee.y };
     bool parked[2];
-    unsigned pm[2];
+    unsigned pm[2], nib[2];
 #pragma unroll
     for (int j = 0; j < 2; j++)
     {
       const u64 k = k2[j];
       const bool occupied = key_is_candidate(k);
-      const bool fin = occupied && winner_is_final(k, P.tau);
-      parked[j] = occupied && !fin;
-      if (occupied) touched++;
+      // a winner at |value| == tau is a free-space candidate: it goes into the voxel's state like the ones
+      // of the free-space phase (a real one of that phase still beats an interpolated one) and is folded
+      // by fmerge_kernel; below tau the voxel is closed: final winner folded here, interpolated one parked
+      const bool open_tau = occupied && key_abs_value(k) >= P.tau;
+      const bool closed = occupied && !open_tau;
+      const bool fin = closed && !key_interpolated(k);
+      parked[j] = closed && !fin;
+      nib[j] = open_tau ? (key_interpolated(k) ? VS_FREE_INT : VS_FREE_REAL)
+                        : (closed ? (VS_CLOSED | (parked[j] ? VS_PARKED : 0u)) : 0u);
+      if (closed) touched++;
       if (fin)
       {
         const int value = key_value(k);
@@ -851,8 +1386,7 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
       pm[j] = __ballot_sync(FULL, parked[j]);
     }
     *reinterpret_cast<uint2 *>(&s_ent[st][2 * tid]) = make_uint2(e2[0], e2[1]);
-    if (lane == 0)
-      *reinterpret_cast<uint2 *>(&g.park_bits[park_word((u64)base + 2u * (unsigned)tid)]) = make_uint2(pm[0], pm[1]);
+    s_state[st][tid] = (unsigned char)(nib[0] | (nib[1] << 4));
     // slots for the parked voxels -- one global atomic per brick (block-aggregated: same-address atomics
     // serialise in L2; reserving slots in per-CTA chunks instead was slower, the gaps cost the replay more)
     if (lane < 2) s_cnt[warp][lane] = (unsigned)__popc(pm[lane]);
@@ -863,7 +1397,7 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
       for (int w = 0; w < 8; w++)
         for (int q = 0; q < 2; q++) { const unsigned c = s_cnt[w][q]; s_cnt[w][q] = tot; tot += c; }
       s_base = tot ? atomicAdd(&ctr->n_pending, tot) : 0u;
-      g.brick_slot_base[base >> 9] = s_base;
+      g.brick_slot_base[base >> 9] = tot ? s_base : NO_PARK;
     }
     __syncthreads();
     u64 nk[2] = { WS_KEY_EMPTY, WS_KEY_EMPTY };
@@ -893,6 +1427,7 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
     {
       bulk_s2g(g.keys + base, s_keys[st], MERGE_KEY_BYTES);
       bulk_s2g(g.grid + base, s_ent[st], MERGE_ENT_BYTES);
+      bulk_s2g(reinterpret_cast<unsigned char *>(g.vstate) + base / 2, s_state[st], WS_BRICK_VOX / 2);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
@@ -910,40 +1445,107 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
   }
 }
 
-// replay list writer: a warp reserves WS_LIST_SPAN entries at a time (one same-address atomic per span) and
-// pads what it does not use with entries whose slot is LIST_NONE
-#define WS_LIST_SPAN 128
-#define LIST_NONE 0xFFFFFFFFFFFFFFFFull
-struct ListWriter
+// ---- free-space merge ------------------------------------------------------------------------------
+// Last kernel of a scan: for every brick the scan touched, the voxels that are not closed and hold a
+// free-space candidate get (tau, +-WEIGHT_RESOLUTION) folded in (update_tsdf.cpp:542-560; real beats
+// interpolated at equal |value|, :508-512), and the brick's per-voxel state is cleared for the next scan.
+// 256 B of state + 2 KB of entries per brick travel as TMA bulk copies, three stages per CTA.
+#ifndef FMERGE_CTAS
+#define FMERGE_CTAS 8
+#endif
+__global__ void __launch_bounds__(256, FMERGE_CTAS)
+fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict__ brick_list, UpdateCounters *__restrict__ ctr)
 {
-  unsigned base, used;
-};
-
-WS_D void list_pad(ListWriter &w, const int lane, Rec *__restrict__ list)
-{
-  for (unsigned t = w.used + (unsigned)lane; t < WS_LIST_SPAN; t += 32u)
+  __shared__ __align__(128) uint32_t s_ent[MERGE_STAGES][WS_BRICK_VOX];
+  __shared__ __align__(128) unsigned char s_state[MERGE_STAGES][WS_BRICK_VOX / 2];
+  __shared__ __align__(128) unsigned char s_zero[WS_BRICK_VOX / 2];
+  __shared__ __align__(8) u64 s_bar[MERGE_STAGES];
+  if (ctr->rec_overflow != 0u && ctr->pending_overflow == 0u) return;       // redone after the regrow
+  const unsigned n_tb = ctr->n_touched_bricks;
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned touched = 0, written = 0;
+  s_zero[tid] = 0;
+  if (tid == 0)
   {
-    Rec e; e.key = 0ull; e.ref = LIST_NONE;
-    list[w.base + t] = e;
+    for (int st = 0; st < MERGE_STAGES; st++) mbar_init(&s_bar[st], 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  w.used = WS_LIST_SPAN;
-}
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
 
-WS_D void list_append(ListWriter &w, const bool want, const Rec e, const int lane, Rec *__restrict__ list, unsigned *counter)
-{
-  const unsigned m = __ballot_sync(FULL, want);
-  if (m == 0u) return;
-  const unsigned n = (unsigned)__popc(m);
-  if (w.used + n > WS_LIST_SPAN)
+  const unsigned n_mine = blockIdx.x < n_tb ? (n_tb - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
+  if (tid == 0)
+    for (unsigned n = 0; n < MERGE_STAGES - 1 && n < n_mine; n++)
+    {
+      const size_t base = (size_t)brick_list[blockIdx.x + n * gridDim.x] * WS_BRICK_VOX;
+      mbar_expect_tx(&s_bar[n], MERGE_ENT_BYTES + WS_BRICK_VOX / 2);
+      bulk_g2s(s_ent[n], g.grid + base, MERGE_ENT_BYTES, &s_bar[n]);
+      bulk_g2s(s_state[n], reinterpret_cast<const unsigned char *>(g.vstate) + base / 2, WS_BRICK_VOX / 2, &s_bar[n]);
+    }
+
+  for (unsigned n = 0; n < n_mine; n++)
   {
-    if (w.used < WS_LIST_SPAN) list_pad(w, lane, list);
-    unsigned b = 0;
-    if (lane == 0) b = atomicAdd(counter, (unsigned)WS_LIST_SPAN);
-    w.base = __shfl_sync(FULL, b, 0);
-    w.used = 0;
+    const int st = (int)(n % MERGE_STAGES);
+    const unsigned parity = (n / MERGE_STAGES) & 1u;
+    const size_t base = (size_t)brick_list[blockIdx.x + n * gridDim.x] * WS_BRICK_VOX;
+    if (tid == 0)
+    {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      const unsigned m = n + MERGE_STAGES - 1;
+      if (m < n_mine)
+      {
+        const int sm = (int)(m % MERGE_STAGES);
+        const size_t bm = (size_t)brick_list[blockIdx.x + m * gridDim.x] * WS_BRICK_VOX;
+        mbar_expect_tx(&s_bar[sm], MERGE_ENT_BYTES + WS_BRICK_VOX / 2);
+        bulk_g2s(s_ent[sm], g.grid + bm, MERGE_ENT_BYTES, &s_bar[sm]);
+        bulk_g2s(s_state[sm], reinterpret_cast<const unsigned char *>(g.vstate) + bm / 2, WS_BRICK_VOX / 2, &s_bar[sm]);
+      }
+    }
+    mbar_wait(&s_bar[st], parity);
+
+    const unsigned sb = s_state[st][tid];
+    bool changed = false;
+    if (sb & 0x33u)            // a free-space bit in either nibble
+    {
+      const uint2 ee = *reinterpret_cast<const uint2 *>(&s_ent[st][2 * tid]);
+      uint32_t e2[2] = { ee.x, ee.y };
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+      {
+        const unsigned nb = (sb >> (4 * j)) & 15u;
+        if ((nb & (VS_FREE_REAL | VS_FREE_INT)) == 0u || (nb & VS_CLOSED)) continue;
+        const int weight = (nb & VS_FREE_REAL) ? WS_WR : -WS_WR;
+        const int ew = entry_weight(e2[j]);
+        touched++;
+        written += ((weight > 0 && ew > 0) || ew <= 0) ? 1u : 0u;
+        const uint32_t ne = merge_entry(e2[j], P.tau, weight, P.max_weight);
+        changed |= ne != e2[j];
+        e2[j] = ne;
+      }
+      if (changed) *reinterpret_cast<uint2 *>(&s_ent[st][2 * tid]) = make_uint2(e2[0], e2[1]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int any_changed = __syncthreads_or(changed ? 1 : 0);
+    if (tid == 0)
+    {
+      if (any_changed) bulk_s2g(g.grid + base, s_ent[st], MERGE_ENT_BYTES);
+      bulk_s2g(reinterpret_cast<unsigned char *>(g.vstate) + base / 2, s_zero, WS_BRICK_VOX / 2);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      g.brick_slot_base[base >> 9] = NO_PARK;
+    }
   }
-  if (want) list[w.base + w.used + (unsigned)__popc(m & ((1u << lane) - 1u))] = e;
-  w.used += n;
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+
+  for (int o = 16; o > 0; o >>= 1)
+  {
+    touched += __shfl_down_sync(FULL, touched, o);
+    written += __shfl_down_sync(FULL, written, o);
+  }
+  if (lane == 0)
+  {
+    if (touched) atomicAdd(&ctr->n_touched, (unsigned long long)touched);
+    if (written) atomicAdd(&ctr->n_written, (unsigned long long)written);
+  }
 }
 
 // Cooperative launch: settles every parked voxel on the device (see the file header, step 4).
@@ -951,7 +1553,7 @@ __global__ void __launch_bounds__(256, 4)
 replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict__ ctr, const unsigned pending_cap,
               u64 *__restrict__ pend_addr, u64 *__restrict__ pend_prev, u64 *__restrict__ pend_key,
               const Rec *__restrict__ rec, const unsigned *__restrict__ chunk_fill, const unsigned cap_chunks,
-              Rec *__restrict__ list, unsigned *__restrict__ active0, unsigned *__restrict__ active1)
+              Rec *__restrict__ list, const unsigned list_cap, unsigned *__restrict__ active0, unsigned *__restrict__ active1)
 {
   cg::grid_group grid = cg::this_grid();
   unsigned n_pend = ctr->n_pending;
@@ -967,8 +1569,8 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
 
   // ---- round 1, candidates: the record, one warp per pair of 64-entry chunks.  Four independent
   // record -> parked bit -> key -> parked-winner chains per lane are in flight at a time (the pass is
-  // latency bound); the parked bitmap (1 bit per voxel, L2 resident) spares the key lookup for the ~80 %
-  // of the records whose voxel is not parked.
+  // latency bound); the per-voxel state (4 bits per voxel, L2 resident) spares the key lookup for the
+  // records whose voxel is not parked.
   unsigned n_chunks = ctr->n_chunks;
   if (n_chunks > cap_chunks) n_chunks = cap_chunks;
   ListWriter lw;
@@ -989,11 +1591,11 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
       if (ok[u]) rr[u] = rec[(size_t)c * WS_REC_CHUNK + j];
     }
 #pragma unroll
-    for (int u = 0; u < 4; u++) pw[u] = ok[u] ? __ldcg(&g.park_bits[park_word(rr[u].ref)]) : 0u;
+    for (int u = 0; u < 4; u++) pw[u] = ok[u] ? __ldcg(&g.vstate[vstate_word(rr[u].ref)]) : 0u;
 #pragma unroll
     for (int u = 0; u < 4; u++)
     {
-      ok[u] = ok[u] && ((pw[u] >> park_bit(rr[u].ref)) & 1u);
+      ok[u] = ok[u] && ((pw[u] >> vstate_shift(rr[u].ref)) & VS_PARKED);
       kv[u] = ok[u] ? __ldcg(&g.keys[rr[u].ref]) : WS_KEY_EMPTY;
     }
     unsigned sb[4];
@@ -1010,10 +1612,10 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
       const bool hit = ok[u] && key_seq(rr[u].key) > (kv[u] & WS_SEQ_MAX);
       if (hit) atomicMin(&pend_key[slot], rr[u].key);
       Rec e; e.key = rr[u].key; e.ref = (u64)slot;
-      list_append(lw, hit, e, lane, list, &ctr->n_list);
+      list_append(lw, hit, e, lane, list, list_cap, ctr);
     }
   }
-  if (lw.used < WS_LIST_SPAN) list_pad(lw, lane, list);
+  if (lw.used < WS_LIST_SPAN) list_pad(lw, lane, list, list_cap);
   grid.sync();
   if (gthread == 0) ctr->t_phase[1] = global_ns();
 
@@ -1095,7 +1697,8 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
       ctr->n_active[(round & 1u) ^ 1u] = 0u;      // next round's output counter (its readers are done)
     }
     if (n_still == 0u) break;
-    const unsigned n_list = ctr->n_list;
+    unsigned n_list = ctr->n_list;
+    if (n_list > list_cap) n_list = list_cap;
     for (unsigned t = gthread; t < n_list; t += gthreads)
     {
       const Rec e = list[t];
@@ -1121,8 +1724,9 @@ __global__ void rec_reset_kernel(UpdateCounters *ctr)
 {
   ctr->n_chunks = 0u;
   ctr->rec_overflow = 0u;
-  ctr->ray_counter = 0u;
-  ctr->n_list = 0u;
+  ctr->item_counter[0] = 0u;
+  ctr->item_counter[1] = 0u;
+  ctr->gen_counter = 0u;
 }
 
 }  // namespace
@@ -1191,8 +1795,11 @@ static void ensure_record(ws_handle *h, size_t chunks)
   WS_CUDA_OK(cudaMalloc(&h->d_rec, chunks * WS_REC_CHUNK * sizeof(Rec)));
   // replay list: every record can land in it, spans are padded (< 32 of 128 entries) and every warp of the
   // replay grid (<= 4 blocks x 8 warps per SM) may leave one span partly used
-  const size_t list_entries = chunks * WS_REC_CHUNK * 3 / 2 + (size_t)h->sm_count * 4 * 8 * WS_LIST_SPAN;
+  // ... and so may every warp of the free-space march, which appends its hits on parked voxels
+  const size_t list_entries = std::min<size_t>(chunks * WS_REC_CHUNK * 3 / 2 + (size_t)h->sm_count * (4 + LS_CTAS) * 8 * WS_LIST_SPAN,
+                                               0xFFFFFF00u);
   WS_CUDA_OK(cudaMalloc(&h->d_list, list_entries * sizeof(Rec)));
+  h->list_cap = list_entries;
   WS_CUDA_OK(cudaMalloc(&h->d_chunk_fill, chunks * sizeof(unsigned)));
   h->rec_cap_chunks = chunks;
 }
@@ -1208,10 +1815,11 @@ static void launch_replay(ws_handle *h, const UpdateParams &P)
     h->replay_blocks = per_sm * h->sm_count;
   }
   unsigned cap_chunks = (unsigned)h->rec_cap_chunks;
+  unsigned list_cap = (unsigned)h->list_cap;
   void *args[] = { (void *)&h->g, (void *)&P, (void *)&h->d_counters, (void *)&h->pending_cap,
                    (void *)&h->d_pend_addr, (void *)&h->d_pend_prev, (void *)&h->d_pend_key,
                    (void *)&h->d_rec, (void *)&h->d_chunk_fill, (void *)&cap_chunks,
-                   (void *)&h->d_list, (void *)&h->d_active[0], (void *)&h->d_active[1] };
+                   (void *)&h->d_list, (void *)&list_cap, (void *)&h->d_active[0], (void *)&h->d_active[1] };
   WS_CUDA_OK(cudaLaunchCooperativeKernel((const void *)replay_kernel, dim3(h->replay_blocks), dim3(256), args, 0, h->stream));
   h->launches++;
 }
@@ -1272,7 +1880,7 @@ void ws_launch_pose(ws_handle *h, const float *d_X, const float prior[16])
   std::memcpy(h_prior, prior, 16 * sizeof(float));
   WS_CUDA_OK(cudaMemcpyAsync(d_prior, h_prior, 16 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
   long long lim = (1ll << 31) / h->res - h->tau - (1ll << 17);
-  if (lim < 0 || std::getenv("WS_MARCH_GENERAL")) lim = 0;
+  if (lim < 0 || std::getenv("WS_MARCH_GENERAL") || h->res < 4) lim = 0;
   pose_kernel<<<1, 32, 0, h->stream>>>(d_X, d_prior, h->res, (int)lim, static_cast<PoseDev *>(h->d_pose));
   h->launches++;
 }
@@ -1316,6 +1924,7 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
     for (int a = 0; a < 3; a++)
       if (std::llabs((long long)P.pos_mm[a]) >= lim) P.coord_lim = 0;
     if (std::getenv("WS_MARCH_GENERAL")) P.coord_lim = 0;   // tests: force the literal-arithmetic path
+    if (h->res < 4) P.coord_lim = 0;                        // the signed 32-bit magic needs a divisor >= 3
   }
   for (int a = 0; a < 3; a++)
   {
@@ -1333,37 +1942,77 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
   if (n > 0)
   {
     const int march_blocks = h->sm_count * MARCH_CTAS;
+    const int lockstep_blocks = h->sm_count * LS_CTAS;
+    const size_t tab_bytes = (size_t)(h->g.size[0] + h->g.size[1] + h->g.size[2]) * sizeof(unsigned);
+    if (tab_bytes > 200 * 1024) throw std::invalid_argument("update_tsdf: map sides too large for the address tables");
+    if (tab_bytes > 48 * 1024 && !h->tab_attr_set)
+    {
+      WS_CUDA_OK(cudaFuncSetAttribute(march_lockstep_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+      WS_CUDA_OK(cudaFuncSetAttribute(march_lockstep_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+      WS_CUDA_OK(cudaFuncSetAttribute(march_lockstep_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+      WS_CUDA_OK(cudaFuncSetAttribute(march_lockstep_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+      WS_CUDA_OK(cudaFuncSetAttribute(march_lockstep_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+      WS_CUDA_OK(cudaFuncSetAttribute(march_lockstep_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tab_bytes));
+      h->tab_attr_set = true;
+    }
     unsigned cap_chunks = (unsigned)h->rec_cap_chunks;
     ws_timer_begin(h, WS_TIMER_MARCH);
     if ((size_t)n > h->rays_cap)
     {
       WS_CUDA_OK(cudaStreamSynchronize(s));
-      cudaFree(h->d_rays);
-      h->d_rays = nullptr; h->rays_cap = 0;
+      cudaFree(h->d_rays); cudaFree(h->d_grp_info); cudaFree(h->d_item_off); cudaFree(h->d_gen_list);
+      h->d_rays = nullptr; h->d_grp_info = nullptr; h->d_item_off = nullptr; h->d_gen_list = nullptr; h->rays_cap = 0;
       const size_t want = std::max<size_t>((size_t)n, 1 << 17);
+      h->grp_cap = want / 32 + 1;
       WS_CUDA_OK(cudaMalloc(&h->d_rays, want * sizeof(RaySetup)));
+      WS_CUDA_OK(cudaMalloc(&h->d_grp_info, 2 * h->grp_cap * sizeof(uint2)));
+      WS_CUDA_OK(cudaMalloc(&h->d_item_off, 2 * (h->grp_cap + 1) * sizeof(unsigned)));
+      WS_CUDA_OK(cudaMalloc(&h->d_gen_list, want * sizeof(unsigned)));
       h->rays_cap = want;
     }
     RaySetup *rays = static_cast<RaySetup *>(h->d_rays);
-    setup_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_pts, rays, h->d_counters, d_pose);
-    march_kernel<true><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_counters, h->d_rec,
+    const unsigned n_groups = (unsigned)((n + 31) / 32);
+    unsigned *list_all = h->d_brick_list, *list_surf = h->d_brick_list + h->g.n_bricks;
+    LsOut out;
+    out.pend_key = h->d_pend_key; out.list = h->d_list; out.pending_cap = h->pending_cap; out.list_cap = (unsigned)h->list_cap;
+    const bool wide = (unsigned long long)h->g.n_bricks * WS_BRICK_VOX > 0xFFFFFFFFull;
+#define LS_LAUNCH(SURF_, ATOMIC_)                                                                                        \
+  do {                                                                                                                   \
+    if (wide) march_lockstep_kernel<SURF_, ATOMIC_, true><<<lockstep_blocks, MARCH_THREADS, tab_bytes, s>>>(             \
+        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out);  \
+    else march_lockstep_kernel<SURF_, ATOMIC_, false><<<lockstep_blocks, MARCH_THREADS, tab_bytes, s>>>(                 \
+        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out);  \
+  } while (0)
+    // surface phase: keys, record, parked voxels
+    setup_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_pts, rays, h->d_grp_info, n_groups, h->d_gen_list, h->d_counters, d_pose);
+    item_scan_kernel<<<1, 1024, 0, s>>>(h->d_grp_info, n_groups, h->d_item_off, h->d_counters);
+    LS_LAUNCH(true, true);
+    march_kernel<true><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_gen_list, h->d_counters, h->d_rec,
                                                               h->d_chunk_fill, cap_chunks, d_pose);
-    h->launches++;
     ws_timer_end(h);
     ws_timer_begin(h, WS_TIMER_MERGE);
-    brick_list_kernel<<<h->sm_count * 4, 256, 0, s>>>(h->g, h->d_brick_list, h->d_counters);
-    merge_kernel<<<h->sm_count * MERGE_CTAS, 256, 0, s>>>(h->g, P, h->d_brick_list, h->d_counters, h->pending_cap,
+    brick_list_kernel<true><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_surf, h->d_counters);
+    merge_kernel<<<h->sm_count * MERGE_CTAS, 256, 0, s>>>(h->g, P, list_surf, h->d_counters, h->pending_cap,
                                                           h->d_pend_addr, h->d_pend_prev, h->d_pend_key);
     ws_timer_end(h);
-    h->launches += 3;
+    // free-space phase: state bits; candidates landing on parked voxels go straight to the replay
+    ws_timer_begin(h, WS_TIMER_MARCH);
+    LS_LAUNCH(false, true);
+    ws_timer_end(h);
     ws_timer_begin(h, WS_TIMER_REPLAY);
     launch_replay(h, P);
     ws_timer_end(h);
+    ws_timer_begin(h, WS_TIMER_MERGE);
+    brick_list_kernel<false><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_all, h->d_counters);
+    fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, list_all, h->d_counters);
+    ws_timer_end(h);
+    h->launches += 9;
     WS_CUDA_OK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
     if (pose_on_device)
       WS_CUDA_OK(cudaMemcpyAsync(h->h_pose, h->d_pose, sizeof(PoseDev), cudaMemcpyDeviceToHost, s));
     WS_CUDA_OK(cudaStreamSynchronize(s));
-    // the record did not fit: grow it, regenerate it from the far part of every ray, settle again
+    // the record did not fit: grow it, regenerate it from the far part of the surface phase, then run what
+    // was held back (free-space phase, replay, free-space merge)
     int guard = 0;
     while (h->h_counters->rec_overflow != 0u && h->h_counters->pending_overflow == 0u)
     {
@@ -1374,11 +2023,16 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
         throw std::runtime_error("update_tsdf: candidate record exceeds WS_RECORD_MAX");
       ensure_record(h, want);
       cap_chunks = (unsigned)h->rec_cap_chunks;
+      out.list = h->d_list; out.list_cap = (unsigned)h->list_cap;
       rec_reset_kernel<<<1, 1, 0, s>>>(h->d_counters);
-      march_kernel<false><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_counters, h->d_rec,
+      LS_LAUNCH(true, false);
+      march_kernel<false><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_gen_list, h->d_counters, h->d_rec,
                                                                  h->d_chunk_fill, cap_chunks, d_pose);
-      h->launches += 2;
+      LS_LAUNCH(false, true);
       launch_replay(h, P);
+      brick_list_kernel<false><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_all, h->d_counters);
+      fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, list_all, h->d_counters);
+      h->launches += 7;
       WS_CUDA_OK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
       WS_CUDA_OK(cudaStreamSynchronize(s));
       h->record_regrows++;
@@ -1399,6 +2053,8 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
     throw std::runtime_error("update_tsdf: parked voxels were left unsettled");
   if (h->last_counters.error & 1u)
     throw std::runtime_error("update_tsdf: ray too long for the candidate order field (march steps > 32768 or fan > 64)");
+  if (h->last_counters.error & 2u)
+    throw std::runtime_error("update_tsdf: replay list overflow (raise WS_RECORD_CAP)");
 }
 
 void ws_update_alloc(ws_handle *h, size_t initial_chunks, size_t max_chunks)

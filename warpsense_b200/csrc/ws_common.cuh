@@ -87,8 +87,9 @@ struct GridDesc
   i64 n_bricks;     // resident bricks
   uint32_t *grid;   // n_bricks * 512 TSDF entries  {int16 value | int16 weight << 16}
   u64 *keys;        // n_bricks * 512 candidate keys (all-ones when idle)
-  unsigned *brick_flag;  // per resident brick: touched by the current scan
-  unsigned *park_bits;   // 1 bit per voxel: parked by the current scan's merge pass (valid for touched bricks)
+  unsigned *brick_flag;  // per resident brick: touched by the surface phase of the current scan's march
+  unsigned *brick_flag2; // per resident brick: touched by the current scan at all (surface or free-space phase)
+  unsigned *vstate;      // 4 bits per voxel (VS_*), all zero between scans
   unsigned *brick_slot_base;   // per resident brick: first pending slot of the voxels it parked in the current scan
   short xslot[WS_MAX_XBRICKS];  // ring-x brick column -> resident slot, -1 if not resident
   unsigned char xown[WS_MAX_XBRICKS];   // 1: this rank owns the column (sums its points in the registration)
@@ -153,10 +154,16 @@ WS_HD u64 make_key(int value, bool interpolated, u64 seq)
   return ((u64)av << 47) | ((u64)(interpolated ? 1 : 0) << 46) | (ord << 1) | (u64)(value < 0 ? 1 : 0);
 }
 
-// bit of voxel `addr` in park_bits: a warp of the merge pass owns 64 consecutive voxels (two per lane) and
-// stores one ballot word per voxel parity
-WS_HD size_t park_word(u64 addr) { return (size_t)((addr >> 6) * 2ull + (addr & 1ull)); }
-WS_HD unsigned park_bit(u64 addr) { return (unsigned)((addr >> 1) & 31ull); }
+// Per-voxel scan state, 4 bits per voxel, eight voxels per 32-bit word in address order:
+//   VS_FREE_REAL / VS_FREE_INT  a free-space candidate (|value| == tau, real / interpolated) arrived
+//   VS_CLOSED                   the voxel has a candidate with |value| < tau: free-space candidates cannot win it
+//   VS_PARKED                   ... and its winner so far is an interpolated one (settled by the replay)
+#define VS_FREE_REAL 1u
+#define VS_FREE_INT 2u
+#define VS_CLOSED 4u
+#define VS_PARKED 8u
+WS_HD size_t vstate_word(u64 addr) { return (size_t)(addr >> 3); }
+WS_HD unsigned vstate_shift(u64 addr) { return (unsigned)(addr & 7ull) << 2; }
 
 WS_HD bool key_is_candidate(u64 k) { return (k >> 62) == 0; }
 WS_HD bool key_is_pending(u64 k) { return (k >> 62) == 2; }

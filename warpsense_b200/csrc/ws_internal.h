@@ -61,26 +61,29 @@ struct UpdateCounters
   unsigned long long n_candidates;
   unsigned long long n_touched;
   unsigned long long n_written;
-  unsigned n_touched_bricks;
+  unsigned n_touched_bricks; // bricks touched by the scan (surface or free-space phase)
   unsigned n_pending;        // voxels whose winner is an interpolated candidate below tau
-  unsigned n_pending_next;
+  unsigned n_surf_bricks;    // bricks touched by the surface phase
   unsigned pending_overflow;
-  unsigned error;            // bit 0: seq field overflow (too many march/fan steps)
+  unsigned error;            // bit 0: seq field overflow (too many march/fan steps); bit 1: replay list overflow
   unsigned rounds;
   unsigned n_parked;         // voxels parked by the merge pass (before any replay round)
-  unsigned n_work;           // rays the set-up pass put on the work list
-  unsigned pad0[18];
-  unsigned ray_counter;      // dynamic ray fetch of the persistent march warps (own 128-byte line)
-  unsigned pad1[31];
+  unsigned n_work;
+  unsigned n_items[2];       // (ray group, step block) work items of the lockstep march: surface / free-space phase
+  unsigned n_general;        // rays outside the 32-bit fast path: marched by the literal-arithmetic kernel
+  unsigned gen_counter;      // ... and its dynamic fetch counter
+  unsigned pad0[14];
+  unsigned item_counter[2];  // dynamic item fetch of the persistent march warps, per phase (own 128-byte line)
+  unsigned pad1[30];
   unsigned n_chunks;         // record chunks handed out (own 128-byte line)
   unsigned pad2[31];
   unsigned rec_overflow;     // the record did not fit its buffer
-  unsigned n_list;           // entries of the replay list (round-1 survivors)
+  unsigned n_list;           // entries of the replay list (round-1 survivors + free-space hits on parked voxels)
   unsigned n_active[2];      // still-pending slots, ping-pong between replay rounds
   unsigned long long t_phase[4];   // %globaltimer at the replay kernel's phase boundaries (diagnostics)
 };
 
-static_assert(offsetof(UpdateCounters, ray_counter) == 128 && offsetof(UpdateCounters, n_chunks) == 256,
+static_assert(offsetof(UpdateCounters, item_counter) == 128 && offsetof(UpdateCounters, n_chunks) == 256,
               "hot counters live on their own 128-byte lines");
 
 struct RegAccum           // 29 exact sums + bookkeeping, device resident
@@ -115,6 +118,12 @@ struct ws_handle
   void *h_pose = nullptr;         // pinned mirror
   void *d_rays = nullptr;         // RaySetup[rays_cap]: the work list written by the set-up pass of update_tsdf
   size_t rays_cap = 0;
+  uint2 *d_grp_info = nullptr;    // [2][groups] per group of 32 rays and phase: first step block with work, number of blocks
+  unsigned *d_item_off = nullptr; // [2][groups + 1] exclusive prefix sums of the groups' block counts (+ the total)
+  size_t grp_cap = 0;             // groups the two tables hold per phase
+  size_t list_cap = 0;            // entries of the replay list
+  bool tab_attr_set = false;      // dynamic shared memory of the lockstep march raised above 48 KB
+  unsigned *d_gen_list = nullptr; // rays for the literal-arithmetic march
   // scan preprocessing scratch (preprocess.cu)
   void *d_pre_tmp = nullptr;      // duplicate-detection keys, scan order
   void *d_pre_val = nullptr;      // points handed on, scan order
@@ -129,7 +138,7 @@ struct ws_handle
   int reg_n = 0;
 
   // update scratch
-  unsigned *d_brick_list = nullptr;     // touched resident brick ids
+  unsigned *d_brick_list = nullptr;     // touched resident brick ids: [n_bricks] all, then [n_bricks] surface phase
   UpdateCounters *d_counters = nullptr;
   UpdateCounters *h_counters = nullptr; // pinned
   // pending (interpolated winner) resolution
@@ -204,6 +213,7 @@ void ws_launch_fill(ws_handle *h, uint32_t entry);
 void ws_launch_upload(ws_handle *h, const uint32_t *d_linear);
 void ws_launch_download(ws_handle *h, uint32_t *d_linear);
 void ws_box_transfer(ws_handle *h, uint32_t *d_buf, const int lo[3], const int ext[3], bool pack);
+void ws_launch_checksum(ws_handle *h, int x_lo, int x_hi, int owned_only, u64 *d_out);
 void ws_launch_test_reduce(ws_handle *h, const i64 *d_jacobis, const int *d_values, int n);
 
 #define WS_TIMER_MARCH 0

@@ -67,6 +67,7 @@ def _signatures():
         "ws_map_get_params": (C.c_int, [hp, i32p, i32p, i32p]),
         "ws_map_fill": (C.c_int, [hp, C.c_int32, C.c_int32]),
         "ws_map_get_voxel": (C.c_int, [hp, C.c_int32, C.c_int32, C.c_int32, u32p]),
+        "ws_map_checksum": (C.c_int, [hp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_uint64)]),
         "ws_map_set_voxel": (C.c_int, [hp, C.c_int32, C.c_int32, C.c_int32, C.c_uint32]),
         "ws_update_tsdf": (C.c_int, [hp, vp, C.c_int64, i32p, i32p]),
         "ws_update_tsdf_device": (C.c_int, [hp, vp, C.c_int64, i32p, i32p]),
