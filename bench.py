@@ -170,6 +170,11 @@ def make_frames(args, count):
     frames = [s.frame(0)]
     for k in range(1, count + 1):
         frames.append(s.frame(k, prior_pose=s.pose(k - 1)))
+    if os.environ.get("WS_BENCH_TRANSPOSE"):      # experiment: column-major scan order (vertical neighbours adjacent)
+        for f in frames:
+            for key in ("points_map", "points_prior"):
+                if key in f and len(f[key]) == args.beams * args.cols:
+                    f[key] = np.ascontiguousarray(f[key].reshape(args.beams, args.cols, 3).transpose(1, 0, 2).reshape(-1, 3))
     return s, frames
 
 

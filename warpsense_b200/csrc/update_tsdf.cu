@@ -772,6 +772,7 @@ struct LsShared        // per CTA: address tables; per warp: ray table and queue
   const unsigned *tx, *ty, *tz;     // voxel - lo (0 .. size-1) -> address parts, see the table set-up in the kernel
   int4 *ray;                        // [32][2] per lane of the group: {hit point, distance}, {interpolation vector, -}
   int4 *queue;                      // [QCAP] {proj x, y, z, march step << 5 | lane}
+  unsigned *pd;                     // [3][32] FREE: state words of the previous batch's candidates (cp.async)
 };
 
 struct LsOut           // where the free-space phase offers candidates that land on parked voxels
@@ -789,40 +790,105 @@ struct LsWarp          // a warp's running state across work items
   ListWriter lw;
   unsigned n_cand, err;
   unsigned last_brick;
-  // FREE: the lane's last candidate, whose old voxel state (returned by its atomic) has not been looked at yet
-  bool pd_valid;
-  unsigned pd_old, pd_info;      // info: state shift [4:0], interpolated [5], fan step [11:6], march step [26:12], lane of the ray [31:27]
-  u64 pd_addr;
+  // FREE: the lane's candidates of the previous batch (fan steps 0..2): the voxel's state word was loaded when
+  // the candidate was written and is looked at one batch later, when the load has long landed
+  unsigned pd_mask;                  // which of the three slots hold a candidate
+  unsigned pd_info[3];               // info: state shift [4:0], interpolated [5], fan step [11:6], march step [26:12], lane of the ray [31:27]
+  u64 pd_addr[3];
 };
 
 // FREE phase, rare: a free-space candidate (|value| == tau) landed on a parked voxel.  What the replay's first
 // round does for a recorded candidate: offer it to the voxel if it follows the parked winner in the
 // reference's order, and keep it for the later rounds.  Warp-collective (list_append).
 WS_D void offer_parked(const GridDesc &g, const UpdateParams &P, const LsOut &out, LsWarp &W,
-                                          const bool chk, const unsigned ray_base, const int lane,
-                                          UpdateCounters *__restrict__ ctr)
+                       const bool chk, const u64 addr, const unsigned info, const unsigned ray_base, const int lane,
+                       UpdateCounters *__restrict__ ctr)
 {
   unsigned slot = 0u;
   bool hit = false;
   u64 key = 0ull;
   if (chk)
   {
-    const unsigned info = W.pd_info;
     const unsigned step = (info >> 6) & 63u, i = (info >> 12) & 0x7FFFu, ray = ray_base + (info >> 27);
     const u64 seq2 = make_seq(ray, i, step) << 1;
     key = (info & 32u) ? (((u64)(unsigned)P.tau << 47) | (1ull << 46) | (((1ull << 46) - 2ull) - seq2))
                        : (((u64)(unsigned)P.tau << 47) | seq2);
-    const u64 kv = __ldcg(&g.keys[W.pd_addr]);
+    const u64 kv = __ldcg(&g.keys[addr]);
     if (key_is_pending(kv))
     {
-      slot = __ldcg(&g.brick_slot_base[W.pd_addr >> 9]) + (unsigned)((kv >> WS_SEQ_BITS) & 0x1FFull);
+      slot = __ldcg(&g.brick_slot_base[addr >> 9]) + (unsigned)((kv >> WS_SEQ_BITS) & 0x1FFull);
       hit = slot < out.pending_cap && key_seq(key) > (kv & WS_SEQ_MAX);
       if (hit) atomicMin(&out.pend_key[slot], key);
     }
   }
   Rec e; e.key = key; e.ref = (u64)slot;
   list_append(W.lw, hit, e, lane, out.list, out.list_cap, ctr);
-  W.pd_valid = false;
+}
+
+// the candidates of the previous batch: did any land on a parked voxel?
+WS_D void free_check_pending(const GridDesc &g, const UpdateParams &P, const LsShared &sh, const LsOut &out, LsWarp &W,
+                             const unsigned ray_base, const int lane, UpdateCounters *__restrict__ ctr)
+{
+  asm volatile("cp.async.wait_all;" ::: "memory");      // issued a batch ago: long landed
+#pragma unroll
+  for (int sl = 0; sl < 3; sl++)
+  {
+    const bool chk = ((W.pd_mask >> sl) & 1u) && ((sh.pd[sl * 32 + lane] >> (W.pd_info[sl] & 31u)) & VS_PARKED) != 0u;
+    if (__any_sync(FULL, chk)) offer_parked(g, P, out, W, chk, W.pd_addr[sl], W.pd_info[sl], ray_base, lane, ctr);
+  }
+  W.pd_mask = 0u;
+}
+
+// FREE phase, one fan step of a batch: OR the candidate's bit into the voxel's state (no return value, the
+// loop never waits for memory); the state word is loaded beside it for the check one batch later
+template <bool WIDE, int SLOT>
+WS_D void free_candidate(const GridDesc &g, const UpdateParams &P, const LsShared &sh, const LsOut &out, LsWarp &W,
+                         const bool have, const int step, const int iter_steps, const int mid, const int low[3],
+                         const int riv[3], const int i, const int rl, const unsigned ray_base, const int lane,
+                         UpdateCounters *__restrict__ ctr)
+{
+  const int nlo[3] = { -P.lo[0], -P.lo[1], -P.lo[2] };
+  int fx = 0, fy = 0, fz = 0;
+  if (step > 0)
+  {
+    const int sr = wmul(step, P.res);
+    fx = div_mr32(sr * riv[0]); fy = div_mr32(sr * riv[1]); fz = div_mr32(sr * riv[2]);
+  }
+  const unsigned tx = (unsigned)(fd32_sdiv_s(low[0] + fx, P.div_res32) + nlo[0]);          // :493
+  const unsigned ty = (unsigned)(fd32_sdiv_s(low[1] + fy, P.div_res32) + nlo[1]);
+  const unsigned tz = (unsigned)(fd32_sdiv_s(low[2] + fz, P.div_res32) + nlo[2]);
+  bool valid = have && step < iter_steps &&
+               !(tx > (unsigned)P.ext[0] || ty > (unsigned)P.ext[1] || tz > (unsigned)P.ext[2]);       // :495-498
+  unsigned ax = TAB_INVALID;
+  if (valid) ax = sh.tx[tx];
+  valid = ax != TAB_INVALID;                       // else: out of bounds, or the column lives on another rank
+  u64 addr = 0ull;
+  unsigned info = 0u;
+  bool chk = false;
+  if (valid)
+  {
+    W.n_cand++;
+    unsigned brick;
+    if (WIDE) { addr = ((u64)ax << 6) + (u64)(sh.ty[ty] + sh.tz[tz]); brick = (unsigned)(addr >> 9); }
+    else { const unsigned a32 = ax + sh.ty[ty] + sh.tz[tz]; addr = (u64)a32; brick = a32 >> 9; }
+    if (brick != W.last_brick) { g.brick_flag2[brick] = 1u; W.last_brick = brick; }
+    const unsigned shft = vstate_shift(addr);
+    unsigned *word = g.vstate + vstate_word(addr);
+    info = shft | ((unsigned)(step == mid ? 0 : 1) << 5) | ((unsigned)step << 6) | ((unsigned)i << 12) | ((unsigned)rl << 27);
+    if (SLOT < 3)
+    {
+      // the state word travels to shared memory by cp.async: no register, no scoreboard to wait on
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&sh.pd[(SLOT < 3 ? SLOT : 0) * 32 + lane])),
+                   "l"(word) : "memory");
+      W.pd_addr[SLOT < 3 ? SLOT : 0] = addr;
+      W.pd_info[SLOT < 3 ? SLOT : 0] = info;
+      W.pd_mask |= 1u << SLOT;
+    }
+    else chk = ((__ldcg(word) >> shft) & VS_PARKED) != 0u;     // long fans (delta_z >= res): checked on the spot
+    // a plain byte store: idempotent, so no atomic and nothing to serialise when many rays hit one voxel
+    g.ffree[(size_t)brick * 1024u + (size_t)((unsigned)addr & 511u) + (step == mid ? 0u : 512u)] = 1;
+  }
+  if (SLOT >= 3 && __any_sync(FULL, chk)) offer_parked(g, P, out, W, chk, addr, info, ray_base, lane, ctr);   // warp-collective
 }
 
 // The heavy part: `take` queued march steps, one per lane, of any of the group's rays.
@@ -873,11 +939,21 @@ WS_D void march_drain(const GridDesc &g, const UpdateParams &P, const LsShared &
   const int iter_steps = (int)fd32_udiv((unsigned)(delta_z * 2), P.div_res32) + 1;           // :486
   const int mid = (int)fd32_udiv((unsigned)delta_z, P.div_res32);                            // :487
   if (have && iter_steps > (1 << WS_SEQ_STEP_BITS)) W.err |= 1u;
-  const int low_x = q.x - div_mr32(delta_z * riv[0]);                                        // :488
-  const int low_y = q.y - div_mr32(delta_z * riv[1]);
-  const int low_z = q.z - div_mr32(delta_z * riv[2]);
+  const int low[3] = { q.x - div_mr32(delta_z * riv[0]), q.y - div_mr32(delta_z * riv[1]), q.z - div_mr32(delta_z * riv[2]) };   // :488
   const bool far = len >= P.far_len;
   const int max_steps = __reduce_max_sync(FULL, have ? iter_steps : 0);
+
+  if (!SURF)
+  {
+    free_check_pending(g, P, sh, out, W, ray_base, lane, ctr);
+    free_candidate<WIDE, 0>(g, P, sh, out, W, have, 0, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
+    if (max_steps > 1) free_candidate<WIDE, 1>(g, P, sh, out, W, have, 1, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
+    if (max_steps > 2) free_candidate<WIDE, 2>(g, P, sh, out, W, have, 2, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
+#pragma unroll 1
+    for (int step = 3; step < max_steps; ++step)
+      free_candidate<WIDE, 3>(g, P, sh, out, W, have, step, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
+    return;
+  }
 
 #pragma unroll 1
   for (int step = 0; step < max_steps; ++step)                                               // :491
@@ -888,35 +964,13 @@ WS_D void march_drain(const GridDesc &g, const UpdateParams &P, const LsShared &
       const int sr = wmul(step, P.res);
       fx = div_mr32(sr * riv[0]); fy = div_mr32(sr * riv[1]); fz = div_mr32(sr * riv[2]);
     }
-    const unsigned tx = LS_VOX(low_x + fx, 0), ty = LS_VOX(low_y + fy, 1), tz = LS_VOX(low_z + fz, 2);   // :493
+    const unsigned tx = LS_VOX(low[0] + fx, 0), ty = LS_VOX(low[1] + fy, 1), tz = LS_VOX(low[2] + fz, 2);   // :493
     bool valid = have && step < iter_steps &&
                  !(tx > (unsigned)P.ext[0] || ty > (unsigned)P.ext[1] || tz > (unsigned)P.ext[2]);       // :495-498
     unsigned ax = TAB_INVALID;
     if (valid) ax = sh.tx[tx];
     valid = ax != TAB_INVALID;                       // else: out of bounds, or the column lives on another rank
     u64 key = 0ull, addr = 0ull;
-    if (!SURF)
-    {
-      // ---- free-space candidate: OR its bit into the voxel's state.  The atomic returns the old state;
-      // whether it shows a PARKED voxel is looked at one candidate later (pd_*), when the answer has long
-      // arrived -- the loop never waits for memory.
-      const bool chk = W.pd_valid && ((W.pd_old >> (W.pd_info & 31u)) & VS_PARKED) != 0u;
-      if (__any_sync(FULL, chk)) offer_parked(g, P, out, W, chk, ray_base, lane, ctr);
-      if (valid)
-      {
-        W.n_cand++;
-        unsigned brick;
-        if (WIDE) { addr = ((u64)ax << 6) + (u64)(sh.ty[ty] + sh.tz[tz]); brick = (unsigned)(addr >> 9); }
-        else { const unsigned a32 = ax + sh.ty[ty] + sh.tz[tz]; addr = (u64)a32; brick = a32 >> 9; }
-        if (brick != W.last_brick) { g.brick_flag2[brick] = 1u; W.last_brick = brick; }
-        const unsigned shft = vstate_shift(addr);
-        W.pd_old = atomicOr(g.vstate + vstate_word(addr), (step == mid ? VS_FREE_REAL : VS_FREE_INT) << shft);
-        W.pd_addr = addr;
-        W.pd_info = shft | ((unsigned)(step == mid ? 0 : 1) << 5) | ((unsigned)step << 6) | ((unsigned)i << 12) | ((unsigned)rl << 27);
-        W.pd_valid = true;
-      }
-      continue;
-    }
     if (valid)
     {
       W.n_cand++;
@@ -1049,13 +1103,7 @@ WS_D void march_block(const GridDesc &g, const UpdateParams &P, const int pos_mm
     }
   }
   if (qn > 0) march_drain<SURF, ATOMIC, WIDE>(g, P, sh, qh, qn, ray_base, lane, W, rec, chunk_fill, cap_chunks, ctr, out);
-  if (!SURF)
-  {
-    // the last candidates' old states, before the ray table changes
-    const bool chk = W.pd_valid && ((W.pd_old >> (W.pd_info & 31u)) & VS_PARKED) != 0u;
-    if (__any_sync(FULL, chk)) offer_parked(g, P, out, W, chk, ray_base, lane, ctr);
-    W.pd_valid = false;
-  }
+  if (!SURF) free_check_pending(g, P, sh, out, W, ray_base, lane, ctr);     // before the ray table changes
 #undef LS_ADVANCE
 #undef LS_VOX
 }
@@ -1070,6 +1118,7 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
   extern __shared__ unsigned s_tab[];               // size[0] + size[1] + size[2] address parts
   __shared__ int4 s_ray[MARCH_WARPS][64];
   __shared__ int4 s_queue[MARCH_WARPS][QCAP];
+  __shared__ unsigned s_pd[MARCH_WARPS][96];
   const unsigned n_items = __ldcg(&ctr->n_items[SURF ? 0 : 1]);
   if (n_items == 0u) return;
   if (!SURF && __ldcg(&ctr->rec_overflow) != 0u && __ldcg(&ctr->pending_overflow) == 0u) return;   // redone after the regrow
@@ -1077,7 +1126,7 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
   const int wib = threadIdx.x >> 5;
   LsShared sh;
   sh.tx = s_tab; sh.ty = s_tab + g.size[0]; sh.tz = sh.ty + g.size[1];
-  sh.ray = s_ray[wib]; sh.queue = s_queue[wib];
+  sh.ray = s_ray[wib]; sh.queue = s_queue[wib]; sh.pd = s_pd[wib];
   for (int t = threadIdx.x; t < g.size[0] + g.size[1] + g.size[2]; t += blockDim.x)
   {
     // ring coordinate (hdf5_local_map.h:140-151) of voxel lo + t, then its share of the bricked address:
@@ -1116,7 +1165,9 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
   if (SURF) rec_init(W.rw, ctr, lane);
   W.lw.base = 0u; W.lw.used = WS_LIST_SPAN;
   W.n_cand = 0u; W.err = 0u; W.last_brick = 0xFFFFFFFFu;
-  W.pd_valid = false; W.pd_old = 0u; W.pd_info = 0u; W.pd_addr = 0ull;
+  W.pd_mask = 0u;
+#pragma unroll
+  for (int sl = 0; sl < 3; sl++) { W.pd_info[sl] = 0u; W.pd_addr[sl] = 0ull; }
 
   // items: the first one by warp index, the others from a global counter, fetched one item ahead
   unsigned k_cur = blockIdx.x * MARCH_WARPS + wib;
@@ -1457,14 +1508,15 @@ __global__ void __launch_bounds__(256, FMERGE_CTAS)
 fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict__ brick_list, UpdateCounters *__restrict__ ctr)
 {
   __shared__ __align__(128) uint32_t s_ent[MERGE_STAGES][WS_BRICK_VOX];
+  __shared__ __align__(128) unsigned char s_free[MERGE_STAGES][2 * WS_BRICK_VOX];
   __shared__ __align__(128) unsigned char s_state[MERGE_STAGES][WS_BRICK_VOX / 2];
-  __shared__ __align__(128) unsigned char s_zero[WS_BRICK_VOX / 2];
+  __shared__ __align__(128) unsigned char s_zero[2 * WS_BRICK_VOX];
   __shared__ __align__(8) u64 s_bar[MERGE_STAGES];
   if (ctr->rec_overflow != 0u && ctr->pending_overflow == 0u) return;       // redone after the regrow
   const unsigned n_tb = ctr->n_touched_bricks;
   const int tid = threadIdx.x, lane = tid & 31;
   unsigned touched = 0, written = 0;
-  s_zero[tid] = 0;
+  reinterpret_cast<unsigned *>(s_zero)[tid] = 0u;
   if (tid == 0)
   {
     for (int st = 0; st < MERGE_STAGES; st++) mbar_init(&s_bar[st], 1u);
@@ -1472,14 +1524,16 @@ fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
+  const unsigned stage_bytes = MERGE_ENT_BYTES + 2 * WS_BRICK_VOX + WS_BRICK_VOX / 2;
 
   const unsigned n_mine = blockIdx.x < n_tb ? (n_tb - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
   if (tid == 0)
     for (unsigned n = 0; n < MERGE_STAGES - 1 && n < n_mine; n++)
     {
       const size_t base = (size_t)brick_list[blockIdx.x + n * gridDim.x] * WS_BRICK_VOX;
-      mbar_expect_tx(&s_bar[n], MERGE_ENT_BYTES + WS_BRICK_VOX / 2);
+      mbar_expect_tx(&s_bar[n], stage_bytes);
       bulk_g2s(s_ent[n], g.grid + base, MERGE_ENT_BYTES, &s_bar[n]);
+      bulk_g2s(s_free[n], g.ffree + base * 2, 2 * WS_BRICK_VOX, &s_bar[n]);
       bulk_g2s(s_state[n], reinterpret_cast<const unsigned char *>(g.vstate) + base / 2, WS_BRICK_VOX / 2, &s_bar[n]);
     }
 
@@ -1496,16 +1550,21 @@ fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict
       {
         const int sm = (int)(m % MERGE_STAGES);
         const size_t bm = (size_t)brick_list[blockIdx.x + m * gridDim.x] * WS_BRICK_VOX;
-        mbar_expect_tx(&s_bar[sm], MERGE_ENT_BYTES + WS_BRICK_VOX / 2);
+        mbar_expect_tx(&s_bar[sm], stage_bytes);
         bulk_g2s(s_ent[sm], g.grid + bm, MERGE_ENT_BYTES, &s_bar[sm]);
+        bulk_g2s(s_free[sm], g.ffree + bm * 2, 2 * WS_BRICK_VOX, &s_bar[sm]);
         bulk_g2s(s_state[sm], reinterpret_cast<const unsigned char *>(g.vstate) + bm / 2, WS_BRICK_VOX / 2, &s_bar[sm]);
       }
     }
     mbar_wait(&s_bar[st], parity);
 
+    // two voxels per thread: state nibbles (free-space winners of the surface phase, closed) + the bytes the
+    // free-space phase stored
     const unsigned sb = s_state[st][tid];
+    const unsigned fr = *reinterpret_cast<const unsigned short *>(&s_free[st][2 * tid]);
+    const unsigned fi = *reinterpret_cast<const unsigned short *>(&s_free[st][WS_BRICK_VOX + 2 * tid]);
     bool changed = false;
-    if (sb & 0x33u)            // a free-space bit in either nibble
+    if ((sb & 0x33u) | fr | fi)
     {
       const uint2 ee = *reinterpret_cast<const uint2 *>(&s_ent[st][2 * tid]);
       uint32_t e2[2] = { ee.x, ee.y };
@@ -1513,8 +1572,10 @@ fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict
       for (int j = 0; j < 2; j++)
       {
         const unsigned nb = (sb >> (4 * j)) & 15u;
-        if ((nb & (VS_FREE_REAL | VS_FREE_INT)) == 0u || (nb & VS_CLOSED)) continue;
-        const int weight = (nb & VS_FREE_REAL) ? WS_WR : -WS_WR;
+        const bool real = (nb & VS_FREE_REAL) || ((fr >> (8 * j)) & 0xFFu);
+        const bool intp = (nb & VS_FREE_INT) || ((fi >> (8 * j)) & 0xFFu);
+        if (!(real || intp) || (nb & VS_CLOSED)) continue;
+        const int weight = real ? WS_WR : -WS_WR;
         const int ew = entry_weight(e2[j]);
         touched++;
         written += ((weight > 0 && ew > 0) || ew <= 0) ? 1u : 0u;
@@ -1529,6 +1590,7 @@ fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict
     if (tid == 0)
     {
       if (any_changed) bulk_s2g(g.grid + base, s_ent[st], MERGE_ENT_BYTES);
+      bulk_s2g(g.ffree + base * 2, s_zero, 2 * WS_BRICK_VOX);
       bulk_s2g(reinterpret_cast<unsigned char *>(g.vstate) + base / 2, s_zero, WS_BRICK_VOX / 2);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       g.brick_slot_base[base >> 9] = NO_PARK;

@@ -90,6 +90,7 @@ struct GridDesc
   unsigned *brick_flag;  // per resident brick: touched by the surface phase of the current scan's march
   unsigned *brick_flag2; // per resident brick: touched by the current scan at all (surface or free-space phase)
   unsigned *vstate;      // 4 bits per voxel (VS_*), all zero between scans
+  unsigned char *ffree;  // per brick 512 + 512 bytes: a real / an interpolated free-space candidate arrived (plain stores), zero between scans
   unsigned *brick_slot_base;   // per resident brick: first pending slot of the voxels it parked in the current scan
   short xslot[WS_MAX_XBRICKS];  // ring-x brick column -> resident slot, -1 if not resident
   unsigned char xown[WS_MAX_XBRICKS];   // 1: this rank owns the column (sums its points in the registration)
