@@ -38,10 +38,6 @@ GN_ITERS = 20
 IT_WEIGHT = 0.1
 EPSILON = 0.0          # |.| < 0 never holds: exactly GN_ITERS iterations
 TAU, MAX_WEIGHT = 1000, 640
-# DRAM bytes of one update_tsdf on the default workload, from the committed ncu capture (profiles/r01p_*):
-# setup 1.6 + 12.5 + march 224.9 + 541.9 + brick_list 1.1 + merge 353.2 + 380.3 + replay 623.9 + 35.5 MB
-NCU_TRAFFIC_BYTES_PER_SCAN = 2174.9e6
-REF_SUBSAMPLE = 8      # --impl reference: every 8th ray per step (bounded sample)
 
 
 def parse_args():
@@ -57,6 +53,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA kernels")
     ap.add_argument("--update-only", action="store_true", help="BASELINE configs[1]: update_tsdf without registration")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short runs of the other BASELINE configs")
+    ap.add_argument("--config3", action="store_true", help="also run BASELINE configs[3] (2049^3 @ 2 cm) below 8 GPUs")
     return ap.parse_args()
 
 
@@ -181,7 +179,9 @@ def make_frames(args, count):
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
     """The reference's CPU implementation of the path (oracle port of src/cpu; the reference itself needs
-    Eigen/HDF5/PCL/ROS and cannot be built here) on this box's host cores, bounded sample per step."""
+    Eigen/HDF5/PCL/ROS and cannot be built here) on this box's host cores: WHOLE scans, every ray, measured
+    wall time per step (update_tsdf single-threaded as the reference launches it, update_tsdf.cpp:405;
+    register_cloud on every OpenMP thread)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -198,36 +198,34 @@ def run_reference(args):
         orc.set_num_threads(os.cpu_count() or 1)
     cores = orc.num_threads()
     pos, up = fp.convert_pose_to_gpu(frames[0]["pose"], res)
-    orc.update_tsdf(om, frames[0]["points_map"][::REF_SUBSAMPLE], pos, up, TAU, MAX_WEIGHT, res)
+    orc.update_tsdf(om, frames[0]["points_map"], pos, up, TAU, MAX_WEIGHT, res)
     I = np.eye(4, dtype=np.float32)
     times = []
+    n_full = len(frames[1]["points_prior"])
     for k in range(1, K + W + 1):
         f = frames[k]
-        cloud = np.ascontiguousarray(f["points_prior"][::REF_SUBSAMPLE])
         t0 = time.perf_counter()
         if not args.update_only:
+            cloud = np.ascontiguousarray(f["points_prior"])
             T, it = orc.register_cloud(om, cloud, I, GN_ITERS, IT_WEIGHT, EPSILON, res)
             pose = (T @ s.pose(k - 1)).astype(np.float32)
         else:
             pose = f["pose"]
-            cloud = np.ascontiguousarray(f["points_map"][::REF_SUBSAMPLE])
+            cloud = np.ascontiguousarray(f["points_map"])
         pos, up = fp.convert_pose_to_gpu(pose, res)
         orc.update_tsdf(om, cloud, pos, up, TAU, MAX_WEIGHT, res)
         dt = time.perf_counter() - t0
         if k > W:
             times.append(dt)
-    n_full = len(frames[1]["points_prior"])
-    n_s = len(frames[1]["points_prior"][::REF_SUBSAMPLE])
     total = sum(times)
-    # a step covers n_s of the n_full rays of a scan: scale to whole scans
-    value = (K * n_s / n_full) / total
-    sample = ("every %dth ray (%d of %d) of each scan per step; update_tsdf single-threaded as launched by the "
-              "reference (update_tsdf.cpp:405), register_cloud %d iterations on %d OpenMP threads; scans/s scaled by "
-              "rays processed" % (REF_SUBSAMPLE, n_s, n_full, GN_ITERS, cores))
+    value = K / total
+    sample = ("%d whole scans of %d rays (every ray), measured wall time; update_tsdf single-threaded as launched by "
+              "the reference (update_tsdf.cpp:405), register_cloud %d iterations on %d OpenMP threads"
+              % (K, n_full, GN_ITERS, cores))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": K, "warmup": W, "ms_per_step": 1000.0 * total / K * (n_full / n_s),
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "steps": K, "warmup": W, "ms_per_step": 1000.0 * total / K,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32+int64", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -247,24 +245,207 @@ def workload_config(args):
         "baseline_config": "configs[1]" if args.update_only else "configs[2]",
         "points_per_scan": args.beams * args.cols,
         "tau_mm": TAU, "max_weight": MAX_WEIGHT,
-        "l2_policy": "working set larger than L2: every step is a different scan and touches ~21 M voxels "
-                     "(12 B key+entry each, ~255 MB) of a 1.6 GB grid+scratch; no explicit flush",
+        "l2_policy": "working set larger than L2: every step is a different scan touching ~56,000 bricks "
+                     "(~20 M voxels: 4 B entry + 2.5 B state each, plus 8 B keys near the surfaces) of a 2 GB "
+                     "grid+scratch; no explicit flush",
         "parallelism": "x-slab spatial sharding of the ring; per-rank culling of march steps; int64[29] sums exchanged per GN iteration inside the kernel over NVLink peer memory",
     }
 
 
 # ------------------------------------------------------------------------------------------------
-class SumsView:
-    """__cuda_array_interface__ view of the handle's int64[29] Gauss-Newton sums (for NCCL)."""
+def traffic_from_profile():
+    """DRAM bytes of one update_tsdf on the default workload, summed from the committed ncu capture
+    (profiles/*_dram_traffic.csv: kernel, dram_read_MB, dram_write_MB per launch of one scan)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_dram_traffic.csv")))
+    if not files:
+        return None, None
+    tot = 0.0
+    with open(files[-1]) as f:
+        for ln in f:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 3 or parts[0].startswith("#") or parts[0] == "kernel":
+                continue
+            if parts[0].startswith("reg_") or parts[0] in ("pose_kernel", "transform_cloud_kernel"):
+                continue
+            tot += float(parts[1]) + float(parts[2])
+    return tot * 1e6, os.path.relpath(files[-1], ROOT)
 
-    def __init__(self, ptr):
-        self.__cuda_array_interface__ = {"shape": (29,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+class Workload:
+    """One map + one synthetic stream on this rank's GPU, stepped through the public API."""
+
+    def __init__(self, torch, dist, args, grid, res, beams, cols, n_frames, update_only, sharded=True, subsample=False):
+        from warpsense_b200 import api, fixedpoint as fp
+        from warpsense_b200.synth import ScanStream
+        self.torch, self.dist, self.api, self.fp = torch, dist, api, fp
+        self.world = int(os.environ.get("WORLD_SIZE", "1")) if sharded else 1
+        self.rank = int(os.environ.get("RANK", "0")) if sharded else 0
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.res, self.update_only = res, update_only
+        self.s = ScanStream(beams, cols, grid, res)
+        self.frames = [self.s.frame(0)]
+        for k in range(1, n_frames + 1):
+            self.frames.append(self.s.frame(k, prior_pose=self.s.pose(k - 1)))
+        size = tuple(v if v % 2 == 1 else v + 1 for v in (grid, grid, grid))
+        self.size = size
+
+        class _View:   # DeviceMap-like view without a host copy of the grid
+            size_ = np.array(size, np.int32)
+            offset_ = np.array([v // 2 for v in size], np.int32)
+            pos_ = np.zeros(3, np.int32)
+            data_ = None
+
+        self.tsdf = api.TSDFCuda(_View(), TAU, MAX_WEIGHT, res, device=self.local_rank, rank=self.rank, world=self.world,
+                                 upload=False)
+        self.reg = api.RegistrationCuda(self.tsdf)
+        self.stream = torch.cuda.Stream()
+        self.tsdf.set_stream(self.stream.cuda_stream)
+        if self.world > 1:
+            # fused exchange: every rank maps every rank's mailbox (CUDA IPC over NVLink); the Gauss-Newton sums
+            # then travel inside the persistent registration kernel -- no NCCL call per iteration
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.reg.peer_export())
+            self.reg.peer_attach_ipc(handles)
+            self.reg.peer_set_timeout(30.0)
+        key = "points_map" if update_only else "points_prior"
+        self.subsample = subsample
+        with torch.cuda.stream(self.stream):
+            pos, up = fp.convert_pose_to_gpu(self.frames[0]["pose"], res)
+            self.tsdf.update_tsdf(self.frames[0]["points_map"], pos, up)      # seed the map with frame 0 (untimed)
+            clouds = [self.frames[k][key] for k in range(1, n_frames + 1)]
+            if subsample:
+                # featsense feed (configs[4]): what Mapping::thread_run hands to update_tsdf_from_ros
+                # (mapping.cpp:128): the cloud in METRES in the map frame + the pose; the voxel-grid subsample
+                # of preprocess_from_ros (tsdf_mapping.cpp:145-163) runs on the device inside the call
+                clouds = [np.ascontiguousarray(c.astype(np.float32) / np.float32(1000.0)) for c in clouds]
+                self.poses_m = [None]
+                for k in range(1, n_frames + 1):
+                    pm = self.frames[k]["pose"].astype(np.float64)
+                    pm[:3, 3] /= 1000.0
+                    self.poses_m.append(pm)
+            self.dev_clouds = [None] + [torch.from_numpy(c).to("cuda") for c in clouds]
+            self.pinned = [None] + [torch.from_numpy(c).pin_memory() for c in clouds]
+            self.host_clouds = [None] + [p.numpy() for p in self.pinned[1:]]
+            self.priors = [None] + [fp.colmajor16(self.s.pose(k - 1)) for k in range(1, n_frames + 1)]
+            self.counts = [0] + [int(c.shape[0]) for c in self.dev_clouds[1:]]
+        self.transforms = []
+
+    def barrier(self):
+        self.stream.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, first, last, host):
+        """Scans first..last through the public API, two in flight: scan k+1 is enqueued (and, from host memory,
+        copied on the second stream) while scan k runs; every scan's transform, pose and counters come back."""
+        fp, res = self.fp, self.res
+        if self.subsample:
+            for k in range(first, last + 1):
+                if host:
+                    self.tsdf.update_tsdf_from_ros(self.host_clouds[k], self.poses_m[k])
+                else:
+                    self.tsdf.update_tsdf_from_ros(None, self.poses_m[k], device_ptr=self.dev_clouds[k].data_ptr(), n=self.counts[k])
+            return
+        if self.update_only:
+            for k in range(first, last + 1):
+                pos, up = fp.convert_pose_to_gpu(self.frames[k]["pose"], res)
+                if host:
+                    self.tsdf.update_tsdf(self.host_clouds[k], pos, up)
+                else:
+                    self.tsdf.update_tsdf_device(self.dev_clouds[k].data_ptr(), self.counts[k], pos, up)
+            return
+        tickets = []
+        for k in range(first, last + 1):
+            if host:
+                t = self.reg.track_submit(self.host_clouds[k], self.priors[k], GN_ITERS, IT_WEIGHT, EPSILON, res)
+            else:
+                t = self.reg.track_submit(None, self.priors[k], GN_ITERS, IT_WEIGHT, EPSILON, res,
+                                          device_ptr=self.dev_clouds[k].data_ptr(), n=self.counts[k])
+            tickets.append(t)
+            if len(tickets) == 2:
+                self.transforms.append(self.reg.track_wait(tickets.pop(0))[0])
+        while tickets:
+            self.transforms.append(self.reg.track_wait(tickets.pop(0))[0])
+
+    def timed(self, W, K, host, first=1):
+        from warpsense_b200 import lib
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            self.run(first, first + W - 1, host)
+            self.barrier()
+            self.tsdf.profile(True)
+            self.tsdf.profile_reset()
+            launches0 = self.tsdf.launch_count()
+            sampler = ClockSampler(self.local_rank)
+            sampler.start()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            self.run(first + W, first + W + K - 1, host)
+            e1.record(self.stream)
+            last = self.tsdf.counters()
+            self.barrier()
+            clocks = sampler.stop()
+            ms = e0.elapsed_time(e1)
+            kern = {name: self.tsdf.profile_get(kind) for name, kind in
+                    (("march", lib.TIMER_MARCH), ("merge", lib.TIMER_MERGE), ("reg", lib.TIMER_REG),
+                     ("replay", lib.TIMER_REPLAY))}
+            self.tsdf.profile(False)
+        if self.world > 1:
+            t = torch.tensor([ms], device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, clocks, kern, self.tsdf.launch_count() - launches0, last
+
+    def n_valid(self):
+        """count of the last registration's last iteration (N_valid of SURVEY 8d) and the per-iteration counts."""
+        if self.update_only:
+            return None, []
+        tr = self.reg.trace()
+        cnt = [int(v) for v in tr[:, 28]]
+        return (cnt[-1] if cnt else None), cnt
+
+    def close(self):
+        self.tsdf.close()
+
+
+def sub_config(torch, dist, args, name, grid, res, beams, cols, K, W, update_only, subsample=False):
+    """A secondary BASELINE config as a short run of its own (value / kernel ms / work counters)."""
+    wl = Workload(torch, dist, args, grid, res, beams, cols, 2 * (K + W), update_only, subsample=subsample)
+    ms_dev, clocks, kern, launches, counters = wl.timed(W, K, host=False)
+    ms_e2e, _, _, _, _ = wl.timed(W, K, host=True, first=1 + K + W)
+    world = wl.world
+    if world > 1:
+        wk = torch.tensor([counters["n_touched"], counters["n_candidates"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(wk)
+        counters = dict(counters)
+        counters["n_touched"], counters["n_candidates"] = (int(v) for v in wk.tolist())
+        km = torch.tensor([kern[k][0] for k in ("march", "merge", "reg", "replay")], dtype=torch.float64, device="cuda")
+        dist.all_reduce(km, op=dist.ReduceOp.MAX)
+        kern = {k: (float(v), kern[k][1]) for k, v in zip(("march", "merge", "reg", "replay"), km.tolist())}
+    nv, _ = wl.n_valid()
+    n_pts = wl.counts[1]
+    out = {
+        "baseline_config": name, "n_gpus": world,
+        "workload": "%dx%d scan -> %d^3 @%dmm, %s%s" % (beams, cols, grid, res,
+                                                         "update_tsdf only" if update_only else "reg %d GN iters + update_tsdf" % GN_ITERS,
+                                                         ", voxel-grid subsampled cloud (featsense feed)" if subsample else ""),
+        "value": K / (ms_dev / 1000.0), "e2e": K / (ms_e2e / 1000.0), "unit": UNIT, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev / K,
+        "kernel_ms_per_scan": {k: kern[k][0] / K for k in ("march", "merge", "replay", "reg")},
+        "work": {"N": n_pts, "C": counters["n_candidates"], "T": counters["n_touched"], "N_valid": nv,
+                 "V": int(np.prod(np.array(wl.size, np.int64)))},
+        "clocks": clocks,
+    }
+    wl.close()
+    return out
 
 
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from warpsense_b200 import api, fixedpoint as fp, lib
+    from warpsense_b200 import api
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -276,120 +457,20 @@ def run_native(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    K, W = args.steps, args.warmup
-    if W < 3:
-        W = 3
-    s, frames = make_frames(args, K + W)
-    side, res = args.grid, args.res
-    N = len(frames[1]["points_prior"])
-
-    size = tuple(v if v % 2 == 1 else v + 1 for v in (side, side, side))
-
-    class _View:   # DeviceMap-like view without a 540 MB host array
-        size_ = np.array(size, np.int32)
-        offset_ = np.array([v // 2 for v in size], np.int32)
-        pos_ = np.zeros(3, np.int32)
-        data_ = None
-
-    tsdf = api.TSDFCuda(_View(), TAU, MAX_WEIGHT, res, device=local_rank, rank=rank, world=world, upload=False)
-    reg = api.RegistrationCuda(tsdf)
-    hd = tsdf.device_map()
-    stream = torch.cuda.Stream()
-    tsdf.set_stream(stream.cuda_stream)
-    if world > 1:
-        # fused exchange: every rank maps every rank's mailbox (CUDA IPC over NVLink); the Gauss-Newton sums
-        # then travel inside the persistent registration kernel -- no NCCL call per iteration
-        handles = [None] * world
-        dist.all_gather_object(handles, reg.peer_export())
-        reg.peer_attach_ipc(handles)
-        reg.peer_set_timeout(20.0)
-
-    I16 = fp.colmajor16(np.eye(4, dtype=np.float32))
-    import ctypes as C
-    f32p = C.POINTER(C.c_float)
-    Tout = np.zeros(16, np.float32)
-    it_out, fin_out = C.c_int32(), C.c_int32()
-
-    def register(n):
-        """20 GN iterations on the cloud already staged with prepare_registration*; returns T (4x4)."""
-        T, _ = reg.register_cloud(None, np.eye(4, dtype=np.float32), GN_ITERS, IT_WEIGHT, EPSILON, res,
-                                  keep_on_device=True)
-        return T
-
-    def step_device(k, dev_cloud):
-        f = frames[k]
-        if args.update_only:
-            pos, up = fp.convert_pose_to_gpu(f["pose"], res)
-            tsdf.update_tsdf_device(dev_cloud.data_ptr(), counts[k], pos, up)
-            return
-        # one fused call per scan: 20 GN iterations -> pose -> update_tsdf, chained on the device
-        reg.track_scan(None, priors[k], GN_ITERS, IT_WEIGHT, EPSILON, res, device_ptr=dev_ptrs[k], n=counts[k])
-
-    def step_host(k, host_cloud):
-        f = frames[k]
-        if args.update_only:
-            pos, up = fp.convert_pose_to_gpu(f["pose"], res)
-            tsdf.update_tsdf(host_cloud, pos, up)
-            return
-        # H2D of the scan, D2H of the transform + pose + work counters, all inside the call
-        reg.track_scan(host_cloud, priors[k], GN_ITERS, IT_WEIGHT, EPSILON, res)
-
-    key = "points_map" if args.update_only else "points_prior"
-    with torch.cuda.stream(stream):
-        # seed the map with frame 0 (untimed)
-        pos, up = fp.convert_pose_to_gpu(frames[0]["pose"], res)
-        tsdf.update_tsdf(frames[0]["points_map"], pos, up)
-
-        dev_clouds = [None] + [torch.from_numpy(frames[k][key]).to("cuda") for k in range(1, K + W + 1)]
-        pinned = [None] + [torch.from_numpy(frames[k][key]).pin_memory() for k in range(1, K + W + 1)]
-        host_clouds = [None] + [p.numpy() for p in pinned[1:]]
-        # step inputs prepared outside the timed region: the odometry prior of every scan in the ABI layout
-        priors = [None] + [fp.colmajor16(s.pose(k - 1)) for k in range(1, K + W + 1)]
-        dev_ptrs = [None] + [c.data_ptr() for c in dev_clouds[1:]]
-        counts = [0] + [int(c.shape[0]) for c in dev_clouds[1:]]
-
-        def barrier():
-            stream.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-
-        def timed(step_fn, inputs):
-            for k in range(1, W + 1):
-                step_fn(k, inputs[k])
-            barrier()
-            tsdf.profile(True)
-            tsdf.profile_reset()
-            launches0 = tsdf.launch_count()
-            sampler = ClockSampler(local_rank)
-            sampler.start()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            for k in range(W + 1, W + K + 1):
-                step_fn(k, inputs[k])          # every call ends with the D2H of its transform, pose and counters
-            e1.record(stream)
-            last = tsdf.counters()             # the last step's work counters (already on the host)
-            barrier()
-            clocks = sampler.stop()
-            ms = e0.elapsed_time(e1)
-            if world > 1:
-                t = torch.tensor([ms], device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms = float(t.item())
-            kern = {name: tsdf.profile_get(kind) for name, kind in
-                    (("march", lib.TIMER_MARCH), ("merge", lib.TIMER_MERGE), ("reg", lib.TIMER_REG),
-                     ("replay", lib.TIMER_REPLAY))}
-            tsdf.profile(False)
-            return ms, clocks, kern, tsdf.launch_count() - launches0, last
-
-        ms_dev, clocks, kern, launches, counters = timed(step_device, dev_clouds)
-        # the end-to-end pass replays the same scans (the map keeps accumulating; the march work is identical)
-        ms_e2e, clocks_e2e, kern_e2e, launches_e2e, counters_e2e = timed(step_host, host_clouds)
+    K, W = args.steps, max(args.warmup, 3)
+    wl = Workload(torch, dist, args, args.grid, args.res, args.beams, args.cols, 2 * (K + W), args.update_only)
+    N = wl.counts[1]
+    size = wl.size
+    ms_dev, clocks, kern, launches, counters = wl.timed(W, K, host=False)
+    n_valid, valid_per_it = wl.n_valid()
+    # the end-to-end pass continues the stream (the map keeps accumulating; the march work is the same)
+    ms_e2e, clocks_e2e, kern_e2e, launches_e2e, counters_e2e = wl.timed(W, K, host=True, first=1 + K + W)
 
     value = K / (ms_dev / 1000.0)
     e2e_value = K / (ms_e2e / 1000.0)
+    parity = None
     if world > 1:
-        # work counters: sum over the slabs (halo columns count twice); kernel times: slowest rank
+        # work counters: sum over the slabs (halo columns count twice); kernel times: slowest and fastest rank
         wk = torch.tensor([counters["n_touched"], counters["n_candidates"], counters["n_touched_bricks"],
                            counters["n_parked"]], dtype=torch.int64, device="cuda")
         dist.all_reduce(wk)
@@ -397,11 +478,16 @@ def run_native(args):
         counters["n_touched"], counters["n_candidates"], counters["n_touched_bricks"], counters["n_parked"] = \
             (int(v) for v in wk.tolist())
         km = torch.tensor([kern[k][0] for k in ("march", "merge", "reg", "replay")], dtype=torch.float64, device="cuda")
+        kmin = km.clone()
         dist.all_reduce(km, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kmin, op=dist.ReduceOp.MIN)
+        kern_min = {k: float(v) / max(1, K) for k, v in zip(("march", "merge", "reg", "replay"), kmin.tolist())}
         kern = {k: (float(v), kern[k][1]) for k, v in zip(("march", "merge", "reg", "replay"), km.tolist())}
+        parity = parity_check(torch, dist, args, wl, K, W)
+    else:
+        kern_min = None
 
     if rank == 0:
-        # T of this rank's slab; for the roofline at N=1 it is the whole scan's T
         T_vox = counters["n_touched"]
         C_cand = counters["n_candidates"]
         march_ms = kern["march"][0] / max(1, K)
@@ -412,49 +498,117 @@ def run_native(args):
         peak, peak_src = peaks()
         upd_ms = march_ms + merge_ms + replay_ms
         achieved = upd_bytes / (upd_ms / 1000.0) / 1e9 if upd_ms > 0 else 0.0
+        traffic, traffic_src = traffic_from_profile()
+        default_shape = (world == 1 and not args.update_only and args.grid == 512 and args.res == 50
+                         and args.beams == 128 and args.cols == 1024)
+        reg_bytes = sum(12 * N + 28 * v + 232 for v in valid_per_it) if valid_per_it else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True,
-            "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "scaling": "strong", "vs_baseline": None,
             "dtype": "int32+int64", "data": "synthetic", "config": workload_config(args),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
-                    "h2d_bytes_per_step": 12 * N, "d2h_bytes_per_step": 352 + 64,
-                    "note": "ws_track_scan with the scan in pinned host memory: H2D -> 20 GN iterations -> pose on the "
-                            "device -> update_tsdf -> transform + pose + counters D2H, one host synchronisation"},
+                    "h2d_bytes_per_step": 12 * N, "d2h_bytes_per_step": 352 + 128 + 64,
+                    "note": "ws_track_submit / ws_track_wait with the scan in pinned host memory, two scans in flight: "
+                            "H2D on a second stream -> 20 GN iterations -> pose on the device -> update_tsdf -> "
+                            "transform + pose + counters D2H; every scan's results are collected"},
             "gpu_launches": launches,
             "roofline": {
-                "bound": "hbm", "kernel": "update_tsdf = march_kernel + brick_list/merge_kernel + replay_kernel (per scan)",
+                "bound": "hbm", "kernel": "update_tsdf = set-up + surface march + surface merge + free-space march + replay + free-space merge (per scan)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-                "traffic": NCU_TRAFFIC_BYTES_PER_SCAN if (world == 1 and not args.update_only and args.grid == 512 and args.res == 50
-                                                          and args.beams == 128 and args.cols == 1024) else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of setup + march + brick_list + merge + replay, one "
-                                  "launch each, ncu --set full capture of this workload (profiles/r01p_summary.md)",
+                "traffic": traffic if default_shape else None,
+                "traffic_source": ("dram__bytes_read.sum + dram__bytes_write.sum of the update kernels, one launch each, ncu capture "
+                                   "of this workload: %s" % traffic_src) if traffic_src else None,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_scan": upd_bytes,
                 "formula": "12*N + 8*T (SURVEY.md 8d), N=%d points, T=%d touched voxels, C=%d candidates" % (N, T_vox, C_cand),
                 "kernel_ms_per_scan": {"march": march_ms, "merge": merge_ms, "replay": replay_ms, "reg_20_iterations": reg_ms,
                                        "step_total": ms_dev / K},
-                "reg_bytes_per_scan": None,
+                "kernel_ms_per_scan_min_over_ranks": kern_min,
+                "reg_bytes_per_scan": reg_bytes,
+                "reg_formula": "sum over the %d GN iterations of 12*N + 28*N_valid + 232 (SURVEY.md 8d)" % len(valid_per_it) if valid_per_it else None,
+                "reg_achieved_gbs": (reg_bytes / (reg_ms / 1000.0) / 1e9) if (reg_bytes and reg_ms > 0) else None,
+                "reg_note": "registration is latency-bound: its per-iteration working set (<= 5 MB) stays L2-resident, "
+                            "the figure is algorithmic bytes over kernel time, not DRAM traffic",
             },
-            "work": {"N": N, "C": C_cand, "T": T_vox, "touched_bricks": counters["n_touched_bricks"],
+            "work": {"N": N, "C": C_cand, "T": T_vox, "N_valid": n_valid, "touched_bricks": counters["n_touched_bricks"],
                      "parked": counters["n_parked"], "replay_rounds": counters["n_rounds"],
                      "replay_list": counters["n_list"], "record_chunks": counters["n_record_chunks"],
                      "replay_phase_us": [v / 1000.0 for v in counters["replay_phase_ns"]],
                      "iterations": GN_ITERS, "V": int(np.prod(np.array(size, np.int64)))},
         }
+        if parity is not None:
+            line["parity_check"] = parity
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, frames, s)
-    tsdf.close()
+            line["cpu_baseline"] = cpu_baseline(args, wl.frames, wl.s)
+    frames_main, s_main = wl.frames, wl.s
+    wl.close()
+    del wl
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, as short runs of their own ------------------------------------------
+    extra = {}
+    if not args.no_extra and not args.update_only:
+        Ke, We = max(5, min(K, 20)), 3
+        if world == 1:
+            extra["configs[1]"] = sub_config(torch, dist, args, "configs[1]", args.grid, args.res, args.beams, args.cols,
+                                             Ke, We, update_only=True)
+            extra["configs[4]"] = sub_config(torch, dist, args, "configs[4]", args.grid, args.res, args.beams, args.cols,
+                                             Ke, We, update_only=True, subsample=True)
+        if world >= 8 or args.config3:
+            extra["configs[3]"] = sub_config(torch, dist, args, "configs[3]", 2048, 20, 128, 2048, 4, 3, update_only=False)
     if rank == 0:
+        if extra:
+            line["extra"] = {"configs": extra}
         if world == 1 and not args.no_ref_cuda:
             try:
-                line["reference_cuda_same_gpu"] = reference_cuda(args, frames, s)
+                line["reference_cuda_same_gpu"] = reference_cuda(args, frames_main, s_main)
             except Exception as exc:   # the secondary baseline must never take the bench line down
                 line["reference_cuda_same_gpu"] = {"unavailable": repr(exc)[:200]}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_check(torch, dist, args, wl, K, W):
+    """N > 1: is the sharded result the single-GPU result?  Rank 0 replays the same 2 * (W + K) scans on an
+    UNSHARDED handle; every rank's owned rows are compared through an order-free device checksum
+    (ws_map_checksum) and every scan's registration transform bit for bit.  Raises on a mismatch."""
+    rank, world = wl.rank, wl.world
+    from warpsense_b200 import api
+    lo, hi, _ = api.slab_layout(wl.size[0], rank, world)
+    mine = torch.tensor([wl.tsdf.checksum(lo, hi, owned_only=True) & 0x7FFFFFFFFFFFFFFF, lo, hi], dtype=torch.int64, device="cuda")
+    allc = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine)
+    ok = torch.ones(1, dtype=torch.int64, device="cuda")
+    info = None
+    if rank == 0:
+        n_frames = 2 * (W + K)
+        full = Workload(torch, dist, args, args.grid, args.res, args.beams, args.cols, n_frames, wl.update_only, sharded=False)
+        full.run(1, n_frames, host=False)
+        full.barrier()
+        rows_ok = True
+        for r in range(world):
+            cs, rlo, rhi = (int(v) for v in allc[r].tolist())
+            if (full.tsdf.checksum(rlo, rhi) & 0x7FFFFFFFFFFFFFFF) != cs:
+                rows_ok = False
+        tf_ok = len(full.transforms) == len(wl.transforms) and all(
+            np.array_equal(a, b) for a, b in zip(full.transforms, wl.transforms))
+        full.close()
+        if not (rows_ok and tf_ok):
+            ok[0] = 0
+        info = {"vs_single_gpu": "bit-exact" if (rows_ok and tf_ok) else "MISMATCH", "scans": n_frames,
+                "owned_rows_checksums": "equal" if rows_ok else "differ", "transforms_compared": len(wl.transforms),
+                "transforms": "equal" if tf_ok else "differ",
+                "how": "rank 0 replays the scans on an unsharded handle; ws_map_checksum of every rank's owned ring-x rows + "
+                       "every scan's registration transform"}
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if int(ok.item()) != 1:
+        if rank == 0:
+            print(json.dumps({"parity_check": info}), file=sys.stderr)
+        raise SystemExit("bench.py: the %d-GPU result differs from the single-GPU result" % world)
+    return info
 
 
 def reference_cuda(args, frames, s, scans=5):

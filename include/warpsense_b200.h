@@ -149,6 +149,22 @@ int ws_preprocess_scan(ws_handle *h, const float *xyz, int64_t n, int32_t point_
                        const float pose_mm[16], int32_t map_resolution, ws_point *out_host, int64_t *n_out);
 const ws_point *ws_scan_points_device(ws_handle *h, int64_t *n);
 
+/* ---- featsense feed ---------------------------------------------------------------------------
+ * ws_voxelgrid_subsample: the pcl::VoxelGrid of cuda::TSDFMapping::preprocess_from_ros
+ *   (src/warpsense/tsdf_mapping.cpp:147-151; PCL 1.10 filters/impl/voxel_grid.hpp applyFilter) on the device: one
+ *   float centroid per occupied leaf, output in ascending leaf index (x fastest), then metres -> int millimetres
+ *   (:153-158).  `xyz`: n points `point_step_bytes` apart, host or device memory.  The millimetre points stay on
+ *   the device (ws_scan_points_device) and are copied to out_mm_host / out_xyz_host (float centroids) if given.
+ * ws_update_tsdf_from_ros: TSDFMapping::update_tsdf_from_ros(cloud, pose) (tsdf_mapping.cpp:165-173):
+ *   preprocess_from_ros (voxel grid; pose_m = column-major 4x4 Isometry3d in metres -> mm Matrix4f through the
+ *   quaternion round trip of :160-161), then update_tsdf(points, mm_pose).  The caller pushes out_mm_pose to
+ *   its pose buffer (:170). */
+int ws_voxelgrid_subsample(ws_handle *h, const float *xyz, int64_t n, int32_t point_step_bytes, int32_t on_device,
+                           float leaf_m, ws_point *out_mm_host, float *out_xyz_host, int64_t *n_out);
+int ws_update_tsdf_from_ros(ws_handle *h, const float *xyz_m, int64_t n, int32_t point_step_bytes, int32_t on_device,
+                            const double pose_m[16], float out_mm_pose[16], int64_t *n_points);
+
+
 int ws_reg_prepare(ws_handle *h, const ws_point *points, int64_t n);
 /* same, the cloud already being in device memory (device-to-device copy on the handle's stream) */
 int ws_reg_prepare_device(ws_handle *h, const ws_point *device_points, int64_t n);
@@ -158,13 +174,32 @@ int ws_register_cloud(ws_handle *h, ws_point *cloud, int64_t n, const float pret
                       int32_t max_iterations, float it_weight_gradient, float epsilon,
                       int32_t map_resolution, int32_t flags, float out_transform[16],
                       int32_t *iterations);
-/* ws_track_scan: the reference's per-scan sequence (App::cloud_callback, src/warpsense/app.cpp:65-112, in the
- *                 order of BASELINE configs[2]: register_cloud with pretransform = identity against the map
- *                 of the earlier scans, pose = X * prior_pose, update_tsdf with the registered cloud and
- *                 convert_pose_to_gpu(pose), tsdf_mapping.cpp:77-85) as one stream of kernels with a single
- *                 host synchronisation: transform, scanner voxel and up vector stay on the device between
- *                 the two halves.  Equivalent to ws_register_cloud + ws_update_tsdf_device with the pose
- *                 product evaluated in float32, accumulating over k = 0..3 in order. */
+/* ---- per-scan pipeline ------------------------------------------------------------------------
+ * The three calls App::cloud_callback makes per scan (src/warpsense/app.cpp:65-112: update_tsdf, register_cloud,
+ * update_pose_estimate) as one stream of kernels, in the order of BASELINE configs[2]: register_cloud against the
+ * map of the earlier scans, pose update, update_tsdf with the registered cloud and convert_pose_to_gpu(pose)
+ * (tsdf_mapping.cpp:77-85); transform, scanner voxel and up vector stay on the device between the two halves.
+ * NOTE the reference's own callback updates the map with the OLD pose first and registers afterwards; callers that
+ * want that order use ws_update_tsdf + ws_register_cloud.
+ *   pretransform  the IMU pre-rotation handed to register_cloud (app.cpp:97-102), NULL = identity
+ *   prior_pose    the pose the scan was placed with; NULL (submit only) = the pose of the previous tracked scan,
+ *                 taken from device memory
+ *   flags         WS_TRACK_REFERENCE_POSE: compose the new pose as App::update_pose_estimate does (app.cpp:172-176,
+ *                 src/cpu/fastsense.cpp:219-221): R = X.R * R, t += X.t.  Default: the full product X * prior_pose
+ *                 (float32, accumulated over k = 0..3 in order).
+ * ws_track_submit enqueues and returns (host points are copied on a second stream; the buffer must stay valid until
+ * the matching ws_track_wait); at most two scans are in flight.  ws_track_wait blocks until the scan is done and
+ * returns the registration transform, the new pose and (ws_get_update_counters) the work counters.
+ * ws_track_scan[_ex] = submit + wait. */
+#define WS_TRACK_REFERENCE_POSE 1
+int ws_track_submit(ws_handle *h, const ws_point *points, int64_t n, int32_t on_device, const float *prior_pose,
+                    const float *pretransform, int32_t max_iterations, float it_weight_gradient, float epsilon,
+                    int32_t map_resolution, int32_t flags, int32_t *ticket);
+int ws_track_wait(ws_handle *h, int32_t ticket, float out_transform[16], float out_pose[16], int32_t *iterations);
+int ws_track_scan_ex(ws_handle *h, const ws_point *points, int64_t n, int32_t on_device, const float prior_pose[16],
+                     const float *pretransform, int32_t max_iterations, float it_weight_gradient, float epsilon,
+                     int32_t map_resolution, int32_t flags, float out_transform[16], float out_pose[16],
+                     int32_t *iterations);
 int ws_track_scan(ws_handle *h, const ws_point *points, int64_t n, int32_t on_device, const float prior_pose[16],
                   int32_t max_iterations, float it_weight_gradient, float epsilon, int32_t map_resolution,
                   float out_transform[16], float out_pose[16], int32_t *iterations);

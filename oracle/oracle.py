@@ -181,6 +181,46 @@ def convert_pose(pose, res):
     return pos, up
 
 
+def update_pose_estimate(pose, transform):
+    """App::update_pose_estimate (src/warpsense/app.cpp:172-176; the CPU node does the same,
+    src/cpu/fastsense.cpp:219-221): R = T.R * R, t += T.t, in float32 (Eigen Matrix4f blocks)."""
+    p = np.array(pose, dtype=np.float32, copy=True)
+    t = np.asarray(transform, dtype=np.float32)
+    R = np.zeros((3, 3), np.float32)
+    for r in range(3):
+        for c in range(3):
+            acc = np.float32(t[r, 0] * p[0, c])
+            acc = np.float32(acc + np.float32(t[r, 1] * p[1, c]))
+            acc = np.float32(acc + np.float32(t[r, 2] * p[2, c]))
+            R[r, c] = acc
+    p[:3, :3] = R
+    p[:3, 3] = (p[:3, 3] + t[:3, 3]).astype(np.float32)
+    return p
+
+
+def voxelgrid(cloud_xyz_m, leaf_m):
+    """pcl::VoxelGrid + metres -> millimetres as preprocess_from_ros does (tsdf_mapping.cpp:145-159).
+    Returns (int32 [m,3] millimetre points, float32 [m,3] centroids)."""
+    a = np.ascontiguousarray(cloud_xyz_m, dtype=np.float32)
+    a = a.reshape(-1, 3) if a.ndim == 1 else a
+    n, stride = a.shape[0], a.shape[1]
+    out_xyz = np.zeros((max(n, 1), 3), np.float32)
+    out_mm = np.zeros((max(n, 1), 3), np.int32)
+    L = lib()
+    L.orc_voxelgrid.restype = C.c_int64
+    m = L.orc_voxelgrid(a.ctypes.data_as(C.c_void_p), C.c_int64(n), C.c_int(stride), C.c_float(leaf_m),
+                        out_xyz.ctypes.data_as(C.c_void_p), out_mm.ctypes.data_as(C.c_void_p))
+    return out_mm[:m].copy(), out_xyz[:m].copy()
+
+
+def mm_pose_from_isometry(pose_m):
+    """tsdf_mapping.cpp:160-161: Isometry3d (4x4, metres) -> Matrix4f in millimetres through Eigen::Quaterniond."""
+    P = np.ascontiguousarray(np.asarray(pose_m, dtype=np.float64).reshape(4, 4).T).reshape(16)
+    out = np.zeros(16, np.float32)
+    lib().orc_mm_pose_from_isometry(P.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return _from_colmajor(out)
+
+
 def transform_point_cloud(pts, m):
     pts = _points(pts).copy()
     cm = _colmajor(m)

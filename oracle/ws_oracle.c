@@ -15,6 +15,7 @@
 #include "ws_oracle.h"
 
 #include <math.h>
+#include <float.h>
 #include <stdlib.h>
 #include <string.h>
 #include <limits.h>
@@ -962,6 +963,122 @@ int orc_register_cloud(const orc_map *m, orc_point *cloud, int64_t n,
   for (int64_t i = 0; i < n; i++) cloud[i] = orc_transform_point(cloud[i], M); /* :168-172 */
   memcpy(out, T, sizeof(T));
   return it;
+}
+
+/* ---- featsense feed (src/warpsense/tsdf_mapping.cpp:145-163) ------------------------------------------------ */
+typedef struct { unsigned idx; unsigned pt; } vg_pair;
+static int vg_cmp(const void *a, const void *b)
+{
+  const vg_pair *x = (const vg_pair *)a, *y = (const vg_pair *)b;
+  if (x->idx != y->idx) return x->idx < y->idx ? -1 : 1;
+  return x->pt < y->pt ? -1 : (x->pt > y->pt ? 1 : 0);          /* the order a stable sort leaves */
+}
+
+int64_t orc_voxelgrid(const float *xyz, int64_t n, int stride, float leaf, float *out_xyz, orc_point *out_mm)
+{
+  if (n <= 0) return 0;
+  const float inv = 1.f / leaf;                                  /* inverse_leaf_size_ */
+  float mn[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, mx[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+  int64_t finite = 0;
+  for (int64_t i = 0; i < n; i++)                                /* getMinMax3D */
+  {
+    const float *p = xyz + i * stride;
+    if (!isfinite(p[0]) || !isfinite(p[1]) || !isfinite(p[2])) continue;
+    finite++;
+    for (int a = 0; a < 3; a++) { if (p[a] < mn[a]) mn[a] = p[a]; if (p[a] > mx[a]) mx[a] = p[a]; }
+  }
+  if (finite == 0) return 0;
+  int64_t d[3]; int min_b[3], div_b[3];
+  for (int a = 0; a < 3; a++)
+  {
+    d[a] = (int64_t)((mx[a] - mn[a]) * inv) + 1;
+    min_b[a] = (int)floorf(mn[a] * inv);
+    div_b[a] = (int)floorf(mx[a] * inv) - min_b[a] + 1;
+  }
+  if (d[0] * d[1] * d[2] > (int64_t)INT32_MAX)                    /* leaf too small: PCL returns its input */
+  {
+    for (int64_t i = 0; i < n; i++)
+    {
+      const float *p = xyz + i * stride;
+      if (out_xyz) { out_xyz[3 * i] = p[0]; out_xyz[3 * i + 1] = p[1]; out_xyz[3 * i + 2] = p[2]; }
+      out_mm[i].x = (int)(p[0] * 1000.f); out_mm[i].y = (int)(p[1] * 1000.f); out_mm[i].z = (int)(p[2] * 1000.f);
+    }
+    return n;
+  }
+  vg_pair *iv = (vg_pair *)malloc((size_t)finite * sizeof(vg_pair));
+  int64_t m = 0;
+  for (int64_t i = 0; i < n; i++)
+  {
+    const float *p = xyz + i * stride;
+    if (!isfinite(p[0]) || !isfinite(p[1]) || !isfinite(p[2])) continue;
+    const int i0 = (int)(floorf(p[0] * inv) - (float)min_b[0]);
+    const int i1 = (int)(floorf(p[1] * inv) - (float)min_b[1]);
+    const int i2 = (int)(floorf(p[2] * inv) - (float)min_b[2]);
+    iv[m].idx = (unsigned)(i0 + i1 * div_b[0] + i2 * div_b[0] * div_b[1]);
+    iv[m].pt = (unsigned)i;
+    m++;
+  }
+  qsort(iv, (size_t)m, sizeof(vg_pair), vg_cmp);
+  int64_t out = 0;
+  for (int64_t a = 0; a < m;)
+  {
+    int64_t b = a;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    while (b < m && iv[b].idx == iv[a].idx)
+    {
+      const float *p = xyz + (int64_t)iv[b].pt * stride;
+      sx += p[0]; sy += p[1]; sz += p[2];                          /* AccumulatorXYZ::add */
+      b++;
+    }
+    const float fm = (float)(b - a);
+    const float cx = sx / fm, cy = sy / fm, cz = sz / fm;          /* AccumulatorXYZ::get: xyz / n */
+    if (out_xyz) { out_xyz[3 * out] = cx; out_xyz[3 * out + 1] = cy; out_xyz[3 * out + 2] = cz; }
+    out_mm[out].x = (int)(cx * 1000.f); out_mm[out].y = (int)(cy * 1000.f); out_mm[out].z = (int)(cz * 1000.f);
+    out++;
+    a = b;
+  }
+  free(iv);
+  return out;
+}
+
+void orc_mm_pose_from_isometry(const double P[16], float out[16])
+{
+#define M_(r, c) P[(c) * 4 + (r)]
+  double q[4];   /* x y z w: Eigen QuaternionBase::operator=(MatrixBase) */
+  double t = M_(0, 0) + M_(1, 1) + M_(2, 2);
+  if (t > 0.0)
+  {
+    t = sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (M_(2, 1) - M_(1, 2)) * t;
+    q[1] = (M_(0, 2) - M_(2, 0)) * t;
+    q[2] = (M_(1, 0) - M_(0, 1)) * t;
+  }
+  else
+  {
+    int i = 0;
+    if (M_(1, 1) > M_(0, 0)) i = 1;
+    if (M_(2, 2) > M_(i, i)) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(M_(i, i) - M_(j, j) - M_(k, k) + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (M_(k, j) - M_(j, k)) * t;
+    q[j] = (M_(j, i) + M_(i, j)) * t;
+    q[k] = (M_(k, i) + M_(i, k)) * t;
+  }
+#undef M_
+  /* QuaternionBase::toRotationMatrix */
+  const double tx = 2.0 * q[0], ty = 2.0 * q[1], tz = 2.0 * q[2];
+  const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+  const double txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+  const double tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+  for (int i = 0; i < 16; i++) out[i] = (i % 5 == 0) ? 1.f : 0.f;
+  out[0] = (float)(1.0 - (tyy + tzz)); out[1] = (float)(txy + twz); out[2] = (float)(txz - twy);
+  out[4] = (float)(txy - twz); out[5] = (float)(1.0 - (txx + tzz)); out[6] = (float)(tyz + twx);
+  out[8] = (float)(txz + twy); out[9] = (float)(tyz - twx); out[10] = (float)(1.0 - (txx + tyy));
+  for (int r = 0; r < 3; r++) out[12 + r] = (float)(P[12 + r] * 1000.0);
 }
 
 int orc_num_threads(void)

@@ -122,6 +122,15 @@ int orc_register_cloud(const orc_map *m, orc_point *cloud, int64_t n,
 /* test/cuda.cpp:837-923 : H += J J^T for one Jacobian */
 void orc_jacobi_2_h(const int64_t J[6], int64_t H[36]);
 
+/* ---- featsense feed: pcl::VoxelGrid<PointXYZI> + metres -> millimetres (src/warpsense/tsdf_mapping.cpp:145-159).
+ * PCL is not vendored in the reference tree (ROS noetic: PCL 1.10); this restates filters/impl/voxel_grid.hpp
+ * applyFilter (leaf index = floor(x * inverse_leaf) - min_b, output sorted by ijk0 + ijk1*div0 + ijk2*div0*div1,
+ * float centroid sums, `xyz / n`).  PARITY UNPINNED: no PCL here to run; runs of equal leaf index are summed in
+ * ascending point index (std::sort leaves that order unspecified).  Returns the number of output points. */
+int64_t orc_voxelgrid(const float *xyz, int64_t n, int stride_floats, float leaf, float *out_xyz, orc_point *out_mm);
+/* Eigen::Quaterniond(pose.rotation()).toRotationMatrix().cast<float>(), translation * 1000 (tsdf_mapping.cpp:160-161) */
+void orc_mm_pose_from_isometry(const double pose_colmajor[16], float out_colmajor[16]);
+
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
 

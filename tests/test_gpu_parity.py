@@ -454,3 +454,86 @@ def test_track_scan_matches_register_then_update():
         assert (c["n_candidates"], c["n_touched"], c["n_written"]) == (st["n_candidates"], st["n_touched"], st["n_written"])
         assert_same_grid(om, tsdf, hm, "frame %d" % k)
     tsdf.close()
+
+
+def _yaw(deg, tx=0.0):
+    T = np.eye(4, dtype=np.float32)
+    a = math.radians(deg)
+    T[0, 0] = math.cos(a); T[0, 1] = -math.sin(a); T[1, 0] = math.sin(a); T[1, 1] = math.cos(a)
+    T[0, 3] = tx
+    return T
+
+
+def test_track_scan_reference_pose_update_and_pretransform():
+    """WS_TRACK_REFERENCE_POSE: the pose is composed as App::update_pose_estimate does (app.cpp:172-176:
+    R = X.R * R, t += X.t -- no X.R * t term) and register_cloud starts from an IMU-like pretransform
+    (app.cpp:97-102).  Oracle: register_cloud -> orc.update_pose_estimate -> convert_pose -> update_tsdf."""
+    res = 100
+    s, om, hm, tsdf, tau, mw = _stream_setup(32, 256, 128, res)
+    reg = api.RegistrationCuda(tsdf)
+    f0 = s.frame(0)
+    pos, up = fp.convert_pose_to_gpu(f0["pose"], res)
+    orc.update_tsdf(om, f0["points_map"], pos, up, tau, mw, res)
+    tsdf.update_tsdf(f0["points_map"], pos, up)
+    pre = _yaw(0.3)
+    for k in range(1, 4):
+        prior = s.pose(k - 1)
+        assert np.abs(prior[:3, 3]).max() > 0 or k == 1      # prior.t != 0: the two compositions differ
+        cloud = s.frame(k, prior_pose=prior)["points_prior"]
+        ocloud = cloud.copy()
+        oX, oit = orc.register_cloud(om, ocloud, pre, 10, 0.1, 0.0, res)
+        opose = orc.update_pose_estimate(prior, oX)
+        opos, oup = orc.convert_pose(opose, res)
+        st = orc.update_tsdf(om, ocloud, opos, oup, tau, mw, res)
+        X, pose, it = reg.track_scan(cloud, prior, 10, 0.1, 0.0, res, pretransform=pre, reference_pose=True)
+        assert it == oit and np.array_equal(X, oX)
+        assert np.array_equal(pose, opose), "reference pose composition differs"
+        if k > 1:
+            assert not np.array_equal(pose, _compose_f32(oX, prior)), "the two compositions should differ here"
+        c = tsdf.counters()
+        assert (c["n_candidates"], c["n_touched"], c["n_written"]) == (st["n_candidates"], st["n_touched"], st["n_written"])
+        assert_same_grid(om, tsdf, hm, "frame %d" % k)
+    tsdf.close()
+
+
+def test_track_submit_wait_two_in_flight_chained_pose():
+    """ws_track_submit / ws_track_wait: scan k+1 is enqueued (host copy on the second stream, prior pose chained
+    on the device) before scan k is collected; results equal the blocking calls and the oracle."""
+    res = 100
+    s, om, hm, tsdf, tau, mw = _stream_setup(32, 256, 128, res)
+    reg = api.RegistrationCuda(tsdf)
+    f0 = s.frame(0)
+    pos, up = fp.convert_pose_to_gpu(f0["pose"], res)
+    orc.update_tsdf(om, f0["points_map"], pos, up, tau, mw, res)
+    tsdf.update_tsdf(f0["points_map"], pos, up)
+    I = np.eye(4, dtype=np.float32)
+    n_scans = 5
+    # oracle: every scan is placed with the ground-truth pose of the scan before; the tracked pose chains
+    clouds = [s.frame(k, prior_pose=s.pose(k - 1))["points_prior"] for k in range(1, n_scans + 1)]
+    want = []
+    opose = s.pose(0)
+    for k in range(n_scans):
+        ocloud = clouds[k].copy()
+        oX, oit = orc.register_cloud(om, ocloud, I, 8, 0.1, 0.0, res)
+        opose = _compose_f32(oX, opose)
+        opos, oup = orc.convert_pose(opose, res)
+        st = orc.update_tsdf(om, ocloud, opos, oup, tau, mw, res)
+        want.append((oX, opose.copy(), oit, st))
+    tickets = []
+    got = []
+    for k in range(n_scans):
+        tickets.append(reg.track_submit(clouds[k], s.pose(0) if k == 0 else None, 8, 0.1, 0.0, res))
+        if len(tickets) == 2:
+            got.append(reg.track_wait(tickets.pop(0)) + (tsdf.counters(),))
+    while tickets:
+        got.append(reg.track_wait(tickets.pop(0)) + (tsdf.counters(),))
+    for k in range(n_scans):
+        X, pose, it, c = got[k]
+        oX, op, oit, st = want[k]
+        assert it == oit and np.array_equal(X, oX), "scan %d: transform" % k
+        assert np.array_equal(pose, op), "scan %d: chained pose" % k
+        assert (c["n_candidates"], c["n_touched"], c["n_written"]) == (st["n_candidates"], st["n_touched"], st["n_written"])
+    assert_same_grid(om, tsdf, hm, "after %d pipelined scans" % n_scans)
+    with pytest.raises(lib.WarpsenseError):
+        reg.track_wait(0)                                   # nothing in flight
+    tsdf.close()

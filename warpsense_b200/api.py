@@ -16,6 +16,8 @@ marshals arguments.  (The same shims exist as C++ in include/warpsense_b200.hpp.
 import ctypes as C
 import threading
 
+import math
+
 import numpy as np
 
 from . import lib as _lib
@@ -262,6 +264,47 @@ class TSDFCuda:
                                          int(map_resolution), out.ctypes.data if fetch else None, C.byref(n_out)))
         return (out[:n_out.value].copy() if fetch else None), n_out.value
 
+    def voxelgrid_subsample(self, cloud_xyz_m, leaf_m, fetch=True, want_xyz=False, device_ptr=None, n=None, point_step_bytes=12):
+        """pcl::VoxelGrid with a cubic leaf + metres -> int millimetres on the device (ws_voxelgrid_subsample,
+        tsdf_mapping.cpp:147-158).  The points stay on the device (scan_points_device); returned as arrays when
+        `fetch`: (int32 [m,3] mm[, float32 [m,3] centroids]), m."""
+        hd = self._hd
+        if device_ptr is None:
+            a = np.ascontiguousarray(cloud_xyz_m, dtype=np.float32)
+            a = a.reshape(-1, 3) if a.ndim == 1 else a
+            ptr, cnt, step, dev = a.ctypes.data, a.shape[0], a.shape[1] * 4, 0
+        else:
+            ptr, cnt, step, dev = C.c_void_p(int(device_ptr)), int(n), int(point_step_bytes), 1
+        out_mm = np.zeros((max(cnt, 1), 3), np.int32) if fetch else None
+        out_xyz = np.zeros((max(cnt, 1), 3), np.float32) if (fetch and want_xyz) else None
+        n_out = C.c_int64()
+        hd.check(hd.L.ws_voxelgrid_subsample(hd.h, ptr, cnt, step, dev, float(leaf_m),
+                                             out_mm.ctypes.data if out_mm is not None else None,
+                                             out_xyz.ctypes.data if out_xyz is not None else None, C.byref(n_out)))
+        m = n_out.value
+        if not fetch:
+            return None, m
+        if want_xyz:
+            return out_mm[:m].copy(), out_xyz[:m].copy(), m
+        return out_mm[:m].copy(), m
+
+    def update_tsdf_from_ros(self, cloud_xyz_m, pose_m, device_ptr=None, n=None, point_step_bytes=12):
+        """TSDFMapping::update_tsdf_from_ros (tsdf_mapping.cpp:165-173) in one call: voxel grid at the map
+        resolution, metres -> millimetres, pose (4x4, metres) -> mm Matrix4f, update_tsdf.  Returns (mm_pose, n_points)."""
+        hd = self._hd
+        if device_ptr is None:
+            a = np.ascontiguousarray(cloud_xyz_m, dtype=np.float32)
+            a = a.reshape(-1, 3) if a.ndim == 1 else a
+            ptr, cnt, step, dev = a.ctypes.data, a.shape[0], a.shape[1] * 4, 0
+        else:
+            ptr, cnt, step, dev = C.c_void_p(int(device_ptr)), int(n), int(point_step_bytes), 1
+        P = np.ascontiguousarray(np.asarray(pose_m, dtype=np.float64).reshape(4, 4).T).reshape(16)
+        out = np.zeros(16, np.float32)
+        n_out = C.c_int64()
+        hd.check(hd.L.ws_update_tsdf_from_ros(hd.h, ptr, cnt, step, dev, P.ctypes.data_as(C.POINTER(C.c_double)),
+                                              out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(n_out)))
+        return from_colmajor16(out), n_out.value
+
     def scan_points_device(self):
         n = C.c_int64()
         ptr = self._hd.L.ws_scan_points_device(self._hd.h, C.byref(n))
@@ -417,31 +460,67 @@ class RegistrationCuda:
                                         out.ctypes.data_as(C.POINTER(C.c_float)), C.byref(it)))
         return from_colmajor16(out), it.value
 
-    def track_scan(self, points, prior_pose, max_iterations, it_weight_gradient, epsilon, map_resolution,
-                   device_ptr=None, n=None):
-        """One scan through the fused pipeline (ws_track_scan): register against the map (pretransform =
-        identity), pose = X @ prior_pose, update_tsdf with the registered cloud -- one host synchronisation.
-        `points`: int32 [n,3] host array, or None with `device_ptr`/`n`.  `prior_pose`: 4x4, or a float32[16]
-        already in the column-major ABI layout (colmajor16).  Returns (X, pose, iterations)."""
-        hd = self._hd
-        f32p = C.POINTER(C.c_float)
-        pp = prior_pose
-        if not (isinstance(pp, np.ndarray) and pp.dtype == np.float32 and pp.shape == (16,) and pp.flags.c_contiguous):
-            pp = colmajor16(prior_pose)
+    def _track_bufs(self):
         buf = getattr(self, "_track_buf", None)
         if buf is None:                              # marshalling buffers, reused from call to call
-            buf = self._track_buf = (np.zeros(16, np.float32), np.zeros(16, np.float32), C.c_int32())
-            self._track_ptrs = (buf[0].ctypes.data_as(f32p), buf[1].ctypes.data_as(f32p), C.byref(buf[2]))
+            f32p = C.POINTER(C.c_float)
+            buf = self._track_buf = (np.zeros(16, np.float32), np.zeros(16, np.float32), C.c_int32(), C.c_int32())
+            self._track_ptrs = (buf[0].ctypes.data_as(f32p), buf[1].ctypes.data_as(f32p), C.byref(buf[2]), C.byref(buf[3]))
+        return buf, self._track_ptrs
+
+    @staticmethod
+    def _mat16(m):
+        if m is None:
+            return None
+        if isinstance(m, np.ndarray) and m.dtype == np.float32 and m.shape == (16,) and m.flags.c_contiguous:
+            return m
+        return colmajor16(m)
+
+    def track_submit(self, points, prior_pose, max_iterations, it_weight_gradient, epsilon, map_resolution,
+                     device_ptr=None, n=None, pretransform=None, reference_pose=False):
+        """Enqueue one scan of the per-scan pipeline (ws_track_submit): register against the map, pose update,
+        update_tsdf with the registered cloud.  Returns a ticket for track_wait; at most two scans in flight.
+        `points`: int32 [n,3] host array (must stay alive until track_wait), or None with `device_ptr`/`n`.
+        `prior_pose`: 4x4 (or float32[16] column-major); None = the pose of the previous tracked scan (on the device).
+        `reference_pose`: compose the pose as App::update_pose_estimate (app.cpp:172-176) instead of X @ prior."""
+        hd = self._hd
+        f32p = C.POINTER(C.c_float)
+        pp, pre = self._mat16(prior_pose), self._mat16(pretransform)
+        _, ptrs = self._track_bufs()
         if points is not None:
             p = _pts(points)
             ptr, cnt, dev = p.ctypes.data, len(p), 0
+            self._track_keep = getattr(self, "_track_keep", {})
         else:
+            p = None
             ptr, cnt, dev = C.c_void_p(int(device_ptr)), int(n), 1
-        hd.check(hd.L.ws_track_scan(hd.h, ptr, cnt, dev, pp.ctypes.data_as(f32p), int(max_iterations),
-                                    float(it_weight_gradient), float(epsilon), int(map_resolution),
-                                    self._track_ptrs[0], self._track_ptrs[1], self._track_ptrs[2]))
+        hd.check(hd.L.ws_track_submit(hd.h, ptr, cnt, dev, pp.ctypes.data_as(f32p) if pp is not None else None,
+                                      pre.ctypes.data_as(f32p) if pre is not None else None, int(max_iterations),
+                                      float(it_weight_gradient), float(epsilon), int(map_resolution),
+                                      _lib.WS_TRACK_REFERENCE_POSE if reference_pose else 0, ptrs[3]))
+        ticket = self._track_buf[3].value
+        if p is not None:
+            self._track_keep[ticket] = p             # the copy is asynchronous: keep the array alive
         self.curr_n_points = cnt
+        return ticket
+
+    def track_wait(self, ticket):
+        """Collect a submitted scan: (X, pose, iterations)."""
+        hd = self._hd
+        buf, ptrs = self._track_bufs()
+        try:
+            hd.check(hd.L.ws_track_wait(hd.h, int(ticket), ptrs[0], ptrs[1], ptrs[2]))
+        finally:
+            getattr(self, "_track_keep", {}).pop(ticket, None)
         return from_colmajor16(buf[0]), from_colmajor16(buf[1]), buf[2].value
+
+    def track_scan(self, points, prior_pose, max_iterations, it_weight_gradient, epsilon, map_resolution,
+                   device_ptr=None, n=None, pretransform=None, reference_pose=False):
+        """One scan through the per-scan pipeline, blocking (ws_track_scan_ex = submit + wait).
+        Returns (X, pose, iterations)."""
+        t = self.track_submit(points, prior_pose, max_iterations, it_weight_gradient, epsilon, map_resolution,
+                              device_ptr=device_ptr, n=n, pretransform=pretransform, reference_pose=reference_pose)
+        return self.track_wait(t)
 
     # -- multi-GPU (SURVEY.md 8e): one handle per rank, the caller supplies the exchange step --
     def sums_device_ptr(self):
@@ -530,6 +609,46 @@ class RegistrationCuda:
         return H.reshape(6, 6).T.copy(), g, e.value, c.value
 
 
+def mm_pose_from_isometry(pose_m):
+    """tsdf_mapping.cpp:160-161: Eigen::Quaterniond(pose.rotation()).toRotationMatrix().cast<float>() and
+    translation * 1000 -- Isometry3d (4x4, metres) -> Matrix4f (millimetres)."""
+    m = np.asarray(pose_m, dtype=np.float64).reshape(4, 4)
+    q = np.zeros(4)                      # x y z w (Eigen QuaternionBase::operator=(MatrixBase))
+    t = m[0, 0] + m[1, 1] + m[2, 2]
+    if t > 0.0:
+        t = math.sqrt(t + 1.0)
+        q[3] = 0.5 * t
+        t = 0.5 / t
+        q[0] = (m[2, 1] - m[1, 2]) * t
+        q[1] = (m[0, 2] - m[2, 0]) * t
+        q[2] = (m[1, 0] - m[0, 1]) * t
+    else:
+        i = 0
+        if m[1, 1] > m[0, 0]:
+            i = 1
+        if m[2, 2] > m[i, i]:
+            i = 2
+        j = (i + 1) % 3
+        k = (j + 1) % 3
+        t = math.sqrt(m[i, i] - m[j, j] - m[k, k] + 1.0)
+        q[i] = 0.5 * t
+        t = 0.5 / t
+        q[3] = (m[k, j] - m[j, k]) * t
+        q[j] = (m[j, i] + m[i, j]) * t
+        q[k] = (m[k, i] + m[i, k]) * t
+    tx, ty, tz = 2.0 * q[0], 2.0 * q[1], 2.0 * q[2]
+    twx, twy, twz = tx * q[3], ty * q[3], tz * q[3]
+    txx, txy, txz = tx * q[0], ty * q[0], tz * q[0]
+    tyy, tyz, tzz = ty * q[1], tz * q[1], tz * q[2]
+    out = np.eye(4, dtype=np.float32)
+    R = np.array([[1.0 - (tyy + tzz), txy - twz, txz + twy],
+                  [txy + twz, 1.0 - (txx + tzz), tyz - twx],
+                  [txz - twy, tyz + twx, 1.0 - (txx + tyy)]])
+    out[:3, :3] = R.astype(np.float32)
+    out[:3, 3] = (m[:3, 3] * 1000.0).astype(np.float32)
+    return out
+
+
 class TSDFMapping:
     """cuda::TSDFMapping(params, local_map) -- tsdf_mapping.h:17-60, tsdf_mapping.cpp:13-205 (no ROS).
 
@@ -574,32 +693,19 @@ class TSDFMapping:
             self.tsdf_.update_tsdf(scan_points, pos, up)
 
     def preprocess_from_ros(self, cloud_xyz_m, pose):
-        """tsdf_mapping.cpp:145-163 without PCL: voxel-grid subsample at the map resolution (one
-        centroid per occupied leaf, like pcl::VoxelGrid), metres -> int millimetres, pose -> mm Matrix4f."""
-        res_m = self.params_.map.resolution / 1000.0
-        pts = np.asarray(cloud_xyz_m, dtype=np.float32).reshape(-1, 3)
-        if len(pts):
-            leaf = np.floor(pts / np.float32(res_m)).astype(np.int64)
-            leaf -= leaf.min(axis=0)
-            dims = leaf.max(axis=0) + 1
-            key = (leaf[:, 0] * dims[1] + leaf[:, 1]) * dims[2] + leaf[:, 2]
-            order = np.argsort(key, kind="stable")
-            ks = key[order]
-            first = np.concatenate([[True], ks[1:] != ks[:-1]])
-            idx = np.cumsum(first) - 1
-            n = int(idx[-1]) + 1
-            sums = np.zeros((n, 3), np.float64)
-            np.add.at(sums, idx, pts[order].astype(np.float64))
-            cnt = np.bincount(idx, minlength=n)[:, None]
-            cent = (sums / cnt).astype(np.float32)
-        else:
-            cent = pts
-        points_rm = np.trunc(cent * np.float32(1000.0)).astype(np.int32)
-        mm_pose = np.eye(4, dtype=np.float32)
-        P = np.asarray(pose, dtype=np.float64).reshape(4, 4)
-        mm_pose[:3, :3] = P[:3, :3].astype(np.float32)
-        mm_pose[:3, 3] = (P[:3, 3] * 1000.0).astype(np.float32)
-        return points_rm, mm_pose
+        """tsdf_mapping.cpp:145-163 without PCL: voxel-grid subsample at the map resolution ON THE DEVICE
+        (ws_voxelgrid_subsample: one float centroid per occupied leaf in pcl::VoxelGrid's leaf order), metres ->
+        int millimetres, pose -> mm Matrix4f (through Eigen::Quaterniond, :160-161)."""
+        res_m = np.float32(self.params_.map.resolution) / np.float32(1000.0)
+        with self.mutex_:
+            points_rm, _ = self.tsdf_.voxelgrid_subsample(cloud_xyz_m, float(res_m))
+        return points_rm, mm_pose_from_isometry(pose)
+
+    def subsample(self, cloud_xyz_m, resolution_m):
+        """pcl::VoxelGrid with a cubic leaf on the device: float32 [m,3] centroids in PCL's leaf order."""
+        with self.mutex_:
+            _, xyz, _ = self.tsdf_.voxelgrid_subsample(cloud_xyz_m, float(resolution_m), want_xyz=True)
+        return xyz
 
     def update_tsdf_from_ros(self, cloud_xyz_m, pose):
         """tsdf_mapping.cpp:165-173: cloud in metres (sensor points already in the map frame), pose in
@@ -688,25 +794,13 @@ class MappingFeed:
         self.poses = []                      # what hdf5_global_map_->write_pose would have stored (:137)
         self.updates = 0
 
-    @staticmethod
-    def subsample(cloud_xyz_m, resolution_m):
-        """mapping.cpp `subsample`: pcl::VoxelGrid with a cubic leaf -- one centroid per occupied leaf."""
+    def subsample(self, cloud_xyz_m, resolution_m):
+        """mapping.cpp `subsample`: pcl::VoxelGrid with a cubic leaf -- one float centroid per occupied leaf
+        (TSDFMapping.subsample: on the device)."""
         pts = np.asarray(cloud_xyz_m, dtype=np.float32).reshape(-1, 3)
         if not len(pts):
             return pts
-        leaf = np.floor(pts / np.float32(resolution_m)).astype(np.int64)
-        leaf -= leaf.min(axis=0)
-        dims = leaf.max(axis=0) + 1
-        key = (leaf[:, 0] * dims[1] + leaf[:, 1]) * dims[2] + leaf[:, 2]
-        order = np.argsort(key, kind="stable")
-        ks = key[order]
-        first = np.concatenate([[True], ks[1:] != ks[:-1]])
-        idx = np.cumsum(first) - 1
-        n = int(idx[-1]) + 1
-        sums = np.zeros((n, 3), np.float64)
-        np.add.at(sums, idx, pts[order].astype(np.float64))
-        cnt = np.bincount(idx, minlength=n)[:, None]
-        return (sums / cnt).astype(np.float32)
+        return self.gpu_.subsample(pts, resolution_m)
 
     def push(self, cloud_xyz_m, pose_m):
         """One (cloud, pose) pair from the odometry front end.  Returns True if the map was updated."""

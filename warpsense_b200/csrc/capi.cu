@@ -67,11 +67,19 @@ void free_handle(ws_handle *h)
   for (auto &t : h->timers) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
   cudaFree(h->g.grid); cudaFree(h->g.keys); cudaFree(h->g.brick_flag); cudaFree(h->g.brick_flag2); cudaFree(h->g.vstate); cudaFree(h->g.ffree); cudaFree(h->g.brick_slot_base);
   cudaFree(h->d_points); cudaFree(h->d_rays); cudaFree(h->d_grp_info); cudaFree(h->d_item_off); cudaFree(h->d_gen_list);
+  cudaFree(h->d_vg_keys); cudaFree(h->d_vg_vals); cudaFree(h->d_vg_hist); cudaFree(h->d_vg_box); cudaFree(h->d_vg_xyz);
   cudaFree(h->d_pre_tmp); cudaFree(h->d_pre_val); cudaFree(h->d_pre_slot); cudaFree(h->d_pre_table); cudaFree(h->d_pre_tiles); cudaFree(h->d_pre_xyz); cudaFree(h->d_reg_points); cudaFree(h->d_brick_list);
   cudaFree(h->d_counters); cudaFreeHost(h->h_counters);
   cudaFree(h->d_pend_addr); cudaFree(h->d_pend_prev); cudaFree(h->d_pend_key);
   cudaFree(h->d_active[0]); cudaFree(h->d_active[1]);
   cudaFree(h->d_rec); cudaFree(h->d_list); cudaFree(h->d_chunk_fill);
+  for (auto &t : h->track)
+  {
+    cudaFree(t.d_pts); cudaFreeHost(t.h_acc); cudaFreeHost(t.h_pose); cudaFreeHost(t.h_ctr);
+    if (t.copied) cudaEventDestroy(t.copied);
+    if (t.done) cudaEventDestroy(t.done);
+  }
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   detach_peers(h); cudaFree(h->d_mail); cudaFree(h->d_pose); cudaFreeHost(h->h_pose);
   cudaFree(h->d_acc); cudaFree(h->d_trace); cudaFreeHost(h->h_acc); cudaFree(h->d_reg_partials);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -607,6 +615,138 @@ int ws_preprocess_scan(ws_handle *h, const float *xyz, int64_t n, int32_t point_
   });
 }
 
+// host: Eigen::Quaterniond(R).toRotationMatrix().cast<float>() (tsdf_mapping.cpp:160), R column-major 3x3 in a 4x4
+static void quat_roundtrip(const double P[16], float R[9])
+{
+  auto m = [&](int r, int c) { return P[c * 4 + r]; };
+  double q[4];   // x y z w
+  double t = m(0, 0) + m(1, 1) + m(2, 2);
+  if (t > 0.0)
+  {
+    t = std::sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (m(2, 1) - m(1, 2)) * t;
+    q[1] = (m(0, 2) - m(2, 0)) * t;
+    q[2] = (m(1, 0) - m(0, 1)) * t;
+  }
+  else
+  {
+    int i = 0;
+    if (m(1, 1) > m(0, 0)) i = 1;
+    if (m(2, 2) > m(i, i)) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (m(k, j) - m(j, k)) * t;
+    q[j] = (m(j, i) + m(i, j)) * t;
+    q[k] = (m(k, i) + m(i, k)) * t;
+  }
+  const double tx = 2.0 * q[0], ty = 2.0 * q[1], tz = 2.0 * q[2];
+  const double twx = tx * q[3], twy = ty * q[3], twz = tz * q[3];
+  const double txx = tx * q[0], txy = ty * q[0], txz = tz * q[0];
+  const double tyy = ty * q[1], tyz = tz * q[1], tzz = tz * q[2];
+  const double r[9] = { 1.0 - (tyy + tzz), txy + twz, txz - twy,      // column 0
+                        txy - twz, 1.0 - (txx + tzz), tyz + twx,      // column 1
+                        txz + twy, tyz - twx, 1.0 - (txx + tyy) };    // column 2
+  for (int i = 0; i < 9; i++) R[i] = (float)r[i];
+}
+
+// include/util/util.h:8-18,52-56 + tsdf_mapping.cpp:77-85 on the host
+static void host_convert_pose(const float pose[16], int res, int pos[3], int up[3])
+{
+  int M[16];
+  for (int i = 0; i < 16; i++) M[i] = (int)(pose[i] * (float)WS_MR);
+  const unsigned z = (unsigned)WS_MR;
+  for (int r = 0; r < 3; r++)
+  {
+    const int acc = (int)((unsigned)M[8 + r] * z);                  // R_int * (0, 0, MR), translation column 0
+    up[r] = acc / WS_MR;
+    pos[r] = (int)std::floor(pose[12 + r] / (float)res);
+  }
+}
+
+static const float *stage_xyz(ws_handle *h, const float *xyz, int64_t n, int stride, int on_device)
+{
+  if (on_device || n == 0) return xyz;
+  const size_t floats = (size_t)n * stride;
+  if (floats > h->pre_xyz_cap)
+  {
+    if (h->d_pre_xyz) WS_CUDA_OK(cudaFree(h->d_pre_xyz));
+    h->d_pre_xyz = nullptr; h->pre_xyz_cap = 0;
+    WS_CUDA_OK(cudaMalloc(&h->d_pre_xyz, floats * sizeof(float)));
+    h->pre_xyz_cap = floats;
+  }
+  WS_CUDA_OK(cudaMemcpyAsync(h->d_pre_xyz, xyz, floats * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  return h->d_pre_xyz;
+}
+
+int ws_voxelgrid_subsample(ws_handle *h, const float *xyz, int64_t n, int32_t point_step_bytes, int32_t on_device, float leaf_m,
+                           ws_point *out_mm_host, float *out_xyz_host, int64_t *n_out)
+{
+  return guarded(h, [&]() {
+    if (n < 0 || (n > 0 && !xyz) || !(leaf_m > 0.f) || point_step_bytes < 12 || (point_step_bytes & 3))
+      throw std::invalid_argument("ws_voxelgrid_subsample: bad argument");
+    if (n > WS_MAX_POINTS) throw std::length_error("ws_voxelgrid_subsample: too many points");
+    ensure_points(&h->d_points, &h->points_cap, (size_t)std::max<int64_t>(n, 1));
+    const int stride = point_step_bytes / 4;
+    const float *d_xyz = stage_xyz(h, xyz, n, stride, on_device);
+    float *d_out = nullptr;
+    if (out_xyz_host && n > 0)
+    {
+      if ((size_t)n * 3 > h->vg_xyz_cap)
+      {
+        if (h->d_vg_xyz) WS_CUDA_OK(cudaFree(h->d_vg_xyz));
+        h->d_vg_xyz = nullptr; h->vg_xyz_cap = 0;
+        const size_t want = std::max<size_t>((size_t)n * 3, 3u << 17);
+        WS_CUDA_OK(cudaMalloc(&h->d_vg_xyz, want * sizeof(float)));
+        h->vg_xyz_cap = want;
+      }
+      d_out = h->d_vg_xyz;
+    }
+    h->scan_n = ws_launch_voxelgrid(h, d_xyz, n, stride, leaf_m, d_out);
+    if (h->scan_n > 0)
+    {
+      if (out_mm_host)
+        WS_CUDA_OK(cudaMemcpyAsync(out_mm_host, h->d_points, (size_t)h->scan_n * sizeof(ws_pt), cudaMemcpyDeviceToHost, h->stream));
+      if (out_xyz_host)
+        WS_CUDA_OK(cudaMemcpyAsync(out_xyz_host, d_out, (size_t)h->scan_n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+      WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+    if (n_out) *n_out = h->scan_n;
+    return WS_OK;
+  });
+}
+
+int ws_update_tsdf_from_ros(ws_handle *h, const float *xyz_m, int64_t n, int32_t point_step_bytes, int32_t on_device,
+                            const double pose_m[16], float out_mm_pose[16], int64_t *n_points)
+{
+  return guarded(h, [&]() {
+    if (n < 0 || (n > 0 && !xyz_m) || !pose_m || point_step_bytes < 12 || (point_step_bytes & 3))
+      throw std::invalid_argument("ws_update_tsdf_from_ros: bad argument");
+    if (n > WS_MAX_POINTS) throw std::length_error("ws_update_tsdf_from_ros: too many points");
+    ensure_points(&h->d_points, &h->points_cap, (size_t)std::max<int64_t>(n, 1));
+    const int stride = point_step_bytes / 4;
+    const float *d_xyz = stage_xyz(h, xyz_m, n, stride, on_device);
+    // preprocess_from_ros (tsdf_mapping.cpp:145-163): voxel grid at the map resolution, metres -> millimetres
+    h->scan_n = ws_launch_voxelgrid(h, d_xyz, n, stride, (float)h->res / 1000.f, nullptr);
+    float mm[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    float R[9];
+    quat_roundtrip(pose_m, R);
+    for (int c = 0; c < 3; c++)
+      for (int r = 0; r < 3; r++) mm[c * 4 + r] = R[c * 3 + r];
+    for (int r = 0; r < 3; r++) mm[12 + r] = (float)(pose_m[12 + r] * 1000.0);
+    if (out_mm_pose) std::memcpy(out_mm_pose, mm, sizeof(mm));
+    if (n_points) *n_points = h->scan_n;
+    int pos[3], up[3];
+    host_convert_pose(mm, h->res, pos, up);
+    h->last_n_points = h->scan_n;
+    ws_launch_update(h, h->d_points, (int)h->scan_n, pos, up);                 // tsdf_mapping.cpp:165-173
+    return WS_OK;
+  });
+}
+
 const ws_point *ws_scan_points_device(ws_handle *h, int64_t *n)
 {
   if (!h) return nullptr;
@@ -637,6 +777,7 @@ int ws_reg_prepare(ws_handle *h, const ws_point *points, int64_t n)
     if (n < 0 || (n > 0 && !points)) throw std::invalid_argument("ws_reg_prepare: bad argument");
     if (n > WS_MAX_POINTS) throw std::length_error("ws_reg_prepare: too many points");
     ensure_points(&h->d_reg_points, &h->reg_points_cap, (size_t)n);
+    h->d_reg_points_last = nullptr;
     if (n > 0)
       WS_CUDA_OK(cudaMemcpyAsync(h->d_reg_points, points, (size_t)n * sizeof(ws_pt), cudaMemcpyHostToDevice, h->stream));
     h->reg_n = (int)n;
@@ -650,6 +791,7 @@ int ws_reg_prepare_device(ws_handle *h, const ws_point *device_points, int64_t n
     if (n < 0 || (n > 0 && !device_points)) throw std::invalid_argument("ws_reg_prepare_device: bad argument");
     if (n > WS_MAX_POINTS) throw std::length_error("ws_reg_prepare_device: too many points");
     ensure_points(&h->d_reg_points, &h->reg_points_cap, (size_t)n);
+    h->d_reg_points_last = nullptr;
     if (n > 0)
       WS_CUDA_OK(cudaMemcpyAsync(h->d_reg_points, device_points, (size_t)n * sizeof(ws_pt), cudaMemcpyDeviceToDevice, h->stream));
     h->reg_n = (int)n;
@@ -681,6 +823,8 @@ int ws_register_cloud(ws_handle *h, ws_point *cloud, int64_t n, const float pret
       if (n < 0) throw std::invalid_argument("ws_register_cloud: bad point count");
       if (n > WS_MAX_POINTS) throw std::length_error("ws_register_cloud: too many points");
       ensure_points(&h->d_reg_points, &h->reg_points_cap, (size_t)n);
+      h->d_reg_points_last = nullptr;
+    h->d_reg_points_last = nullptr;
       if (n > 0)
         WS_CUDA_OK(cudaMemcpyAsync(h->d_reg_points, cloud, (size_t)n * sizeof(ws_pt), cudaMemcpyHostToDevice, h->stream));
       h->reg_n = (int)n;
@@ -811,42 +955,112 @@ int ws_peer_set_timeout(ws_handle *h, double seconds)
   return WS_OK;
 }
 
-// The reference's per-scan sequence (App::cloud_callback, src/warpsense/app.cpp:65-112: register_cloud,
-// pose update, update_tsdf) as ONE stream of kernels with a single host synchronisation at the end: the
-// registration leaves its transform on the device, pose_kernel turns X * prior into the scanner voxel and
-// the up vector there, and update_tsdf's kernels read them from device memory.
-int ws_track_scan(ws_handle *h, const ws_point *points, int64_t n, int32_t on_device, const float prior_pose[16],
-                  int32_t max_iterations, float it_weight_gradient, float epsilon, int32_t map_resolution,
-                  float out_transform[16], float out_pose[16], int32_t *iterations)
+// ---- per-scan pipeline ------------------------------------------------------------------------------
+// register_cloud -> pose update -> update_tsdf as ONE stream of kernels per scan (the calls App::cloud_callback
+// makes, src/warpsense/app.cpp:65-112, in the order of BASELINE configs[2]): the registration leaves its
+// transform on the device, pose_kernel turns it and the prior pose into the scanner voxel and the up vector
+// there, and update_tsdf's kernels read them from device memory.  ws_track_submit only ENQUEUES (the scan is
+// copied from host memory on a second stream into one of two device buffers); ws_track_wait collects the
+// transform, the pose and the work counters.  With two scans in flight the host never idles the GPU.
+static void track_slot_init(ws_handle *h, ws_handle::TrackSlot &t)
+{
+  if (t.h_acc) return;
+  WS_CUDA_OK(cudaMallocHost(&t.h_acc, sizeof(RegAccum)));
+  WS_CUDA_OK(cudaMallocHost(&t.h_pose, sizeof(PoseDev)));
+  WS_CUDA_OK(cudaMallocHost(&t.h_ctr, sizeof(UpdateCounters)));
+  std::memset(t.h_acc, 0, sizeof(RegAccum)); std::memset(t.h_pose, 0, sizeof(PoseDev)); std::memset(t.h_ctr, 0, sizeof(UpdateCounters));
+  WS_CUDA_OK(cudaEventCreateWithFlags(&t.copied, cudaEventDisableTiming));
+  WS_CUDA_OK(cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming));
+  if (!h->copy_stream) WS_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+}
+
+int ws_track_submit(ws_handle *h, const ws_point *points, int64_t n, int32_t on_device, const float *prior_pose,
+                    const float *pretransform, int32_t max_iterations, float it_weight_gradient, float epsilon,
+                    int32_t map_resolution, int32_t flags, int32_t *ticket)
 {
   return guarded(h, [&]() {
-    if (!prior_pose || !out_transform || map_resolution < 1 || max_iterations < 0 || n < 0 || (n > 0 && !points))
-      throw std::invalid_argument("ws_track_scan: bad argument");
-    if (n > WS_MAX_POINTS) throw std::length_error("ws_track_scan: too many points");
-    if (map_resolution != h->res) throw std::invalid_argument("ws_track_scan: map_resolution differs from the map's");
-    ensure_points(&h->d_reg_points, &h->reg_points_cap, (size_t)std::max<int64_t>(n, 1));
+    if (!ticket || map_resolution < 1 || max_iterations < 0 || n < 0 || (n > 0 && !points))
+      throw std::invalid_argument("ws_track_submit: bad argument");
+    if (n > WS_MAX_POINTS) throw std::length_error("ws_track_submit: too many points");
+    if (map_resolution != h->res) throw std::invalid_argument("ws_track_submit: map_resolution differs from the map's");
+    if (!prior_pose && !h->track_has_pose) throw std::logic_error("ws_track_submit: no previous pose on the device to chain from");
+    ws_handle::TrackSlot &t = h->track[h->track_next];
+    if (t.busy) throw std::logic_error("ws_track_submit: two scans already in flight (call ws_track_wait)");
+    track_slot_init(h, t);
+    ensure_points(&t.d_pts, &t.cap, (size_t)std::max<int64_t>(n, 1));
     if (n > 0)
-      WS_CUDA_OK(cudaMemcpyAsync(h->d_reg_points, points, (size_t)n * sizeof(ws_pt),
-                                 on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    {
+      if (on_device)
+        WS_CUDA_OK(cudaMemcpyAsync(t.d_pts, points, (size_t)n * sizeof(ws_pt), cudaMemcpyDeviceToDevice, h->stream));
+      else
+      {
+        // host -> device on the copy stream: overlaps the kernels of the scan before
+        WS_CUDA_OK(cudaMemcpyAsync(t.d_pts, points, (size_t)n * sizeof(ws_pt), cudaMemcpyHostToDevice, h->copy_stream));
+        WS_CUDA_OK(cudaEventRecord(t.copied, h->copy_stream));
+        WS_CUDA_OK(cudaStreamWaitEvent(h->stream, t.copied, 0));
+      }
+    }
+    // the registration works on (and transforms in place) the slot's buffer
+    h->d_reg_points_alias = t.d_pts;
     h->reg_n = (int)n;
     h->last_reg_host = false;
     h->host_trace.clear();
     const float I16[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
-    ws_launch_reg_reset(h, I16, 0.f);
+    ws_launch_reg_reset(h, pretransform ? pretransform : I16, 0.f);
     if (max_iterations > 0) ws_launch_reg_loop(h, (int)n, map_resolution, max_iterations, it_weight_gradient, epsilon);
-    ws_launch_transform_cloud(h, h->d_reg_points, (int)n);
-    ws_launch_pose(h, h->d_acc->T, prior_pose);
-    WS_CUDA_OK(cudaMemcpyAsync(h->h_acc, h->d_acc, sizeof(RegAccum), cudaMemcpyDeviceToHost, h->stream));
-    h->last_n_points = n;
-    ws_launch_update(h, h->d_reg_points, (int)n, nullptr, nullptr, true);     // synchronises once, at its end
-    if (h->h_acc->finished == 2u)
-      throw std::logic_error("track_scan: a peer rank did not deliver its Gauss-Newton sums in time");
-    std::memcpy(out_transform, h->h_acc->T, 16 * sizeof(float));
-    if (out_pose) std::memcpy(out_pose, static_cast<const PoseDev *>(h->h_pose)->pose, 16 * sizeof(float));
-    h->last_reg_iterations = (int)h->h_acc->iterations;
-    if (iterations) *iterations = h->last_reg_iterations;
+    ws_launch_transform_cloud(h, t.d_pts, (int)n);
+    ws_launch_pose(h, h->d_acc->T, prior_pose, (flags & WS_TRACK_REFERENCE_POSE) ? 1 : 0);
+    h->track_has_pose = true;
+    WS_CUDA_OK(cudaMemcpyAsync(t.h_acc, h->d_acc, sizeof(RegAccum), cudaMemcpyDeviceToHost, h->stream));
+    ws_update_enqueue(h, t.d_pts, (int)n, nullptr, nullptr, true, t.h_ctr, t.h_pose);
+    WS_CUDA_OK(cudaEventRecord(t.done, h->stream));
+    h->d_reg_points_alias = nullptr;
+    t.busy = true; t.n = n;
+    h->track_in_flight++;
+    *ticket = h->track_next;
+    h->track_next ^= 1;
     return WS_OK;
   });
+}
+
+int ws_track_wait(ws_handle *h, int32_t ticket, float out_transform[16], float out_pose[16], int32_t *iterations)
+{
+  return guarded(h, [&]() {
+    if (ticket < 0 || ticket > 1 || !h->track[ticket].busy) throw std::invalid_argument("ws_track_wait: no such scan in flight");
+    ws_handle::TrackSlot &t = h->track[ticket];
+    struct Release { ws_handle *h; ws_handle::TrackSlot &t; ~Release() { t.busy = false; h->track_in_flight--; } } release{ h, t };
+    h->last_n_points = t.n;
+    ws_update_finish(h, t.h_ctr, t.h_pose, t.done);
+    if (t.h_acc->finished == 2u)
+      throw std::logic_error("track_scan: a peer rank did not deliver its Gauss-Newton sums in time");
+    if (out_transform) std::memcpy(out_transform, t.h_acc->T, 16 * sizeof(float));
+    if (out_pose) std::memcpy(out_pose, static_cast<const PoseDev *>(t.h_pose)->pose, 16 * sizeof(float));
+    h->last_reg_iterations = (int)t.h_acc->iterations;
+    if (iterations) *iterations = h->last_reg_iterations;
+    // the registered cloud of this scan (ws_reg_points_device)
+    h->d_reg_points_last = t.d_pts;
+    return WS_OK;
+  });
+}
+
+int ws_track_scan_ex(ws_handle *h, const ws_point *points, int64_t n, int32_t on_device, const float prior_pose[16],
+                     const float *pretransform, int32_t max_iterations, float it_weight_gradient, float epsilon,
+                     int32_t map_resolution, int32_t flags, float out_transform[16], float out_pose[16], int32_t *iterations)
+{
+  if (!prior_pose || !out_transform) return WS_ERR_INVALID;
+  int32_t ticket = -1;
+  int rc = ws_track_submit(h, points, n, on_device, prior_pose, pretransform, max_iterations, it_weight_gradient, epsilon,
+                           map_resolution, flags, &ticket);
+  if (rc != WS_OK) return rc;
+  return ws_track_wait(h, ticket, out_transform, out_pose, iterations);
+}
+
+int ws_track_scan(ws_handle *h, const ws_point *points, int64_t n, int32_t on_device, const float prior_pose[16],
+                  int32_t max_iterations, float it_weight_gradient, float epsilon, int32_t map_resolution,
+                  float out_transform[16], float out_pose[16], int32_t *iterations)
+{
+  return ws_track_scan_ex(h, points, n, on_device, prior_pose, nullptr, max_iterations, it_weight_gradient, epsilon,
+                          map_resolution, 0, out_transform, out_pose, iterations);
 }
 
 int ws_reg_get_trace(ws_handle *h, int64_t *out, int32_t max_iterations)
@@ -877,7 +1091,7 @@ const ws_point *ws_reg_points_device(ws_handle *h, int64_t *n)
 {
   if (!h) return nullptr;
   if (n) *n = h->reg_n;
-  return reinterpret_cast<const ws_point *>(h->d_reg_points);
+  return reinterpret_cast<const ws_point *>(h->d_reg_points_last ? h->d_reg_points_last : h->d_reg_points);
 }
 
 int ws_reg_begin(ws_handle *h, const float pretransform[16])

@@ -864,7 +864,7 @@ void ws_launch_reg_iteration(ws_handle *h, int n, int res, int fused_solve, floa
   int blocks = (n + 255) / 256;
   if (blocks < 1) blocks = 1;
   ws_timer_begin(h, WS_TIMER_REG);
-  reg_accum_kernel<<<blocks, 256, 0, h->stream>>>(h->g, h->d_reg_points, n, make_fastdiv((unsigned)res), h->d_acc,
+  reg_accum_kernel<<<blocks, 256, 0, h->stream>>>(h->g, h->d_reg_points_alias ? h->d_reg_points_alias : h->d_reg_points, n, make_fastdiv((unsigned)res), h->d_acc,
                                                   h->d_trace, h->trace_cap, fused_solve, it_weight_gradient, epsilon);
   ws_timer_end(h);
   h->launches++;
@@ -908,7 +908,8 @@ void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float 
     pp.timeout_ns = h->peer_timeout_ns;
     for (int p = 0; p < h->world; p++) pp.mail[p] = static_cast<uint2 *>(h->peer_mail[p]);
   }
-  void *args[] = { (void *)&h->g, (void *)&h->d_reg_points, (void *)&rp, (void *)&h->d_acc,
+  ws_pt *reg_pts = h->d_reg_points_alias ? h->d_reg_points_alias : h->d_reg_points;
+  void *args[] = { (void *)&h->g, (void *)&reg_pts, (void *)&rp, (void *)&h->d_acc,
                    (void *)&h->d_reg_partials, (void *)&h->d_trace, (void *)&h->trace_cap, (void *)&pp };
 #ifndef WS_REG_GRIDSYNC
   WS_CUDA_OK(cudaMemsetAsync(h->d_reg_partials, 0, (size_t)4 * REG_NSLOT * sizeof(u64), h->stream));   // accumulators + tickets

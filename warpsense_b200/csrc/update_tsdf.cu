@@ -771,7 +771,7 @@ struct LsShared        // per CTA: address tables; per warp: ray table and queue
 {
   const unsigned *tx, *ty, *tz;     // voxel - lo (0 .. size-1) -> address parts, see the table set-up in the kernel
   int4 *ray;                        // [32][2] per lane of the group: {hit point, distance}, {interpolation vector, -}
-  int4 *queue;                      // [QCAP] {proj x, y, z, march step << 5 | lane}
+  unsigned queue_s;                 // shared-memory address of the warp's queue: [QCAP] {proj x, y, z, march step << 5 | lane}
   unsigned *pd;                     // [3][32] FREE: state words of the previous batch's candidates (cp.async)
 };
 
@@ -874,19 +874,19 @@ WS_D void free_candidate(const GridDesc &g, const UpdateParams &P, const LsShare
     if (brick != W.last_brick) { g.brick_flag2[brick] = 1u; W.last_brick = brick; }
     const unsigned shft = vstate_shift(addr);
     unsigned *word = g.vstate + vstate_word(addr);
-    info = shft | ((unsigned)(step == mid ? 0 : 1) << 5) | ((unsigned)step << 6) | ((unsigned)i << 12) | ((unsigned)rl << 27);
-    if (SLOT < 3)
+    if (SLOT >= 0) info = shft | ((unsigned)(step == mid ? 0 : 1) << 5) | ((unsigned)step << 6) | ((unsigned)i << 12) | ((unsigned)rl << 27);
+    if (SLOT >= 0 && SLOT < 3)
     {
       // the state word travels to shared memory by cp.async: no register, no scoreboard to wait on
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&sh.pd[(SLOT < 3 ? SLOT : 0) * 32 + lane])),
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(&sh.pd[(SLOT >= 0 && SLOT < 3 ? SLOT : 0) * 32 + lane])),
                    "l"(word) : "memory");
-      W.pd_addr[SLOT < 3 ? SLOT : 0] = addr;
-      W.pd_info[SLOT < 3 ? SLOT : 0] = info;
-      W.pd_mask |= 1u << SLOT;
+      W.pd_addr[SLOT >= 0 && SLOT < 3 ? SLOT : 0] = addr;
+      W.pd_info[SLOT >= 0 && SLOT < 3 ? SLOT : 0] = info;
+      W.pd_mask |= 1u << (SLOT >= 0 ? SLOT : 0);
     }
-    else chk = ((__ldcg(word) >> shft) & VS_PARKED) != 0u;     // long fans (delta_z >= res): checked on the spot
+    else if (SLOT >= 3) chk = ((__ldcg(word) >> shft) & VS_PARKED) != 0u;     // long fans (delta_z >= res): checked on the spot
     // a plain byte store: idempotent, so no atomic and nothing to serialise when many rays hit one voxel
-    g.ffree[(size_t)brick * 1024u + (size_t)((unsigned)addr & 511u) + (step == mid ? 0u : 512u)] = 1;
+    g.ffree[2 * addr - (addr & 511ull) + (step == mid ? 0u : 512u)] = 1;     // brick * 1024 + local (+ 512: interpolated)
   }
   if (SLOT >= 3 && __any_sync(FULL, chk)) offer_parked(g, P, out, W, chk, addr, info, ray_base, lane, ctr);   // warp-collective
 }
@@ -900,7 +900,9 @@ WS_D void march_drain(const GridDesc &g, const UpdateParams &P, const LsShared &
                       const LsOut &out)
 {
   bool have = lane < take;
-  const int4 q = sh.queue[(qh + lane) & (QCAP - 1)];
+  int4 q;
+  asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(sh.queue_s + (unsigned)(((qh + lane) & (QCAP - 1)) << 4)) : "memory");
   const int rl = q.w & 31, i = q.w >> 5;
   const int4 r1 = sh.ray[2 * rl + 1];
   const int riv[3] = { r1.x, r1.y, r1.z };
@@ -945,6 +947,15 @@ WS_D void march_drain(const GridDesc &g, const UpdateParams &P, const LsShared &
 
   if (!SURF)
   {
+    // near field (before far_start_len): no voxel there can be parked, the candidates are stored and forgotten
+    if (!__any_sync(FULL, have && far))
+    {
+      free_candidate<WIDE, -1>(g, P, sh, out, W, have, 0, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
+#pragma unroll 1
+      for (int step = 1; step < max_steps; ++step)
+        free_candidate<WIDE, -1>(g, P, sh, out, W, have, step, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
+      return;
+    }
     free_check_pending(g, P, sh, out, W, ray_base, lane, ctr);
     free_candidate<WIDE, 0>(g, P, sh, out, W, have, 0, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
     if (max_steps > 1) free_candidate<WIDE, 1>(g, P, sh, out, W, have, 1, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
@@ -1091,7 +1102,9 @@ WS_D void march_block(const GridDesc &g, const UpdateParams &P, const int pos_mm
     if (ix > (unsigned)P.ext[0] || iy > (unsigned)P.ext[1] || iz > (unsigned)P.ext[2]) act = false;   // :460-463
     const unsigned m = __ballot_sync(FULL, act);
     if (m == 0u) continue;
-    if (act) sh.queue[(qh + qn + __popc(m & lt)) & (QCAP - 1)] = make_int4(cx, cy, cz, (i << 5) | lane);
+    if (act)
+      asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};"
+                   ::"r"(sh.queue_s + (unsigned)(((qh + qn + __popc(m & lt)) & (QCAP - 1)) << 4)), "r"(cx), "r"(cy), "r"(cz), "r"((i << 5) | lane) : "memory");
     qn += __popc(m);
     __syncwarp();
     if (qn >= 32)
@@ -1117,7 +1130,7 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
 {
   extern __shared__ unsigned s_tab[];               // size[0] + size[1] + size[2] address parts
   __shared__ int4 s_ray[MARCH_WARPS][64];
-  __shared__ int4 s_queue[MARCH_WARPS][QCAP];
+  __shared__ __align__(16) int4 s_queue[MARCH_WARPS][QCAP];
   __shared__ unsigned s_pd[MARCH_WARPS][96];
   const unsigned n_items = __ldcg(&ctr->n_items[SURF ? 0 : 1]);
   if (n_items == 0u) return;
@@ -1126,7 +1139,9 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
   const int wib = threadIdx.x >> 5;
   LsShared sh;
   sh.tx = s_tab; sh.ty = s_tab + g.size[0]; sh.tz = sh.ty + g.size[1];
-  sh.ray = s_ray[wib]; sh.queue = s_queue[wib]; sh.pd = s_pd[wib];
+  sh.ray = s_ray[wib]; sh.pd = s_pd[wib];
+  sh.queue_s = (unsigned)__cvta_generic_to_shared(s_queue[wib]);
+  asm volatile("" : "+r"(sh.queue_s));              // opaque: kept in a register instead of being re-derived every turn
   for (int t = threadIdx.x; t < g.size[0] + g.size[1] + g.size[2]; t += blockDim.x)
   {
     // ring coordinate (hdf5_local_map.h:140-151) of voxel lo + t, then its share of the bricked address:
@@ -1886,23 +1901,34 @@ static void launch_replay(ws_handle *h, const UpdateParams &P)
   h->launches++;
 }
 
-// src/warpsense/tsdf_mapping.cpp:77-85 + include/util/util.h:52-56 on the device: pose = X * prior (float32, the
-// accumulation order of ws_compose_pose_host), scanner voxel = floor(t / res), up = third column of
-// to_int_mat(pose) -- so update_tsdf can follow register_cloud on the stream without the host in between
-__global__ void pose_kernel(const float *__restrict__ X, const float *__restrict__ prior, const int res,
-                            const int coord_lim, PoseDev *__restrict__ out)
+// src/warpsense/tsdf_mapping.cpp:77-85 + include/util/util.h:52-56 on the device, so update_tsdf can follow
+// register_cloud on the stream without the host in between: new pose from the registration result X and the
+// prior pose, scanner voxel = floor(t / res), up = third column of to_int_mat(pose).
+//   compose_reference == 0: pose = X * prior (float32, the accumulation order of ws_compose_pose_host);
+//   compose_reference != 0: App::update_pose_estimate (src/warpsense/app.cpp:172-176, same in
+//                           src/cpu/fastsense.cpp:219-221): R = X.R * prior.R, t = prior.t + X.t.
+// The prior comes by value, or (chain) is the pose this kernel left in `out` for the previous scan.
+struct Mat16 { float m[16]; };
+__global__ void pose_kernel(const float *__restrict__ X, const Mat16 prior_in, const int chain, const int compose_reference,
+                            const int res, const int coord_lim, PoseDev *__restrict__ out)
 {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  float pose[16];
+  float prior[16], pose[16];
+  for (int i = 0; i < 16; i++) prior[i] = chain ? out->pose[i] : prior_in.m[i];
   for (int c = 0; c < 4; c++)
     for (int r = 0; r < 4; r++)
     {
       float acc = X[0 * 4 + r] * prior[c * 4 + 0];
       acc = acc + X[1 * 4 + r] * prior[c * 4 + 1];
       acc = acc + X[2 * 4 + r] * prior[c * 4 + 2];
-      acc = acc + X[3 * 4 + r] * prior[c * 4 + 3];
+      if (!compose_reference) acc = acc + X[3 * 4 + r] * prior[c * 4 + 3];
       pose[c * 4 + r] = acc;
     }
+  if (compose_reference)
+  {
+    for (int r = 0; r < 3; r++) pose[12 + r] = prior[12 + r] + X[12 + r];
+    for (int c = 0; c < 4; c++) pose[c * 4 + 3] = prior[c * 4 + 3];
+  }
   bool ok = true;
   for (int a = 0; a < 3; a++)
   {
@@ -1930,25 +1956,36 @@ void ws_compose_pose_host(const float X[16], const float prior[16], float pose[1
     }
 }
 
-void ws_launch_pose(ws_handle *h, const float *d_X, const float prior[16])
+// prior == nullptr: chain from the pose the previous ws_launch_pose left on the device
+void ws_launch_pose(ws_handle *h, const float *d_X, const float *prior, int compose_reference)
 {
   if (!h->d_pose)
   {
-    WS_CUDA_OK(cudaMalloc(&h->d_pose, sizeof(PoseDev) + 16 * sizeof(float)));
-    WS_CUDA_OK(cudaMallocHost(&h->h_pose, sizeof(PoseDev) + 16 * sizeof(float)));
+    WS_CUDA_OK(cudaMalloc(&h->d_pose, sizeof(PoseDev)));
+    WS_CUDA_OK(cudaMemsetAsync(h->d_pose, 0, sizeof(PoseDev), h->stream));
+    WS_CUDA_OK(cudaMallocHost(&h->h_pose, sizeof(PoseDev)));
   }
-  float *d_prior = reinterpret_cast<float *>(reinterpret_cast<char *>(h->d_pose) + sizeof(PoseDev));
-  float *h_prior = reinterpret_cast<float *>(reinterpret_cast<char *>(h->h_pose) + sizeof(PoseDev));
-  std::memcpy(h_prior, prior, 16 * sizeof(float));
-  WS_CUDA_OK(cudaMemcpyAsync(d_prior, h_prior, 16 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  Mat16 pm;
+  for (int i = 0; i < 16; i++) pm.m[i] = prior ? prior[i] : 0.f;
   long long lim = (1ll << 31) / h->res - h->tau - (1ll << 17);
   if (lim < 0 || std::getenv("WS_MARCH_GENERAL") || h->res < 4) lim = 0;
-  pose_kernel<<<1, 32, 0, h->stream>>>(d_X, d_prior, h->res, (int)lim, static_cast<PoseDev *>(h->d_pose));
+  pose_kernel<<<1, 32, 0, h->stream>>>(d_X, pm, prior ? 0 : 1, compose_reference, h->res, (int)lim, static_cast<PoseDev *>(h->d_pose));
   h->launches++;
 }
 
-void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos_in[3], const int up_in[3],
-                      bool pose_on_device)
+#define LS_LAUNCH(SURF_, ATOMIC_)                                                                                        \
+  do {                                                                                                                   \
+    if (wide) march_lockstep_kernel<SURF_, ATOMIC_, true><<<lockstep_blocks, MARCH_THREADS, tab_bytes, s>>>(             \
+        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out);  \
+    else march_lockstep_kernel<SURF_, ATOMIC_, false><<<lockstep_blocks, MARCH_THREADS, tab_bytes, s>>>(                 \
+        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out);  \
+  } while (0)
+
+// Enqueues one update_tsdf on the handle's stream; the work counters (and the device-side pose) land in
+// `h_ctr` / `h_pose_out` (pinned) behind it.  ws_update_finish() waits, regrows the record if it overflowed and
+// reports errors.
+void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos_in[3], const int up_in[3],
+                       bool pose_on_device, UpdateCounters *h_ctr, void *h_pose_out)
 {
   // pose_on_device: the scanner pose was left in h->d_pose by ws_launch_pose on this stream; the host copy
   // (needed only if the candidate record has to be regenerated) is read back with the counters
@@ -2038,13 +2075,6 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
     LsOut out;
     out.pend_key = h->d_pend_key; out.list = h->d_list; out.pending_cap = h->pending_cap; out.list_cap = (unsigned)h->list_cap;
     const bool wide = (unsigned long long)h->g.n_bricks * WS_BRICK_VOX > 0xFFFFFFFFull;
-#define LS_LAUNCH(SURF_, ATOMIC_)                                                                                        \
-  do {                                                                                                                   \
-    if (wide) march_lockstep_kernel<SURF_, ATOMIC_, true><<<lockstep_blocks, MARCH_THREADS, tab_bytes, s>>>(             \
-        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out);  \
-    else march_lockstep_kernel<SURF_, ATOMIC_, false><<<lockstep_blocks, MARCH_THREADS, tab_bytes, s>>>(                 \
-        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out);  \
-  } while (0)
     // surface phase: keys, record, parked voxels
     setup_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_pts, rays, h->d_grp_info, n_groups, h->d_gen_list, h->d_counters, d_pose);
     item_scan_kernel<<<1, 1024, 0, s>>>(h->d_grp_info, n_groups, h->d_item_off, h->d_counters);
@@ -2069,17 +2099,45 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
     fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, list_all, h->d_counters);
     ws_timer_end(h);
     h->launches += 9;
-    WS_CUDA_OK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
-    if (pose_on_device)
-      WS_CUDA_OK(cudaMemcpyAsync(h->h_pose, h->d_pose, sizeof(PoseDev), cudaMemcpyDeviceToHost, s));
-    WS_CUDA_OK(cudaStreamSynchronize(s));
+  }
+  WS_CUDA_OK(cudaMemcpyAsync(h_ctr, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
+  if (pose_on_device)
+    WS_CUDA_OK(cudaMemcpyAsync(h_pose_out, h->d_pose, sizeof(PoseDev), cudaMemcpyDeviceToHost, s));
+  // what ws_update_finish needs should the record have to grow
+  h->upd_P = P; h->upd_n = n; h->upd_pose_on_device = pose_on_device;
+}
+
+// Second half of an update: wait for the stream (or `done`), regrow + regenerate the record if it overflowed,
+// publish the counters, throw on errors.
+void ws_update_finish(ws_handle *h, UpdateCounters *h_ctr, void *h_pose_out, cudaEvent_t done)
+{
+  cudaStream_t s = h->stream;
+  if (done) WS_CUDA_OK(cudaEventSynchronize(done));
+  else WS_CUDA_OK(cudaStreamSynchronize(s));
+  const UpdateParams &P = h->upd_P;
+  const int n = h->upd_n;
+  if (n > 0)
+  {
+    const PoseDev *d_pose = h->upd_pose_on_device ? static_cast<const PoseDev *>(h->d_pose) : nullptr;
+    const int march_blocks = h->sm_count * MARCH_CTAS;
+    const int lockstep_blocks = h->sm_count * LS_CTAS;
+    const size_t tab_bytes = (size_t)(h->g.size[0] + h->g.size[1] + h->g.size[2]) * sizeof(unsigned);
+    RaySetup *rays = static_cast<RaySetup *>(h->d_rays);
+    const unsigned n_groups = (unsigned)((n + 31) / 32);
+    unsigned *list_all = h->d_brick_list;
+    const bool wide = (unsigned long long)h->g.n_bricks * WS_BRICK_VOX > 0xFFFFFFFFull;
+    unsigned cap_chunks = (unsigned)h->rec_cap_chunks;
+    LsOut out;
+    out.pend_key = h->d_pend_key; out.list = h->d_list; out.pending_cap = h->pending_cap; out.list_cap = (unsigned)h->list_cap;
     // the record did not fit: grow it, regenerate it from the far part of the surface phase, then run what
     // was held back (free-space phase, replay, free-space merge)
     int guard = 0;
-    while (h->h_counters->rec_overflow != 0u && h->h_counters->pending_overflow == 0u)
+    while (h_ctr->rec_overflow != 0u && h_ctr->pending_overflow == 0u)
     {
+      if (h->track_in_flight > 1)
+        throw std::logic_error("update_tsdf: candidate record overflow with another scan already enqueued (raise WS_RECORD_CAP)");
       if (++guard > 8) throw std::runtime_error("update_tsdf: candidate record keeps overflowing");
-      size_t want = (size_t)h->h_counters->n_chunks + (size_t)h->h_counters->n_chunks / 4 + 1024;
+      size_t want = (size_t)h_ctr->n_chunks + (size_t)h_ctr->n_chunks / 4 + 1024;
       if (want > h->rec_max_chunks) want = h->rec_max_chunks;
       if (want <= h->rec_cap_chunks)
         throw std::runtime_error("update_tsdf: candidate record exceeds WS_RECORD_MAX");
@@ -2095,20 +2153,14 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
       brick_list_kernel<false><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_all, h->d_counters);
       fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, list_all, h->d_counters);
       h->launches += 7;
-      WS_CUDA_OK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
+      WS_CUDA_OK(cudaMemcpyAsync(h_ctr, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
       WS_CUDA_OK(cudaStreamSynchronize(s));
       h->record_regrows++;
     }
   }
-  else
-  {
-    WS_CUDA_OK(cudaMemcpyAsync(h->h_counters, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
-    if (pose_on_device)
-      WS_CUDA_OK(cudaMemcpyAsync(h->h_pose, h->d_pose, sizeof(PoseDev), cudaMemcpyDeviceToHost, s));
-    WS_CUDA_OK(cudaStreamSynchronize(s));
-  }
+  (void)h_pose_out;
   WS_CUDA_OK(cudaGetLastError());
-  h->last_counters = *h->h_counters;
+  h->last_counters = *h_ctr;
   if (h->last_counters.pending_overflow)
     throw std::runtime_error("update_tsdf: pending-voxel capacity exceeded (raise WS_PENDING_CAP)");
   if (h->last_counters.n_pending != 0u)
@@ -2117,6 +2169,12 @@ void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner
     throw std::runtime_error("update_tsdf: ray too long for the candidate order field (march steps > 32768 or fan > 64)");
   if (h->last_counters.error & 2u)
     throw std::runtime_error("update_tsdf: replay list overflow (raise WS_RECORD_CAP)");
+}
+
+void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3], bool pose_on_device)
+{
+  ws_update_enqueue(h, d_pts, n, scanner_pos, up, pose_on_device, h->h_counters, h->h_pose);
+  ws_update_finish(h, h->h_counters, h->h_pose, nullptr);
 }
 
 void ws_update_alloc(ws_handle *h, size_t initial_chunks, size_t max_chunks)

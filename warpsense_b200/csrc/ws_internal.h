@@ -122,7 +122,22 @@ struct ws_handle
   unsigned *d_item_off = nullptr; // [2][groups + 1] exclusive prefix sums of the groups' block counts (+ the total)
   size_t grp_cap = 0;             // groups the two tables hold per phase
   size_t list_cap = 0;            // entries of the replay list
-  bool tab_attr_set = false;      // dynamic shared memory of the lockstep march raised above 48 KB
+  bool tab_attr_set = false;
+  // context of the last enqueued update (ws_update_finish regrows the record with it)
+  UpdateParams upd_P{};
+  int upd_n = 0;
+  bool upd_pose_on_device = false;
+  // asynchronous per-scan pipeline (ws_track_submit / ws_track_wait): two scans may be in flight
+  struct TrackSlot
+  {
+    ws_pt *d_pts = nullptr; size_t cap = 0;
+    RegAccum *h_acc = nullptr; void *h_pose = nullptr; UpdateCounters *h_ctr = nullptr;   // pinned
+    cudaEvent_t copied = nullptr, done = nullptr;
+    bool busy = false; int64_t n = 0;
+  } track[2];
+  cudaStream_t copy_stream = nullptr;
+  int track_next = 0, track_in_flight = 0;
+  bool track_has_pose = false;      // d_pose holds the pose of the previous tracked scan      // dynamic shared memory of the lockstep march raised above 48 KB
   unsigned *d_gen_list = nullptr; // rays for the literal-arithmetic march
   // scan preprocessing scratch (preprocess.cu)
   void *d_pre_tmp = nullptr;      // duplicate-detection keys, scan order
@@ -132,8 +147,15 @@ struct ws_handle
   unsigned *d_pre_tiles = nullptr;// survivors per 1024-point tile (+ the total)
   float *d_pre_xyz = nullptr;     // staging of a host PointCloud2 payload
   size_t pre_cap = 0, pre_xyz_cap = 0;
-  int64_t scan_n = 0;             // points the last ws_preprocess_scan left in d_points
+  int64_t scan_n = 0;             // points the last ws_preprocess_scan / ws_voxelgrid_subsample left in d_points
+  // voxel-grid subsample scratch (voxelgrid.cu)
+  unsigned *d_vg_keys = nullptr, *d_vg_vals = nullptr, *d_vg_hist = nullptr;
+  void *d_vg_box = nullptr;
+  float *d_vg_xyz = nullptr;      // float centroids (optional output)
+  size_t vg_cap = 0, vg_xyz_cap = 0;
   ws_pt *d_reg_points = nullptr;  // registration cloud
+  ws_pt *d_reg_points_alias = nullptr;   // set while a tracked scan is enqueued: the registration works on the slot's buffer
+  ws_pt *d_reg_points_last = nullptr;    // registered cloud of the last ws_track_wait
   size_t reg_points_cap = 0;
   int reg_n = 0;
 
@@ -195,7 +217,10 @@ struct ws_handle
 // update_tsdf.cu
 void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3],
                       bool pose_on_device = false);
-void ws_launch_pose(ws_handle *h, const float *d_X, const float prior[16]);
+void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3],
+                       bool pose_on_device, UpdateCounters *h_ctr, void *h_pose_out);
+void ws_update_finish(ws_handle *h, UpdateCounters *h_ctr, void *h_pose_out, cudaEvent_t done);
+void ws_launch_pose(ws_handle *h, const float *d_X, const float *prior, int compose_reference);
 void ws_compose_pose_host(const float X[16], const float prior[16], float pose[16]);
 void ws_update_alloc(ws_handle *h, size_t initial_chunks, size_t max_chunks);
 // registration.cu
@@ -208,6 +233,8 @@ void ws_host_solve(const i64 H[36], const i64 g[6], int err, int cnt, float alph
 // preprocess.cu
 int64_t ws_launch_preprocess(ws_handle *h, const float *d_xyz, int64_t n, int stride_floats, const float pose_mm[16], int res,
                              int mode);
+// voxelgrid.cu
+int64_t ws_launch_voxelgrid(ws_handle *h, const float *d_xyz, int64_t n, int stride_floats, float leaf_m, float *d_out_xyz);
 // map_ops.cu
 void ws_launch_fill(ws_handle *h, uint32_t entry);
 void ws_launch_upload(ws_handle *h, const uint32_t *d_linear);

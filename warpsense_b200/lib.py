@@ -17,6 +17,7 @@ WS_ERR_CAPACITY = -3
 WS_ERR_STATE = -4
 WS_MAX_POINTS = 1 << 24
 WS_REG_DEVICE_SOLVE = 0
+WS_TRACK_REFERENCE_POSE = 1
 WS_REG_HOST_SOLVE = 1
 
 TIMER_MARCH, TIMER_MERGE, TIMER_REG, TIMER_REPLAY = 0, 1, 2, 3
@@ -74,6 +75,8 @@ def _signatures():
         "ws_get_update_counters": (C.c_int, [hp, C.POINTER(UpdateCounters)]),
         "ws_preprocess_scan": (C.c_int, [hp, vp, C.c_int64, C.c_int32, C.c_int32, f32p, C.c_int32, vp, i64p]),
         "ws_scan_points_device": (vp, [hp, i64p]),
+        "ws_voxelgrid_subsample": (C.c_int, [hp, vp, C.c_int64, C.c_int32, C.c_int32, C.c_float, vp, vp, i64p]),
+        "ws_update_tsdf_from_ros": (C.c_int, [hp, vp, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_double), f32p, i64p]),
         "ws_reg_prepare": (C.c_int, [hp, vp, C.c_int64]),
         "ws_reg_prepare_device": (C.c_int, [hp, vp, C.c_int64]),
         "ws_reg_step": (C.c_int, [hp, f32p, C.c_int32, i64p, i64p, i32p, i32p]),
@@ -81,6 +84,11 @@ def _signatures():
                                         C.c_int32, C.c_int32, f32p, i32p]),
         "ws_track_scan": (C.c_int, [hp, vp, C.c_int64, C.c_int32, f32p, C.c_int32, C.c_float, C.c_float, C.c_int32,
                                     f32p, f32p, i32p]),
+        "ws_track_scan_ex": (C.c_int, [hp, vp, C.c_int64, C.c_int32, f32p, f32p, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                                       C.c_int32, f32p, f32p, i32p]),
+        "ws_track_submit": (C.c_int, [hp, vp, C.c_int64, C.c_int32, f32p, f32p, C.c_int32, C.c_float, C.c_float, C.c_int32,
+                                      C.c_int32, i32p]),
+        "ws_track_wait": (C.c_int, [hp, C.c_int32, f32p, f32p, i32p]),
         "ws_reg_get_trace": (C.c_int, [hp, i64p, C.c_int32]),
         "ws_reg_points_device": (vp, [hp, i64p]),
         "ws_reg_begin": (C.c_int, [hp, f32p]),
