@@ -266,6 +266,14 @@ int64_t ws_store_num_chunks(const ws_handle *h);
 int ws_store_chunk_list(const ws_handle *h, int32_t *xyz, int64_t cap);
 /* copy one 64^3 chunk (index x*4096 + y*64 + z, hdf5_global_map.cpp:53-57); WS_ERR_INVALID if absent */
 int ws_store_get_chunk(const ws_handle *h, int32_t cx, int32_t cy, int32_t cz, uint32_t *out);
+/* put a chunk into the store (what loading a map file does chunk by chunk) */
+int ws_store_set_chunk(ws_handle *h, int32_t cx, int32_t cy, int32_t cz, const uint32_t *data);
+/* HDF5GlobalMap keeps 64 active chunks and writes the least recently used one to its file
+ * (hdf5_global_map.h:78, hdf5_global_map.cpp:59-137).  Here at most `max_chunks_in_memory` chunks (default 4096,
+ * WS_STORE_CHUNKS) stay in memory; the least recently used one goes to a spill file (WS_STORE_SPILL_DIR, default
+ * /tmp) and is read back on its next activation. */
+int ws_store_configure(ws_handle *h, int64_t max_chunks_in_memory);
+int64_t ws_store_evictions(const ws_handle *h);
 
 /* ---- global-map file ----------------------------------------------------------------------------
  * ws_export_hdf5: what HDF5GlobalMap leaves on disk (src/map/hdf5_global_map.cpp): /map/<cx>_<cy>_<cz> = 64^3
@@ -285,6 +293,16 @@ int ws_export_hdf5(ws_handle *h, const char *path, const ws_map_meta *meta, cons
 /* the same file from caller-held chunks (host only, no handle): chunk_xyz[n][3], chunk_data[n][64^3] */
 int ws_hdf5_write_chunks(const char *path, const ws_map_meta *meta, const int32_t *chunk_xyz,
                          const uint32_t *chunk_data, int64_t n_chunks, const float *poses7, int64_t n_poses);
+
+/* ws_import_hdf5: read such a file back (the reference cannot: HDF5GlobalMap truncates its file on open,
+ * hdf5_global_map.cpp:5,24 -- no resume).  Every /map/<cx>_<cy>_<cz> chunk goes into the handle's chunk store
+ * (one at a time: bounded memory), *meta receives the /map attributes, poses7 the first poses_cap rows of
+ * /poses/<n>/pose in ascending n.  ws_map_reload then fills the device-resident local map from the store. */
+int ws_import_hdf5(ws_handle *h, const char *path, ws_map_meta *meta, float *poses7, int64_t poses_cap,
+                   int64_t *n_chunks, int64_t *n_poses);
+/* (re)load the whole local map window from the chunk store: what HDF5LocalMap's constructor does for a fresh map
+ * (src/map/hdf5_local_map.cpp:5-20: save_load_area(..., false) over the window). */
+int ws_map_reload(ws_handle *h);
 
 /* ---- timing -------------------------------------------------------------------------------- */
 /* record cudaEvents around the hot kernels on the handle's stream (kind: 0 march, 1 brick list + merge, 2 registration

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include "warpsense_b200.hpp"
 
 #define CHECK(cond)                                                              \
@@ -124,6 +125,85 @@ int main()
       std::fclose(fp);
       std::remove(path);
     }
+  }
+  // ---- featsense feed in C++: background map-shift thread, accumulate-while-shifting, flush ---------------------
+  {
+    Params params;
+    params.map.resolution = 100; params.map.tau = 1000; params.map.max_weight = 10 * WEIGHT_RESOLUTION;
+    params.map.shift = 1.0f; params.map.update_distance = 0.2f;
+    auto local_map = std::make_shared<HostLocalMap>(96, 96, 96, params.map.tau, 0);
+    auto pose_buffer = std::make_shared<ConcurrentRingBuffer<Matrix4f>>(16);
+    cuda::TSDFMapping gpu(params, pose_buffer, local_map);
+    featsense::MappingFeed feed(gpu);
+    // a box room around the sensor, in metres, map frame
+    std::vector<float> cloud;
+    for (int a = -30; a <= 30; a++)
+      for (int b = -10; b <= 10; b++)
+      {
+        const float u = a * 0.1f, v = b * 0.1f;
+        const float w[4][3] = { { 3.f, u, v }, { -3.f, u, v }, { u, 3.f, v }, { u, -3.f, v } };
+        for (auto &p : w) { cloud.push_back(p[0]); cloud.push_back(p[1]); cloud.push_back(p[2]); cloud.push_back(p[0] + 0.01f); cloud.push_back(p[1]); cloud.push_back(p[2]); }
+      }
+    const int64_t n = (int64_t)(cloud.size() / 3);
+    auto pose_at = [](double x, double out[16]) { for (int i = 0; i < 16; i++) out[i] = (i % 5 == 0) ? 1.0 : 0.0; out[12] = x; };
+    double P[16];
+    // the voxel grid halves the doubled points
+    std::vector<float> sub;
+    gpu.subsample(cloud.data(), n, 12, 0.1f, sub);
+    CHECK(sub.size() / 3 < (size_t)n * 3 / 4 && sub.size() / 3 > (size_t)n / 4);
+    pose_at(0.0, P);
+    CHECK(feed.push(cloud.data(), n, P));                                       // initialises (:66-75)
+    pose_at(0.1, P);
+    CHECK(!feed.push(cloud.data(), n, P));                                      // below update_distance (:81)
+    // while the shift thread is inside map_shift, the feed must accumulate instead of updating
+    std::atomic<int> pushed_during_shift{ 0 };
+    std::atomic<bool> saw_flag{ false };
+    gpu.set_shift_hook([&] {
+      saw_flag = gpu.is_shifting().load();
+      double Q[16];
+      pose_at(1.6, Q);
+      if (!feed.push(cloud.data(), n, Q)) pushed_during_shift++;                // accumulated (:115-119)
+    });
+    pose_at(1.3, P);                                                            // 1.3 m > map.shift (1 m): pose reaches the thread
+    CHECK(feed.push(cloud.data(), n, P));
+    for (int spin = 0; spin < 5000 && !gpu.shifted(); spin++) std::this_thread::sleep_for(std::chrono::milliseconds(1));
+    CHECK(gpu.shifted() && !gpu.is_shifting());
+    CHECK(saw_flag && pushed_during_shift == 1 && feed.accumulated_points() == (size_t)n);
+    gpu.set_shift_hook(nullptr);
+    CHECK(local_map->get_pos()[0] == 13);                                       // floor(1300 / 100)
+    pose_at(1.9, P);
+    const int before = feed.updates();
+    CHECK(feed.push(cloud.data(), n, P));                                       // flush: concatenated + subsampled (:121-126)
+    CHECK(feed.updates() == before + 1 && feed.accumulated_points() == 0);
+    CHECK(feed.poses().size() / 16 == 3);
+    gpu.join_mapping_thread();
+    gpu.get_tsdf_map();
+    int seen = 0;
+    for (int x = 20; x <= 40; x++) seen += local_map->in_bounds(x, 0, 0) && local_map->value(x, 0, 0).weight() != 0;
+    CHECK(seen > 5);                                                            // the wall at x = 3 m is in the map
+  }
+  // ---- asynchronous per-scan pipeline from C++ -----------------------------------------------------------------
+  {
+    Params params;
+    params.map.resolution = 64; params.map.tau = 600; params.map.max_weight = 10 * WEIGHT_RESOLUTION;
+    params.registration.max_iterations = 10; params.registration.epsilon = 0.f;
+    auto local_map = std::make_shared<HostLocalMap>(128, 128, 64, params.map.tau, 0);
+    cuda::TSDFRegistration gpu(params, local_map);
+    std::vector<rmagine::Pointi> scan;
+    for (int a = -40; a <= 40; a++)
+      for (int b = -12; b <= 12; b++) { scan.emplace_back(2500, a * 40, b * 40); scan.emplace_back(a * 40, 2200, b * 40); scan.emplace_back(-2300, a * 40, b * 40); }
+    gpu.update_tsdf(scan, Matrix4f::Identity());
+    const Matrix4f I = Matrix4f::Identity();
+    const int t0 = gpu.track_submit(scan, &I);
+    const int t1 = gpu.track_submit(scan, nullptr);                             // prior chained on the device
+    Matrix4f X0{}, X1{};
+    int it = 0;
+    const Matrix4f p0 = gpu.track_wait(t0, &X0, &it);
+    CHECK(it == 10);
+    const Matrix4f p1 = gpu.track_wait(t1, &X1, &it);
+    CHECK(it == 10);
+    CHECK(std::fabs(p0(0, 3) - X0(0, 3)) < 1e-3f);                              // pose0 = X0 * I
+    CHECK(std::fabs(p1(0, 3) - (X1(0, 0) * p0(0, 3) + X1(0, 1) * p0(1, 3) + X1(0, 2) * p0(2, 3) + X1(0, 3))) < 1e-2f);
   }
   std::printf("cpp shim ok\n");
   return 0;

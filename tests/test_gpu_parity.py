@@ -413,6 +413,54 @@ def test_shift_random_walk_matches_oracle():
         assert np.array_equal(tsdf.chunk(*c), om.chunk(*c)), "chunk %r" % (c,)
 
 
+def test_shift_walk_with_bounded_chunk_store_and_file_round_trip(tmp_path):
+    """hdf5_global_map.cpp:59-137: only a few chunks stay in memory (here 3), the least recently used one is spilled
+    and read back on demand -- a long walk must still agree with the oracle's unbounded store; then the file the
+    writer leaves is read back by ws_import_hdf5 into a fresh handle and reloaded into its local map."""
+    rng = np.random.default_rng(33)
+    tau, res, mw = 600, 64, 640
+    om, hm, tsdf = make_pair((33, 25, 17), tau, mw, res)
+    tsdf.store_configure(3)
+    up = np.array([0, 0, MR], np.int32)
+    pos = np.zeros(3, np.int64)
+    for step in range(10):
+        pts = (pos * res + rng.integers(-700, 700, size=(300, 3))).astype(np.int32)
+        orc.update_tsdf(om, pts, pos, up, tau, mw, res)
+        tsdf.update_tsdf(pts, pos, up)
+        pos = pos + rng.integers(-16, 17, size=3)              # crosses 64-voxel chunk borders often
+        om.shift(pos)
+        tsdf.shift(pos)
+        assert_same_grid(om, tsdf, hm, "after shift %d" % step)
+    # walk back to the start: everything that was stored must come back
+    while np.abs(pos).max() > 0:
+        pos = pos - np.clip(pos, -12, 12)                      # a shift may not exceed the map size (:63-65)
+        om.shift(pos)
+        tsdf.shift(pos)
+        assert_same_grid(om, tsdf, hm, "walking back to %r" % (list(pos),))
+    assert tsdf.store_evictions() > 0, "the walk was meant to overflow the 3-chunk store"
+    om.write_back()
+    tsdf.write_back()
+    assert sorted(tsdf.chunk_list()) == sorted(om.chunk_list())
+    for c in om.chunk_list():
+        assert np.array_equal(tsdf.chunk(*c), om.chunk(*c)), "chunk %r" % (c,)
+    # file round trip
+    path = str(tmp_path / "walk.h5")
+    poses = np.round(rng.normal(size=(5, 7)).astype(np.float32) * 1000) / 1000
+    tsdf.export_hdf5(path, tau, (33, 25, 17), 0.6, res, mw, poses)
+    hm2 = api.HostLocalMap(33, 25, 17, tau, 0)
+    fresh = api.TSDFCuda(api.DeviceMap(hm2), tau, mw, res)
+    fresh.store_configure(2)
+    meta, poses_back, n_chunks = fresh.import_hdf5(path)
+    assert n_chunks == len(om.chunk_list()) and np.array_equal(poses_back, poses)
+    assert meta == {"tau": tau, "map_size": (33, 25, 17), "max_distance": np.float32(0.6), "map_resolution": res, "max_weight": mw}
+    for c in om.chunk_list():
+        assert np.array_equal(fresh.chunk(*c), om.chunk(*c)), "imported chunk %r" % (c,)
+    fresh.reload()                                              # the window around pos = 0 out of the imported chunks
+    assert_same_grid(om, fresh, hm2, "reloaded from the file")
+    fresh.close()
+    tsdf.close()
+
+
 # ----------------------------------------------------------------------------- fused per-scan pipeline
 def _compose_f32(X, prior):
     """pose = X * prior in float32, accumulating over k = 0..3 in order (ws_track_scan's definition)."""

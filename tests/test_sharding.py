@@ -211,6 +211,79 @@ def test_sharded_handles_match_oracle_on_one_gpu(world, ring_offset, stripe, mon
         t.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,stripe", [(2, 0), (3, 0), (4, 0), (2, 2)])
+def test_shift_on_sharded_handles(world, stripe, monkeypatch):
+    """HDF5LocalMap::shift (src/map/hdf5_local_map.cpp:53-118) on a map sharded over `world` handles: slabs are
+    in ring (storage) coordinates, so a shift never re-partitions -- after every shift each rank's owned rows equal
+    the oracle's, and the ranks' chunk stores, merged by row owner, equal the oracle's chunk store."""
+    if stripe:
+        monkeypatch.setenv("WS_STRIPE_COLS", str(stripe))
+    rng = np.random.default_rng(5 + world)
+    tau, res, mw = 600, 64, 640
+    size = (41, 25, 17)
+    om = orc.LocalMap(*size, tau, 0)
+    hm = api.HostLocalMap(*size, tau, 0)
+    ranks = [api.TSDFCuda(api.DeviceMap(hm), tau, mw, res, device=0, rank=r, world=world) for r in range(world)]
+    up = np.array([0, 0, MR], np.int32)
+    pos = np.zeros(3, np.int64)
+    row = int(hm.size[1]) * int(hm.size[2])
+
+    def check(what):
+        covered = np.zeros(int(hm.size[0]), np.int32)
+        for r, t in enumerate(ranks):
+            rows = t.owned_rows()
+            covered += rows
+            back = api.HostLocalMap(*size, tau, 0)
+            t.avg_map().to_host(api.DeviceMap(back))
+            assert list(back.pos) == list(om.pos) and list(back.offset) == list(om.offset)
+            assert np.array_equal(back.data.reshape(-1, row)[rows], om.data.reshape(-1, row)[rows]), \
+                "%s: rank %d owned rows differ from the oracle" % (what, r)
+        assert (covered == 1).all()
+
+    for step in range(7):
+        pts = (pos * res + rng.integers(-900, 900, size=(400, 3))).astype(np.int32)
+        orc.update_tsdf(om, pts, pos, up, tau, mw, res)
+        for t in ranks:
+            t.update_tsdf(pts, pos, up)
+        pos = pos + np.array([int(rng.integers(-30, 31)), int(rng.integers(-20, 21)), int(rng.integers(-5, 6))])
+        om.shift(pos)
+        for t in ranks:
+            t.shift(pos)
+        check("after shift %d to %r" % (step, list(pos)))
+    # back to the start: what left the window comes back from each rank's own store
+    while np.abs(pos).max() > 0:
+        pos = pos - np.clip(pos, -12, 12)                      # a shift may not exceed the map size (:63-65)
+        om.shift(pos)
+        for t in ranks:
+            t.shift(pos)
+    check("back at the origin")
+    # chunk stores: merge the ranks' chunks row by row (ring-x owner of the world row) and compare with the oracle's
+    om.write_back()
+    for t in ranks:
+        t.write_back()
+    owned = [t.owned_rows() for t in ranks]
+    sx = int(hm.size[0])
+    for c in om.chunk_list():
+        want = om.chunk(*c).reshape(64, 64 * 64)
+        got = np.full_like(want, want[0, 0])
+        have = [t.chunk(*c) for t in ranks]
+        for i in range(64):
+            x = c[0] * 64 + i
+            ring = (x - int(om.pos[0]) + int(om.offset[0]) + 2 * sx) % sx
+            in_window = abs(x - int(om.pos[0])) <= sx // 2
+            # a world row outside the final window was saved by the rank that owned its ring row when it left
+            owners = [r for r in range(world) if owned[r][ring] and have[r] is not None]
+            assert owners or not in_window
+            if owners:
+                got[i] = have[owners[0]].reshape(64, 64 * 64)[i]
+            else:
+                got[i] = want[i]
+        assert np.array_equal(got, want), "merged chunk %r differs from the oracle" % (c,)
+    for t in ranks:
+        t.close()
+
+
 # ----------------------------------------------------------------------------- GPU: fused peer exchange
 def _build_sharded_scene(world, device_of_rank, frames=2):
     res, tau, mw, side = 100, 1000, 640, 96

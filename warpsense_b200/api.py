@@ -384,6 +384,31 @@ class TSDFCuda:
         self._hd.check(self._hd.L.ws_export_hdf5(self._hd.h, str(path).encode(), C.byref(meta),
                                                  p.ctypes.data_as(C.POINTER(C.c_float)), len(p)))
 
+    def import_hdf5(self, path, max_poses=4096):
+        """Read a global-map file back into the chunk store (ws_import_hdf5).  Returns (meta dict, poses [n,7], n_chunks);
+        `reload()` then brings the stored chunks into the device-resident local map."""
+        meta = _lib.MapMeta()
+        poses = np.zeros((max_poses, 7), np.float32)
+        nc, npz = C.c_int64(), C.c_int64()
+        self._hd.check(self._hd.L.ws_import_hdf5(self._hd.h, str(path).encode(), C.byref(meta),
+                                                 poses.ctypes.data_as(C.POINTER(C.c_float)), max_poses, C.byref(nc), C.byref(npz)))
+        m = {"tau": meta.tau, "map_size": tuple(meta.map_size), "max_distance": meta.max_distance,
+             "map_resolution": meta.map_resolution, "max_weight": meta.max_weight}
+        return m, poses[:min(npz.value, max_poses)].copy(), nc.value
+
+    def reload(self):
+        self._hd.check(self._hd.L.ws_map_reload(self._hd.h))
+
+    def store_configure(self, max_chunks_in_memory):
+        self._hd.check(self._hd.L.ws_store_configure(self._hd.h, int(max_chunks_in_memory)))
+
+    def store_evictions(self):
+        return int(self._hd.L.ws_store_evictions(self._hd.h))
+
+    def set_chunk(self, cx, cy, cz, data):
+        a = np.ascontiguousarray(data, np.uint32).reshape(64 ** 3)
+        self._hd.check(self._hd.L.ws_store_set_chunk(self._hd.h, int(cx), int(cy), int(cz), a.ctypes.data_as(C.POINTER(C.c_uint32))))
+
     def sync(self):
         self._hd.check(self._hd.L.ws_sync(self._hd.h))
 

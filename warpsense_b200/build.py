@@ -6,7 +6,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libwarpsense_b200.so")
-SOURCES = ["capi.cu", "update_tsdf.cu", "registration.cu", "map_ops.cu", "preprocess.cu", "voxelgrid.cu", "hdf5_export.cu"]
+SOURCES = ["capi.cu", "update_tsdf.cu", "registration.cu", "map_ops.cu", "preprocess.cu", "voxelgrid.cu", "hdf5_export.cu", "hdf5_import.cu"]
 HEADERS = ["ws_common.cuh", "ws_internal.h", "march_math.cuh", os.path.join("..", "..", "include", "warpsense_b200.h")]
 
 NVCC_FLAGS = [

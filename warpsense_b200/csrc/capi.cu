@@ -3,6 +3,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <cstdio>
+#include <unistd.h>
 #include "../../include/warpsense_b200.h"
 #include "ws_internal.h"
 
@@ -80,6 +82,8 @@ void free_handle(ws_handle *h)
     if (t.done) cudaEventDestroy(t.done);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  cudaFree(h->d_shift_buf); cudaFreeHost(h->h_shift_buf);
+  if (h->spill_fp) { std::fclose(h->spill_fp); std::remove(h->spill_path.c_str()); }
   detach_peers(h); cudaFree(h->d_mail); cudaFree(h->d_pose); cudaFreeHost(h->h_pose);
   cudaFree(h->d_acc); cudaFree(h->d_trace); cudaFreeHost(h->h_acc); cudaFree(h->d_reg_partials);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -228,6 +232,7 @@ int create_impl(const int32_t size[3], int tau, int max_weight, int res, int dev
     std::memset(h->h_acc, 0, sizeof(RegAccum));
     h->trace_cap = WS_TRACE_CAP;
     WS_CUDA_OK(cudaMalloc(&h->d_trace, (size_t)WS_TRACE_CAP * WS_NSUM * sizeof(u64)));
+    if (const char *env = std::getenv("WS_STORE_CHUNKS")) h->store_max_chunks = std::max<size_t>(1, (size_t)std::strtoull(env, nullptr, 10));
     ws_launch_fill(h, h->default_entry);
     WS_CUDA_OK(cudaStreamSynchronize(h->stream));
   }
@@ -259,14 +264,79 @@ inline void chunk_unkey(u64 k, int &x, int &y, int &z)
 // include/map/util.h:5-12
 inline int floor_divide(int a, int b) { return (int)std::floor((float)a / (float)b); }
 
-// hdf5_global_map.cpp:59-137 (activate_chunk): default-filled on first use
-std::vector<uint32_t> &activate_chunk(ws_handle *h, int cx, int cy, int cz)
+// hdf5_global_map.cpp:59-137 (activate_chunk): default-filled on first use.  Like the reference's 64 active
+// chunks (hdf5_global_map.h:78) the store keeps a bounded number of chunks in memory (WS_STORE_CHUNKS, default
+// 4096 = 4 GiB); the least recently used one is written to a spill file (WS_STORE_SPILL_DIR, default /tmp) and read
+// back on its next activation -- the reference writes it to its HDF5 dataset at that point (:96-107).
+constexpr size_t CHUNK_ENTRIES = (size_t)WS_CHUNK * WS_CHUNK * WS_CHUNK;
+
+void store_spill_open(ws_handle *h)
 {
-  auto it = h->store.find(chunk_key(cx, cy, cz));
-  if (it != h->store.end()) return it->second;
-  auto &v = h->store[chunk_key(cx, cy, cz)];
-  v.assign((size_t)WS_CHUNK * WS_CHUNK * WS_CHUNK, h->default_entry);
-  return v;
+  if (h->spill_fp) return;
+  const char *dir = std::getenv("WS_STORE_SPILL_DIR");
+  char path[512];
+  std::snprintf(path, sizeof(path), "%s/ws_chunk_spill_%d_%p.bin", dir ? dir : "/tmp", (int)getpid(), (void *)h);
+  h->spill_path = path;
+  h->spill_fp = std::fopen(path, "w+b");
+  if (!h->spill_fp) throw std::runtime_error(std::string("chunk store: cannot open spill file ") + path);
+}
+
+void store_evict_one(ws_handle *h)
+{
+  const u64 key = h->lru.back();
+  auto it = h->store.find(key);
+  store_spill_open(h);
+  long slot;
+  auto sp = h->spilled.find(key);
+  if (sp != h->spilled.end()) slot = sp->second;                 // rewrite in place
+  else { slot = (long)h->spill_slots++; h->spilled[key] = slot; }
+  if (std::fseek(h->spill_fp, slot * (long)(CHUNK_ENTRIES * sizeof(uint32_t)), SEEK_SET) != 0 ||
+      std::fwrite(it->second.data.data(), sizeof(uint32_t), CHUNK_ENTRIES, h->spill_fp) != CHUNK_ENTRIES)
+    throw std::runtime_error("chunk store: spill write failed");
+  h->lru.pop_back();
+  h->store.erase(it);
+  h->store_evictions++;
+}
+
+uint32_t *activate_chunk(ws_handle *h, int cx, int cy, int cz)
+{
+  const u64 key = chunk_key(cx, cy, cz);
+  auto it = h->store.find(key);
+  if (it != h->store.end())
+  {
+    h->lru.splice(h->lru.begin(), h->lru, it->second.pos);       // most recently used
+    return it->second.data.data();
+  }
+  while (h->store.size() >= h->store_max_chunks && !h->lru.empty()) store_evict_one(h);
+  StoredChunk &c = h->store[key];
+  auto sp = h->spilled.find(key);
+  if (sp != h->spilled.end())
+  {
+    c.data.resize(CHUNK_ENTRIES);
+    if (std::fseek(h->spill_fp, sp->second * (long)(CHUNK_ENTRIES * sizeof(uint32_t)), SEEK_SET) != 0 ||
+        std::fread(c.data.data(), sizeof(uint32_t), CHUNK_ENTRIES, h->spill_fp) != CHUNK_ENTRIES)
+      throw std::runtime_error("chunk store: spill read failed");
+  }
+  else c.data.assign(CHUNK_ENTRIES, h->default_entry);
+  h->lru.push_front(key);
+  c.pos = h->lru.begin();
+  return c.data.data();
+}
+
+// every chunk the store knows (in memory or spilled), visited in turn with its data
+template <typename F>
+void store_for_each(ws_handle *h, F &&f)
+{
+  std::vector<u64> keys;
+  for (const auto &kv : h->store) keys.push_back(kv.first);
+  for (const auto &kv : h->spilled) if (!h->store.count(kv.first)) keys.push_back(kv.first);
+  std::sort(keys.begin(), keys.end());
+  for (u64 k : keys)
+  {
+    int x, y, z;
+    chunk_unkey(k, x, y, z);
+    f(x, y, z, activate_chunk(h, x, y, z));
+  }
 }
 
 bool column_resident(const GridDesc &g, int x)
@@ -275,71 +345,78 @@ bool column_resident(const GridDesc &g, int x)
   return g.xslot[ring_coord(x, g.pos[0], g.offset[0], g.size[0]) >> 3] >= 0;
 }
 
-// hdf5_local_map.cpp:120-198 (save_load_area) on the device-resident grid, in x-slices of bounded size
+// hdf5_local_map.cpp:120-198 (save_load_area) on the device-resident grid, in x-slices of bounded size.
+// Staging buffers (device + pinned host) live in the handle; chunk <-> slab copies go a z-run at a time.
+void ensure_shift_buffers(ws_handle *h, size_t entries)
+{
+  if (entries <= h->shift_cap) return;
+  WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+  cudaFree(h->d_shift_buf); cudaFreeHost(h->h_shift_buf);
+  h->d_shift_buf = nullptr; h->h_shift_buf = nullptr; h->shift_cap = 0;
+  WS_CUDA_OK(cudaMalloc(&h->d_shift_buf, entries * sizeof(uint32_t)));
+  if (cudaMallocHost(&h->h_shift_buf, entries * sizeof(uint32_t)) != cudaSuccess)
+  {
+    cudaFree(h->d_shift_buf); h->d_shift_buf = nullptr;
+    throw std::runtime_error("cudaMallocHost(shift buffer)");
+  }
+  h->shift_cap = entries;
+}
+
 void save_load_area(ws_handle *h, const int bottom[3], const int top[3], bool save)
 {
   int start[3], end[3];
   for (int a = 0; a < 3; a++) { start[a] = std::min(bottom[a], top[a]); end[a] = std::max(bottom[a], top[a]); }
   const i64 plane = (i64)(end[1] - start[1] + 1) * (end[2] - start[2] + 1);
   const int max_nx = (int)std::max<i64>(1, (i64)(32 << 20) / plane);
-  uint32_t *d_buf = nullptr, *h_buf = nullptr;
-  const size_t cap = (size_t)plane * std::min(max_nx, end[0] - start[0] + 1);
-  WS_CUDA_OK(cudaMalloc(&d_buf, cap * sizeof(uint32_t)));
-  if (cudaMallocHost(&h_buf, cap * sizeof(uint32_t)) != cudaSuccess) { cudaFree(d_buf); throw std::runtime_error("cudaMallocHost(shift buffer)"); }
-  try
+  ensure_shift_buffers(h, (size_t)plane * std::min(max_nx, end[0] - start[0] + 1));
+  uint32_t *d_buf = h->d_shift_buf, *h_buf = h->h_shift_buf;
+  for (int x0 = start[0]; x0 <= end[0]; x0 += max_nx)
   {
-    for (int x0 = start[0]; x0 <= end[0]; x0 += max_nx)
+    const int x1 = std::min(end[0], x0 + max_nx - 1);
+    const int lo[3] = { x0, start[1], start[2] };
+    const int ext[3] = { x1 - x0 + 1, end[1] - start[1] + 1, end[2] - start[2] + 1 };
+    const size_t n = (size_t)ext[0] * ext[1] * ext[2];
+    if (save)
     {
-      const int x1 = std::min(end[0], x0 + max_nx - 1);
-      const int lo[3] = { x0, start[1], start[2] };
-      const int ext[3] = { x1 - x0 + 1, end[1] - start[1] + 1, end[2] - start[2] + 1 };
-      const size_t n = (size_t)ext[0] * ext[1] * ext[2];
-      if (save)
-      {
-        ws_box_transfer(h, d_buf, lo, ext, true);
-        WS_CUDA_OK(cudaMemcpyAsync(h_buf, d_buf, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
-        WS_CUDA_OK(cudaStreamSynchronize(h->stream));
-      }
-      // chunk-wise traversal, as the reference does (touch each chunk once)
-      const int cs[3] = { floor_divide(lo[0], WS_CHUNK), floor_divide(lo[1], WS_CHUNK), floor_divide(lo[2], WS_CHUNK) };
-      const int ce[3] = { floor_divide(x1, WS_CHUNK), floor_divide(end[1], WS_CHUNK), floor_divide(end[2], WS_CHUNK) };
-      for (int cx = cs[0]; cx <= ce[0]; ++cx)
-        for (int cy = cs[1]; cy <= ce[1]; ++cy)
-          for (int cz = cs[2]; cz <= ce[2]; ++cz)
+      ws_box_transfer(h, d_buf, lo, ext, true);
+      WS_CUDA_OK(cudaMemcpyAsync(h_buf, d_buf, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+      WS_CUDA_OK(cudaStreamSynchronize(h->stream));
+    }
+    // chunk-wise traversal, as the reference does (touch each chunk once)
+    const int cs[3] = { floor_divide(lo[0], WS_CHUNK), floor_divide(lo[1], WS_CHUNK), floor_divide(lo[2], WS_CHUNK) };
+    const int ce[3] = { floor_divide(x1, WS_CHUNK), floor_divide(end[1], WS_CHUNK), floor_divide(end[2], WS_CHUNK) };
+    for (int cx = cs[0]; cx <= ce[0]; ++cx)
+      for (int cy = cs[1]; cy <= ce[1]; ++cy)
+        for (int cz = cs[2]; cz <= ce[2]; ++cz)
+        {
+          const int xs = std::max(lo[0], cx * WS_CHUNK), xe = std::min(x1, cx * WS_CHUNK + WS_CHUNK - 1);
+          const int ys = std::max(lo[1], cy * WS_CHUNK), ye = std::min(end[1], cy * WS_CHUNK + WS_CHUNK - 1);
+          const int zs = std::max(lo[2], cz * WS_CHUNK), ze = std::min(end[2], cz * WS_CHUNK + WS_CHUNK - 1);
+          // a sharded handle only holds (and stores) the columns resident on its rank
+          bool any_resident = false;
+          for (int x = xs; x <= xe && !any_resident; ++x) any_resident = column_resident(h->g, x);
+          if (!any_resident) continue;
+          uint32_t *chunk = activate_chunk(h, cx, cy, cz);
+          const size_t run = (size_t)(ze - zs + 1);
+          for (int x = xs; x <= xe; ++x)
           {
-            std::vector<uint32_t> &chunk = activate_chunk(h, cx, cy, cz);
-            const int xs = std::max(lo[0], cx * WS_CHUNK), xe = std::min(x1, cx * WS_CHUNK + WS_CHUNK - 1);
-            const int ys = std::max(lo[1], cy * WS_CHUNK), ye = std::min(end[1], cy * WS_CHUNK + WS_CHUNK - 1);
-            const int zs = std::max(lo[2], cz * WS_CHUNK), ze = std::min(end[2], cz * WS_CHUNK + WS_CHUNK - 1);
-            for (int x = xs; x <= xe; ++x)
+            if (!column_resident(h->g, x)) continue;
+            for (int y = ys; y <= ye; ++y)
             {
-              if (!column_resident(h->g, x)) continue;
-              for (int y = ys; y <= ye; ++y)
-              {
-                const size_t brow = ((size_t)(x - lo[0]) * ext[1] + (size_t)(y - lo[1])) * ext[2];
-                const size_t crow = ((size_t)(x - cx * WS_CHUNK) * WS_CHUNK + (size_t)(y - cy * WS_CHUNK)) * WS_CHUNK;
-                for (int z = zs; z <= ze; ++z)
-                {
-                  if (save) chunk[crow + (z - cz * WS_CHUNK)] = h_buf[brow + (z - lo[2])];
-                  else h_buf[brow + (z - lo[2])] = chunk[crow + (z - cz * WS_CHUNK)];
-                }
-              }
+              uint32_t *b = h_buf + ((size_t)(x - lo[0]) * ext[1] + (size_t)(y - lo[1])) * ext[2] + (zs - lo[2]);
+              uint32_t *c = chunk + ((size_t)(x - cx * WS_CHUNK) * WS_CHUNK + (size_t)(y - cy * WS_CHUNK)) * WS_CHUNK + (zs - cz * WS_CHUNK);
+              if (save) std::memcpy(c, b, run * sizeof(uint32_t));
+              else std::memcpy(b, c, run * sizeof(uint32_t));
             }
           }
-      if (!save)
-      {
-        WS_CUDA_OK(cudaMemcpyAsync(d_buf, h_buf, n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
-        ws_box_transfer(h, d_buf, lo, ext, false);
-        WS_CUDA_OK(cudaStreamSynchronize(h->stream));
-      }
+        }
+    if (!save)
+    {
+      WS_CUDA_OK(cudaMemcpyAsync(d_buf, h_buf, n * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
+      ws_box_transfer(h, d_buf, lo, ext, false);
+      WS_CUDA_OK(cudaStreamSynchronize(h->stream));
     }
   }
-  catch (...)
-  {
-    cudaFree(d_buf); cudaFreeHost(h_buf);
-    throw;
-  }
-  cudaFree(d_buf); cudaFreeHost(h_buf);
 }
 
 void read_acc(ws_handle *h)
@@ -389,6 +466,17 @@ void ws_timer_end(ws_handle *h)
     h->timers_used++;
   }
 }
+
+std::vector<unsigned long long> ws_store_keys(ws_handle *h)
+{
+  std::vector<unsigned long long> keys;
+  for (const auto &kv : h->store) keys.push_back(kv.first);
+  for (const auto &kv : h->spilled) if (!h->store.count(kv.first)) keys.push_back(kv.first);
+  std::sort(keys.begin(), keys.end());
+  return keys;
+}
+
+const uint32_t *ws_store_chunk(ws_handle *h, int cx, int cy, int cz) { return activate_chunk(h, cx, cy, cz); }
 
 extern "C" {
 
@@ -1269,31 +1357,68 @@ int ws_write_back(ws_handle *h)
   });
 }
 
-int64_t ws_store_num_chunks(const ws_handle *h) { return h ? (int64_t)h->store.size() : 0; }
+int ws_map_reload(ws_handle *h)
+{
+  return guarded(h, [&]() {
+    int start[3], end[3];
+    for (int a = 0; a < 3; a++) { start[a] = h->g.pos[a] - h->g.half[a]; end[a] = h->g.pos[a] + h->g.half[a]; }
+    save_load_area(h, start, end, false);
+    return WS_OK;
+  });
+}
+
+int64_t ws_store_num_chunks(const ws_handle *h)
+{
+  if (!h) return 0;
+  int64_t n = (int64_t)h->store.size();
+  for (const auto &kv : h->spilled) if (!h->store.count(kv.first)) n++;
+  return n;
+}
 
 int ws_store_chunk_list(const ws_handle *h, int32_t *xyz, int64_t cap)
 {
   if (!h || !xyz) return WS_ERR_INVALID;
   int64_t k = 0;
-  for (const auto &kv : h->store)
+  for (unsigned long long key : ws_store_keys(const_cast<ws_handle *>(h)))
   {
     if (k >= cap) break;
     int x, y, z;
-    chunk_unkey(kv.first, x, y, z);
+    chunk_unkey(key, x, y, z);
     xyz[3 * k] = x; xyz[3 * k + 1] = y; xyz[3 * k + 2] = z;
     k++;
   }
   return (int)k;
 }
 
-int ws_store_get_chunk(const ws_handle *h, int32_t cx, int32_t cy, int32_t cz, uint32_t *out)
+int ws_store_get_chunk(const ws_handle *h_, int32_t cx, int32_t cy, int32_t cz, uint32_t *out)
 {
+  ws_handle *h = const_cast<ws_handle *>(h_);
   if (!h || !out) return WS_ERR_INVALID;
-  auto it = h->store.find(chunk_key(cx, cy, cz));
-  if (it == h->store.end()) return WS_ERR_INVALID;
-  std::memcpy(out, it->second.data(), it->second.size() * sizeof(uint32_t));
+  const u64 key = chunk_key(cx, cy, cz);
+  if (!h->store.count(key) && !h->spilled.count(key)) return WS_ERR_INVALID;
+  try { std::memcpy(out, activate_chunk(h, cx, cy, cz), CHUNK_ENTRIES * sizeof(uint32_t)); }
+  catch (const std::exception &e) { h->last_error = e.what(); return WS_ERR_STATE; }
   return WS_OK;
 }
+
+int ws_store_set_chunk(ws_handle *h, int32_t cx, int32_t cy, int32_t cz, const uint32_t *data)
+{
+  if (!h || !data) return WS_ERR_INVALID;
+  try { std::memcpy(activate_chunk(h, cx, cy, cz), data, CHUNK_ENTRIES * sizeof(uint32_t)); }
+  catch (const std::exception &e) { h->last_error = e.what(); return WS_ERR_STATE; }
+  return WS_OK;
+}
+
+int ws_store_configure(ws_handle *h, int64_t max_chunks_in_memory)
+{
+  if (!h || max_chunks_in_memory < 1) return WS_ERR_INVALID;
+  h->store_max_chunks = (size_t)max_chunks_in_memory;
+  try { while (h->store.size() > h->store_max_chunks && !h->lru.empty()) store_evict_one(h); }
+  catch (const std::exception &e) { h->last_error = e.what(); return WS_ERR_STATE; }
+  return WS_OK;
+}
+
+int64_t ws_store_evictions(const ws_handle *h) { return h ? h->store_evictions : 0; }
 
 int64_t ws_launch_count(const ws_handle *h) { return h ? h->launches : 0; }
 

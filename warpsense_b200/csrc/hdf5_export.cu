@@ -10,8 +10,8 @@
 //                               (write_pose :175-200)
 // written directly in the HDF5 file format as libhdf5's default (earliest) settings would: version-0
 // superblock, version-1 object headers, groups as symbol tables (v1 B-tree of SNOD leaves + local heap),
-// contiguous little-endian datasets, version-1 attribute messages.  The file is assembled in memory in one
-// pass (every group's names are known up front) and written once.
+// contiguous little-endian datasets, version-1 attribute messages.  One pass: the 1 MiB chunk payloads are
+// streamed to disk as they come, only headers / B-trees / heaps are assembled in memory.
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -29,18 +29,50 @@ const uint64_t UNDEF = ~0ull;
 const int LEAF_K = 4;        // symbol table node holds 2K entries      (libhdf5 defaults)
 const int INTERNAL_K = 16;   // B-tree node holds 2K children
 
+// Append-only byte sink.  Small pieces (headers, B-trees, heaps) collect in memory; with a file attached
+// (streaming mode) the big dataset payloads go straight to disk and the memory part is flushed in front of
+// them, so the file never has to exist in memory as a whole.
 struct Buf
 {
   std::vector<uint8_t> b;
-  uint64_t size() const { return b.size(); }
+  FILE *fp = nullptr;          // streaming: everything before `base` is already on disk
+  uint64_t base = 0;
+  uint64_t size() const { return base + b.size(); }
   void u8(uint8_t v) { b.push_back(v); }
   void u16(uint16_t v) { for (int i = 0; i < 2; i++) b.push_back((uint8_t)(v >> (8 * i))); }
   void u32(uint32_t v) { for (int i = 0; i < 4; i++) b.push_back((uint8_t)(v >> (8 * i))); }
   void u64(uint64_t v) { for (int i = 0; i < 8; i++) b.push_back((uint8_t)(v >> (8 * i))); }
   void bytes(const void *p, size_t n) { const uint8_t *q = static_cast<const uint8_t *>(p); b.insert(b.end(), q, q + n); }
   void zeros(size_t n) { b.insert(b.end(), n, 0); }
-  void align8() { while (b.size() & 7) b.push_back(0); }
-  void put_u64_at(uint64_t off, uint64_t v) { for (int i = 0; i < 8; i++) b[off + i] = (uint8_t)(v >> (8 * i)); }
+  void align8() { while (size() & 7) b.push_back(0); }
+  void flush()
+  {
+    if (!fp || b.empty()) return;
+    if (std::fseek(fp, (long)base, SEEK_SET) != 0 || std::fwrite(b.data(), 1, b.size(), fp) != b.size())
+      throw std::runtime_error("short write");
+    base += b.size();
+    b.clear();
+  }
+  // a large payload: in memory without a file, else written through
+  void payload(const void *p, size_t n)
+  {
+    if (!fp) { bytes(p, n); return; }
+    flush();
+    if (std::fseek(fp, (long)base, SEEK_SET) != 0 || std::fwrite(p, 1, n, fp) != n) throw std::runtime_error("short write");
+    base += n;
+  }
+  void patch(uint64_t off, const void *p, size_t n)
+  {
+    if (off >= base) { std::memcpy(b.data() + (off - base), p, n); return; }
+    if (off + n > base) throw std::runtime_error("patch straddles the flushed part");
+    if (std::fseek(fp, (long)off, SEEK_SET) != 0 || std::fwrite(p, 1, n, fp) != n) throw std::runtime_error("short write");
+  }
+  void put_u64_at(uint64_t off, uint64_t v)
+  {
+    uint8_t t[8];
+    for (int i = 0; i < 8; i++) t[i] = (uint8_t)(v >> (8 * i));
+    patch(off, t, 8);
+  }
 };
 
 // ---- header messages ------------------------------------------------------------------------------
@@ -255,7 +287,7 @@ Entry write_dataset(Buf &f, const std::string &name, int kind, const void *data,
 {
   f.align8();
   const uint64_t data_addr = f.size();
-  f.bytes(data, n * 4);
+  f.payload(data, n * 4);
   std::vector<Msg> msgs;
   msgs.push_back(msg_dataspace_1d(n));
   msgs.push_back(msg_datatype(kind));
@@ -271,17 +303,25 @@ namespace {
 
 struct ChunkRef { int x, y, z; const uint32_t *data; };
 
-void write_map_file(const char *path, const ws_map_meta *meta, const std::vector<ChunkRef> &chunk_refs,
+// `fetch(i)` returns the 64^3 entries of chunk i (valid until the next call): the chunks are streamed to disk
+// one at a time, only headers / B-trees / heaps are assembled in memory.
+template <typename Fetch>
+void write_map_file(const char *path, const ws_map_meta *meta, const std::vector<ChunkRef> &chunk_refs, Fetch &&fetch,
                     const float *poses7, int64_t n_poses)
 {
+  FILE *fp = std::fopen(path, "w+b");
+  if (!fp) throw std::runtime_error(std::string("cannot open ") + path);
+  struct Closer { FILE *fp; ~Closer() { if (fp) std::fclose(fp); } } closer{ fp };
   Buf f;
+  f.fp = fp;
   f.zeros(96);                                            // superblock, filled in at the end
   // /map/<cx>_<cy>_<cz>
   std::vector<Entry> chunks;
-  for (const ChunkRef &c : chunk_refs)
+  for (size_t i = 0; i < chunk_refs.size(); i++)
   {
+    const ChunkRef &c = chunk_refs[i];
     const std::string tag = std::to_string(c.x) + "_" + std::to_string(c.y) + "_" + std::to_string(c.z);   // :46-51
-    chunks.push_back(write_dataset(f, tag, 0, c.data, (uint64_t)64 * 64 * 64));
+    chunks.push_back(write_dataset(f, tag, 0, fetch(i), (uint64_t)64 * 64 * 64));
   }
   std::vector<Msg> attrs;                                 // write_meta, :208-221
   attrs.push_back(msg_attribute("tau", 1, &meta->tau));
@@ -317,13 +357,9 @@ void write_map_file(const char *path, const ws_map_meta *meta, const std::vector
   s.u64(0); s.u64(UNDEF); s.u64(f.size()); s.u64(UNDEF);  // base, free-space info, end of file, driver info
   write_symbol_entry(s, 0, root);                         // root group symbol table entry
   if (s.size() != 96) throw std::runtime_error("superblock size");
-  std::memcpy(f.b.data(), s.b.data(), 96);
-
-  FILE *fp = std::fopen(path, "wb");
-  if (!fp) throw std::runtime_error(std::string("cannot open ") + path);
-  const size_t w = std::fwrite(f.b.data(), 1, f.b.size(), fp);
-  std::fclose(fp);
-  if (w != f.b.size()) throw std::runtime_error("short write");
+  f.flush();
+  f.patch(0, s.b.data(), 96);
+  if (std::fflush(fp) != 0) throw std::runtime_error("short write");
 }
 
 }  // namespace
@@ -334,15 +370,17 @@ extern "C" int ws_export_hdf5(ws_handle *h, const char *path, const ws_map_meta 
   try
   {
     std::vector<ChunkRef> refs;
-    for (const auto &kv : h->store)
+    std::vector<unsigned long long> keys = ws_store_keys(h);
+    for (unsigned long long k : keys)
     {
       ChunkRef c;
-      c.x = (int)((kv.first >> 42) & 0x1FFFFF) - (1 << 20); c.y = (int)((kv.first >> 21) & 0x1FFFFF) - (1 << 20);
-      c.z = (int)(kv.first & 0x1FFFFF) - (1 << 20);
-      c.data = kv.second.data();
+      c.x = (int)((k >> 42) & 0x1FFFFF) - (1 << 20); c.y = (int)((k >> 21) & 0x1FFFFF) - (1 << 20);
+      c.z = (int)(k & 0x1FFFFF) - (1 << 20);
+      c.data = nullptr;
       refs.push_back(c);
     }
-    write_map_file(path, meta, refs, poses7, n_poses);
+    // one chunk at a time through the bounded store (spilled chunks are read back in turn)
+    write_map_file(path, meta, refs, [&](size_t i) { return ws_store_chunk(h, refs[i].x, refs[i].y, refs[i].z); }, poses7, n_poses);
     return WS_OK;
   }
   catch (const std::exception &e)
@@ -351,6 +389,7 @@ extern "C" int ws_export_hdf5(ws_handle *h, const char *path, const ws_map_meta 
     return WS_ERR_STATE;
   }
 }
+
 
 // the same file from caller-held chunks (no map handle, no GPU): chunk_xyz[n_chunks][3], chunk_data[n_chunks][64^3]
 extern "C" int ws_hdf5_write_chunks(const char *path, const ws_map_meta *meta, const int32_t *chunk_xyz,
@@ -368,7 +407,7 @@ extern "C" int ws_hdf5_write_chunks(const char *path, const ws_map_meta *meta, c
       c.data = chunk_data + (size_t)i * 64 * 64 * 64;
       refs.push_back(c);
     }
-    write_map_file(path, meta, refs, poses7, n_poses);
+    write_map_file(path, meta, refs, [&](size_t i) { return refs[i].data; }, poses7, n_poses);
     return WS_OK;
   }
   catch (const std::exception &) { return WS_ERR_STATE; }

@@ -4,6 +4,8 @@
 #include <stdexcept>
 #include <string>
 #include <algorithm>
+#include <cstdio>
+#include <list>
 #include <unordered_map>
 #include <vector>
 #include "ws_common.cuh"
@@ -100,6 +102,12 @@ struct RegAccum           // 29 exact sums + bookkeeping, device resident
 struct WsTimer
 {
   cudaEvent_t start, stop;
+};
+
+struct StoredChunk
+{
+  std::vector<uint32_t> data;
+  std::list<u64>::iterator pos;             // place in ws_handle::lru
 };
 
 struct ws_handle
@@ -209,9 +217,20 @@ struct ws_handle
   int last_reg_iterations = 0;
   bool last_reg_host = false;
 
-  // in-memory global chunk store (src/map/hdf5_global_map.cpp): 64^3 raw entries per chunk
-  std::unordered_map<u64, std::vector<uint32_t>> store;
+  // global chunk store (src/map/hdf5_global_map.cpp): 64^3 raw entries per chunk, a bounded number of them in
+  // memory (LRU), the rest in a spill file
+  std::unordered_map<u64, StoredChunk> store;
+  std::list<u64> lru;                       // most recently used first
+  std::unordered_map<u64, long> spilled;    // chunk key -> slot in the spill file
+  size_t store_max_chunks = 4096;
+  size_t spill_slots = 0;
+  int64_t store_evictions = 0;
+  FILE *spill_fp = nullptr;
+  std::string spill_path;
   uint32_t default_entry = 0;
+  // shift staging (device + pinned host), kept between calls
+  uint32_t *d_shift_buf = nullptr, *h_shift_buf = nullptr;
+  size_t shift_cap = 0;
 };
 
 // update_tsdf.cu
@@ -235,6 +254,9 @@ int64_t ws_launch_preprocess(ws_handle *h, const float *d_xyz, int64_t n, int st
                              int mode);
 // voxelgrid.cu
 int64_t ws_launch_voxelgrid(ws_handle *h, const float *d_xyz, int64_t n, int stride_floats, float leaf_m, float *d_out_xyz);
+// capi.cu: the chunk store (bounded, LRU, spill file)
+std::vector<unsigned long long> ws_store_keys(ws_handle *h);
+const uint32_t *ws_store_chunk(ws_handle *h, int cx, int cy, int cz);
 // map_ops.cu
 void ws_launch_fill(ws_handle *h, uint32_t entry);
 void ws_launch_upload(ws_handle *h, const uint32_t *d_linear);

@@ -113,8 +113,13 @@ def _signatures():
         "ws_store_num_chunks": (C.c_int64, [hp]),
         "ws_store_chunk_list": (C.c_int, [hp, i32p, C.c_int64]),
         "ws_store_get_chunk": (C.c_int, [hp, C.c_int32, C.c_int32, C.c_int32, u32p]),
+        "ws_store_set_chunk": (C.c_int, [hp, C.c_int32, C.c_int32, C.c_int32, u32p]),
+        "ws_store_configure": (C.c_int, [hp, C.c_int64]),
+        "ws_store_evictions": (C.c_int64, [hp]),
         "ws_export_hdf5": (C.c_int, [hp, C.c_char_p, C.POINTER(MapMeta), f32p, C.c_int64]),
         "ws_hdf5_write_chunks": (C.c_int, [C.c_char_p, C.POINTER(MapMeta), i32p, u32p, C.c_int64, f32p, C.c_int64]),
+        "ws_import_hdf5": (C.c_int, [hp, C.c_char_p, C.POINTER(MapMeta), f32p, C.c_int64, i64p, i64p]),
+        "ws_map_reload": (C.c_int, [hp]),
         "ws_launch_count": (C.c_int64, [hp]),
         "ws_profile_enable": (C.c_int, [hp, C.c_int32]),
         "ws_profile_reset": (C.c_int, [hp]),
