@@ -208,7 +208,9 @@ int create_impl(const int32_t size[3], int tau, int max_weight, int res, int dev
     WS_CUDA_OK(cudaMalloc(&h->d_counters, sizeof(UpdateCounters)));
     WS_CUDA_OK(cudaMallocHost(&h->h_counters, sizeof(UpdateCounters)));
     std::memset(h->h_counters, 0, sizeof(UpdateCounters));
-    size_t pcap = 16u << 20;
+    // parked voxels per scan: a fraction of the voxels near the surfaces; 1/8 of the resident voxels (at least
+    // 16 Mi, at most 512 Mi slots of 32 bytes) unless WS_PENDING_CAP says otherwise
+    size_t pcap = std::min<size_t>(std::max<size_t>(16u << 20, n_vox / 8), (size_t)512 << 20);
     if (const char *env = std::getenv("WS_PENDING_CAP")) pcap = (size_t)std::strtoull(env, nullptr, 10);
     pcap = std::min(pcap, n_vox);
     pcap = std::max<size_t>(pcap, 1);
@@ -1062,6 +1064,19 @@ static void track_slot_init(ws_handle *h, ws_handle::TrackSlot &t)
   if (!h->copy_stream) WS_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
 }
 
+// complete a tracked scan on the host side (wait, regrow the record if needed, error checks); errors are kept
+// for the scan's ws_track_wait
+static void track_finish_slot(ws_handle *h, ws_handle::TrackSlot &t)
+{
+  try { ws_update_finish(h, t.h_ctr, t.h_pose, t.done); }
+  catch (const std::exception &e) { t.error = e.what(); }
+  t.finished = true;
+  // room to spare: the record used less than 60 % of its chunks and did not have to grow
+  const size_t used = t.h_ctr->n_chunks;
+  if (t.h_ctr->rec_overflow == 0u && h->record_regrows == t.regrows_at_submit && used * 10 < h->rec_cap_chunks * 6) h->rec_headroom_ok = true;
+  else if (h->record_regrows != t.regrows_at_submit || used * 10 >= h->rec_cap_chunks * 9) h->rec_headroom_ok = false;
+}
+
 int ws_track_submit(ws_handle *h, const ws_point *points, int64_t n, int32_t on_device, const float *prior_pose,
                     const float *pretransform, int32_t max_iterations, float it_weight_gradient, float epsilon,
                     int32_t map_resolution, int32_t flags, int32_t *ticket)
@@ -1074,6 +1089,11 @@ int ws_track_submit(ws_handle *h, const ws_point *points, int64_t n, int32_t on_
     if (!prior_pose && !h->track_has_pose) throw std::logic_error("ws_track_submit: no previous pose on the device to chain from");
     ws_handle::TrackSlot &t = h->track[h->track_next];
     if (t.busy) throw std::logic_error("ws_track_submit: two scans already in flight (call ws_track_wait)");
+    // A scan whose candidate record overflows is finished by the host (regrow + regenerate); nothing may be
+    // queued behind it.  Until a scan has shown that the record has room to spare, the scan in flight is
+    // completed here before the next one is enqueued.
+    ws_handle::TrackSlot &prev = h->track[h->track_next ^ 1];
+    if (prev.busy && !prev.finished && !h->rec_headroom_ok) track_finish_slot(h, prev);
     track_slot_init(h, t);
     ensure_points(&t.d_pts, &t.cap, (size_t)std::max<int64_t>(n, 1));
     if (n > 0)
@@ -1103,7 +1123,7 @@ int ws_track_submit(ws_handle *h, const ws_point *points, int64_t n, int32_t on_
     ws_update_enqueue(h, t.d_pts, (int)n, nullptr, nullptr, true, t.h_ctr, t.h_pose);
     WS_CUDA_OK(cudaEventRecord(t.done, h->stream));
     h->d_reg_points_alias = nullptr;
-    t.busy = true; t.n = n;
+    t.busy = true; t.finished = false; t.error.clear(); t.n = n; t.regrows_at_submit = h->record_regrows;
     h->track_in_flight++;
     *ticket = h->track_next;
     h->track_next ^= 1;
@@ -1118,7 +1138,9 @@ int ws_track_wait(ws_handle *h, int32_t ticket, float out_transform[16], float o
     ws_handle::TrackSlot &t = h->track[ticket];
     struct Release { ws_handle *h; ws_handle::TrackSlot &t; ~Release() { t.busy = false; h->track_in_flight--; } } release{ h, t };
     h->last_n_points = t.n;
-    ws_update_finish(h, t.h_ctr, t.h_pose, t.done);
+    if (!t.finished) track_finish_slot(h, t);
+    h->last_counters = *t.h_ctr;
+    if (!t.error.empty()) throw std::runtime_error(t.error);
     if (t.h_acc->finished == 2u)
       throw std::logic_error("track_scan: a peer rank did not deliver its Gauss-Newton sums in time");
     if (out_transform) std::memcpy(out_transform, t.h_acc->T, 16 * sizeof(float));

@@ -1841,7 +1841,9 @@ static void resident_x_intervals(const ws_handle *h, UpdateParams &P)
   }
   const double len_max = 1.7320508 * (double)std::max(g.size[0], std::max(g.size[1], g.size[2])) * h->res + P.tau + h->res;
   const long long dz_max = (long long)((double)P.dz_per_distance * len_max / WS_MR) + 1;
-  const int margin = (int)((3 * dz_max + h->res) / h->res) + 3;
+  // a candidate lies within delta_z (fan offset, |iv| = MR) + res (truncating divisions) + 1 (proj rounding) of the
+  // ray point: voxels beyond that margin of a resident column cannot be reached
+  const int margin = (int)((dz_max + 2 * (long long)h->res + 1) / h->res) + 1;
   struct Iv { long long lo, hi; };
   std::vector<Iv> ivs;
   for (int t = 0; t < size; )

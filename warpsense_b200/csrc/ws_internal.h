@@ -141,10 +141,12 @@ struct ws_handle
     ws_pt *d_pts = nullptr; size_t cap = 0;
     RegAccum *h_acc = nullptr; void *h_pose = nullptr; UpdateCounters *h_ctr = nullptr;   // pinned
     cudaEvent_t copied = nullptr, done = nullptr;
-    bool busy = false; int64_t n = 0;
+    bool busy = false, finished = false; int64_t n = 0, regrows_at_submit = 0;
+    std::string error;
   } track[2];
   cudaStream_t copy_stream = nullptr;
   int track_next = 0, track_in_flight = 0;
+  bool rec_headroom_ok = false;     // a finished scan left the candidate record well below its capacity
   bool track_has_pose = false;      // d_pose holds the pose of the previous tracked scan      // dynamic shared memory of the lockstep march raised above 48 KB
   unsigned *d_gen_list = nullptr; // rays for the literal-arithmetic march
   // scan preprocessing scratch (preprocess.cu)
