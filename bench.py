@@ -410,6 +410,25 @@ class Workload:
         self.tsdf.close()
 
 
+def shift_timing(torch, dist, args):
+    """HDF5LocalMap::shift on the device-resident map (ws_shift): wall time of 1-, 8- and 64-voxel shifts along each
+    axis of a map that holds a few scans (leaving slabs go to the chunk store, entering ones come back from it)."""
+    wl = Workload(torch, dist, args, args.grid, args.res, args.beams, args.cols, 3, True)
+    wl.run(1, 3, host=False)
+    wl.barrier()
+    out = {}
+    pos = np.zeros(3, np.int64)
+    for d in (1, 8, 64):
+        for axis, name in enumerate("xyz"):
+            pos[axis] += d
+            t0 = time.perf_counter()
+            wl.tsdf.shift(pos)
+            out["%s+%d" % (name, d)] = 1000.0 * (time.perf_counter() - t0)
+    slab_mb = {d: d * wl.size[1] * wl.size[2] * 4 / 1e6 for d in (1, 8, 64)}
+    wl.close()
+    return {"ms": out, "slab_MB_each_way": slab_mb, "unit": "ms per ws_shift call (device pack -> D2H -> chunk store, store -> H2D -> unpack)"}
+
+
 def sub_config(torch, dist, args, name, grid, res, beams, cols, K, W, update_only, subsample=False):
     """A secondary BASELINE config as a short run of its own (value / kernel ms / work counters)."""
     wl = Workload(torch, dist, args, grid, res, beams, cols, 2 * (K + W), update_only, subsample=subsample)
@@ -556,11 +575,15 @@ def run_native(args):
                                              Ke, We, update_only=True)
             extra["configs[4]"] = sub_config(torch, dist, args, "configs[4]", args.grid, args.res, args.beams, args.cols,
                                              Ke, We, update_only=True, subsample=True)
+            extra["shift"] = shift_timing(torch, dist, args)
         if world >= 8 or args.config3:
             extra["configs[3]"] = sub_config(torch, dist, args, "configs[3]", 2048, 20, 128, 2048, 4, 3, update_only=False)
     if rank == 0:
         if extra:
+            shift = extra.pop("shift", None)
             line["extra"] = {"configs": extra}
+            if shift is not None:
+                line["extra"]["shift"] = shift
         if world == 1 and not args.no_ref_cuda:
             try:
                 line["reference_cuda_same_gpu"] = reference_cuda(args, frames_main, s_main)

@@ -422,6 +422,7 @@ int64_t orc_preprocess(const float *xyz, int64_t n, int stride_floats, const flo
   {
     const float x = xyz[i * stride_floats], y = xyz[i * stride_floats + 1], z = xyz[i * stride_floats + 2];
     if (x < 0.3 && y < 0.3 && z < 0.3) continue;                              /* :128-131 */
+    if (!isfinite(x) || !isfinite(y) || !isfinite(z)) continue;    /* (int)NaN is undefined behaviour in the reference: dropped, as on the device */
     const float mm[3] = { x * 1000.f, y * 1000.f, z * 1000.f };               /* :133 */
     orc_point c;
     int32_t cc[3];
@@ -466,6 +467,7 @@ int64_t orc_preprocess_cpu_node(const float *xyz, int64_t n, int stride_floats, 
   {
     const float x = xyz[i * stride_floats], y = xyz[i * stride_floats + 1], z = xyz[i * stride_floats + 2];
     if (x < 0.3 && y < 0.3 && z < 0.3) continue;                              /* :152-155 */
+    if (!isfinite(x) || !isfinite(y) || !isfinite(z)) continue;    /* (int)NaN is undefined behaviour in the reference: dropped, as on the device */
     orc_point pt = { f2i(x * 1000), f2i(y * 1000), f2i(z * 1000) };           /* :156-159 */
     const orc_point k = { pt.x / map_resolution, pt.y / map_resolution, pt.z / map_resolution };   /* :160 */
     uint64_t h = ((uint64_t)(uint32_t)k.x * 0x9E3779B97F4A7C15ull) ^ ((uint64_t)(uint32_t)k.y * 0xC2B2AE3D27D4EB4Full) ^

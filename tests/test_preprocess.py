@@ -118,6 +118,17 @@ def test_preprocess_scan_device_matches_oracle(n, res):
     want4 = orc.preprocess(cloud, pose, res, cpu_node=True)          # the CPU node's variant, its own order
     got4, m4 = tsdf.preprocess_scan(cloud, pose, res, cpu_node=True)
     assert m4 == len(want4) and np.array_equal(got4, want4)
+    # NaN / inf returns (is_dense == false) are dropped, on the device as in the oracle, in both variants
+    bad = cloud.copy()
+    bad[::5, 0] = np.nan
+    bad[1::7, 2] = np.inf
+    bad[2::11, 1] = -np.inf
+    for cpu_node in (False, True):
+        want5 = orc.preprocess(bad, pose, res, cpu_node=cpu_node)
+        keep = np.isfinite(bad).all(axis=1)
+        assert np.array_equal(want5, orc.preprocess(np.ascontiguousarray(bad[keep]), pose, res, cpu_node=cpu_node))
+        got5, m5 = tsdf.preprocess_scan(bad, pose, res, cpu_node=cpu_node)
+        assert m5 == len(want5) and np.array_equal(got5, want5)
     tsdf.close()
 
 

@@ -3,7 +3,7 @@
 out=gpurun_out; mkdir -p $out
 for rep in 1 2; do
 for name in "$@"; do
-  WS_LIB_PATH=$PWD/build/variants/libws_$name.so timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-ref-cuda ${AB_ARGS} > $out/ab_$name.json 2> $out/ab_$name.err || tail -3 $out/ab_$name.err
+  WS_LIB_PATH=$PWD/build/variants/libws_$name.so timeout 300 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-ref-cuda --no-extra ${AB_ARGS} > $out/ab_$name.json 2> $out/ab_$name.err || tail -3 $out/ab_$name.err
   python - <<PY
 import json
 d=json.loads(open("$out/ab_$name.json").read().strip().splitlines()[-1])

@@ -4,7 +4,7 @@ tag=${1:-r02x}; shift
 out=gpurun_out; mkdir -p $out
 timeout 600 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,lts__t_sector_hit_rate.pct \
    --clock-control none -s 70 -c 34 --csv --log-file $out/${tag}_list.csv \
-   python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-ref-cuda "$@" > $out/${tag}_list.log 2>&1
+   python bench.py --steps 6 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-extra "$@" > $out/${tag}_list.log 2>&1
 python - <<PY
 import csv
 rows=[r for r in csv.reader(open("$out/${tag}_list.csv")) if len(r)>10]

@@ -7,6 +7,7 @@
 #include <unistd.h>
 #include "../../include/warpsense_b200.h"
 #include "ws_internal.h"
+#include <nvtx3/nvToolsExt.h>      // header-only NVTX: ranges around the phases of a scan (Nsight Systems / ncu --nvtx)
 
 static_assert(sizeof(ws_point) == sizeof(ws_pt), "point layout");
 #define WS_NSUM 29
@@ -157,6 +158,15 @@ int create_impl(const int32_t size[3], int tau, int max_weight, int res, int dev
   if (size[0] % 2 == 0 || size[1] % 2 == 0 || size[2] % 2 == 0) return WS_ERR_INVALID;  // hdf5_local_map.cpp:6-8
   if (tau < 1 || tau > 32767 || res < 2 || max_weight < 0 || max_weight > 32767) return WS_ERR_INVALID;
   if (world < 1 || rank < 0 || rank >= world) return WS_ERR_INVALID;
+  {
+    // the candidate order field holds 2^15 march steps and 2^6 fan steps: a ray across the whole map (the longest
+    // a point inside the map can give with the sensor inside it too) must fit, or every scan would fail AFTER
+    // it has changed the map.  Rays from a sensor far outside the map are still checked per scan.
+    const double diag = std::sqrt((double)size[0] * size[0] + (double)size[1] * size[1] + (double)size[2] * size[2]) * res;
+    const double steps = (diag + tau) / (double)(res / 2 > 0 ? res / 2 : 1);
+    const double dz = std::tan((double)(45.f / 128.f / 180.f) * M_PI) / 2.0 * WS_MR * (diag + tau) / WS_MR;
+    if (steps > 32768.0 || 2.0 * dz / res + 1.0 > 64.0) return WS_ERR_INVALID;
+  }
   int n_dev = 0;
   if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return WS_ERR_CUDA;
 
@@ -446,6 +456,8 @@ void sums_to_hg(const u64 sums[32], int64_t H[36], int64_t g[6], int32_t *err, i
 
 void ws_timer_begin(ws_handle *h, int kind)
 {
+  static const char *const names[] = { "ws:march", "ws:merge", "ws:register", "ws:replay" };
+  nvtxRangePushA(names[kind & 3]);
   if (!h->profile) return;
   if (h->timers_used >= h->timers.size())
   {
@@ -461,6 +473,7 @@ void ws_timer_begin(ws_handle *h, int kind)
 
 void ws_timer_end(ws_handle *h)
 {
+  nvtxRangePop();
   if (!h->profile) return;
   if (h->timers_used < h->timers.size())
   {

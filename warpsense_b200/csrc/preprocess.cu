@@ -40,6 +40,9 @@ WS_D bool pre_point(const PreParams &P, const float *__restrict__ xyz, int i, ws
   const float x = xyz[(size_t)i * P.stride_floats], y = xyz[(size_t)i * P.stride_floats + 1],
               z = xyz[(size_t)i * P.stride_floats + 2];
   if (x < 0.3 && y < 0.3 && z < 0.3) return false;                       // app.cpp:128-131 / fastsense.cpp:152-155
+  // NaN / inf returns (PointCloud2 with is_dense == false): the reference casts them to int -- undefined behaviour,
+  // INT_MIN on x86, normally out of bounds and dropped later; here they are dropped explicitly (the oracle does the same)
+  if (!isfinite(x) || !isfinite(y) || !isfinite(z)) return false;
   int c[3];
   if (P.mode == 0)
   {

@@ -320,8 +320,12 @@ reg_accum_kernel(const GridDesc g, const ws_pt *__restrict__ pts, const int n, c
 //     deterministic FP64 solve (warp 0), so each block owns the next transform without a second barrier;
 //   * the solve is inverse6()/gn_solve() above with the row operations spread over six lanes and the six
 //     columns of the inverse over six lanes: operation order per element unchanged, results bit-identical.
+#ifndef REG_THREADS
 #define REG_THREADS 256
+#endif
+#ifndef REG_PTS
 #define REG_PTS 2
+#endif
 #define REG_NSLOT 32
 
 struct RegLoopParams

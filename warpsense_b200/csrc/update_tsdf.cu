@@ -757,7 +757,7 @@ WS_D void list_append(ListWriter &w, const bool want, const Rec e, const int lan
 // Voxel addresses come from three per-axis tables in shared memory (ring wrap, residency, bricking).
 // Rays outside the bounds of the 32-bit arithmetic (march_math.cuh) are left to march_kernel.
 #ifndef LS_CTAS
-#define LS_CTAS 3
+#define LS_CTAS 2
 #endif
 #define TAB_INVALID 0xFFFFFFFFu
 
