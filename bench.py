@@ -122,7 +122,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         try:
             for ln in proc.stdout:
-                parts = [p.strip() for p in ln.split(",")]
+                parts = [p.strip() for p in ln.rsplit(",", 3)]       # kernel names may hold commas (template arguments)
                 if len(parts) >= 9:
                     try:
                         self.sm.append(float(parts[1])); self.mx.append(float(parts[2]))
@@ -263,7 +263,7 @@ def traffic_from_profile():
     tot = 0.0
     with open(files[-1]) as f:
         for ln in f:
-            parts = [p.strip() for p in ln.split(",")]
+            parts = [p.strip() for p in ln.rsplit(",", 3)]       # kernel names may hold commas (template arguments)
             if len(parts) < 3 or parts[0].startswith("#") or parts[0] == "kernel":
                 continue
             if parts[0].startswith("reg_") or parts[0] in ("pose_kernel", "transform_cloud_kernel"):

@@ -34,3 +34,10 @@ def test_reference_arm_prints_the_contract_line():
 
 def test_reference_arm_is_silent_on_other_ranks():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, ("--gpus", "2")) == []
+
+
+def test_committed_traffic_profile_parses():
+    """bench.py reads roofline.traffic from the committed ncu capture; template arguments put commas into kernel names."""
+    import bench
+    total, src = bench.traffic_from_profile()
+    assert src and src.startswith("profiles/") and 1e8 < total < 1e10

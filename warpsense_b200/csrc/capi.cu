@@ -83,6 +83,7 @@ void free_handle(ws_handle *h)
     if (t.done) cudaEventDestroy(t.done);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  if (h->stream2) { cudaStreamDestroy(h->stream2); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
   cudaFree(h->d_shift_buf); cudaFreeHost(h->h_shift_buf);
   if (h->spill_fp) { std::fclose(h->spill_fp); std::remove(h->spill_path.c_str()); }
   detach_peers(h); cudaFree(h->d_mail); cudaFree(h->d_pose); cudaFreeHost(h->h_pose);
@@ -454,7 +455,7 @@ void sums_to_hg(const u64 sums[32], int64_t H[36], int64_t g[6], int32_t *err, i
 
 }  // namespace
 
-void ws_timer_begin(ws_handle *h, int kind)
+void ws_timer_begin(ws_handle *h, int kind, cudaStream_t stream)
 {
   static const char *const names[] = { "ws:march", "ws:merge", "ws:register", "ws:replay" };
   nvtxRangePushA(names[kind & 3]);
@@ -468,16 +469,16 @@ void ws_timer_begin(ws_handle *h, int kind)
     h->timer_kind.push_back(kind);
   }
   h->timer_kind[h->timers_used] = kind;
-  cudaEventRecord(h->timers[h->timers_used].start, h->stream);
+  cudaEventRecord(h->timers[h->timers_used].start, stream ? stream : h->stream);
 }
 
-void ws_timer_end(ws_handle *h)
+void ws_timer_end(ws_handle *h, cudaStream_t stream)
 {
   nvtxRangePop();
   if (!h->profile) return;
   if (h->timers_used < h->timers.size())
   {
-    cudaEventRecord(h->timers[h->timers_used].stop, h->stream);
+    cudaEventRecord(h->timers[h->timers_used].stop, stream ? stream : h->stream);
     h->timers_used++;
   }
 }

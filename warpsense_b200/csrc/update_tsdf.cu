@@ -619,9 +619,14 @@ setup_kernel(const UpdateParams Pin, const ws_pt *__restrict__ pts, RaySetup *__
     unsigned b_lo = hi_s > lo_s ? (unsigned)lo_s / LS_BLOCK : 0u;
     unsigned nb = hi_s > lo_s ? ((unsigned)hi_s + LS_BLOCK - 1u) / LS_BLOCK - b_lo : 0u;
     grp_info[ray_id >> 5] = make_uint2(b_lo, nb);
+    // free space: the blocks before the far field need nothing from the surface phase, the others wait for
+    // its merge (they look for parked voxels)
     b_lo = hi_f > lo_f ? (unsigned)lo_f / LS_BLOCK : 0u;
-    nb = hi_f > lo_f ? ((unsigned)hi_f + LS_BLOCK - 1u) / LS_BLOCK - b_lo : 0u;
-    grp_info[grp_stride + (ray_id >> 5)] = make_uint2(b_lo, nb);
+    const unsigned b_hi = hi_f > lo_f ? ((unsigned)hi_f + LS_BLOCK - 1u) / LS_BLOCK : 0u;
+    const unsigned b_far = (unsigned)P.far_block;
+    const unsigned near_hi = b_hi < b_far ? b_hi : b_far, far_lo = b_lo > b_far ? b_lo : b_far;
+    grp_info[grp_stride + (ray_id >> 5)] = make_uint2(b_lo, near_hi > b_lo ? near_hi - b_lo : 0u);
+    grp_info[2u * grp_stride + (ray_id >> 5)] = make_uint2(far_lo, b_hi > far_lo ? b_hi - far_lo : 0u);
   }
   if (valid && !small) gen_list[atomicAdd(&ctr->n_general, 1u)] = (unsigned)ray_id;
 }
@@ -1126,15 +1131,17 @@ __global__ void __launch_bounds__(MARCH_THREADS, LS_CTAS)
 march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__restrict__ rays,
                       const uint2 *__restrict__ grp_info, const unsigned *__restrict__ item_off, const unsigned n_groups,
                       UpdateCounters *__restrict__ ctr, Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill,
-                      const unsigned cap_chunks, const PoseDev *__restrict__ pose, const LsOut out)
+                      const unsigned cap_chunks, const PoseDev *__restrict__ pose, const LsOut out, const unsigned tab)
 {
   extern __shared__ unsigned s_tab[];               // size[0] + size[1] + size[2] address parts
   __shared__ int4 s_ray[MARCH_WARPS][64];
   __shared__ __align__(16) int4 s_queue[MARCH_WARPS][QCAP];
   __shared__ unsigned s_pd[MARCH_WARPS][96];
-  const unsigned n_items = __ldcg(&ctr->n_items[SURF ? 0 : 1]);
+  // item tables: 0 = surface phase; free-space phase: 1 = near field (needs nothing from the surface phase, runs beside
+  // it on a second stream), 2 = far field (looks for parked voxels: launched after the surface merge)
+  const unsigned n_items = __ldcg(&ctr->n_items[tab]);
   if (n_items == 0u) return;
-  if (!SURF && __ldcg(&ctr->rec_overflow) != 0u && __ldcg(&ctr->pending_overflow) == 0u) return;   // redone after the regrow
+  if (tab == 2u && __ldcg(&ctr->rec_overflow) != 0u && __ldcg(&ctr->pending_overflow) == 0u) return;   // redone after the regrow
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   LsShared sh;
@@ -1172,9 +1179,9 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
 #pragma unroll
   for (int a = 0; a < 3; a++) pos_mm[a] = pose ? pose->pos_mm[a] : P.pos_mm[a];
   const unsigned total_warps = gridDim.x * MARCH_WARPS;
-  const uint2 *ginfo = grp_info + (SURF ? 0u : n_groups);
-  const unsigned *ioff = item_off + (SURF ? 0u : n_groups + 1u);
-  unsigned *counter = &ctr->item_counter[SURF ? 0 : 1];
+  unsigned *counter = &ctr->item_counter[tab];
+  const uint2 *ginfo = grp_info + (size_t)tab * n_groups;
+  const unsigned *ioff = item_off + (size_t)tab * (n_groups + 1u);
 
   LsWarp W;
   if (SURF) rec_init(W.rw, ctr, lane);
@@ -1228,7 +1235,7 @@ item_scan_kernel(const uint2 *__restrict__ grp_info, const unsigned n_groups, un
   __shared__ unsigned s_warp[32];
   __shared__ unsigned s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int phase = 0; phase < 2; phase++)
+  for (int phase = 0; phase < 3; phase++)
   {
     const uint2 *gi = grp_info + (size_t)phase * n_groups;
     unsigned *io = item_off + (size_t)phase * (n_groups + 1u);
@@ -1802,11 +1809,19 @@ __global__ void rec_reset_kernel(UpdateCounters *ctr)
   ctr->n_chunks = 0u;
   ctr->rec_overflow = 0u;
   ctr->item_counter[0] = 0u;
-  ctr->item_counter[1] = 0u;
+  ctr->item_counter[2] = 0u;
   ctr->gen_counter = 0u;
 }
 
 }  // namespace
+
+// CTAs per SM of one lockstep launch (tuning knob for A/B runs; the default is what the launcher was tuned to)
+static int ls_ctas_env(const char *name, int dflt)
+{
+  const char *e = std::getenv(name);
+  const int v = e ? std::atoi(e) : dflt;
+  return v >= 1 && v <= LS_CTAS ? v : dflt;
+}
 
 static int far_start_len(int res, int dz)
 {
@@ -1975,12 +1990,13 @@ void ws_launch_pose(ws_handle *h, const float *d_X, const float *prior, int comp
   h->launches++;
 }
 
-#define LS_LAUNCH(SURF_, ATOMIC_)                                                                                        \
+#define LS_LAUNCH_ON(SURF_, ATOMIC_, TAB_, STREAM_) LS_LAUNCH_GRID(SURF_, ATOMIC_, TAB_, STREAM_, lockstep_blocks)
+#define LS_LAUNCH_GRID(SURF_, ATOMIC_, TAB_, STREAM_, GRID_)                                                             \
   do {                                                                                                                   \
-    if (wide) march_lockstep_kernel<SURF_, ATOMIC_, true><<<lockstep_blocks, MARCH_THREADS, tab_bytes, s>>>(             \
-        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out);  \
-    else march_lockstep_kernel<SURF_, ATOMIC_, false><<<lockstep_blocks, MARCH_THREADS, tab_bytes, s>>>(                 \
-        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out);  \
+    if (wide) march_lockstep_kernel<SURF_, ATOMIC_, true><<<GRID_, MARCH_THREADS, tab_bytes, STREAM_>>>(                 \
+        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out, TAB_);  \
+    else march_lockstep_kernel<SURF_, ATOMIC_, false><<<GRID_, MARCH_THREADS, tab_bytes, STREAM_>>>(                     \
+        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out, TAB_);  \
   } while (0)
 
 // Enqueues one update_tsdf on the handle's stream; the work counters (and the device-side pose) land in
@@ -2036,6 +2052,7 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
   }
   P.n_points = n;
   P.far_len = far_start_len(h->res, P.dz_per_distance);
+  P.far_block = (P.far_len > 1 ? (P.far_len - 2) / P.half_res + 1 : 0) / LS_BLOCK;      // block of the first far step
   resident_x_intervals(h, P);
 
   cudaStream_t s = h->stream;
@@ -2066,8 +2083,8 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
       const size_t want = std::max<size_t>((size_t)n, 1 << 17);
       h->grp_cap = want / 32 + 1;
       WS_CUDA_OK(cudaMalloc(&h->d_rays, want * sizeof(RaySetup)));
-      WS_CUDA_OK(cudaMalloc(&h->d_grp_info, 2 * h->grp_cap * sizeof(uint2)));
-      WS_CUDA_OK(cudaMalloc(&h->d_item_off, 2 * (h->grp_cap + 1) * sizeof(unsigned)));
+      WS_CUDA_OK(cudaMalloc(&h->d_grp_info, 3 * h->grp_cap * sizeof(uint2)));
+      WS_CUDA_OK(cudaMalloc(&h->d_item_off, 3 * (h->grp_cap + 1) * sizeof(unsigned)));
       WS_CUDA_OK(cudaMalloc(&h->d_gen_list, want * sizeof(unsigned)));
       h->rays_cap = want;
     }
@@ -2077,22 +2094,40 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
     LsOut out;
     out.pend_key = h->d_pend_key; out.list = h->d_list; out.pending_cap = h->pending_cap; out.list_cap = (unsigned)h->list_cap;
     const bool wide = (unsigned long long)h->g.n_bricks * WS_BRICK_VOX > 0xFFFFFFFFull;
-    // surface phase: keys, record, parked voxels
+    if (!h->stream2)
+    {
+      WS_CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+      WS_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+      WS_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    }
+    cudaStream_t s2 = h->stream2;
     setup_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_pts, rays, h->d_grp_info, n_groups, h->d_gen_list, h->d_counters, d_pose);
     item_scan_kernel<<<1, 1024, 0, s>>>(h->d_grp_info, n_groups, h->d_item_off, h->d_counters);
-    LS_LAUNCH(true, true);
+    ws_timer_end(h);
+    // Two streams from here.  Surface phase (this stream): keys, record, merge -> parked voxels.  The near-field part
+    // of the free-space phase needs nothing from it and runs beside it on the second stream (both marches are
+    // persistent grids; the block scheduler fills the SMs with whatever fits, nobody waits on the device); the
+    // far-field part looks for parked voxels and follows the surface merge.
+    WS_CUDA_OK(cudaEventRecord(h->ev_fork, s));
+    WS_CUDA_OK(cudaStreamWaitEvent(s2, h->ev_fork, 0));
+    ws_timer_begin(h, WS_TIMER_MARCH);
+    LS_LAUNCH_GRID(true, true, 0u, s, h->sm_count * ls_ctas_env("WS_LS_GRID_S", LS_CTAS));
     march_kernel<true><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_gen_list, h->d_counters, h->d_rec,
                                                               h->d_chunk_fill, cap_chunks, d_pose);
     ws_timer_end(h);
+    ws_timer_begin(h, WS_TIMER_MARCH, s2);
+    LS_LAUNCH_GRID(false, true, 1u, s2, h->sm_count * ls_ctas_env("WS_LS_GRID_N", LS_CTAS));
+    ws_timer_end(h, s2);
+    WS_CUDA_OK(cudaEventRecord(h->ev_join, s2));
     ws_timer_begin(h, WS_TIMER_MERGE);
     brick_list_kernel<true><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_surf, h->d_counters);
     merge_kernel<<<h->sm_count * MERGE_CTAS, 256, 0, s>>>(h->g, P, list_surf, h->d_counters, h->pending_cap,
                                                           h->d_pend_addr, h->d_pend_prev, h->d_pend_key);
     ws_timer_end(h);
-    // free-space phase: state bits; candidates landing on parked voxels go straight to the replay
     ws_timer_begin(h, WS_TIMER_MARCH);
-    LS_LAUNCH(false, true);
+    LS_LAUNCH_ON(false, true, 2u, s);
     ws_timer_end(h);
+    WS_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
     ws_timer_begin(h, WS_TIMER_REPLAY);
     launch_replay(h, P);
     ws_timer_end(h);
@@ -2100,7 +2135,7 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
     brick_list_kernel<false><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_all, h->d_counters);
     fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, list_all, h->d_counters);
     ws_timer_end(h);
-    h->launches += 9;
+    h->launches += 11;
   }
   WS_CUDA_OK(cudaMemcpyAsync(h_ctr, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
   if (pose_on_device)
@@ -2147,10 +2182,10 @@ void ws_update_finish(ws_handle *h, UpdateCounters *h_ctr, void *h_pose_out, cud
       cap_chunks = (unsigned)h->rec_cap_chunks;
       out.list = h->d_list; out.list_cap = (unsigned)h->list_cap;
       rec_reset_kernel<<<1, 1, 0, s>>>(h->d_counters);
-      LS_LAUNCH(true, false);
+      LS_LAUNCH_ON(true, false, 0u, s);
       march_kernel<false><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_gen_list, h->d_counters, h->d_rec,
                                                                  h->d_chunk_fill, cap_chunks, d_pose);
-      LS_LAUNCH(false, true);
+      LS_LAUNCH_ON(false, true, 2u, s);
       launch_replay(h, P);
       brick_list_kernel<false><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_all, h->d_counters);
       fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, list_all, h->d_counters);

@@ -23,6 +23,7 @@ struct UpdateParams
   int half_res;        // map_resolution / 2
   int n_points;
   int far_len;         // march lengths >= far_len can meet an interpolated winner: their candidates are recorded
+  int far_block;       // first step block (LS_BLOCK steps) that holds a far-field step
   // fast path of the march (march_math.cuh)
   FastDiv div_half;    // / (map_resolution / 2)
   FastDiv32 div_res32; // / map_resolution, 32-bit magic
@@ -71,12 +72,12 @@ struct UpdateCounters
   unsigned rounds;
   unsigned n_parked;         // voxels parked by the merge pass (before any replay round)
   unsigned n_work;
-  unsigned n_items[2];       // (ray group, step block) work items of the lockstep march: surface / free-space phase
+  unsigned n_items[3];       // (ray group, step block) work items of the lockstep march: surface / free space near / free space far
   unsigned n_general;        // rays outside the 32-bit fast path: marched by the literal-arithmetic kernel
   unsigned gen_counter;      // ... and its dynamic fetch counter
-  unsigned pad0[14];
-  unsigned item_counter[2];  // dynamic item fetch of the persistent march warps, per phase (own 128-byte line)
-  unsigned pad1[30];
+  unsigned pad0[13];
+  unsigned item_counter[3];  // dynamic item fetch of the persistent march warps, per item table (own 128-byte line)
+  unsigned pad1[29];
   unsigned n_chunks;         // record chunks handed out (own 128-byte line)
   unsigned pad2[31];
   unsigned rec_overflow;     // the record did not fit its buffer
@@ -145,6 +146,8 @@ struct ws_handle
     std::string error;
   } track[2];
   cudaStream_t copy_stream = nullptr;
+  cudaStream_t stream2 = nullptr;   // the free-space march runs here, beside the surface march + merge
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_f0 = nullptr, ev_f1 = nullptr;
   int track_next = 0, track_in_flight = 0;
   bool rec_headroom_ok = false;     // a finished scan left the candidate record well below its capacity
   bool track_has_pose = false;      // d_pose holds the pose of the previous tracked scan      // dynamic shared memory of the lockstep march raised above 48 KB
@@ -271,8 +274,8 @@ void ws_launch_test_reduce(ws_handle *h, const i64 *d_jacobis, const int *d_valu
 #define WS_TIMER_MERGE 1
 #define WS_TIMER_REG 2
 #define WS_TIMER_REPLAY 3
-void ws_timer_begin(ws_handle *h, int kind);
-void ws_timer_end(ws_handle *h);
+void ws_timer_begin(ws_handle *h, int kind, cudaStream_t stream = nullptr);
+void ws_timer_end(ws_handle *h, cudaStream_t stream = nullptr);
 
 size_t ws_reg_mailbox_bytes(int world);
 
