@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--ref-update", default="omp", choices=["omp", "seq"],
+                    help="reference arm: which of the reference's CPU update_tsdf variants is timed")
     ap.add_argument("--grid", type=int, default=512, help="local map side in voxels")
     ap.add_argument("--res", type=int, default=50, help="voxel size in mm")
     ap.add_argument("--beams", type=int, default=128)
@@ -180,8 +182,9 @@ def make_frames(args, count):
 def run_reference(args):
     """The reference's CPU implementation of the path (oracle port of src/cpu; the reference itself needs
     Eigen/HDF5/PCL/ROS and cannot be built here) on this box's host cores: WHOLE scans, every ray, measured
-    wall time per step (update_tsdf single-threaded as the reference launches it, update_tsdf.cpp:405;
-    register_cloud on every OpenMP thread)."""
+    wall time per step.  update_tsdf = the reference's OpenMP overload (update_tsdf.cpp:566-724) on every host
+    thread -- the faster of its two CPU variants; --ref-update seq times the sequential one (update_tsdf.cpp:397-564,
+    thread_count = 1, the parity target) instead.  register_cloud on every OpenMP thread."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -197,10 +200,19 @@ def run_reference(args):
     except (AttributeError, OSError):
         orc.set_num_threads(os.cpu_count() or 1)
     cores = orc.num_threads()
+    use_omp = args.ref_update == "omp" and cores > 1
+
+    def update(cloud, pos, up):
+        if use_omp:
+            return orc.update_tsdf_omp(om, cloud, pos, up, TAU, MAX_WEIGHT, res, cores)
+        return orc.update_tsdf(om, cloud, pos, up, TAU, MAX_WEIGHT, res)
+
     pos, up = fp.convert_pose_to_gpu(frames[0]["pose"], res)
-    orc.update_tsdf(om, frames[0]["points_map"], pos, up, TAU, MAX_WEIGHT, res)
+    t0 = time.perf_counter()
+    orc.update_tsdf(om, frames[0]["points_map"], pos, up, TAU, MAX_WEIGHT, res)      # first scan: sequential variant, timed once
+    t_seq = time.perf_counter() - t0
     I = np.eye(4, dtype=np.float32)
-    times = []
+    times, t_updates = [], []
     n_full = len(frames[1]["points_prior"])
     for k in range(1, K + W + 1):
         f = frames[k]
@@ -213,22 +225,27 @@ def run_reference(args):
             pose = f["pose"]
             cloud = np.ascontiguousarray(f["points_map"])
         pos, up = fp.convert_pose_to_gpu(pose, res)
-        orc.update_tsdf(om, cloud, pos, up, TAU, MAX_WEIGHT, res)
-        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        update(cloud, pos, up)
+        t2 = time.perf_counter()
         if k > W:
-            times.append(dt)
+            times.append(t2 - t0)
+            t_updates.append(t2 - t1)
     total = sum(times)
     value = K / total
-    sample = ("%d whole scans of %d rays (every ray), measured wall time; update_tsdf single-threaded as launched by "
-              "the reference (update_tsdf.cpp:405), register_cloud %d iterations on %d OpenMP threads"
-              % (K, n_full, GN_ITERS, cores))
+    variant = ("OpenMP overload (update_tsdf.cpp:566-724) on %d threads" % cores) if use_omp else \
+        "sequential variant (update_tsdf.cpp:397-564, thread_count = 1)"
+    sample = ("%d whole scans of %d rays (every ray), measured wall time; update_tsdf: %s, register_cloud %d "
+              "iterations on %d OpenMP threads" % (K, n_full, variant, GN_ITERS, cores))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": K, "warmup": W, "ms_per_step": 1000.0 * total / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32+int64", "data": "synthetic",
         "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "update_variant": "omp" if use_omp else "sequential",
+                         "update_s": sum(t_updates) / K, "sequential_update_s": t_seq},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -679,31 +696,42 @@ def reference_cuda(args, frames, s, scans=5):
 
 
 def cpu_baseline(args, frames, s):
-    """The oracle on this box's host cores: ONE full scan (update_tsdf of frame 0 single-threaded, as the
-    reference launches it, + register_cloud of frame 1, 20 iterations on all cores)."""
+    """The oracle on this box's host cores: ONE full scan -- update_tsdf of frame 0 by both of the reference's CPU
+    variants (sequential :397-564, the parity target; OpenMP overload :566-724 on all cores) + register_cloud of
+    frame 1, 20 iterations on all cores.  `value` uses the faster update."""
     from oracle import oracle as orc
     from warpsense_b200 import fixedpoint as fp
     side, res = args.grid, args.res
-    om = orc.LocalMap(side, side, side, TAU, 0)
     try:
         orc.set_num_threads(len(os.sched_getaffinity(0)))
     except (AttributeError, OSError):
         orc.set_num_threads(os.cpu_count() or 1)
+    cores = orc.num_threads()
     pos, up = fp.convert_pose_to_gpu(frames[0]["pose"], res)
+    t_omp = None
+    if cores > 1:
+        om = orc.LocalMap(side, side, side, TAU, 0)
+        t0 = time.perf_counter()
+        orc.update_tsdf_omp(om, frames[0]["points_map"], pos, up, TAU, MAX_WEIGHT, res, cores)
+        t_omp = time.perf_counter() - t0
+        del om
+    om = orc.LocalMap(side, side, side, TAU, 0)
     t0 = time.perf_counter()
     st = orc.update_tsdf(om, frames[0]["points_map"], pos, up, TAU, MAX_WEIGHT, res)
-    t_upd = time.perf_counter() - t0
+    t_seq = time.perf_counter() - t0
+    t_upd = min(t_seq, t_omp) if t_omp is not None else t_seq
     t_reg = 0.0
     if not args.update_only:
         cloud = frames[1]["points_prior"].copy()
         t0 = time.perf_counter()
         orc.register_cloud(om, cloud, np.eye(4, dtype=np.float32), GN_ITERS, IT_WEIGHT, EPSILON, res)
         t_reg = time.perf_counter() - t0
-    return {"value": 1.0 / (t_upd + t_reg), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
-            "sample": "1 full scan: update_tsdf of frame 0 single-threaded (%.2f s, C=%d, T=%d) + register_cloud of "
-                      "frame 1, %d iterations on %d OpenMP threads (%.2f s)"
-                      % (t_upd, st["n_candidates"], st["n_touched"], GN_ITERS, orc.num_threads(), t_reg),
-            "update_s": t_upd, "reg_s": t_reg}
+    return {"value": 1.0 / (t_upd + t_reg), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "1 full scan: update_tsdf of frame 0 (sequential variant %.2f s, OpenMP overload on %d threads "
+                      "%s; C=%d, T=%d) + register_cloud of frame 1, %d iterations on %d OpenMP threads (%.2f s)"
+                      % (t_seq, cores, "%.2f s" % t_omp if t_omp is not None else "n/a", st["n_candidates"],
+                         st["n_touched"], GN_ITERS, cores, t_reg),
+            "update_s": t_upd, "sequential_update_s": t_seq, "omp_update_s": t_omp, "reg_s": t_reg}
 
 
 if __name__ == "__main__":

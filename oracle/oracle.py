@@ -88,6 +88,8 @@ def lib():
         "orc_calc_weight": (C.c_int, [C.c_int, C.c_int, C.c_int]),
         "orc_update_tsdf": (None, [vp, vp, C.c_int64, i32p, i32p, C.c_int, C.c_int, C.c_int,
                                    C.POINTER(UpdateStats)]),
+        "orc_update_tsdf_omp": (None, [vp, vp, C.c_int64, i32p, i32p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.POINTER(UpdateStats)]),
         "orc_reg_step": (None, [vp, vp, C.c_int64, f32p, C.c_int, i64p, i64p, i32p, i32p]),
         "orc_reg_solve": (C.c_float, [i64p, i64p, C.c_int32, C.c_int32, C.c_float, f32p, f64p]),
         "orc_xi_to_transform": (None, [f64p, i32p, f32p]),
@@ -366,6 +368,17 @@ def update_tsdf(m, points, scanner_pos, up, tau, max_weight, map_resolution):
     st = UpdateStats()
     lib().orc_update_tsdf(m._h, pts.ctypes.data, len(pts), _p(sp, C.c_int32), _p(u, C.c_int32),
                           int(tau), int(max_weight), int(map_resolution), C.byref(st))
+    return st.as_dict()
+
+
+def update_tsdf_omp(m, points, scanner_pos, up, tau, max_weight, map_resolution, threads=0):
+    """src/cpu/update_tsdf.cpp:566-724, the OpenMP overload (threads = 0: all cores).  For timing: with more than
+    one thread its result differs from update_tsdf's wherever two threads reach the same voxel."""
+    pts = _points(points)
+    sp, u = _i3(scanner_pos), _i3(up)
+    st = UpdateStats()
+    lib().orc_update_tsdf_omp(m._h, pts.ctypes.data, len(pts), _p(sp, C.c_int32), _p(u, C.c_int32),
+                              int(tau), int(max_weight), int(map_resolution), int(threads), C.byref(st))
     return st.as_dict()
 
 

@@ -611,132 +611,251 @@ static inline int64_t scan_map_emplace(scan_map *s, int64_t key, orc_entry val, 
 
 /* ------------------------------------------------------- update_tsdf oracle */
 
+/* One scan point: the ray march with its fan of interpolated voxels into `values`
+ * (update_tsdf.cpp:418-514; the rmagine/OpenMP variant's loop body :589-669 is the same code minus the
+ * scan-point bounds check :430-434, which `check_point` switches) */
+typedef struct {
+  int res, tau, weight_epsilon, dz_per_distance;
+  int32_t pos[3];
+  int64_t upl[3];
+} march_consts;
+
+static void march_point(const orc_map *m, const march_consts *k, const orc_point *pt, int check_point,
+                        scan_map *values, orc_update_stats *st)
+{
+  const int res = k->res, tau = k->tau, weight_epsilon = k->weight_epsilon;
+  const int32_t *pos = k->pos;
+  const int64_t *upl = k->upl;
+  const int32_t p[3] = { pt->x, pt->y, pt->z };
+  int32_t d[3] = { wrap_sub(p[0], pos[0]), wrap_sub(p[1], pos[1]), wrap_sub(p[2], pos[2]) }; /* :422 */
+  int32_t distance = norm_i32(d[0], d[1], d[2]);                            /* :423 */
+  if (distance == 0) return;                                                /* :424-428 */
+
+  if (check_point && !orc_map_in_bounds(m, p[0] / res, p[1] / res, p[2] / res)) return;  /* :430-434 */
+  st->n_marched++;
+
+  int64_t nd[3], c1[3], iv[3];
+  for (int a = 0; a < 3; a++) nd[a] = ((int64_t)d[a] * MR) / distance;      /* :438 */
+  c1[0] = nd[1] * upl[2] - nd[2] * upl[1];                                  /* :439 inner cross */
+  c1[1] = nd[2] * upl[0] - nd[0] * upl[2];
+  c1[2] = nd[0] * upl[1] - nd[1] * upl[0];
+  for (int a = 0; a < 3; a++) c1[a] /= MR;
+  iv[0] = nd[1] * c1[2] - nd[2] * c1[1];                                    /* :439 outer cross */
+  iv[1] = nd[2] * c1[0] - nd[0] * c1[2];
+  iv[2] = nd[0] * c1[1] - nd[1] * c1[0];
+  int64_t inorm = norm_i64(iv[0], iv[1], iv[2]);                            /* :440 */
+  if (inorm == 0) return;                                                   /* :441-445 */
+  for (int a = 0; a < 3; a++) iv[a] = (iv[a] * MR) / inorm;                 /* :446 */
+
+  int have_prev = 0;                                                        /* :448 (uninitialised) */
+  int32_t prev[2] = { 0, 0 };
+
+  for (int32_t len = 1; len <= distance + tau; len += res / 2)              /* :450 */
+  {
+    int32_t proj[3], index[3];
+    for (int a = 0; a < 3; a++)
+    {
+      proj[a] = wrap_add(pos[a], wrap_mul(d[a], len) / distance);           /* :452 */
+      index[a] = proj[a] / res;                                             /* :453 */
+    }
+    if (have_prev && index[0] == prev[0] && index[1] == prev[1]) continue;  /* :455-458 */
+    prev[0] = index[0]; prev[1] = index[1]; have_prev = 1;                  /* :459 */
+    if (!orc_map_in_bounds(m, index[0], index[1], index[2])) continue;      /* :460-463 */
+
+    int32_t tc[3];
+    for (int a = 0; a < 3; a++) tc[a] = wrap_add(wrap_mul(index[a], res), res / 2); /* :466 */
+    long long value = norm_i32(wrap_sub(p[0], tc[0]), wrap_sub(p[1], tc[1]), wrap_sub(p[2], tc[2])); /* :467 */
+    if (value > (long long)tau) value = tau;                                /* :468 */
+    if (len > distance) value = -value;                                     /* :469-472 */
+
+    int weight = WR;                                                        /* :475 */
+    if (value < -weight_epsilon)
+      weight = (int)(WR * (tau + value) / (tau - weight_epsilon));          /* :476-479 */
+    if (weight == 0) continue;                                              /* :480-483 */
+
+    int32_t delta_z = wrap_mul(k->dz_per_distance, len) / MR;               /* :485 */
+    int32_t iter_steps = (delta_z * 2) / res + 1;                           /* :486 */
+    int32_t mid = delta_z / res;                                            /* :487 */
+    int32_t lowest[3];
+    for (int a = 0; a < 3; a++)
+      lowest[a] = wrap_sub(proj[a], (int32_t)(((int64_t)delta_z * iv[a]) / MR)); /* :488 */
+
+    for (int32_t step = 0; step < iter_steps; ++step)                       /* :491 */
+    {
+      int32_t idx[3];
+      for (int a = 0; a < 3; a++)
+        idx[a] = wrap_add(lowest[a], (int32_t)(((int64_t)wrap_mul(step, res) * iv[a]) / MR)) / res; /* :493 */
+      if (!orc_map_in_bounds(m, idx[0], idx[1], idx[2])) continue;          /* :495-498 */
+
+      int w = (step != mid) ? -weight : weight;                             /* :503-506 */
+      orc_entry tmp = orc_make_entry((int)value, w);
+      st->n_candidates++;
+      if (w < 0) st->n_neg_candidates++;
+
+      int inserted;
+      int64_t slot = scan_map_emplace(values, orc_map_index(m, idx[0], idx[1], idx[2]), tmp, &inserted); /* :508 */
+      if (!inserted)
+      {
+        orc_entry ex = values->vals[slot];
+        long long av = value < 0 ? -value : value;
+        if (av < abs(orc_entry_value(ex)) || orc_entry_weight(ex) < 0)      /* :509 */
+          values->vals[slot] = tmp;                                         /* :511 */
+      }
+    }
+  }
+}
+
+/* one winner into the grid: update_tsdf.cpp:542-560 (= :708-721); returns 1 if the entry was written */
+static int merge_winner(orc_entry *e, orc_entry win, int max_weight)
+{
+  int value = orc_entry_value(win);
+  int weight = orc_entry_weight(win);
+  int ev = orc_entry_value(*e), ew = orc_entry_weight(*e);
+  if (weight > 0 && ew > 0)                                                 /* :546-551 */
+  {
+    int nv = (ev * ew + value * weight) / (ew + weight);
+    int nw = (ew + weight) < max_weight ? (ew + weight) : max_weight;
+    *e = orc_make_entry(nv, nw);
+    return 1;
+  }
+  if (weight != 0 && ew <= 0)                                               /* :553-557 */
+  {
+    *e = orc_make_entry(value, weight);
+    return 1;
+  }
+  return 0;
+}
+
+static void march_consts_init(march_consts *k, const int scanner_pos[3], const int up[3], int tau, int res)
+{
+  float angle = 45.f / 128.f;                                                 /* :400 */
+  k->dz_per_distance = d2i(tan((double)(angle / 180) * M_PI) / 2.0 * MR);     /* :401 */
+  k->weight_epsilon = tau / 10;                                               /* :403 */
+  k->res = res; k->tau = tau;
+  for (int a = 0; a < 3; a++)
+  {
+    k->pos[a] = wrap_mul(scanner_pos[a], res);                                /* :410 */
+    k->upl[a] = up[a];
+  }
+}
+
 /* src/cpu/update_tsdf.cpp:397-564 (up-vector ray march, Eigen variant, thread_count = 1) */
 void orc_update_tsdf(orc_map *m, const orc_point *pts, int64_t n,
                      const int scanner_pos[3], const int up[3],
                      int tau, int max_weight, int map_resolution,
                      orc_update_stats *stats)
 {
-  const int res = map_resolution;
-  float angle = 45.f / 128.f;                                                 /* :400 */
-  int dz_per_distance = d2i(tan((double)(angle / 180) * M_PI) / 2.0 * MR);    /* :401 */
-  int weight_epsilon = tau / 10;                                              /* :403 */
-
+  march_consts k;
+  march_consts_init(&k, scanner_pos, up, tau, map_resolution);
   orc_update_stats st;
   memset(&st, 0, sizeof(st));
   st.n_points = n;
 
   scan_map values;
   scan_map_init(&values, 1 << 16);
-
-  const int32_t pos[3] = { wrap_mul(scanner_pos[0], res), wrap_mul(scanner_pos[1], res),
-                           wrap_mul(scanner_pos[2], res) };                   /* :410 */
-  const int64_t upl[3] = { up[0], up[1], up[2] };
-
-  for (int64_t pi = 0; pi < n; pi++)
-  {
-    const int32_t p[3] = { pts[pi].x, pts[pi].y, pts[pi].z };
-    int32_t d[3] = { wrap_sub(p[0], pos[0]), wrap_sub(p[1], pos[1]), wrap_sub(p[2], pos[2]) }; /* :422 */
-    int32_t distance = norm_i32(d[0], d[1], d[2]);                            /* :423 */
-    if (distance == 0) continue;                                              /* :424-428 */
-
-    if (!orc_map_in_bounds(m, p[0] / res, p[1] / res, p[2] / res)) continue;  /* :430-434 */
-    st.n_marched++;
-
-    int64_t nd[3], c1[3], iv[3];
-    for (int a = 0; a < 3; a++) nd[a] = ((int64_t)d[a] * MR) / distance;      /* :438 */
-    c1[0] = nd[1] * upl[2] - nd[2] * upl[1];                                  /* :439 inner cross */
-    c1[1] = nd[2] * upl[0] - nd[0] * upl[2];
-    c1[2] = nd[0] * upl[1] - nd[1] * upl[0];
-    for (int a = 0; a < 3; a++) c1[a] /= MR;
-    iv[0] = nd[1] * c1[2] - nd[2] * c1[1];                                    /* :439 outer cross */
-    iv[1] = nd[2] * c1[0] - nd[0] * c1[2];
-    iv[2] = nd[0] * c1[1] - nd[1] * c1[0];
-    int64_t inorm = norm_i64(iv[0], iv[1], iv[2]);                            /* :440 */
-    if (inorm == 0) continue;                                                 /* :441-445 */
-    for (int a = 0; a < 3; a++) iv[a] = (iv[a] * MR) / inorm;                 /* :446 */
-
-    int have_prev = 0;                                                        /* :448 (uninitialised) */
-    int32_t prev[2] = { 0, 0 };
-
-    for (int32_t len = 1; len <= distance + tau; len += res / 2)              /* :450 */
-    {
-      int32_t proj[3], index[3];
-      for (int a = 0; a < 3; a++)
-      {
-        proj[a] = wrap_add(pos[a], wrap_mul(d[a], len) / distance);           /* :452 */
-        index[a] = proj[a] / res;                                             /* :453 */
-      }
-      if (have_prev && index[0] == prev[0] && index[1] == prev[1]) continue;  /* :455-458 */
-      prev[0] = index[0]; prev[1] = index[1]; have_prev = 1;                  /* :459 */
-      if (!orc_map_in_bounds(m, index[0], index[1], index[2])) continue;      /* :460-463 */
-
-      int32_t tc[3];
-      for (int a = 0; a < 3; a++) tc[a] = wrap_add(wrap_mul(index[a], res), res / 2); /* :466 */
-      long long value = norm_i32(wrap_sub(p[0], tc[0]), wrap_sub(p[1], tc[1]), wrap_sub(p[2], tc[2])); /* :467 */
-      if (value > (long long)tau) value = tau;                                /* :468 */
-      if (len > distance) value = -value;                                     /* :469-472 */
-
-      int weight = WR;                                                        /* :475 */
-      if (value < -weight_epsilon)
-        weight = (int)(WR * (tau + value) / (tau - weight_epsilon));          /* :476-479 */
-      if (weight == 0) continue;                                              /* :480-483 */
-
-      int32_t delta_z = wrap_mul(dz_per_distance, len) / MR;                  /* :485 */
-      int32_t iter_steps = (delta_z * 2) / res + 1;                           /* :486 */
-      int32_t mid = delta_z / res;                                            /* :487 */
-      int32_t lowest[3];
-      for (int a = 0; a < 3; a++)
-        lowest[a] = wrap_sub(proj[a], (int32_t)(((int64_t)delta_z * iv[a]) / MR)); /* :488 */
-
-      for (int32_t step = 0; step < iter_steps; ++step)                       /* :491 */
-      {
-        int32_t idx[3];
-        for (int a = 0; a < 3; a++)
-          idx[a] = wrap_add(lowest[a], (int32_t)(((int64_t)wrap_mul(step, res) * iv[a]) / MR)) / res; /* :493 */
-        if (!orc_map_in_bounds(m, idx[0], idx[1], idx[2])) continue;          /* :495-498 */
-
-        int w = (step != mid) ? -weight : weight;                             /* :503-506 */
-        orc_entry tmp = orc_make_entry((int)value, w);
-        st.n_candidates++;
-        if (w < 0) st.n_neg_candidates++;
-
-        int inserted;
-        int64_t slot = scan_map_emplace(&values, orc_map_index(m, idx[0], idx[1], idx[2]), tmp, &inserted); /* :508 */
-        if (!inserted)
-        {
-          orc_entry ex = values.vals[slot];
-          long long av = value < 0 ? -value : value;
-          if (av < abs(orc_entry_value(ex)) || orc_entry_weight(ex) < 0)      /* :509 */
-            values.vals[slot] = tmp;                                          /* :511 */
-        }
-      }
-    }
-  }
+  for (int64_t pi = 0; pi < n; pi++) march_point(m, &k, &pts[pi], 1, &values, &st);
 
   /* merge into the grid: update_tsdf.cpp:517-561 (single thread => no cross-thread skip) */
   st.n_touched = values.count;
   for (int64_t s = 0; s < values.cap; s++)
   {
     if (values.keys[s] < 0) continue;
-    int value = orc_entry_value(values.vals[s]);
-    int weight = orc_entry_weight(values.vals[s]);
-    orc_entry *e = &m->data[values.keys[s]];
-    int ev = orc_entry_value(*e), ew = orc_entry_weight(*e);
-    if (weight > 0 && ew > 0)                                                 /* :546-551 */
-    {
-      int nv = (ev * ew + value * weight) / (ew + weight);
-      int nw = (ew + weight) < max_weight ? (ew + weight) : max_weight;
-      *e = orc_make_entry(nv, nw);
-      st.n_written++;
-    }
-    else if (weight != 0 && ew <= 0)                                          /* :553-557 */
-    {
-      *e = orc_make_entry(value, weight);
-      st.n_written++;
-    }
+    st.n_written += merge_winner(&m->data[values.keys[s]], values.vals[s], max_weight);
   }
   scan_map_free(&values);
+  if (stats) *stats = st;
+}
+
+static int64_t scan_map_find(const scan_map *s, int64_t key)
+{
+  uint64_t j = mix64((uint64_t)key) & (uint64_t)(s->cap - 1);
+  while (s->keys[j] >= 0)
+  {
+    if (s->keys[j] == key) return (int64_t)j;
+    j = (j + 1) & (uint64_t)(s->cap - 1);
+  }
+  return -1;
+}
+
+/* src/cpu/update_tsdf.cpp:566-724: the rmagine-point overload, the reference's only multi-threaded CPU update
+ * (thread_count = omp_get_max_threads(), :575).  The scan is split statically over the threads (:586), each with
+ * its own candidate map; after a barrier every thread applies those of its winners that no other thread beats
+ * with a strictly smaller |value| (:674-693) -- a tie between threads is applied by both, and the preference for
+ * real over interpolated winners does not cross threads, so its result differs from the sequential variant's
+ * except with one thread.  No scan-point bounds check here (:589-599).  Kept for TIMING (bench.py's
+ * cpu_baseline "omp_variant"); the parity oracle is orc_update_tsdf.
+ * The reference applies the winners from all threads concurrently (a race on ties); here every voxel has one
+ * owner thread that applies its winners in thread order, so the port is deterministic and as parallel. */
+void orc_update_tsdf_omp(orc_map *m, const orc_point *pts, int64_t n,
+                         const int scanner_pos[3], const int up[3],
+                         int tau, int max_weight, int map_resolution, int threads,
+                         orc_update_stats *stats)
+{
+  march_consts k;
+  march_consts_init(&k, scanner_pos, up, tau, map_resolution);
+  if (threads < 1) threads = omp_get_max_threads();                           /* :575 */
+  scan_map *values = (scan_map *)malloc((size_t)threads * sizeof(scan_map));
+  orc_update_stats *sts = (orc_update_stats *)calloc((size_t)threads, sizeof(orc_update_stats));
+  char *skip_flags = NULL;
+  for (int t = 0; t < threads; t++) scan_map_init(&values[t], 1 << 14);
+
+#pragma omp parallel num_threads(threads)
+  {
+    const int t = omp_get_thread_num();
+    /* schedule(static), :586: contiguous blocks of the scan in thread order */
+    const int64_t per = n / threads, extra = n % threads;
+    const int64_t lo = t * per + (t < extra ? t : extra), hi = lo + per + (t < extra ? 1 : 0);
+    for (int64_t pi = lo; pi < hi; pi++) march_point(m, &k, &pts[pi], 0, &values[t], &sts[t]);
+  }
+
+  /* :674-693 the cross-thread rule, evaluated in parallel (read-only) ... */
+  int64_t total_cap = 0;
+  int64_t *cap_off = (int64_t *)malloc((size_t)(threads + 1) * sizeof(int64_t));
+  for (int t = 0; t < threads; t++) { cap_off[t] = total_cap; total_cap += values[t].cap; }
+  cap_off[threads] = total_cap;
+  skip_flags = (char *)calloc((size_t)total_cap, 1);
+#pragma omp parallel num_threads(threads)
+  {
+    const int t = omp_get_thread_num();
+    for (int64_t s = 0; s < values[t].cap; s++)
+    {
+      if (values[t].keys[s] < 0) continue;
+      const int mine = abs(orc_entry_value(values[t].vals[s]));
+      for (int i = 0; i < threads; i++)
+      {
+        if (i == t) continue;
+        int64_t o = scan_map_find(&values[i], values[t].keys[s]);
+        if (o >= 0 && abs(orc_entry_value(values[i].vals[o])) < mine) { skip_flags[cap_off[t] + s] = 1; break; }
+      }
+    }
+  }
+  /* ... :695-721 applied by all threads; each owns the voxels with key % threads == its number and walks the
+   * maps in thread order, which is the sequential thread-order result without the reference's race on ties */
+  orc_update_stats st;
+  memset(&st, 0, sizeof(st));
+  st.n_points = n;
+  int64_t written = 0;
+#pragma omp parallel num_threads(threads) reduction(+ : written)
+  {
+    const int me = omp_get_thread_num();
+    for (int t = 0; t < threads; t++)
+      for (int64_t s = 0; s < values[t].cap; s++)
+      {
+        const int64_t key = values[t].keys[s];
+        if (key < 0 || (int)(key % threads) != me || skip_flags[cap_off[t] + s]) continue;
+        written += merge_winner(&m->data[key], values[t].vals[s], max_weight);
+      }
+  }
+  st.n_written = written;
+  for (int t = 0; t < threads; t++)
+  {
+    st.n_marched += sts[t].n_marched;
+    st.n_candidates += sts[t].n_candidates;
+    st.n_neg_candidates += sts[t].n_neg_candidates;
+    st.n_touched += values[t].count;          /* per-thread maps: a voxel two threads reached counts twice */
+    scan_map_free(&values[t]);
+  }
+  free(values); free(sts); free(skip_flags); free(cap_off);
   if (stats) *stats = st;
 }
 

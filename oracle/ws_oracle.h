@@ -100,6 +100,12 @@ void orc_update_tsdf(orc_map *m, const orc_point *pts, int64_t n,
                      const int scanner_pos[3], const int up[3],
                      int tau, int max_weight, int map_resolution,
                      orc_update_stats *stats /* may be NULL */);
+/* src/cpu/update_tsdf.cpp:566-724: the OpenMP overload (per-thread candidate maps + cross-thread rule); equals
+ * orc_update_tsdf with threads = 1 and every scan point inside the map; for timing.  threads < 1: all cores */
+void orc_update_tsdf_omp(orc_map *m, const orc_point *pts, int64_t n,
+                         const int scanner_pos[3], const int up[3],
+                         int tau, int max_weight, int map_resolution, int threads,
+                         orc_update_stats *stats /* may be NULL */);
 
 /* ---- the registration oracle: src/cpu/registration.cpp:14-177 ---- */
 /* one Gauss-Newton accumulation pass (registration.cpp:52-118): H column-major 6x6 */

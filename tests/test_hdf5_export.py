@@ -56,6 +56,25 @@ def test_writer_against_independent_reader(tmp_path, n_chunks, n_poses):
         list(g.walk())
 
 
+def test_writer_against_libhdf5(tmp_path):
+    """Where h5py (libhdf5) exists: the file the writer produces opens with it and holds the same datasets and
+    attributes.  Neither exists in the build image, so there this test skips and the format stays checked by
+    tools/h5min.py and the C++ loader only (HDF5 parity unpinned)."""
+    h5py = pytest.importorskip("h5py")
+    rng = np.random.default_rng(11)
+    chunks = {(i - 5, 2 * i, -i): rng.integers(0, 2 ** 32, 64 ** 3, dtype=np.uint32) for i in range(12)}
+    poses = np.round(rng.normal(size=(5, 7)).astype(np.float32) * 1000) / 1000
+    path = str(tmp_path / "m.h5")
+    api.write_map_hdf5(path, chunks, 600, (20, 20, 5), 0.6, 64, 640, poses)
+    with h5py.File(path, "r") as f:
+        assert set(f["/map"].keys()) == {"%d_%d_%d" % c for c in chunks}
+        assert int(f["/map"].attrs["tau"]) == 600 and int(f["/map"].attrs["map_resolution"]) == 64
+        for c, want in chunks.items():
+            assert np.array_equal(f["/map/%d_%d_%d" % c][...].view(np.uint32).reshape(-1), want)
+        for i in range(5):
+            assert np.array_equal(f["/poses/%d/pose" % i][...].reshape(-1), poses[i])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_poses", [0, 3])
 def test_export_roundtrip(tmp_path, n_poses):

@@ -144,3 +144,29 @@ def test_entry_packing():
     assert orc.make_entry(-1, 2) == (0xFFFF | (2 << 16))
     assert orc.make_entry(3000, 0) == 3000
     assert orc.make_entry(5, -64) == (5 | (0xFFC0 << 16))
+
+
+def test_update_tsdf_omp_variant():
+    """src/cpu/update_tsdf.cpp:566-724, the OpenMP overload (timing only): with one thread it is the
+    sequential variant; with several it reaches the same voxels with the same candidates, and differs only where
+    two threads met on a voxel."""
+    rng = np.random.default_rng(17)
+    size, res, tau = 65, 64, 600
+    d = rng.normal(size=(3000, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pts = (d * rng.uniform(400, 1900, (3000, 1))).astype(np.int32)
+    pos, up = (0, 0, 0), (0, 0, 1024)
+    maps, stats = [], []
+    for kind in ("seq", 1, 4):
+        m = orc.LocalMap(size, size, size, tau, 0)
+        if kind == "seq":
+            st = orc.update_tsdf(m, pts, pos, up, tau, 640, res)
+        else:
+            st = orc.update_tsdf_omp(m, pts, pos, up, tau, 640, res, kind)
+        maps.append(np.array(m.data, copy=True))
+        stats.append(st)
+    assert np.array_equal(maps[0], maps[1]) and stats[0] == stats[1]
+    assert stats[2]["n_candidates"] == stats[0]["n_candidates"] and stats[2]["n_touched"] >= stats[0]["n_touched"]
+    touched = lambda a: (a >> 16).astype(np.int16) != 0                      # weight != 0
+    assert np.array_equal(touched(maps[0]), touched(maps[2]))
+    assert (maps[0] != maps[2]).mean() < 0.05
