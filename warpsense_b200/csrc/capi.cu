@@ -83,7 +83,11 @@ void free_handle(ws_handle *h)
     if (t.done) cudaEventDestroy(t.done);
   }
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-  if (h->stream2) { cudaStreamDestroy(h->stream2); cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); }
+  if (h->stream2)
+  {
+    cudaStreamDestroy(h->stream2); cudaStreamDestroy(h->stream3);
+    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_merged); cudaEventDestroy(h->ev_scanned);
+  }
   cudaFree(h->d_shift_buf); cudaFreeHost(h->h_shift_buf);
   if (h->spill_fp) { std::fclose(h->spill_fp); std::remove(h->spill_path.c_str()); }
   detach_peers(h); cudaFree(h->d_mail); cudaFree(h->d_pose); cudaFreeHost(h->h_pose);

@@ -1632,29 +1632,22 @@ fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict
   }
 }
 
-// Cooperative launch: settles every parked voxel on the device (see the file header, step 4).
+// Replay, first half (plain launch, runs beside the far-field free-space march on its own stream): the surface
+// record against the parked voxels.  One warp per pair of 64-entry chunks; four independent
+// record -> parked bit -> key -> parked-winner chains per lane are in flight at a time (the pass streams the
+// record at DRAM speed and is otherwise latency bound); the per-voxel state (4 bits per voxel, L2 resident)
+// spares the key lookup for the records whose voxel is not parked.
 __global__ void __launch_bounds__(256, 4)
-replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict__ ctr, const unsigned pending_cap,
-              u64 *__restrict__ pend_addr, u64 *__restrict__ pend_prev, u64 *__restrict__ pend_key,
-              const Rec *__restrict__ rec, const unsigned *__restrict__ chunk_fill, const unsigned cap_chunks,
-              Rec *__restrict__ list, const unsigned list_cap, unsigned *__restrict__ active0, unsigned *__restrict__ active1)
+replay_scan_kernel(const GridDesc g, UpdateCounters *__restrict__ ctr, const unsigned pending_cap,
+                   u64 *__restrict__ pend_key, const Rec *__restrict__ rec, const unsigned *__restrict__ chunk_fill,
+                   const unsigned cap_chunks, Rec *__restrict__ list, const unsigned list_cap)
 {
-  cg::grid_group grid = cg::this_grid();
-  unsigned n_pend = ctr->n_pending;
-  if (n_pend > pending_cap) n_pend = pending_cap;
-  if (n_pend == 0u || ctr->rec_overflow != 0u || ctr->pending_overflow != 0u) return;   // grid-uniform
-
+  if (ctr->n_pending == 0u || ctr->rec_overflow != 0u || ctr->pending_overflow != 0u) return;   // grid-uniform
   const int lane = threadIdx.x & 31;
   const unsigned gthread = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned gthreads = gridDim.x * blockDim.x;
   const unsigned gwarp = gthread >> 5, gwarps = gthreads >> 5;
-  unsigned written = 0;
   if (gthread == 0) ctr->t_phase[0] = global_ns();
-
-  // ---- round 1, candidates: the record, one warp per pair of 64-entry chunks.  Four independent
-  // record -> parked bit -> key -> parked-winner chains per lane are in flight at a time (the pass is
-  // latency bound); the per-voxel state (4 bits per voxel, L2 resident) spares the key lookup for the
-  // records whose voxel is not parked.
   unsigned n_chunks = ctr->n_chunks;
   if (n_chunks > cap_chunks) n_chunks = cap_chunks;
   ListWriter lw;
@@ -1693,14 +1686,30 @@ replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict
     for (int u = 0; u < 4; u++)
     {
       const unsigned slot = sb[u] + (unsigned)((kv[u] >> WS_SEQ_BITS) & 0x1FFull);
-      const bool hit = ok[u] && key_seq(rr[u].key) > (kv[u] & WS_SEQ_MAX);
+      const bool hit = ok[u] && slot < pending_cap && key_seq(rr[u].key) > (kv[u] & WS_SEQ_MAX);
       if (hit) atomicMin(&pend_key[slot], rr[u].key);
       Rec e; e.key = rr[u].key; e.ref = (u64)slot;
       list_append(lw, hit, e, lane, list, list_cap, ctr);
     }
   }
   if (lw.used < WS_LIST_SPAN) list_pad(lw, lane, list, list_cap);
-  grid.sync();
+}
+
+// Replay, second half.  Cooperative launch: settles every parked voxel on the device (see the file header, step 4).
+__global__ void __launch_bounds__(256, 4)
+replay_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict__ ctr, const unsigned pending_cap,
+              u64 *__restrict__ pend_addr, u64 *__restrict__ pend_prev, u64 *__restrict__ pend_key,
+              const Rec *__restrict__ list, const unsigned list_cap, unsigned *__restrict__ active0, unsigned *__restrict__ active1)
+{
+  cg::grid_group grid = cg::this_grid();
+  unsigned n_pend = ctr->n_pending;
+  if (n_pend > pending_cap) n_pend = pending_cap;
+  if (n_pend == 0u || ctr->rec_overflow != 0u || ctr->pending_overflow != 0u) return;   // grid-uniform
+
+  const int lane = threadIdx.x & 31;
+  const unsigned gthread = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned gthreads = gridDim.x * blockDim.x;
+  unsigned written = 0;
   if (gthread == 0) ctr->t_phase[1] = global_ns();
 
   // ---- rounds: resolve, then offer the short list to what is still pending ----------------------
@@ -1898,6 +1907,14 @@ static void ensure_record(ws_handle *h, size_t chunks)
   h->rec_cap_chunks = chunks;
 }
 
+// first half of the replay (the surface record against the parked voxels) on `stream`
+static void launch_replay_scan(ws_handle *h, cudaStream_t stream)
+{
+  replay_scan_kernel<<<h->sm_count * 4, 256, 0, stream>>>(h->g, h->d_counters, h->pending_cap, h->d_pend_key, h->d_rec, h->d_chunk_fill,
+                                                         (unsigned)h->rec_cap_chunks, h->d_list, (unsigned)h->list_cap);
+  h->launches++;
+}
+
 static void launch_replay(ws_handle *h, const UpdateParams &P)
 {
   if (h->replay_blocks == 0)
@@ -1908,11 +1925,9 @@ static void launch_replay(ws_handle *h, const UpdateParams &P)
     if (per_sm > 4) per_sm = 4;
     h->replay_blocks = per_sm * h->sm_count;
   }
-  unsigned cap_chunks = (unsigned)h->rec_cap_chunks;
   unsigned list_cap = (unsigned)h->list_cap;
   void *args[] = { (void *)&h->g, (void *)&P, (void *)&h->d_counters, (void *)&h->pending_cap,
                    (void *)&h->d_pend_addr, (void *)&h->d_pend_prev, (void *)&h->d_pend_key,
-                   (void *)&h->d_rec, (void *)&h->d_chunk_fill, (void *)&cap_chunks,
                    (void *)&h->d_list, (void *)&list_cap, (void *)&h->d_active[0], (void *)&h->d_active[1] };
   WS_CUDA_OK(cudaLaunchCooperativeKernel((const void *)replay_kernel, dim3(h->replay_blocks), dim3(256), args, 0, h->stream));
   h->launches++;
@@ -2097,8 +2112,11 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
     if (!h->stream2)
     {
       WS_CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+      WS_CUDA_OK(cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
       WS_CUDA_OK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
       WS_CUDA_OK(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+      WS_CUDA_OK(cudaEventCreateWithFlags(&h->ev_merged, cudaEventDisableTiming));
+      WS_CUDA_OK(cudaEventCreateWithFlags(&h->ev_scanned, cudaEventDisableTiming));
     }
     cudaStream_t s2 = h->stream2;
     setup_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_pts, rays, h->d_grp_info, n_groups, h->d_gen_list, h->d_counters, d_pose);
@@ -2124,10 +2142,18 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
     merge_kernel<<<h->sm_count * MERGE_CTAS, 256, 0, s>>>(h->g, P, list_surf, h->d_counters, h->pending_cap,
                                                           h->d_pend_addr, h->d_pend_prev, h->d_pend_key);
     ws_timer_end(h);
+    // the record pass of the replay (streams the record, DRAM bound) beside the far-field march (compute bound)
+    WS_CUDA_OK(cudaEventRecord(h->ev_merged, s));
+    WS_CUDA_OK(cudaStreamWaitEvent(h->stream3, h->ev_merged, 0));
+    ws_timer_begin(h, WS_TIMER_REPLAY, h->stream3);
+    launch_replay_scan(h, h->stream3);
+    ws_timer_end(h, h->stream3);
+    WS_CUDA_OK(cudaEventRecord(h->ev_scanned, h->stream3));
     ws_timer_begin(h, WS_TIMER_MARCH);
     LS_LAUNCH_ON(false, true, 2u, s);
     ws_timer_end(h);
     WS_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
+    WS_CUDA_OK(cudaStreamWaitEvent(s, h->ev_scanned, 0));
     ws_timer_begin(h, WS_TIMER_REPLAY);
     launch_replay(h, P);
     ws_timer_end(h);
@@ -2135,7 +2161,7 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
     brick_list_kernel<false><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_all, h->d_counters);
     fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, list_all, h->d_counters);
     ws_timer_end(h);
-    h->launches += 11;
+    h->launches += 11;       // + the two replay launches counted where they are made
   }
   WS_CUDA_OK(cudaMemcpyAsync(h_ctr, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
   if (pose_on_device)
@@ -2186,6 +2212,7 @@ void ws_update_finish(ws_handle *h, UpdateCounters *h_ctr, void *h_pose_out, cud
       march_kernel<false><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_gen_list, h->d_counters, h->d_rec,
                                                                  h->d_chunk_fill, cap_chunks, d_pose);
       LS_LAUNCH_ON(false, true, 2u, s);
+      launch_replay_scan(h, s);
       launch_replay(h, P);
       brick_list_kernel<false><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_all, h->d_counters);
       fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, list_all, h->d_counters);

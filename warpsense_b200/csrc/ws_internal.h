@@ -146,8 +146,9 @@ struct ws_handle
     std::string error;
   } track[2];
   cudaStream_t copy_stream = nullptr;
-  cudaStream_t stream2 = nullptr;   // the free-space march runs here, beside the surface march + merge
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_f0 = nullptr, ev_f1 = nullptr;
+  cudaStream_t stream2 = nullptr;   // the near-field free-space march runs here, beside the surface march + merge
+  cudaStream_t stream3 = nullptr;   // the record pass of the replay runs here, beside the far-field free-space march
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_merged = nullptr, ev_scanned = nullptr;
   int track_next = 0, track_in_flight = 0;
   bool rec_headroom_ok = false;     // a finished scan left the candidate record well below its capacity
   bool track_has_pose = false;      // d_pose holds the pose of the previous tracked scan      // dynamic shared memory of the lockstep march raised above 48 KB
