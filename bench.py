@@ -270,6 +270,12 @@ def workload_config(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# the timed ranges of one update_tsdf in launch order (ws_profile_timeline; update_tsdf.cu ws_update_enqueue)
+TIMELINE_NAMES = ["update_tsdf (whole)", "set-up + item scan", "surface march [stream 1]", "free-space march, near field [stream 2]",
+                  "brick list + surface merge [stream 1]", "replay record pass [stream 3]", "free-space march, far field [stream 1]",
+                  "replay rounds [stream 1]", "brick list + free-space merge [stream 1]"]
+
+
 def traffic_from_profile():
     """DRAM bytes of one update_tsdf on the default workload, summed from the committed ncu capture
     (profiles/*_dram_traffic.csv: kernel, dram_read_MB, dram_write_MB per launch of one scan)."""
@@ -407,7 +413,8 @@ class Workload:
             ms = e0.elapsed_time(e1)
             kern = {name: self.tsdf.profile_get(kind) for name, kind in
                     (("march", lib.TIMER_MARCH), ("merge", lib.TIMER_MERGE), ("reg", lib.TIMER_REG),
-                     ("replay", lib.TIMER_REPLAY))}
+                     ("replay", lib.TIMER_REPLAY), ("update", lib.TIMER_UPDATE))}
+            self.timeline = self.tsdf.profile_timeline()
             self.tsdf.profile(False)
         if self.world > 1:
             t = torch.tensor([ms], device="cuda")
@@ -457,9 +464,10 @@ def sub_config(torch, dist, args, name, grid, res, beams, cols, K, W, update_onl
         dist.all_reduce(wk)
         counters = dict(counters)
         counters["n_touched"], counters["n_candidates"] = (int(v) for v in wk.tolist())
-        km = torch.tensor([kern[k][0] for k in ("march", "merge", "reg", "replay")], dtype=torch.float64, device="cuda")
+        kinds = ("march", "merge", "reg", "replay", "update")
+        km = torch.tensor([kern[k][0] for k in kinds], dtype=torch.float64, device="cuda")
         dist.all_reduce(km, op=dist.ReduceOp.MAX)
-        kern = {k: (float(v), kern[k][1]) for k, v in zip(("march", "merge", "reg", "replay"), km.tolist())}
+        kern = {k: (float(v), kern[k][1]) for k, v in zip(kinds, km.tolist())}
     nv, _ = wl.n_valid()
     n_pts = wl.counts[1]
     out = {
@@ -469,7 +477,8 @@ def sub_config(torch, dist, args, name, grid, res, beams, cols, K, W, update_onl
                                                          ", voxel-grid subsampled cloud (featsense feed)" if subsample else ""),
         "value": K / (ms_dev / 1000.0), "e2e": K / (ms_e2e / 1000.0), "unit": UNIT, "steps": K, "warmup": W,
         "ms_per_step": ms_dev / K,
-        "kernel_ms_per_scan": {k: kern[k][0] / K for k in ("march", "merge", "replay", "reg")},
+        "kernel_ms_per_scan": {("update_tsdf" if k == "update" else k): kern[k][0] / K
+                               for k in ("update", "reg", "march", "merge", "replay")},
         "work": {"N": n_pts, "C": counters["n_candidates"], "T": counters["n_touched"], "N_valid": nv,
                  "V": int(np.prod(np.array(wl.size, np.int64)))},
         "clocks": clocks,
@@ -513,12 +522,13 @@ def run_native(args):
         counters = dict(counters)
         counters["n_touched"], counters["n_candidates"], counters["n_touched_bricks"], counters["n_parked"] = \
             (int(v) for v in wk.tolist())
-        km = torch.tensor([kern[k][0] for k in ("march", "merge", "reg", "replay")], dtype=torch.float64, device="cuda")
+        kinds = ("march", "merge", "reg", "replay", "update")
+        km = torch.tensor([kern[k][0] for k in kinds], dtype=torch.float64, device="cuda")
         kmin = km.clone()
         dist.all_reduce(km, op=dist.ReduceOp.MAX)
         dist.all_reduce(kmin, op=dist.ReduceOp.MIN)
-        kern_min = {k: float(v) / max(1, K) for k, v in zip(("march", "merge", "reg", "replay"), kmin.tolist())}
-        kern = {k: (float(v), kern[k][1]) for k, v in zip(("march", "merge", "reg", "replay"), km.tolist())}
+        kern_min = {k: float(v) / max(1, K) for k, v in zip(kinds, kmin.tolist())}
+        kern = {k: (float(v), kern[k][1]) for k, v in zip(kinds, km.tolist())}
         parity = parity_check(torch, dist, args, wl, K, W)
     else:
         kern_min = None
@@ -532,7 +542,7 @@ def run_native(args):
         replay_ms = kern["replay"][0] / max(1, K)
         upd_bytes = 12 * N + 8 * T_vox
         peak, peak_src = peaks()
-        upd_ms = march_ms + merge_ms + replay_ms
+        upd_ms = kern["update"][0] / max(1, K)          # elapsed, set-up to free-space merge (the phases overlap on three streams)
         achieved = upd_bytes / (upd_ms / 1000.0) / 1e9 if upd_ms > 0 else 0.0
         traffic, traffic_src = traffic_from_profile()
         default_shape = (world == 1 and not args.update_only and args.grid == 512 and args.res == 50
@@ -559,8 +569,13 @@ def run_native(args):
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_scan": upd_bytes,
                 "formula": "12*N + 8*T (SURVEY.md 8d), N=%d points, T=%d touched voxels, C=%d candidates" % (N, T_vox, C_cand),
-                "kernel_ms_per_scan": {"march": march_ms, "merge": merge_ms, "replay": replay_ms, "reg_20_iterations": reg_ms,
-                                       "step_total": ms_dev / K},
+                "kernel_ms_per_scan": {"update_tsdf": upd_ms, "reg_20_iterations": reg_ms, "step_total": ms_dev / K,
+                                       "march": march_ms, "merge": merge_ms, "replay": replay_ms,
+                                       "note": "update_tsdf = elapsed on the handle's stream; march / merge / replay = busy "
+                                               "ranges on three streams that run side by side, their sum exceeds it"},
+                "update_timeline_ms": [{"range": TIMELINE_NAMES[i] if i < len(TIMELINE_NAMES) else "kind %d" % kd,
+                                        "start": round(a, 4), "stop": round(b, 4)}
+                                       for i, (kd, a, b) in enumerate(wl.timeline)],
                 "kernel_ms_per_scan_min_over_ranks": kern_min,
                 "reg_bytes_per_scan": reg_bytes,
                 "reg_formula": "sum over the %d GN iterations of 12*N + 28*N_valid + 232 (SURVEY.md 8d)" % len(valid_per_it) if valid_per_it else None,

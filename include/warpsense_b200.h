@@ -305,12 +305,17 @@ int ws_import_hdf5(ws_handle *h, const char *path, ws_map_meta *meta, float *pos
 int ws_map_reload(ws_handle *h);
 
 /* ---- timing -------------------------------------------------------------------------------- */
-/* record cudaEvents around the hot kernels on the handle's stream (kind: 0 march, 1 brick list + merge, 2 registration
- * iteration, 3 replay) */
+/* record cudaEvents around the hot kernels (kind: 0 march, 1 brick list + merge, 2 registration loop, 3 replay,
+ * 4 the whole update_tsdf of one scan on the handle's stream).  Kinds 0, 1 and 3 are ranges on three streams that
+ * run side by side (surface march + merge | near-field free-space march | record pass of the replay): their sums
+ * exceed kind 4, which is the elapsed time of the update. */
 int ws_profile_enable(ws_handle *h, int32_t on);
 int ws_profile_reset(ws_handle *h);
 /* sum of elapsed ms and launch count per kind since the last reset (synchronises the stream) */
 int ws_profile_get(ws_handle *h, int32_t kind, double *total_ms, int64_t *launches);
+/* the ranges of the last update_tsdf as (kind, start_ms, stop_ms) triples relative to its start, in launch order
+ * (first the kind-4 span itself); returns the number of ranges written, -1 on error.  Shows what ran side by side. */
+int64_t ws_profile_timeline(ws_handle *h, double *out, int64_t cap_ranges);
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int64_t ws_launch_count(const ws_handle *h);

@@ -1,6 +1,13 @@
 #!/bin/bash
-for cfg in "1 1" "2 1" "1 2" "2 2"; do
-  set -- $cfg
-  echo "== S=$1 N=$2"
-  WS_LS_GRID_S=$1 WS_LS_GRID_N=$2 bash tools/gpu_b.sh r02B_g$1$2 --no-extra 2>&1 | grep "^value\|exit"
-done
+# A/B of launch geometry knobs: lines of "ENV=VAL ..." are tried one after the other
+while read -r cfg; do
+  [ -z "$cfg" ] && continue
+  echo "== $cfg"
+  env $cfg bash tools/gpu_b.sh r02ab --no-extra 2>&1 | grep "^value\|exit\|replay rounds\|free-space merge"
+done <<CFGS
+WS_REPLAY_CTAS=2 WS_FMERGE_GRID=4
+WS_REPLAY_CTAS=1 WS_FMERGE_GRID=6
+WS_REPLAY_CTAS=1 WS_FMERGE_GRID=4
+WS_REPLAY_CTAS=2 WS_FMERGE_GRID=3
+WS_REPLAY_CTAS=4 WS_FMERGE_GRID=8
+CFGS

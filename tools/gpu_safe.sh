@@ -16,7 +16,7 @@ python - <<PY
 import json
 d=json.loads(open("$out/${tag}_bench.json").read().strip().splitlines()[-1])
 k=d["roofline"]["kernel_ms_per_scan"]
-print("value %.1f e2e %.1f march %.3f merge %.3f replay %.3f reg %.3f step %.3f" % (d["value"], d["e2e"]["value"], k["march"], k["merge"], k["replay"], k["reg_20_iterations"], k["step_total"]))
+print("value %.1f e2e %.1f update %.3f (march %.3f merge %.3f replay %.3f) reg %.3f step %.3f frac %.4f" % (d["value"], d["e2e"]["value"], k["update_tsdf"], k["march"], k["merge"], k["replay"], k["reg_20_iterations"], k["step_total"], d["roofline"]["frac"]))
 print(d["work"])
 PY
 tail -3 $out/${tag}_bench.err

@@ -429,6 +429,12 @@ class TSDFCuda:
         self._hd.check(self._hd.L.ws_profile_get(self._hd.h, int(kind), C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def profile_timeline(self, cap=64):
+        """(kind, start_ms, stop_ms) of every timed range of the last update_tsdf, relative to its start."""
+        buf = (C.c_double * (3 * cap))()
+        n = self._hd.check(self._hd.L.ws_profile_timeline(self._hd.h, buf, cap))
+        return [(int(buf[3 * i]), buf[3 * i + 1], buf[3 * i + 2]) for i in range(n)]
+
     def close(self):
         self._hd.close()
 

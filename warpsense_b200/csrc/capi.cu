@@ -487,6 +487,30 @@ void ws_timer_end(ws_handle *h, cudaStream_t stream)
   }
 }
 
+// a range that spans others (the whole update_tsdf of one scan): takes its own slot, returns it for ws_span_end
+long ws_span_begin(ws_handle *h, int kind)
+{
+  if (!h->profile) return -1;
+  if (h->timers_used >= h->timers.size())
+  {
+    if (h->timers.size() >= (1u << 16)) return -1;
+    WsTimer t;
+    if (cudaEventCreate(&t.start) != cudaSuccess || cudaEventCreate(&t.stop) != cudaSuccess) return -1;
+    h->timers.push_back(t);
+    h->timer_kind.push_back(kind);
+  }
+  const long idx = (long)h->timers_used++;
+  h->timer_kind[idx] = kind;
+  cudaEventRecord(h->timers[idx].start, h->stream);
+  return idx;
+}
+
+void ws_span_end(ws_handle *h, long idx)
+{
+  if (idx < 0 || (size_t)idx >= h->timers.size()) return;
+  cudaEventRecord(h->timers[idx].stop, h->stream);
+}
+
 std::vector<unsigned long long> ws_store_keys(ws_handle *h)
 {
   std::vector<unsigned long long> keys;
@@ -1476,6 +1500,30 @@ int ws_profile_reset(ws_handle *h)
     h->timers_used = 0;
     return WS_OK;
   });
+}
+
+int64_t ws_profile_timeline(ws_handle *h, double *out, int64_t cap_ranges)
+{
+  // ranges of the LAST update_tsdf span, as (kind, start_ms, stop_ms) relative to the span's start
+  int64_t n = 0;
+  const int rc = guarded(h, [&]() {
+    WS_CUDA_OK(cudaDeviceSynchronize());
+    const size_t used = std::min(h->timers_used, h->timers.size());
+    long span = -1;
+    for (size_t i = 0; i < used; i++)
+      if (h->timer_kind[i] == WS_TIMER_UPDATE) span = (long)i;
+    if (span < 0) return WS_OK;
+    for (size_t i = (size_t)span; i < used && n < cap_ranges; i++)
+    {
+      float a = 0.f, b = 0.f;
+      if (cudaEventElapsedTime(&a, h->timers[span].start, h->timers[i].start) != cudaSuccess) continue;
+      if (cudaEventElapsedTime(&b, h->timers[span].start, h->timers[i].stop) != cudaSuccess) continue;
+      out[3 * n] = (double)h->timer_kind[i]; out[3 * n + 1] = a; out[3 * n + 2] = b;
+      n++;
+    }
+    return WS_OK;
+  });
+  return rc == WS_OK ? n : -1;
 }
 
 int ws_profile_get(ws_handle *h, int32_t kind, double *total_ms, int64_t *launches)

@@ -1227,7 +1227,7 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
 }
 
 // exclusive prefix sums of the groups' block counts, per phase -> item_off[phase][0 .. n_groups], n_items[phase]
-// (one CTA)
+// (one CTA per table)
 __global__ void __launch_bounds__(1024)
 item_scan_kernel(const uint2 *__restrict__ grp_info, const unsigned n_groups, unsigned *__restrict__ item_off,
                  UpdateCounters *__restrict__ ctr)
@@ -1235,8 +1235,8 @@ item_scan_kernel(const uint2 *__restrict__ grp_info, const unsigned n_groups, un
   __shared__ unsigned s_warp[32];
   __shared__ unsigned s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int phase = 0; phase < 3; phase++)
   {
+    const int phase = blockIdx.x;          // one CTA per item table
     const uint2 *gi = grp_info + (size_t)phase * n_groups;
     unsigned *io = item_off + (size_t)phase * (n_groups + 1u);
     __syncthreads();
@@ -1522,7 +1522,8 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
 // Last kernel of a scan: for every brick the scan touched, the voxels that are not closed and hold a
 // free-space candidate get (tau, +-WEIGHT_RESOLUTION) folded in (update_tsdf.cpp:542-560; real beats
 // interpolated at equal |value|, :508-512), and the brick's per-voxel state is cleared for the next scan.
-// 256 B of state + 2 KB of entries per brick travel as TMA bulk copies, three stages per CTA.
+// 256 B of state + 1 KB of free-space bytes + 2 KB of entries per brick arrive as TMA bulk copies, three stages per
+// CTA; the changed entries go back one by one (see below), the state is cleared by bulk stores of zeros.
 #ifndef FMERGE_CTAS
 #define FMERGE_CTAS 8
 #endif
@@ -1566,7 +1567,6 @@ fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict
     const size_t base = (size_t)brick_list[blockIdx.x + n * gridDim.x] * WS_BRICK_VOX;
     if (tid == 0)
     {
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       const unsigned m = n + MERGE_STAGES - 1;
       if (m < n_mine)
       {
@@ -1585,11 +1585,11 @@ fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict
     const unsigned sb = s_state[st][tid];
     const unsigned fr = *reinterpret_cast<const unsigned short *>(&s_free[st][2 * tid]);
     const unsigned fi = *reinterpret_cast<const unsigned short *>(&s_free[st][WS_BRICK_VOX + 2 * tid]);
-    bool changed = false;
     if ((sb & 0x33u) | fr | fi)
     {
       const uint2 ee = *reinterpret_cast<const uint2 *>(&s_ent[st][2 * tid]);
       uint32_t e2[2] = { ee.x, ee.y };
+      unsigned changed = 0u;
 #pragma unroll
       for (int j = 0; j < 2; j++)
       {
@@ -1602,16 +1602,18 @@ fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict
         touched++;
         written += ((weight > 0 && ew > 0) || ew <= 0) ? 1u : 0u;
         const uint32_t ne = merge_entry(e2[j], P.tau, weight, P.max_weight);
-        changed |= ne != e2[j];
+        if (ne != e2[j]) changed |= 1u << j;
         e2[j] = ne;
       }
-      if (changed) *reinterpret_cast<uint2 *>(&s_ent[st][2 * tid]) = make_uint2(e2[0], e2[1]);
+      // entry by entry, never the whole brick: only the sectors that changed go back to DRAM
+      uint32_t *dst = g.grid + base + 2 * tid;
+      if (changed == 3u) *reinterpret_cast<uint2 *>(dst) = make_uint2(e2[0], e2[1]);
+      else if (changed == 1u) dst[0] = e2[0];
+      else if (changed == 2u) dst[1] = e2[1];
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const int any_changed = __syncthreads_or(changed ? 1 : 0);
+    __syncthreads();                       // everybody is done with this stage before it is refilled
     if (tid == 0)
     {
-      if (any_changed) bulk_s2g(g.grid + base, s_ent[st], MERGE_ENT_BYTES);
       bulk_s2g(g.ffree + base * 2, s_zero, 2 * WS_BRICK_VOX);
       bulk_s2g(reinterpret_cast<unsigned char *>(g.vstate) + base / 2, s_zero, WS_BRICK_VOX / 2);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -1824,14 +1826,6 @@ __global__ void rec_reset_kernel(UpdateCounters *ctr)
 
 }  // namespace
 
-// CTAs per SM of one lockstep launch (tuning knob for A/B runs; the default is what the launcher was tuned to)
-static int ls_ctas_env(const char *name, int dflt)
-{
-  const char *e = std::getenv(name);
-  const int v = e ? std::atoi(e) : dflt;
-  return v >= 1 && v <= LS_CTAS ? v : dflt;
-}
-
 static int far_start_len(int res, int dz)
 {
   // interpolated candidates need iter_steps >= 2  <=>  delta_z >= ceil(res/2)  <=>  len >= L0.
@@ -1907,6 +1901,14 @@ static void ensure_record(ws_handle *h, size_t chunks)
   h->rec_cap_chunks = chunks;
 }
 
+// CTAs per SM of one launch (tuning knob for A/B runs; the default is what the launcher was tuned to)
+static int ls_ctas_env(const char *name, int dflt)
+{
+  const char *e = std::getenv(name);
+  const int v = e ? std::atoi(e) : dflt;
+  return v >= 1 && v <= 8 ? v : dflt;
+}
+
 // first half of the replay (the surface record against the parked voxels) on `stream`
 static void launch_replay_scan(ws_handle *h, cudaStream_t stream)
 {
@@ -1922,7 +1924,8 @@ static void launch_replay(ws_handle *h, const UpdateParams &P)
     int per_sm = 0;
     WS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, replay_kernel, 256, 0));
     if (per_sm < 1) throw std::runtime_error("replay_kernel does not fit on an SM");
-    if (per_sm > 4) per_sm = 4;
+    const int want = ls_ctas_env("WS_REPLAY_CTAS", 4);
+    if (per_sm > want) per_sm = want;
     h->replay_blocks = per_sm * h->sm_count;
   }
   unsigned list_cap = (unsigned)h->list_cap;
@@ -2089,6 +2092,7 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
       h->tab_attr_set = true;
     }
     unsigned cap_chunks = (unsigned)h->rec_cap_chunks;
+    const long span = ws_span_begin(h, WS_TIMER_UPDATE);
     ws_timer_begin(h, WS_TIMER_MARCH);
     if ((size_t)n > h->rays_cap)
     {
@@ -2120,7 +2124,7 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
     }
     cudaStream_t s2 = h->stream2;
     setup_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_pts, rays, h->d_grp_info, n_groups, h->d_gen_list, h->d_counters, d_pose);
-    item_scan_kernel<<<1, 1024, 0, s>>>(h->d_grp_info, n_groups, h->d_item_off, h->d_counters);
+    item_scan_kernel<<<3, 1024, 0, s>>>(h->d_grp_info, n_groups, h->d_item_off, h->d_counters);
     ws_timer_end(h);
     // Two streams from here.  Surface phase (this stream): keys, record, merge -> parked voxels.  The near-field part
     // of the free-space phase needs nothing from it and runs beside it on the second stream (both marches are
@@ -2154,6 +2158,8 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
     ws_timer_end(h);
     WS_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
     WS_CUDA_OK(cudaStreamWaitEvent(s, h->ev_scanned, 0));
+    // (the replay rounds and the free-space merge write disjoint voxels and could run side by side, but the rounds
+    // need every register of the SMs to hide their latency and the merge every CTA slot: measured, no gain)
     ws_timer_begin(h, WS_TIMER_REPLAY);
     launch_replay(h, P);
     ws_timer_end(h);
@@ -2161,6 +2167,7 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
     brick_list_kernel<false><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_all, h->d_counters);
     fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, list_all, h->d_counters);
     ws_timer_end(h);
+    ws_span_end(h, span);
     h->launches += 11;       // + the two replay launches counted where they are made
   }
   WS_CUDA_OK(cudaMemcpyAsync(h_ctr, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));

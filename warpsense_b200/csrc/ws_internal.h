@@ -275,6 +275,9 @@ void ws_launch_test_reduce(ws_handle *h, const i64 *d_jacobis, const int *d_valu
 #define WS_TIMER_MERGE 1
 #define WS_TIMER_REG 2
 #define WS_TIMER_REPLAY 3
+#define WS_TIMER_UPDATE 4   // the whole update_tsdf of one scan on the handle's stream (the phases above overlap on three streams)
+long ws_span_begin(ws_handle *h, int kind);
+void ws_span_end(ws_handle *h, long idx);
 void ws_timer_begin(ws_handle *h, int kind, cudaStream_t stream = nullptr);
 void ws_timer_end(ws_handle *h, cudaStream_t stream = nullptr);
 

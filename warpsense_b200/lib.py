@@ -20,7 +20,7 @@ WS_REG_DEVICE_SOLVE = 0
 WS_TRACK_REFERENCE_POSE = 1
 WS_REG_HOST_SOLVE = 1
 
-TIMER_MARCH, TIMER_MERGE, TIMER_REG, TIMER_REPLAY = 0, 1, 2, 3
+TIMER_MARCH, TIMER_MERGE, TIMER_REG, TIMER_REPLAY, TIMER_UPDATE = 0, 1, 2, 3, 4
 
 
 class UpdateCounters(C.Structure):
@@ -124,6 +124,7 @@ def _signatures():
         "ws_profile_enable": (C.c_int, [hp, C.c_int32]),
         "ws_profile_reset": (C.c_int, [hp]),
         "ws_profile_get": (C.c_int, [hp, C.c_int32, C.POINTER(C.c_double), i64p]),
+        "ws_profile_timeline": (C.c_int64, [hp, C.POINTER(C.c_double), C.c_int64]),
     }
 
 
