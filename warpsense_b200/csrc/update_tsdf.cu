@@ -762,7 +762,7 @@ WS_D void list_append(ListWriter &w, const bool want, const Rec e, const int lan
 // Voxel addresses come from three per-axis tables in shared memory (ring wrap, residency, bricking).
 // Rays outside the bounds of the 32-bit arithmetic (march_math.cuh) are left to march_kernel.
 #ifndef LS_CTAS
-#define LS_CTAS 2
+#define LS_CTAS 3
 #endif
 #define TAB_INVALID 0xFFFFFFFFu
 
@@ -2133,12 +2133,12 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
     WS_CUDA_OK(cudaEventRecord(h->ev_fork, s));
     WS_CUDA_OK(cudaStreamWaitEvent(s2, h->ev_fork, 0));
     ws_timer_begin(h, WS_TIMER_MARCH);
-    LS_LAUNCH_GRID(true, true, 0u, s, h->sm_count * ls_ctas_env("WS_LS_GRID_S", LS_CTAS));
+    LS_LAUNCH_GRID(true, true, 0u, s, h->sm_count * ls_ctas_env("WS_LS_GRID_S", 2));
     march_kernel<true><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_gen_list, h->d_counters, h->d_rec,
                                                               h->d_chunk_fill, cap_chunks, d_pose);
     ws_timer_end(h);
     ws_timer_begin(h, WS_TIMER_MARCH, s2);
-    LS_LAUNCH_GRID(false, true, 1u, s2, h->sm_count * ls_ctas_env("WS_LS_GRID_N", LS_CTAS));
+    LS_LAUNCH_GRID(false, true, 1u, s2, h->sm_count * ls_ctas_env("WS_LS_GRID_N", 3));
     ws_timer_end(h, s2);
     WS_CUDA_OK(cudaEventRecord(h->ev_join, s2));
     ws_timer_begin(h, WS_TIMER_MERGE);
@@ -2154,7 +2154,7 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
     ws_timer_end(h, h->stream3);
     WS_CUDA_OK(cudaEventRecord(h->ev_scanned, h->stream3));
     ws_timer_begin(h, WS_TIMER_MARCH);
-    LS_LAUNCH_ON(false, true, 2u, s);
+    LS_LAUNCH_GRID(false, true, 2u, s, h->sm_count * ls_ctas_env("WS_LS_GRID_F", 2));
     ws_timer_end(h);
     WS_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
     WS_CUDA_OK(cudaStreamWaitEvent(s, h->ev_scanned, 0));
