@@ -237,6 +237,28 @@ def test_update_tsdf_record_overflow_regenerates(monkeypatch):
         assert_same_grid(om, tsdf, hm, "record overflow, scan %d" % scan)
 
 
+def test_update_tsdf_64bit_address_path(monkeypatch):
+    """Maps beyond 2^32 voxels take the kernels' 64-bit address path (x table holds address / 64, record chunks carry
+    the addresses' high words).  WS_FORCE_WIDE puts a small map on that path: replay rounds, general rays and two
+    scans, against the oracle."""
+    monkeypatch.setenv("WS_FORCE_WIDE", "1")
+    rng = np.random.default_rng(14)
+    tau, res, mw = 400, 10, 10 * WR
+    om, hm, tsdf = make_pair((257, 65, 65), tau, mw, res)
+    monkeypatch.delenv("WS_FORCE_WIDE")
+    up = np.array([0, 0, MR], np.int32)
+    spos = (-120, 0, 0)
+    for scan in range(2):
+        base = np.stack([rng.integers(900, 1250, 2500), rng.integers(-250, 250, 2500), rng.integers(-250, 250, 2500)], 1)
+        pts = np.concatenate([base, base[::-1]]).astype(np.int32)
+        st = orc.update_tsdf(om, pts, spos, up, tau, mw, res)
+        tsdf.update_tsdf(pts, spos, up)
+        c = tsdf.counters()
+        assert c["n_candidates"] == st["n_candidates"] and c["n_touched"] == st["n_touched"]
+        assert c["n_parked"] > 0
+        assert_same_grid(om, tsdf, hm, "64-bit address path, scan %d" % scan)
+
+
 def test_update_tsdf_empty_and_over_capacity():
     tau, res, mw = 600, 64, 640
     om, hm, tsdf = make_pair((17, 17, 17), tau, mw, res)

@@ -205,6 +205,7 @@ int create_impl(const int32_t size[3], int tau, int max_weight, int res, int dev
     g.n_bricks = (i64)cols.size() * g.nb[1] * g.nb[2];
     if (g.n_bricks >= (1ll << 31)) throw std::invalid_argument("map too large");
     const size_t n_vox = (size_t)g.n_bricks * WS_BRICK_VOX;
+    g.wide = (n_vox > 0xFFFFFFFFull || std::getenv("WS_FORCE_WIDE")) ? 1 : 0;
 
     WS_CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;

@@ -186,6 +186,14 @@ WS_D void step_index(const UpdateParams &P, const int pos_mm[3], const int d[3],
   }
 }
 
+// A record chunk (1 KB): 64 keys (512 B), the low words of the 64 voxel addresses (256 B) and -- for maps beyond 2^32
+// voxels -- their high words (256 B; never touched otherwise, so a record costs 12 bytes of traffic, and the replay's
+// record pass reads the keys only where a voxel turns out to be parked).
+WS_D u64 *rec_keys(Rec *rec, unsigned chunk) { return reinterpret_cast<u64 *>(rec + (size_t)chunk * WS_REC_CHUNK); }
+WS_D const u64 *rec_keys(const Rec *rec, unsigned chunk) { return reinterpret_cast<const u64 *>(rec + (size_t)chunk * WS_REC_CHUNK); }
+WS_D unsigned *rec_refs(Rec *rec, unsigned chunk) { return reinterpret_cast<unsigned *>(rec_keys(rec, chunk) + WS_REC_CHUNK); }
+WS_D const unsigned *rec_refs(const Rec *rec, unsigned chunk) { return reinterpret_cast<const unsigned *>(rec_keys(rec, chunk) + WS_REC_CHUNK); }
+
 // Record writer.  The record is a sequence of 64-entry chunks with a fill count each.  A warp reserves
 // WS_REC_SPAN consecutive chunks at a time (one same-address atomic per 2048 records -- the allocation
 // counter is a single L2 word, and same-address atomics serialise), fills them in order, and on its way
@@ -207,7 +215,7 @@ WS_D void rec_init(RecWriter &w, UpdateCounters *ctr, int lane)
 }
 
 // warp-collective append of one record per lane with want == true
-WS_D void rec_append(RecWriter &w, const bool want, const u64 key, const u64 addr, const int lane,
+WS_D void rec_append(RecWriter &w, const bool want, const u64 key, const u64 addr, const bool wide, const int lane,
                      Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill, const unsigned cap_chunks,
                      UpdateCounters *__restrict__ ctr)
 {
@@ -224,8 +232,10 @@ WS_D void rec_append(RecWriter &w, const bool want, const u64 key, const u64 add
     const unsigned chunk = slot < WS_REC_CHUNK ? w.cur : after;
     if (chunk < cap_chunks)
     {
-      Rec e; e.key = key; e.ref = addr;
-      rec[(size_t)chunk * WS_REC_CHUNK + (unsigned)(slot & (WS_REC_CHUNK - 1))] = e;
+      const unsigned j = (unsigned)(slot & (WS_REC_CHUNK - 1));
+      rec_keys(rec, chunk)[j] = key;
+      rec_refs(rec, chunk)[j] = (unsigned)addr;
+      if (wide) rec_refs(rec, chunk)[WS_REC_CHUNK + j] = (unsigned)(addr >> 32);    // maps beyond 2^32 voxels only
     }
   }
   w.fill += n;
@@ -510,7 +520,7 @@ WS_D void march_ray(const GridDesc &g, const UpdateParams &P, const int pos_mm[3
         }
       }
 #ifndef WHATIF_NOREC
-      rec_append(cx.rw, resident && far, key, addr, lane, rec, chunk_fill, cap_chunks, ctr);
+      rec_append(cx.rw, resident && far, key, addr, g.wide != 0, lane, rec, chunk_fill, cap_chunks, ctr);
 #endif
     }
   }
@@ -1001,7 +1011,7 @@ WS_D void march_drain(const GridDesc &g, const UpdateParams &P, const LsShared &
         if (brick != W.last_brick) { g.brick_flag[brick] = 1u; W.last_brick = brick; }
       }
     }
-    rec_append(W.rw, valid && far, key, addr, lane, rec, chunk_fill, cap_chunks, ctr);     // warp-collective
+    rec_append(W.rw, valid && far, key, addr, WIDE, lane, rec, chunk_fill, cap_chunks, ctr);     // warp-collective
   }
 #undef LS_VOX
 }
@@ -1458,7 +1468,9 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
       }
       pm[j] = __ballot_sync(FULL, parked[j]);
     }
-    *reinterpret_cast<uint2 *>(&s_ent[st][2 * tid]) = make_uint2(e2[0], e2[1]);
+    // entries and keys go back sector by sector, only where they changed (a surface brick is mostly empty space:
+    // the bulk store of the whole brick wrote 6 KB where a few hundred bytes had changed)
+    if (e2[0] != ee.x || e2[1] != ee.y) *reinterpret_cast<uint2 *>(g.grid + base + 2 * tid) = make_uint2(e2[0], e2[1]);
     s_state[st][tid] = (unsigned char)(nib[0] | (nib[1] << 4));
     // slots for the parked voxels -- one global atomic per brick (block-aggregated: same-address atomics
     // serialise in L2; reserving slots in per-CTA chunks instead was slower, the gaps cost the replay more)
@@ -1492,14 +1504,12 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
         else atomicAdd(&ctr->pending_overflow, 1u);
       }
     }
-    *reinterpret_cast<ulonglong2 *>(&s_keys[st][2 * tid]) = make_ulonglong2(nk[0], nk[1]);
-    // generic-proxy writes to the stage -> visible to the async proxy, then one thread stores the brick
+    if (kk.x != nk[0] || kk.y != nk[1]) *reinterpret_cast<ulonglong2 *>(g.keys + base + 2 * tid) = make_ulonglong2(nk[0], nk[1]);
+    // generic-proxy writes to the state stage -> visible to the async proxy, then one thread stores it
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid == 0)
     {
-      bulk_s2g(g.keys + base, s_keys[st], MERGE_KEY_BYTES);
-      bulk_s2g(g.grid + base, s_ent[st], MERGE_ENT_BYTES);
       bulk_s2g(reinterpret_cast<unsigned char *>(g.vstate) + base / 2, s_state[st], WS_BRICK_VOX / 2);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
@@ -1652,6 +1662,7 @@ replay_scan_kernel(const GridDesc g, UpdateCounters *__restrict__ ctr, const uns
   if (gthread == 0) ctr->t_phase[0] = global_ns();
   unsigned n_chunks = ctr->n_chunks;
   if (n_chunks > cap_chunks) n_chunks = cap_chunks;
+  const bool wide = g.wide != 0;
   ListWriter lw;
   lw.base = 0u; lw.used = WS_LIST_SPAN;
   for (unsigned c0 = gwarp * 2u; c0 < n_chunks; c0 += gwarps * 2u)
@@ -1667,7 +1678,11 @@ replay_scan_kernel(const GridDesc g, UpdateCounters *__restrict__ ctr, const uns
       const unsigned j = (unsigned)(u & 1) * 32u + (unsigned)lane;
       ok[u] = c < n_chunks && j < chunk_fill[c < n_chunks ? c : c0];
       rr[u].key = 0ull; rr[u].ref = 0ull;
-      if (ok[u]) rr[u] = rec[(size_t)c * WS_REC_CHUNK + j];
+      if (ok[u])
+      {
+        rr[u].ref = (u64)rec_refs(rec, c)[j];
+        if (wide) rr[u].ref |= (u64)rec_refs(rec, c)[WS_REC_CHUNK + j] << 32;
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) pw[u] = ok[u] ? __ldcg(&g.vstate[vstate_word(rr[u].ref)]) : 0u;
@@ -1676,6 +1691,7 @@ replay_scan_kernel(const GridDesc g, UpdateCounters *__restrict__ ctr, const uns
     {
       ok[u] = ok[u] && ((pw[u] >> vstate_shift(rr[u].ref)) & VS_PARKED);
       kv[u] = ok[u] ? __ldcg(&g.keys[rr[u].ref]) : WS_KEY_EMPTY;
+      if (ok[u]) rr[u].key = rec_keys(rec, c0 + (unsigned)(u >> 1))[(unsigned)(u & 1) * 32u + (unsigned)lane];
     }
     unsigned sb[4];
 #pragma unroll
@@ -2112,7 +2128,7 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
     unsigned *list_all = h->d_brick_list, *list_surf = h->d_brick_list + h->g.n_bricks;
     LsOut out;
     out.pend_key = h->d_pend_key; out.list = h->d_list; out.pending_cap = h->pending_cap; out.list_cap = (unsigned)h->list_cap;
-    const bool wide = (unsigned long long)h->g.n_bricks * WS_BRICK_VOX > 0xFFFFFFFFull;
+    const bool wide = h->g.wide != 0;
     if (!h->stream2)
     {
       WS_CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
@@ -2195,7 +2211,7 @@ void ws_update_finish(ws_handle *h, UpdateCounters *h_ctr, void *h_pose_out, cud
     RaySetup *rays = static_cast<RaySetup *>(h->d_rays);
     const unsigned n_groups = (unsigned)((n + 31) / 32);
     unsigned *list_all = h->d_brick_list;
-    const bool wide = (unsigned long long)h->g.n_bricks * WS_BRICK_VOX > 0xFFFFFFFFull;
+    const bool wide = h->g.wide != 0;
     unsigned cap_chunks = (unsigned)h->rec_cap_chunks;
     LsOut out;
     out.pend_key = h->d_pend_key; out.list = h->d_list; out.pending_cap = h->pending_cap; out.list_cap = (unsigned)h->list_cap;

@@ -84,6 +84,7 @@ struct GridDesc
   int offset[3];    // ring offset of the centre (hdf5_local_map.h:59-70)
   int nb[3];        // bricks per axis = ceil(size / 8)
   int full;         // 1: every ring-x brick column is resident and slot == column
+  int wide;         // 1: voxel addresses need more than 32 bits (n_bricks * 512 > 2^32; WS_FORCE_WIDE=1 forces the 64-bit path on small maps, for tests)
   i64 n_bricks;     // resident bricks
   uint32_t *grid;   // n_bricks * 512 TSDF entries  {int16 value | int16 weight << 16}
   u64 *keys;        // n_bricks * 512 candidate keys (all-ones when idle)
