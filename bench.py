@@ -276,6 +276,19 @@ TIMELINE_NAMES = ["update_tsdf (whole)", "set-up + item scan", "surface march [s
                   "replay rounds [stream 1]", "brick list + free-space merge [stream 1]"]
 
 
+def timeline_rows(timeline):
+    """ws_profile_timeline -> named rows (kind 2 = the registration loop of the same scan, before the update)."""
+    rows, k = [], 0
+    for kd, a, b in timeline:
+        if kd == 2:
+            name = "registration loop (20 iterations) [stream 1]"
+        else:
+            name = TIMELINE_NAMES[k] if k < len(TIMELINE_NAMES) else "kind %d" % kd
+            k += 1
+        rows.append({"range": name, "start": round(a, 4), "stop": round(b, 4)})
+    return rows
+
+
 def traffic_from_profile():
     """DRAM bytes of one update_tsdf on the default workload, summed from the committed ncu capture
     (profiles/*_dram_traffic.csv: kernel, dram_read_MB, dram_write_MB per launch of one scan)."""
@@ -573,9 +586,7 @@ def run_native(args):
                                        "march": march_ms, "merge": merge_ms, "replay": replay_ms,
                                        "note": "update_tsdf = elapsed on the handle's stream; march / merge / replay = busy "
                                                "ranges on three streams that run side by side, their sum exceeds it"},
-                "update_timeline_ms": [{"range": TIMELINE_NAMES[i] if i < len(TIMELINE_NAMES) else "kind %d" % kd,
-                                        "start": round(a, 4), "stop": round(b, 4)}
-                                       for i, (kd, a, b) in enumerate(wl.timeline)],
+                "update_timeline_ms": timeline_rows(wl.timeline),
                 "kernel_ms_per_scan_min_over_ranks": kern_min,
                 "reg_bytes_per_scan": reg_bytes,
                 "reg_formula": "sum over the %d GN iterations of 12*N + 28*N_valid + 232 (SURVEY.md 8d)" % len(valid_per_it) if valid_per_it else None,

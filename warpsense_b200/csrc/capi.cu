@@ -1157,13 +1157,15 @@ int ws_track_submit(ws_handle *h, const ws_point *points, int64_t n, int32_t on_
     h->last_reg_host = false;
     h->host_trace.clear();
     const float I16[16] = { 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1 };
+    // registration -> pose -> update_tsdf, whose set-up kernel transforms the cloud by the registration result first
+    // (registration.cpp:164-174); results read back at the end.  (The pose stays a kernel of its own: computed in
+    // the registration kernel's epilogue it cost that kernel 12 % -- its loop is sensitive to what follows it.)
     ws_launch_reg_reset(h, pretransform ? pretransform : I16, 0.f);
-    if (max_iterations > 0) ws_launch_reg_loop(h, (int)n, map_resolution, max_iterations, it_weight_gradient, epsilon);
-    ws_launch_transform_cloud(h, t.d_pts, (int)n);
+    if (max_iterations > 0 && n > 0) ws_launch_reg_loop(h, (int)n, map_resolution, max_iterations, it_weight_gradient, epsilon);
     ws_launch_pose(h, h->d_acc->T, prior_pose, (flags & WS_TRACK_REFERENCE_POSE) ? 1 : 0);
     h->track_has_pose = true;
+    ws_update_enqueue(h, t.d_pts, (int)n, nullptr, nullptr, true, t.h_ctr, t.h_pose, h->d_acc->T);
     WS_CUDA_OK(cudaMemcpyAsync(t.h_acc, h->d_acc, sizeof(RegAccum), cudaMemcpyDeviceToHost, h->stream));
-    ws_update_enqueue(h, t.d_pts, (int)n, nullptr, nullptr, true, t.h_ctr, t.h_pose);
     WS_CUDA_OK(cudaEventRecord(t.done, h->stream));
     h->d_reg_points_alias = nullptr;
     t.busy = true; t.finished = false; t.error.clear(); t.n = n; t.regrows_at_submit = h->record_regrows;
@@ -1505,16 +1507,19 @@ int ws_profile_reset(ws_handle *h)
 
 int64_t ws_profile_timeline(ws_handle *h, double *out, int64_t cap_ranges)
 {
-  // ranges of the LAST update_tsdf span, as (kind, start_ms, stop_ms) relative to the span's start
+  // ranges of the LAST update_tsdf span (and the registration before it), as (kind, start_ms, stop_ms) relative to the span's start
   int64_t n = 0;
   const int rc = guarded(h, [&]() {
     WS_CUDA_OK(cudaDeviceSynchronize());
     const size_t used = std::min(h->timers_used, h->timers.size());
-    long span = -1;
+    long span = -1, first = -1;
     for (size_t i = 0; i < used; i++)
       if (h->timer_kind[i] == WS_TIMER_UPDATE) span = (long)i;
     if (span < 0) return WS_OK;
-    for (size_t i = (size_t)span; i < used && n < cap_ranges; i++)
+    // ... preceded by the ranges since the end of the update before (the registration of this scan): negative offsets
+    first = span;
+    while (first > 0 && h->timer_kind[first - 1] == WS_TIMER_REG) first--;
+    for (size_t i = (size_t)first; i < used && n < cap_ranges; i++)
     {
       float a = 0.f, b = 0.f;
       if (cudaEventElapsedTime(&a, h->timers[span].start, h->timers[i].start) != cudaSuccess) continue;

@@ -21,27 +21,6 @@ namespace cg = cooperative_groups;
 #define FULL 0xFFFFFFFFu
 #define WS_NSUM 29
 
-namespace {
-
-// include/util/util.h:8-11
-WS_HD void to_int_mat(const float T[16], int M[16])
-{
-  for (int i = 0; i < 16; i++) M[i] = (int)(T[i] * (float)WS_MR);
-}
-
-// include/util/util.h:13-18 (column-major M)
-WS_HD void transform_point(const int M[16], int x, int y, int z, int out[3])
-{
-#pragma unroll
-  for (int r = 0; r < 3; r++)
-  {
-    int acc = wadd(wadd(wadd(wmul(M[r], x), wmul(M[4 + r], y)), wmul(M[8 + r], z)), M[12 + r]);
-    out[r] = div_mr32(acc);
-  }
-}
-
-}  // namespace
-
 // ------------------------------------------------------------------------------------------------
 // FP64 damped solve + pose update, compiled for host and device from one source so the two agree.
 // Mirrors Eigen's PartialPivLU-based Matrix<double,6,6>::inverse().
@@ -823,11 +802,15 @@ __global__ void reg_solve_kernel(RegAccum *acc, u64 *trace, int trace_cap, float
   finish_iteration(acc, trace, trace_cap, it_weight_gradient, epsilon);
 }
 
-__global__ void reg_reset_kernel(RegAccum *acc, const float *T, float alpha0)
+// (the start transform comes by value: nothing staged in host memory that a second scan in flight could overwrite;
+// the rotating accumulators + ticket counter of reg_loop_kernel are cleared here too)
+struct RegMat16 { float m[16]; };
+__global__ void reg_reset_kernel(RegAccum *acc, const RegMat16 T0, float alpha0, u64 *partials, int n_partials)
 {
   const int t = threadIdx.x;
+  for (int i = t; i < n_partials; i += blockDim.x) partials[i] = 0ull;
   if (t < 32) acc->sums[t] = 0ull;
-  if (t < 16) acc->T[t] = T[t];
+  if (t < 16) acc->T[t] = T0.m[t];
   if (t < 4) acc->prev_err[t] = 0.f;
   if (t == 0) { acc->ticket = 0u; acc->finished = 0u; acc->iterations = 0u; acc->alpha = alpha0; }
 }
@@ -853,13 +836,29 @@ transform_cloud_kernel(ws_pt *pts, int n, const RegAccum *acc)
 
 }  // namespace
 
+static void ensure_reg_loop_buffers(ws_handle *h)
+{
+  if (h->reg_loop_blocks != 0) return;
+  int per_sm = 0;
+  WS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reg_loop_kernel<true>, REG_THREADS, 0));
+  if (per_sm < 1) throw std::runtime_error("reg_loop_kernel does not fit on an SM");
+  if (per_sm > 2) per_sm = 2;
+  h->reg_loop_blocks = per_sm * h->sm_count;
+  // tests that run several ranks' persistent kernels side by side on ONE GPU need them co-resident
+  if (const char *e = std::getenv("WS_REG_BLOCKS"))
+  {
+    const int v = std::atoi(e);
+    if (v >= 1 && v < h->reg_loop_blocks) h->reg_loop_blocks = v;
+  }
+  WS_CUDA_OK(cudaMalloc(&h->d_reg_partials, ((size_t)2 * h->reg_loop_blocks + 4) * REG_NSLOT * sizeof(u64)));
+}
+
 void ws_launch_reg_reset(ws_handle *h, const float T[16], float alpha0)
 {
-  // T is staged through the pinned mirror so the copy is asynchronous on the handle's stream
-  std::memcpy(h->h_acc->T, T, 16 * sizeof(float));
-  float *d_T_stage = reinterpret_cast<float *>(reinterpret_cast<char *>(h->d_acc) + sizeof(RegAccum));
-  WS_CUDA_OK(cudaMemcpyAsync(d_T_stage, h->h_acc->T, 16 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-  reg_reset_kernel<<<1, 32, 0, h->stream>>>(h->d_acc, d_T_stage, alpha0);
+  ensure_reg_loop_buffers(h);
+  RegMat16 T0;
+  std::memcpy(T0.m, T, sizeof(T0.m));
+  reg_reset_kernel<<<1, 128, 0, h->stream>>>(h->d_acc, T0, alpha0, h->d_reg_partials, 4 * REG_NSLOT);
   h->launches++;
 }
 
@@ -878,21 +877,7 @@ size_t ws_reg_mailbox_bytes(int world) { return (size_t)4 * world * WS_MAIL_WORD
 
 void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float it_weight_gradient, float epsilon)
 {
-  if (h->reg_loop_blocks == 0)
-  {
-    int per_sm = 0;
-    WS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reg_loop_kernel<true>, REG_THREADS, 0));
-    if (per_sm < 1) throw std::runtime_error("reg_loop_kernel does not fit on an SM");
-    if (per_sm > 2) per_sm = 2;
-    h->reg_loop_blocks = per_sm * h->sm_count;
-    // tests that run several ranks' persistent kernels side by side on ONE GPU need them co-resident
-    if (const char *e = std::getenv("WS_REG_BLOCKS"))
-    {
-      const int v = std::atoi(e);
-      if (v >= 1 && v < h->reg_loop_blocks) h->reg_loop_blocks = v;
-    }
-    WS_CUDA_OK(cudaMalloc(&h->d_reg_partials, ((size_t)2 * h->reg_loop_blocks + 4) * REG_NSLOT * sizeof(u64)));
-  }
+  ensure_reg_loop_buffers(h);
   RegLoopParams rp;
   rp.n = n;
   rp.div_res = make_fastdiv((unsigned)res);
@@ -915,9 +900,7 @@ void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float 
   ws_pt *reg_pts = h->d_reg_points_alias ? h->d_reg_points_alias : h->d_reg_points;
   void *args[] = { (void *)&h->g, (void *)&reg_pts, (void *)&rp, (void *)&h->d_acc,
                    (void *)&h->d_reg_partials, (void *)&h->d_trace, (void *)&h->trace_cap, (void *)&pp };
-#ifndef WS_REG_GRIDSYNC
-  WS_CUDA_OK(cudaMemsetAsync(h->d_reg_partials, 0, (size_t)4 * REG_NSLOT * sizeof(u64), h->stream));   // accumulators + tickets
-#endif
+  // (the accumulators + tickets were cleared by reg_reset_kernel, which every caller runs first)
   ws_timer_begin(h, WS_TIMER_REG);
   const void *fn = h->world > 1 ? (const void *)reg_loop_kernel<true> : (const void *)reg_loop_kernel<false>;
   WS_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(h->reg_loop_blocks), dim3(REG_THREADS), args, 0, h->stream));

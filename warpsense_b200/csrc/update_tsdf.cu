@@ -536,9 +536,9 @@ WS_D void ray_segments(const UpdateParams &P, const Ray &r, int seg[2 * RAY_SEGS
 // Set-up pass: one THREAD per ray (the march needs the result warp-uniform; computing it there costs every
 // lane of a warp the same ~600 instructions).  Rays without work on this rank get empty step ranges.
 __global__ void __launch_bounds__(256)
-setup_kernel(const UpdateParams Pin, const ws_pt *__restrict__ pts, RaySetup *__restrict__ rays,
+setup_kernel(const UpdateParams Pin, ws_pt *__restrict__ pts, RaySetup *__restrict__ rays,
              uint2 *__restrict__ grp_info, const unsigned grp_stride, unsigned *__restrict__ gen_list,
-             UpdateCounters *__restrict__ ctr, const PoseDev *__restrict__ pose)
+             UpdateCounters *__restrict__ ctr, const PoseDev *__restrict__ pose, const float *__restrict__ xform)
 {
   // the sensor pose comes from the host (kernel parameters) or, in the fused per-scan pipeline, from the
   // registration that ran just before on the same stream (device memory)
@@ -555,7 +555,21 @@ setup_kernel(const UpdateParams Pin, const ws_pt *__restrict__ pts, RaySetup *__
   if (ray_id < P.n_points)
   {
     Ray r;
-    if (ray_setup(P, pts[ray_id], r))
+    ws_pt pt = pts[ray_id];
+    if (xform)
+    {
+      // the registered cloud (registration.cpp:164-174): transformed here instead of by a kernel of its own, and
+      // written back for the callers that read it (ws_reg_points_device)
+      float T[16];
+#pragma unroll
+      for (int i = 0; i < 16; i++) T[i] = __ldg(&xform[i]);
+      int M[16], q[3];
+      to_int_mat(T, M);
+      transform_point(M, pt.x, pt.y, pt.z, q);
+      pt.x = q[0]; pt.y = q[1]; pt.z = q[2];
+      pts[ray_id] = pt;
+    }
+    if (ray_setup(P, pt, r))
     {
 #pragma unroll
       for (int a = 0; a < 3; a++) { o.p[a] = r.p[a]; o.d[a] = r.d[a]; o.iv[a] = r.iv[a]; }
@@ -1959,39 +1973,10 @@ static void launch_replay(ws_handle *h, const UpdateParams &P)
 //   compose_reference != 0: App::update_pose_estimate (src/warpsense/app.cpp:172-176, same in
 //                           src/cpu/fastsense.cpp:219-221): R = X.R * prior.R, t = prior.t + X.t.
 // The prior comes by value, or (chain) is the pose this kernel left in `out` for the previous scan.
-struct Mat16 { float m[16]; };
-__global__ void pose_kernel(const float *__restrict__ X, const Mat16 prior_in, const int chain, const int compose_reference,
-                            const int res, const int coord_lim, PoseDev *__restrict__ out)
+__global__ void pose_kernel(const float *__restrict__ X, const PoseArgs pa)
 {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  float prior[16], pose[16];
-  for (int i = 0; i < 16; i++) prior[i] = chain ? out->pose[i] : prior_in.m[i];
-  for (int c = 0; c < 4; c++)
-    for (int r = 0; r < 4; r++)
-    {
-      float acc = X[0 * 4 + r] * prior[c * 4 + 0];
-      acc = acc + X[1 * 4 + r] * prior[c * 4 + 1];
-      acc = acc + X[2 * 4 + r] * prior[c * 4 + 2];
-      if (!compose_reference) acc = acc + X[3 * 4 + r] * prior[c * 4 + 3];
-      pose[c * 4 + r] = acc;
-    }
-  if (compose_reference)
-  {
-    for (int r = 0; r < 3; r++) pose[12 + r] = prior[12 + r] + X[12 + r];
-    for (int c = 0; c < 4; c++) pose[c * 4 + 3] = prior[c * 4 + 3];
-  }
-  bool ok = true;
-  for (int a = 0; a < 3; a++)
-  {
-    const int vox = (int)floorf(pose[12 + a] / (float)res);
-    out->pos_mm[a] = (int)((unsigned)vox * (unsigned)res);
-    out->up[a] = (long long)(int)(pose[8 + a] * (float)WS_MR);
-    const long long ap = out->pos_mm[a] < 0 ? -(long long)out->pos_mm[a] : (long long)out->pos_mm[a];
-    if (ap >= (long long)coord_lim) ok = false;
-    out->pos_vox[a] = vox;
-  }
-  out->coord_lim = ok ? coord_lim : 0;
-  for (int i = 0; i < 16; i++) out->pose[i] = pose[i];
+  pose_compute(X, pa);
 }
 
 void ws_compose_pose_host(const float X[16], const float prior[16], float pose[16])
@@ -2007,8 +1992,8 @@ void ws_compose_pose_host(const float X[16], const float prior[16], float pose[1
     }
 }
 
-// prior == nullptr: chain from the pose the previous ws_launch_pose left on the device
-void ws_launch_pose(ws_handle *h, const float *d_X, const float *prior, int compose_reference)
+// prior == nullptr: chain from the pose the previous scan left on the device
+PoseArgs ws_pose_args(ws_handle *h, const float *prior, int compose_reference)
 {
   if (!h->d_pose)
   {
@@ -2016,11 +2001,22 @@ void ws_launch_pose(ws_handle *h, const float *d_X, const float *prior, int comp
     WS_CUDA_OK(cudaMemsetAsync(h->d_pose, 0, sizeof(PoseDev), h->stream));
     WS_CUDA_OK(cudaMallocHost(&h->h_pose, sizeof(PoseDev)));
   }
-  Mat16 pm;
-  for (int i = 0; i < 16; i++) pm.m[i] = prior ? prior[i] : 0.f;
+  PoseArgs pa;
+  pa.out = static_cast<PoseDev *>(h->d_pose);
+  for (int i = 0; i < 16; i++) pa.prior[i] = prior ? prior[i] : 0.f;
+  pa.chain = prior ? 0 : 1;
+  pa.compose_reference = compose_reference;
+  pa.res = h->res;
   long long lim = (1ll << 31) / h->res - h->tau - (1ll << 17);
   if (lim < 0 || std::getenv("WS_MARCH_GENERAL") || h->res < 4) lim = 0;
-  pose_kernel<<<1, 32, 0, h->stream>>>(d_X, pm, prior ? 0 : 1, compose_reference, h->res, (int)lim, static_cast<PoseDev *>(h->d_pose));
+  pa.coord_lim = (int)lim;
+  return pa;
+}
+
+void ws_launch_pose(ws_handle *h, const float *d_X, const float *prior, int compose_reference)
+{
+  const PoseArgs pa = ws_pose_args(h, prior, compose_reference);
+  pose_kernel<<<1, 32, 0, h->stream>>>(d_X, pa);
   h->launches++;
 }
 
@@ -2036,8 +2032,8 @@ void ws_launch_pose(ws_handle *h, const float *d_X, const float *prior, int comp
 // Enqueues one update_tsdf on the handle's stream; the work counters (and the device-side pose) land in
 // `h_ctr` / `h_pose_out` (pinned) behind it.  ws_update_finish() waits, regrows the record if it overflowed and
 // reports errors.
-void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos_in[3], const int up_in[3],
-                       bool pose_on_device, UpdateCounters *h_ctr, void *h_pose_out)
+void ws_update_enqueue(ws_handle *h, ws_pt *d_pts, int n, const int scanner_pos_in[3], const int up_in[3],
+                       bool pose_on_device, UpdateCounters *h_ctr, void *h_pose_out, const float *d_xform)
 {
   // pose_on_device: the scanner pose was left in h->d_pose by ws_launch_pose on this stream; the host copy
   // (needed only if the candidate record has to be regenerated) is read back with the counters
@@ -2139,7 +2135,7 @@ void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanne
       WS_CUDA_OK(cudaEventCreateWithFlags(&h->ev_scanned, cudaEventDisableTiming));
     }
     cudaStream_t s2 = h->stream2;
-    setup_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_pts, rays, h->d_grp_info, n_groups, h->d_gen_list, h->d_counters, d_pose);
+    setup_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_pts, rays, h->d_grp_info, n_groups, h->d_gen_list, h->d_counters, d_pose, d_xform);
     item_scan_kernel<<<3, 1024, 0, s>>>(h->d_grp_info, n_groups, h->d_item_off, h->d_counters);
     ws_timer_end(h);
     // Two streams from here.  Surface phase (this stream): keys, record, merge -> parked voxels.  The near-field part
@@ -2260,7 +2256,7 @@ void ws_update_finish(ws_handle *h, UpdateCounters *h_ctr, void *h_pose_out, cud
 
 void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3], bool pose_on_device)
 {
-  ws_update_enqueue(h, d_pts, n, scanner_pos, up, pose_on_device, h->h_counters, h->h_pose);
+  ws_update_enqueue(h, const_cast<ws_pt *>(d_pts), n, scanner_pos, up, pose_on_device, h->h_counters, h->h_pose);   // no transform: read only
   ws_update_finish(h, h->h_counters, h->h_pose, nullptr);
 }
 

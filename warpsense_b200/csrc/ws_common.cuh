@@ -64,6 +64,23 @@ WS_HD int wmul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
 WS_HD int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
 WS_HD int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
 
+// include/util/util.h:8-11
+WS_HD void to_int_mat(const float T[16], int M[16])
+{
+  for (int i = 0; i < 16; i++) M[i] = (int)(T[i] * (float)WS_MR);
+}
+
+// include/util/util.h:13-18 (column-major M)
+WS_HD void transform_point(const int M[16], int x, int y, int z, int out[3])
+{
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+  {
+    int acc = wadd(wadd(wadd(wmul(M[r], x), wmul(M[4 + r], y)), wmul(M[8 + r], z)), M[12 + r]);
+    out[r] = div_mr32(acc);
+  }
+}
+
 // (int)std::sqrt((double)sq) for 0 <= sq < 2^31 == floor(sqrt(sq)) (Eigen Vector3i::norm()).
 WS_D int isqrt31(int sq)
 {

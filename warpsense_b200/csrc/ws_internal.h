@@ -49,6 +49,54 @@ struct PoseDev
   float pose[16];      // X * prior, column-major
 };
 
+// what the device needs to turn a registration result X into the scanner pose of update_tsdf
+struct PoseArgs
+{
+  PoseDev *out;            // nullptr: no pose wanted
+  float prior[16];         // prior pose (column-major), unless chain
+  int chain;               // 1: the prior is the pose left in `out` by the scan before
+  int compose_reference;   // 1: App::update_pose_estimate (R = X.R * R, t += X.t); 0: the full product X * prior
+  int res;
+  int coord_lim;
+};
+
+#ifdef __CUDACC__
+// src/warpsense/tsdf_mapping.cpp:77-85 + include/util/util.h:52-56: new pose from the registration result X and the
+// prior pose, scanner voxel = floor(t / res), up = third column of to_int_mat(pose).  One thread.
+__device__ inline void pose_compute(const float *X, const PoseArgs &pa)
+{
+  PoseDev *out = pa.out;
+  float prior[16], pose[16];
+  for (int i = 0; i < 16; i++) prior[i] = pa.chain ? out->pose[i] : pa.prior[i];
+  for (int c = 0; c < 4; c++)
+    for (int r = 0; r < 4; r++)
+    {
+      float acc = X[0 * 4 + r] * prior[c * 4 + 0];
+      acc = acc + X[1 * 4 + r] * prior[c * 4 + 1];
+      acc = acc + X[2 * 4 + r] * prior[c * 4 + 2];
+      if (!pa.compose_reference) acc = acc + X[3 * 4 + r] * prior[c * 4 + 3];
+      pose[c * 4 + r] = acc;
+    }
+  if (pa.compose_reference)
+  {
+    for (int r = 0; r < 3; r++) pose[12 + r] = prior[12 + r] + X[12 + r];
+    for (int c = 0; c < 4; c++) pose[c * 4 + 3] = prior[c * 4 + 3];
+  }
+  bool ok = true;
+  for (int a = 0; a < 3; a++)
+  {
+    const int vox = (int)floorf(pose[12 + a] / (float)pa.res);
+    out->pos_mm[a] = (int)((unsigned)vox * (unsigned)pa.res);
+    out->up[a] = (long long)(int)(pose[8 + a] * (float)WS_MR);
+    const long long ap = out->pos_mm[a] < 0 ? -(long long)out->pos_mm[a] : (long long)out->pos_mm[a];
+    if (ap >= (long long)pa.coord_lim) ok = false;
+    out->pos_vox[a] = vox;
+  }
+  out->coord_lim = ok ? pa.coord_lim : 0;
+  for (int i = 0; i < 16; i++) out->pose[i] = pose[i];
+}
+#endif
+
 // one recorded candidate: its key and the voxel address (record) or the pending slot (replay list)
 struct Rec
 {
@@ -242,8 +290,10 @@ struct ws_handle
 // update_tsdf.cu
 void ws_launch_update(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3],
                       bool pose_on_device = false);
-void ws_update_enqueue(ws_handle *h, const ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3],
-                       bool pose_on_device, UpdateCounters *h_ctr, void *h_pose_out);
+// d_xform != nullptr: the scan is first transformed in place by that column-major float[16] in device memory
+// (registration.cpp:164-174, the registration result left in RegAccum::T) -- inside the set-up kernel
+void ws_update_enqueue(ws_handle *h, ws_pt *d_pts, int n, const int scanner_pos[3], const int up[3],
+                       bool pose_on_device, UpdateCounters *h_ctr, void *h_pose_out, const float *d_xform = nullptr);
 void ws_update_finish(ws_handle *h, UpdateCounters *h_ctr, void *h_pose_out, cudaEvent_t done);
 void ws_launch_pose(ws_handle *h, const float *d_X, const float *prior, int compose_reference);
 void ws_compose_pose_host(const float X[16], const float prior[16], float pose[16]);
@@ -253,6 +303,8 @@ void ws_launch_reg_reset(ws_handle *h, const float T[16], float alpha0);
 void ws_launch_reg_iteration(ws_handle *h, int n, int res, int fused_solve, float it_weight_gradient, float epsilon);
 void ws_launch_reg_solve(ws_handle *h, float it_weight_gradient, float epsilon);
 void ws_launch_reg_loop(ws_handle *h, int n, int res, int max_iterations, float it_weight_gradient, float epsilon);
+// the PoseArgs of ws_launch_pose (allocates the device pose on first use)
+PoseArgs ws_pose_args(ws_handle *h, const float *prior, int compose_reference);
 void ws_launch_transform_cloud(ws_handle *h, ws_pt *d_pts, int n);
 void ws_host_solve(const i64 H[36], const i64 g[6], int err, int cnt, float alpha, float T[16], double xi_out[6]);
 // preprocess.cu
