@@ -308,7 +308,8 @@ int ws_map_reload(ws_handle *h);
 /* record cudaEvents around the hot kernels (kind: 0 march, 1 brick list + merge, 2 registration loop, 3 replay,
  * 4 the whole update_tsdf of one scan on the handle's stream).  Kinds 0, 1 and 3 are ranges on three streams that
  * run side by side (surface march + merge | near-field free-space march | record pass of the replay): their sums
- * exceed kind 4, which is the elapsed time of the update. */
+ * exceed kind 4, which is the elapsed time of the update.  on: 0 off, 1 every range (~20 event records per scan:
+ * measured 3 % of the scan rate), 2 kinds 2 and 4 only (what a timed run can afford). */
 int ws_profile_enable(ws_handle *h, int32_t on);
 int ws_profile_reset(ws_handle *h);
 /* sum of elapsed ms and launch count per kind since the last reset (synchronises the stream) */

@@ -43,6 +43,30 @@ int main()
       CHECK(fd32_sdiv((int)-n, f) == (int)((-n) / (long long)d) && fd32_udiv((unsigned)n, f) == (unsigned)(n / d), "small %lld / %u", n, d);
   }
 
+  // 1b. the merge's running average (update_tsdf.cpp:549): float estimate + one correction == C++ `/`
+  for (int t = 0; t < 4000000; t++)
+  {
+    int n, d;
+    switch (t & 3)
+    {
+      case 0: { const int ev = (int)uni(-32768, 32767), ew = (int)uni(1, 32767), v = (int)uni(-32767, 32767), w = (int)uni(1, 64);
+                n = ev * ew + v * w; d = ew + w; break; }                                   // what merge_entry feeds it
+      case 1: d = (int)uni(1, 800); n = (int)uni(-(1ll << 31) + 1, (1ll << 31) - 1); break; // quotients above 2^20: falls back
+      case 2: d = (int)uni(1, (1 << 25)); n = (int)uni(-(1ll << 31) + 1, (1ll << 31) - 1); break;
+      default: { d = (int)uni(1, 70000); const long long k = uni(0, ((1ll << 31) - 2) / d); n = (int)(k * d + uni(-1, 1));
+                 if (t & 4) n = -n; break; }                                                // multiples and their neighbours
+    }
+    CHECK(div_trunc_small(n, d) == n / d, "div_trunc_small %d / %d -> %d", n, d, div_trunc_small(n, d));
+  }
+  // 1c. the candidate weight (update_tsdf.cpp:475-479) through the per-scan magic
+  for (int tau : { 1, 2, 9, 10, 11, 100, 600, 1000, 1234, 32767 })
+  {
+    const int eps = tau / 10;
+    const FastDiv fw = make_fastdiv((unsigned)(tau - eps > 0 ? tau - eps : 1));
+    for (int v = -tau; v <= tau; v++)
+      CHECK(tsdf_weight_fd(v, tau, eps, fw) == tsdf_weight(v, tau, eps), "tsdf_weight tau %d value %d", tau, v);
+  }
+
   // 2. reciprocal-based division with remainder
   for (int t = 0; t < 2000000; t++)
   {

@@ -419,7 +419,10 @@ class TSDFCuda:
         return int(self._hd.L.ws_launch_count(self._hd.h))
 
     def profile(self, on=True):
-        self._hd.check(self._hd.L.ws_profile_enable(self._hd.h, 1 if on else 0))
+        """False / 0: off; True / 1: every range (about 20 event records per scan); 2: the registration loop and the
+        whole update only (what a timed run can afford)."""
+        level = int(on) if not isinstance(on, bool) else (1 if on else 0)
+        self._hd.check(self._hd.L.ws_profile_enable(self._hd.h, level))
 
     def profile_reset(self):
         self._hd.check(self._hd.L.ws_profile_reset(self._hd.h))

@@ -464,7 +464,8 @@ void ws_timer_begin(ws_handle *h, int kind, cudaStream_t stream)
 {
   static const char *const names[] = { "ws:march", "ws:merge", "ws:register", "ws:replay" };
   nvtxRangePushA(names[kind & 3]);
-  if (!h->profile) return;
+  h->timer_open = false;
+  if (!h->profile || (h->profile == 2 && kind != WS_TIMER_REG)) return;      // level 2: registration + whole update only
   if (h->timers_used >= h->timers.size())
   {
     if (h->timers.size() >= (1u << 16)) { h->timers_used = h->timers.size() + 1; return; }
@@ -475,12 +476,14 @@ void ws_timer_begin(ws_handle *h, int kind, cudaStream_t stream)
   }
   h->timer_kind[h->timers_used] = kind;
   cudaEventRecord(h->timers[h->timers_used].start, stream ? stream : h->stream);
+  h->timer_open = true;
 }
 
 void ws_timer_end(ws_handle *h, cudaStream_t stream)
 {
   nvtxRangePop();
-  if (!h->profile) return;
+  if (!h->profile || !h->timer_open) return;
+  h->timer_open = false;
   if (h->timers_used < h->timers.size())
   {
     cudaEventRecord(h->timers[h->timers_used].stop, stream ? stream : h->stream);
@@ -1492,7 +1495,7 @@ int64_t ws_launch_count(const ws_handle *h) { return h ? h->launches : 0; }
 int ws_profile_enable(ws_handle *h, int32_t on)
 {
   if (!h) return WS_ERR_INVALID;
-  h->profile = on != 0;
+  h->profile = on == 2 ? 2 : (on != 0 ? 1 : 0);
   return WS_OK;
 }
 

@@ -57,7 +57,9 @@ namespace cg = cooperative_groups;
 #endif
 #define MARCH_THREADS (MARCH_WARPS * 32)
 #define QCAP 64
+#ifndef LS_BLOCK
 #define LS_BLOCK 64          // march steps per work item of the lockstep march
+#endif
 #ifndef RAY_BATCH
 #define RAY_BATCH 1          // same-box A/B on B200: 1 -> 0.77 ms, 2 -> 0.79, 4 -> 0.91, 8 -> 1.07 (tail of long rays)
 #endif
@@ -1332,7 +1334,7 @@ brick_list_kernel(const GridDesc g, unsigned *__restrict__ brick_list, UpdateCou
 WS_D unsigned apply_winner_to(uint32_t *slot, const uint32_t e, const UpdateParams &P, const u64 key)
 {
   const int value = key_value(key);
-  int weight = tsdf_weight(value, P.tau, P.weight_epsilon);
+  int weight = tsdf_weight_fd(value, P.tau, P.weight_epsilon, P.div_weps);
   if (key_interpolated(key)) weight = -weight;
   const uint32_t n = merge_entry(e, value, weight, P.max_weight);
   if (n != e) *slot = n;
@@ -1474,7 +1476,7 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
       if (fin)
       {
         const int value = key_value(k);
-        int weight = tsdf_weight(value, P.tau, P.weight_epsilon);
+        int weight = tsdf_weight_fd(value, P.tau, P.weight_epsilon, P.div_weps);
         if (key_interpolated(k)) weight = -weight;
         const int ew = entry_weight(e2[j]);
         written += ((weight > 0 && ew > 0) || (weight != 0 && ew <= 0)) ? 1u : 0u;

@@ -255,7 +255,8 @@ struct ws_handle
   unsigned long long peer_timeout_ns = 5000000000ull;
 
   // timing of the dominant kernels (cudaEvents on `stream`)
-  bool profile = false;
+  int profile = 0;            // 0 off, 1 every range, 2 registration loop + whole update only
+  bool timer_open = false;
   std::vector<WsTimer> timers;
   std::vector<int> timer_kind;
   size_t timers_used = 0;
