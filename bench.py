@@ -273,8 +273,8 @@ def workload_config(args):
 # ------------------------------------------------------------------------------------------------
 # the timed ranges of one update_tsdf in launch order (ws_profile_timeline; update_tsdf.cu ws_update_enqueue)
 TIMELINE_NAMES = ["update_tsdf (whole)", "set-up + item scan", "surface march [stream 1]", "free-space march, near field [stream 2]",
-                  "brick list + surface merge [stream 1]", "replay record pass [stream 3]", "free-space march, far field [stream 1]",
-                  "replay rounds [stream 1]", "brick list + free-space merge [stream 1]"]
+                  "surface merge (flag compaction inside) [stream 1]", "replay record pass [stream 3]", "free-space march, far field [stream 1]",
+                  "replay rounds [stream 1]", "free-space merge (flag compaction inside) [stream 1]"]
 
 
 def timeline_rows(timeline):
@@ -407,15 +407,16 @@ class Workload:
             self.transforms.append(self.reg.track_wait(tickets.pop(0))[0])
 
     def timed(self, W, K, host, first=1, detail=False):
-        """W warm-up scans, then K timed ones.  The timed region carries only the coarse CUDA events (registration
-        loop + whole update_tsdf per scan: ws_profile_enable level 2); the per-phase ranges on the three streams cost
-        ~3 % of the scan rate (~20 event records per scan, measured) and are taken by a separate pass (detail=True)."""
+        """W warm-up scans, then K timed ones.  The device-resident pass carries only the coarse CUDA events
+        (registration loop + whole update_tsdf per scan: ws_profile_enable level 2, ~1 % of the scan rate), the
+        end-to-end pass none; the per-phase ranges on the three streams cost ~3 % (~20 event records per scan,
+        same-box A/B 798 -> 823 scans/s without them) and are taken by a separate pass (detail=True)."""
         from warpsense_b200 import lib
         torch = self.torch
         with torch.cuda.stream(self.stream):
             self.run(first, first + W - 1, host)
             self.barrier()
-            self.tsdf.profile(1 if detail else 2)
+            self.tsdf.profile(1 if detail else (0 if host else 2))
             self.tsdf.profile_reset()
             launches0 = self.tsdf.launch_count()
             sampler = ClockSampler(self.local_rank)

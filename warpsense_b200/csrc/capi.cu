@@ -71,7 +71,7 @@ void free_handle(ws_handle *h)
   cudaFree(h->g.grid); cudaFree(h->g.keys); cudaFree(h->g.brick_flag); cudaFree(h->g.brick_flag2); cudaFree(h->g.vstate); cudaFree(h->g.ffree); cudaFree(h->g.brick_slot_base);
   cudaFree(h->d_points); cudaFree(h->d_rays); cudaFree(h->d_grp_info); cudaFree(h->d_item_off); cudaFree(h->d_gen_list);
   cudaFree(h->d_vg_keys); cudaFree(h->d_vg_vals); cudaFree(h->d_vg_hist); cudaFree(h->d_vg_box); cudaFree(h->d_vg_xyz);
-  cudaFree(h->d_pre_tmp); cudaFree(h->d_pre_val); cudaFree(h->d_pre_slot); cudaFree(h->d_pre_table); cudaFree(h->d_pre_tiles); cudaFree(h->d_pre_xyz); cudaFree(h->d_reg_points); cudaFree(h->d_brick_list);
+  cudaFree(h->d_pre_tmp); cudaFree(h->d_pre_val); cudaFree(h->d_pre_slot); cudaFree(h->d_pre_table); cudaFree(h->d_pre_tiles); cudaFree(h->d_pre_xyz); cudaFree(h->d_reg_points);
   cudaFree(h->d_counters); cudaFreeHost(h->h_counters);
   cudaFree(h->d_pend_addr); cudaFree(h->d_pend_prev); cudaFree(h->d_pend_key);
   cudaFree(h->d_active[0]); cudaFree(h->d_active[1]);
@@ -220,7 +220,6 @@ int create_impl(const int32_t size[3], int tau, int max_weight, int res, int dev
     WS_CUDA_OK(cudaMemsetAsync(g.vstate, 0, n_vox / 2, h->stream));
     WS_CUDA_OK(cudaMalloc(&g.ffree, n_vox * 2));
     WS_CUDA_OK(cudaMemsetAsync(g.ffree, 0, n_vox * 2, h->stream));
-    WS_CUDA_OK(cudaMalloc(&h->d_brick_list, 2 * (size_t)g.n_bricks * sizeof(unsigned)));
     WS_CUDA_OK(cudaMalloc(&h->d_counters, sizeof(UpdateCounters)));
     WS_CUDA_OK(cudaMallocHost(&h->h_counters, sizeof(UpdateCounters)));
     std::memset(h->h_counters, 0, sizeof(UpdateCounters));

@@ -21,8 +21,8 @@
 //                           store that flags the voxel's 8x8x8 brick.  Far-field candidates (the only ones
 //                           that can meet an interpolated winner) are also appended to a record list in
 //                           64-entry chunks owned by the warp.
-//   2. brick_list_kernel    touched-brick flags -> compact list (and flags reset for the next scan).
-//   3. merge_kernel         moves the touched bricks (4 KB keys + 2 KB entries each) through shared memory
+//   2./3. merge_kernel      every CTA compacts its share of the touched-brick flags into shared memory, then
+//                           moves those bricks (4 KB keys + 2 KB entries each) through shared memory
 //                           with TMA bulk copies (cp.async.bulk + mbarrier, three stages per CTA), folds final
 //                           winners into the grid (:542-560), resets the keys, and parks the voxels whose
 //                           winner is an interpolated candidate below tau ("pending"): their key word then
@@ -1301,35 +1301,6 @@ item_scan_kernel(const uint2 *__restrict__ grp_info, const unsigned n_groups, un
   }
 }
 
-// touched-brick flags -> compact list; flags are reset for the next scan.  SURF: the bricks of the surface
-// phase (they are also marked as touched at all); !SURF: every brick the scan touched.
-template <bool SURF>
-__global__ void __launch_bounds__(256)
-brick_list_kernel(const GridDesc g, unsigned *__restrict__ brick_list, UpdateCounters *__restrict__ ctr)
-{
-  if (!SURF && ctr->rec_overflow != 0u && ctr->pending_overflow == 0u) return;     // redone after the regrow
-  const int lane = threadIdx.x & 31;
-  const i64 stride = (i64)gridDim.x * blockDim.x;
-  const i64 n_round = (g.n_bricks + 31) & ~31ll;
-  unsigned *flag = SURF ? g.brick_flag : g.brick_flag2;
-  unsigned *count = SURF ? &ctr->n_surf_bricks : &ctr->n_touched_bricks;
-  for (i64 b = (i64)blockIdx.x * blockDim.x + threadIdx.x; b < n_round; b += stride)
-  {
-    const bool set = b < g.n_bricks && flag[b] != 0u;
-    const unsigned m = __ballot_sync(FULL, set);
-    if (m == 0u) continue;
-    unsigned first = 0;
-    if (lane == 0) first = atomicAdd(count, (unsigned)__popc(m));
-    first = __shfl_sync(FULL, first, 0);
-    if (set)
-    {
-      brick_list[first + (unsigned)__popc(m & ((1u << lane) - 1u))] = (unsigned)b;
-      flag[b] = 0u;
-      if (SURF) g.brick_flag2[b] = 1u;
-    }
-  }
-}
-
 // final winner -> grid entry (update_tsdf.cpp:542-560); returns 1 if the reference writes the entry
 WS_D unsigned apply_winner_to(uint32_t *slot, const uint32_t e, const UpdateParams &P, const u64 key)
 {
@@ -1397,8 +1368,43 @@ WS_D void bulk_s2g(void *dst_gmem, const void *src_smem, unsigned bytes)
                ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
 
+// The bricks a merge CTA folds: every gridDim.x-th brick of the map whose touched flag is set (the marches set the
+// flags with plain stores), compacted into shared memory, BRICK_SHARE_CAP map bricks per round; the flags are cleared
+// for the next scan.  This used to be a kernel of its own (flags -> global list, 8.5 us plus a launch gap in front of
+// either merge); the strided assignment spreads the touched bricks evenly (they cluster in space).
+#ifndef BRICK_SHARE_CAP
+#define BRICK_SHARE_CAP 512
+#endif
+template <bool SURF>
+WS_D unsigned collect_bricks(const GridDesc &g, const unsigned first, unsigned *s_list, unsigned *s_n)
+{
+  unsigned *flag = SURF ? g.brick_flag : g.brick_flag2;
+  const int tid = threadIdx.x, lane = tid & 31;
+  __syncthreads();                                  // everybody is done with the previous round's list
+  if (tid == 0) *s_n = 0u;
+  __syncthreads();
+  for (unsigned k = (unsigned)tid; k < BRICK_SHARE_CAP; k += 256u)
+  {
+    const i64 b = (i64)blockIdx.x + (i64)(first + k) * (i64)gridDim.x;
+    const bool set = b < (i64)g.n_bricks && flag[b] != 0u;
+    const unsigned m = __ballot_sync(FULL, set);
+    if (m == 0u) continue;
+    unsigned at = 0u;
+    if (lane == 0) at = atomicAdd(s_n, (unsigned)__popc(m));
+    at = __shfl_sync(FULL, at, 0);
+    if (set)
+    {
+      s_list[at + (unsigned)__popc(m & ((1u << lane) - 1u))] = (unsigned)b;
+      flag[b] = 0u;
+      if (SURF) g.brick_flag2[b] = 1u;              // a surface brick is a touched brick
+    }
+  }
+  __syncthreads();
+  return *s_n;
+}
+
 __global__ void __launch_bounds__(256, MERGE_CTAS)
-merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict__ brick_list,
+merge_kernel(const GridDesc g, const UpdateParams P,
                  UpdateCounters *__restrict__ ctr, const unsigned pending_cap,
                  u64 *__restrict__ pend_addr, u64 *__restrict__ pend_prev, u64 *__restrict__ pend_key)
 {
@@ -1408,7 +1414,8 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
   __shared__ unsigned s_cnt[8][2];
   __shared__ unsigned s_base;
   __shared__ __align__(128) unsigned char s_state[MERGE_STAGES][WS_BRICK_VOX / 2];
-  const unsigned n_tb = ctr->n_surf_bricks;
+  __shared__ unsigned s_list[BRICK_SHARE_CAP];
+  __shared__ unsigned s_n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned touched = 0, written = 0;
 
@@ -1419,22 +1426,31 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
   }
   __syncthreads();
 
-  // bricks of this CTA: blockIdx.x, + gridDim.x, ...; iteration n uses stage n % MERGE_STAGES
-  const unsigned n_mine = blockIdx.x < n_tb ? (n_tb - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
+  // bricks of this CTA: the flagged ones among blockIdx.x, + gridDim.x, ... (collect_bricks, BRICK_SHARE_CAP map
+  // bricks per round); the it-th brick the CTA folds uses stage it % MERGE_STAGES, the mbarrier phases run on across rounds
+  const unsigned share = (i64)blockIdx.x < (i64)g.n_bricks ? (unsigned)(((i64)g.n_bricks - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+  unsigned it0 = 0u;
+  for (unsigned r0 = 0u; r0 < share; r0 += BRICK_SHARE_CAP)
+  {
+  const unsigned n_mine = collect_bricks<true>(g, r0, s_list, &s_n);
   if (tid == 0)
+  {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     for (unsigned n = 0; n < MERGE_STAGES - 1 && n < n_mine; n++)
     {
-      const size_t base = (size_t)brick_list[blockIdx.x + n * gridDim.x] * WS_BRICK_VOX;
-      mbar_expect_tx(&s_bar[n], MERGE_KEY_BYTES + MERGE_ENT_BYTES);
-      bulk_g2s(s_keys[n], g.keys + base, MERGE_KEY_BYTES, &s_bar[n]);
-      bulk_g2s(s_ent[n], g.grid + base, MERGE_ENT_BYTES, &s_bar[n]);
+      const int sn = (int)((it0 + n) % MERGE_STAGES);
+      const size_t base = (size_t)s_list[n] * WS_BRICK_VOX;
+      mbar_expect_tx(&s_bar[sn], MERGE_KEY_BYTES + MERGE_ENT_BYTES);
+      bulk_g2s(s_keys[sn], g.keys + base, MERGE_KEY_BYTES, &s_bar[sn]);
+      bulk_g2s(s_ent[sn], g.grid + base, MERGE_ENT_BYTES, &s_bar[sn]);
     }
+  }
 
   for (unsigned n = 0; n < n_mine; n++)
   {
-    const int st = (int)(n % MERGE_STAGES);
-    const unsigned parity = (n / MERGE_STAGES) & 1u;
-    const size_t base = (size_t)brick_list[blockIdx.x + n * gridDim.x] * WS_BRICK_VOX;
+    const int st = (int)((it0 + n) % MERGE_STAGES);
+    const unsigned parity = ((it0 + n) / MERGE_STAGES) & 1u;
+    const size_t base = (size_t)s_list[n] * WS_BRICK_VOX;
     if (tid == 0)
     {
       // the stage brick n-1 was stored from becomes the landing zone of brick n + STAGES - 1
@@ -1442,8 +1458,8 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
       const unsigned m = n + MERGE_STAGES - 1;
       if (m < n_mine)
       {
-        const int sm = (int)(m % MERGE_STAGES);
-        const size_t bm = (size_t)brick_list[blockIdx.x + m * gridDim.x] * WS_BRICK_VOX;
+        const int sm = (int)((it0 + m) % MERGE_STAGES);
+        const size_t bm = (size_t)s_list[m] * WS_BRICK_VOX;
         mbar_expect_tx(&s_bar[sm], MERGE_KEY_BYTES + MERGE_ENT_BYTES);
         bulk_g2s(s_keys[sm], g.keys + bm, MERGE_KEY_BYTES, &s_bar[sm]);
         bulk_g2s(s_ent[sm], g.grid + bm, MERGE_ENT_BYTES, &s_bar[sm]);
@@ -1530,7 +1546,13 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
   }
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  it0 += n_mine;
+  }
+  if (tid == 0)
+  {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (it0) atomicAdd(&ctr->n_surf_bricks, it0);
+  }
 
   for (int o = 16; o > 0; o >>= 1)
   {
@@ -1554,15 +1576,16 @@ merge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict_
 #define FMERGE_CTAS 8
 #endif
 __global__ void __launch_bounds__(256, FMERGE_CTAS)
-fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict__ brick_list, UpdateCounters *__restrict__ ctr)
+fmerge_kernel(const GridDesc g, const UpdateParams P, UpdateCounters *__restrict__ ctr)
 {
   __shared__ __align__(128) uint32_t s_ent[MERGE_STAGES][WS_BRICK_VOX];
   __shared__ __align__(128) unsigned char s_free[MERGE_STAGES][2 * WS_BRICK_VOX];
   __shared__ __align__(128) unsigned char s_state[MERGE_STAGES][WS_BRICK_VOX / 2];
   __shared__ __align__(128) unsigned char s_zero[2 * WS_BRICK_VOX];
   __shared__ __align__(8) u64 s_bar[MERGE_STAGES];
+  __shared__ unsigned s_list[BRICK_SHARE_CAP];
+  __shared__ unsigned s_n;
   if (ctr->rec_overflow != 0u && ctr->pending_overflow == 0u) return;       // redone after the regrow
-  const unsigned n_tb = ctr->n_touched_bricks;
   const int tid = threadIdx.x, lane = tid & 31;
   unsigned touched = 0, written = 0;
   reinterpret_cast<unsigned *>(s_zero)[tid] = 0u;
@@ -1575,29 +1598,34 @@ fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict
   __syncthreads();
   const unsigned stage_bytes = MERGE_ENT_BYTES + 2 * WS_BRICK_VOX + WS_BRICK_VOX / 2;
 
-  const unsigned n_mine = blockIdx.x < n_tb ? (n_tb - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
+  const unsigned share = (i64)blockIdx.x < (i64)g.n_bricks ? (unsigned)(((i64)g.n_bricks - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+  unsigned it0 = 0u;
+  for (unsigned r0 = 0u; r0 < share; r0 += BRICK_SHARE_CAP)
+  {
+  const unsigned n_mine = collect_bricks<false>(g, r0, s_list, &s_n);
   if (tid == 0)
     for (unsigned n = 0; n < MERGE_STAGES - 1 && n < n_mine; n++)
     {
-      const size_t base = (size_t)brick_list[blockIdx.x + n * gridDim.x] * WS_BRICK_VOX;
-      mbar_expect_tx(&s_bar[n], stage_bytes);
-      bulk_g2s(s_ent[n], g.grid + base, MERGE_ENT_BYTES, &s_bar[n]);
-      bulk_g2s(s_free[n], g.ffree + base * 2, 2 * WS_BRICK_VOX, &s_bar[n]);
-      bulk_g2s(s_state[n], reinterpret_cast<const unsigned char *>(g.vstate) + base / 2, WS_BRICK_VOX / 2, &s_bar[n]);
+      const int sn = (int)((it0 + n) % MERGE_STAGES);
+      const size_t base = (size_t)s_list[n] * WS_BRICK_VOX;
+      mbar_expect_tx(&s_bar[sn], stage_bytes);
+      bulk_g2s(s_ent[sn], g.grid + base, MERGE_ENT_BYTES, &s_bar[sn]);
+      bulk_g2s(s_free[sn], g.ffree + base * 2, 2 * WS_BRICK_VOX, &s_bar[sn]);
+      bulk_g2s(s_state[sn], reinterpret_cast<const unsigned char *>(g.vstate) + base / 2, WS_BRICK_VOX / 2, &s_bar[sn]);
     }
 
   for (unsigned n = 0; n < n_mine; n++)
   {
-    const int st = (int)(n % MERGE_STAGES);
-    const unsigned parity = (n / MERGE_STAGES) & 1u;
-    const size_t base = (size_t)brick_list[blockIdx.x + n * gridDim.x] * WS_BRICK_VOX;
+    const int st = (int)((it0 + n) % MERGE_STAGES);
+    const unsigned parity = ((it0 + n) / MERGE_STAGES) & 1u;
+    const size_t base = (size_t)s_list[n] * WS_BRICK_VOX;
     if (tid == 0)
     {
       const unsigned m = n + MERGE_STAGES - 1;
       if (m < n_mine)
       {
-        const int sm = (int)(m % MERGE_STAGES);
-        const size_t bm = (size_t)brick_list[blockIdx.x + m * gridDim.x] * WS_BRICK_VOX;
+        const int sm = (int)((it0 + m) % MERGE_STAGES);
+        const size_t bm = (size_t)s_list[m] * WS_BRICK_VOX;
         mbar_expect_tx(&s_bar[sm], stage_bytes);
         bulk_g2s(s_ent[sm], g.grid + bm, MERGE_ENT_BYTES, &s_bar[sm]);
         bulk_g2s(s_free[sm], g.ffree + bm * 2, 2 * WS_BRICK_VOX, &s_bar[sm]);
@@ -1646,7 +1674,13 @@ fmerge_kernel(const GridDesc g, const UpdateParams P, const unsigned *__restrict
       g.brick_slot_base[base >> 9] = NO_PARK;
     }
   }
-  if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  it0 += n_mine;
+  }
+  if (tid == 0)
+  {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (it0) atomicAdd(&ctr->n_touched_bricks, it0);
+  }
 
   for (int o = 16; o > 0; o >>= 1)
   {
@@ -2123,7 +2157,6 @@ void ws_update_enqueue(ws_handle *h, ws_pt *d_pts, int n, const int scanner_pos_
     }
     RaySetup *rays = static_cast<RaySetup *>(h->d_rays);
     const unsigned n_groups = (unsigned)((n + 31) / 32);
-    unsigned *list_all = h->d_brick_list, *list_surf = h->d_brick_list + h->g.n_bricks;
     LsOut out;
     out.pend_key = h->d_pend_key; out.list = h->d_list; out.pending_cap = h->pending_cap; out.list_cap = (unsigned)h->list_cap;
     const bool wide = h->g.wide != 0;
@@ -2148,6 +2181,9 @@ void ws_update_enqueue(ws_handle *h, ws_pt *d_pts, int n, const int scanner_pos_
     WS_CUDA_OK(cudaStreamWaitEvent(s2, h->ev_fork, 0));
     ws_timer_begin(h, WS_TIMER_MARCH);
     LS_LAUNCH_GRID(true, true, 0u, s, h->sm_count * ls_ctas_env("WS_LS_GRID_S", 2));
+    // (the rays outside the fast path -- none on a sane scan, the kernel returns at once -- stay on this stream: on a
+    // side stream the kernel cannot become resident before a persistent march CTA retires, and the merge behind it
+    // started 45 us late: 776 instead of 821 scans/s, same-box A/B)
     march_kernel<true><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_gen_list, h->d_counters, h->d_rec,
                                                               h->d_chunk_fill, cap_chunks, d_pose);
     ws_timer_end(h);
@@ -2156,8 +2192,7 @@ void ws_update_enqueue(ws_handle *h, ws_pt *d_pts, int n, const int scanner_pos_
     ws_timer_end(h, s2);
     WS_CUDA_OK(cudaEventRecord(h->ev_join, s2));
     ws_timer_begin(h, WS_TIMER_MERGE);
-    brick_list_kernel<true><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_surf, h->d_counters);
-    merge_kernel<<<h->sm_count * MERGE_CTAS, 256, 0, s>>>(h->g, P, list_surf, h->d_counters, h->pending_cap,
+    merge_kernel<<<h->sm_count * MERGE_CTAS, 256, 0, s>>>(h->g, P, h->d_counters, h->pending_cap,
                                                           h->d_pend_addr, h->d_pend_prev, h->d_pend_key);
     ws_timer_end(h);
     // the record pass of the replay (streams the record, DRAM bound) beside the far-field march (compute bound)
@@ -2178,11 +2213,10 @@ void ws_update_enqueue(ws_handle *h, ws_pt *d_pts, int n, const int scanner_pos_
     launch_replay(h, P);
     ws_timer_end(h);
     ws_timer_begin(h, WS_TIMER_MERGE);
-    brick_list_kernel<false><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_all, h->d_counters);
-    fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, list_all, h->d_counters);
+    fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, h->d_counters);
     ws_timer_end(h);
     ws_span_end(h, span);
-    h->launches += 11;       // + the two replay launches counted where they are made
+    h->launches += 9;        // + the two replay launches counted where they are made
   }
   WS_CUDA_OK(cudaMemcpyAsync(h_ctr, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
   if (pose_on_device)
@@ -2208,7 +2242,6 @@ void ws_update_finish(ws_handle *h, UpdateCounters *h_ctr, void *h_pose_out, cud
     const size_t tab_bytes = (size_t)(h->g.size[0] + h->g.size[1] + h->g.size[2]) * sizeof(unsigned);
     RaySetup *rays = static_cast<RaySetup *>(h->d_rays);
     const unsigned n_groups = (unsigned)((n + 31) / 32);
-    unsigned *list_all = h->d_brick_list;
     const bool wide = h->g.wide != 0;
     unsigned cap_chunks = (unsigned)h->rec_cap_chunks;
     LsOut out;
@@ -2235,9 +2268,8 @@ void ws_update_finish(ws_handle *h, UpdateCounters *h_ctr, void *h_pose_out, cud
       LS_LAUNCH_ON(false, true, 2u, s);
       launch_replay_scan(h, s);
       launch_replay(h, P);
-      brick_list_kernel<false><<<h->sm_count * 4, 256, 0, s>>>(h->g, list_all, h->d_counters);
-      fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, list_all, h->d_counters);
-      h->launches += 7;
+      fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, h->d_counters);
+      h->launches += 6;
       WS_CUDA_OK(cudaMemcpyAsync(h_ctr, h->d_counters, sizeof(UpdateCounters), cudaMemcpyDeviceToHost, s));
       WS_CUDA_OK(cudaStreamSynchronize(s));
       h->record_regrows++;

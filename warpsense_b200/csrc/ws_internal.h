@@ -222,7 +222,6 @@ struct ws_handle
   int reg_n = 0;
 
   // update scratch
-  unsigned *d_brick_list = nullptr;     // touched resident brick ids: [n_bricks] all, then [n_bricks] surface phase
   UpdateCounters *d_counters = nullptr;
   UpdateCounters *h_counters = nullptr; // pinned
   // pending (interpolated winner) resolution
