@@ -649,10 +649,14 @@ setup_kernel(const UpdateParams Pin, ws_pt *__restrict__ pts, RaySetup *__restri
     // its merge (they look for parked voxels)
     b_lo = hi_f > lo_f ? (unsigned)lo_f / LS_BLOCK : 0u;
     const unsigned b_hi = hi_f > lo_f ? ((unsigned)hi_f + LS_BLOCK - 1u) / LS_BLOCK : 0u;
-    const unsigned b_far = (unsigned)P.far_block;
+    const unsigned b_far = (unsigned)P.far_block, b_split = (unsigned)P.near_split_block;
     const unsigned near_hi = b_hi < b_far ? b_hi : b_far, far_lo = b_lo > b_far ? b_lo : b_far;
-    grp_info[grp_stride + (ray_id >> 5)] = make_uint2(b_lo, near_hi > b_lo ? near_hi - b_lo : 0u);
+    // the near field in two parts: blocks before near_split_block run beside the surface phase, the rest beside the
+    // far field (whose launch otherwise leaves 40 % of the issue slots idle)
+    const unsigned a_hi = near_hi < b_split ? near_hi : b_split, b2_lo = b_lo > b_split ? b_lo : b_split;
+    grp_info[grp_stride + (ray_id >> 5)] = make_uint2(b_lo, a_hi > b_lo ? a_hi - b_lo : 0u);
     grp_info[2u * grp_stride + (ray_id >> 5)] = make_uint2(far_lo, b_hi > far_lo ? b_hi - far_lo : 0u);
+    grp_info[3u * grp_stride + (ray_id >> 5)] = make_uint2(b2_lo, near_hi > b2_lo ? near_hi - b2_lo : 0u);
   }
   if (valid && !small) gen_list[atomicAdd(&ctr->n_general, 1u)] = (unsigned)ray_id;
 }
@@ -791,6 +795,7 @@ WS_D void list_append(ListWriter &w, const bool want, const Rec e, const int lan
 #define LS_CTAS 3
 #endif
 #define TAB_INVALID 0xFFFFFFFFu
+#define LS_NO_TAB 0xFFFFFFFFu      // march_lockstep_kernel: no second item table
 
 WS_D u64 step_bits(int a, int b)   // bits [a, b) of a 64-bit mask, 0 <= a < b <= 64
 {
@@ -1152,12 +1157,19 @@ WS_D void march_block(const GridDesc &g, const UpdateParams &P, const int pos_mm
 #undef LS_VOX
 }
 
+// (CTAs per SM of the free-space instantiations: 4 fits -- 64 registers, 20 bytes of spills -- and is slower, 794
+// against 822 scans/s in a same-box A/B; so is 4 for the surface phase: the march is bound by the ALU pipe, not by
+// latency that more resident warps could hide)
+#ifndef LS_CTAS_FREE
+#define LS_CTAS_FREE LS_CTAS
+#endif
 template <bool SURF, bool ATOMIC, bool WIDE>
-__global__ void __launch_bounds__(MARCH_THREADS, LS_CTAS)
+__global__ void __launch_bounds__(MARCH_THREADS, SURF ? LS_CTAS : LS_CTAS_FREE)
 march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__restrict__ rays,
                       const uint2 *__restrict__ grp_info, const unsigned *__restrict__ item_off, const unsigned n_groups,
                       UpdateCounters *__restrict__ ctr, Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill,
-                      const unsigned cap_chunks, const PoseDev *__restrict__ pose, const LsOut out, const unsigned tab)
+                      const unsigned cap_chunks, const PoseDev *__restrict__ pose, const LsOut out, const unsigned tab,
+                      const unsigned tab_b)
 {
   extern __shared__ unsigned s_tab[];               // size[0] + size[1] + size[2] address parts
   __shared__ int4 s_ray[MARCH_WARPS][64];
@@ -1165,8 +1177,8 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
   __shared__ unsigned s_pd[MARCH_WARPS][96];
   // item tables: 0 = surface phase; free-space phase: 1 = near field (needs nothing from the surface phase, runs beside
   // it on a second stream), 2 = far field (looks for parked voxels: launched after the surface merge)
-  const unsigned n_items = __ldcg(&ctr->n_items[tab]);
-  if (n_items == 0u) return;
+  // ... 3 = the second part of the near field, marched by the far-field launch after its own items (tab_b)
+  if (__ldcg(&ctr->n_items[tab]) == 0u && (tab_b == LS_NO_TAB || __ldcg(&ctr->n_items[tab_b]) == 0u)) return;
   if (tab == 2u && __ldcg(&ctr->rec_overflow) != 0u && __ldcg(&ctr->pending_overflow) == 0u) return;   // redone after the regrow
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
@@ -1205,9 +1217,6 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
 #pragma unroll
   for (int a = 0; a < 3; a++) pos_mm[a] = pose ? pose->pos_mm[a] : P.pos_mm[a];
   const unsigned total_warps = gridDim.x * MARCH_WARPS;
-  unsigned *counter = &ctr->item_counter[tab];
-  const uint2 *ginfo = grp_info + (size_t)tab * n_groups;
-  const unsigned *ioff = item_off + (size_t)tab * (n_groups + 1u);
 
   LsWarp W;
   if (SURF) rec_init(W.rw, ctr, lane);
@@ -1217,6 +1226,15 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
 #pragma unroll
   for (int sl = 0; sl < 3; sl++) { W.pd_info[sl] = 0u; W.pd_addr[sl] = 0ull; }
 
+  for (int pass = 0; pass < 2; pass++)
+  {
+  const unsigned tb = pass == 0 ? tab : tab_b;
+  if (tb == LS_NO_TAB) break;
+  const unsigned n_items = __ldcg(&ctr->n_items[tb]);
+  if (n_items == 0u) continue;
+  unsigned *counter = &ctr->item_counter[tb];
+  const uint2 *ginfo = grp_info + (size_t)tb * n_groups;
+  const unsigned *ioff = item_off + (size_t)tb * (n_groups + 1u);
   // items: the first one by warp index, the others from a global counter, fetched one item ahead
   unsigned k_cur = blockIdx.x * MARCH_WARPS + wib;
   unsigned k_nxt = 0;
@@ -1239,6 +1257,7 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
     asm volatile("" : "+r"(fetched) : "r"(W.n_cand), "r"(W.lw.used));   // keep the fetch in flight behind the march
     k_cur = k_nxt;
     k_nxt = total_warps + __shfl_sync(FULL, fetched, 0);
+  }
   }
 
   if (SURF) rec_finish(W.rw, lane, chunk_fill, cap_chunks, ctr);
@@ -1887,6 +1906,7 @@ __global__ void rec_reset_kernel(UpdateCounters *ctr)
   ctr->rec_overflow = 0u;
   ctr->item_counter[0] = 0u;
   ctr->item_counter[2] = 0u;
+  ctr->item_counter[3] = 0u;
   ctr->gen_counter = 0u;
 }
 
@@ -2057,12 +2077,13 @@ void ws_launch_pose(ws_handle *h, const float *d_X, const float *prior, int comp
 }
 
 #define LS_LAUNCH_ON(SURF_, ATOMIC_, TAB_, STREAM_) LS_LAUNCH_GRID(SURF_, ATOMIC_, TAB_, STREAM_, lockstep_blocks)
-#define LS_LAUNCH_GRID(SURF_, ATOMIC_, TAB_, STREAM_, GRID_)                                                             \
+#define LS_LAUNCH_GRID(SURF_, ATOMIC_, TAB_, STREAM_, GRID_) LS_LAUNCH_GRID2(SURF_, ATOMIC_, TAB_, LS_NO_TAB, STREAM_, GRID_)
+#define LS_LAUNCH_GRID2(SURF_, ATOMIC_, TAB_, TABB_, STREAM_, GRID_)                                                     \
   do {                                                                                                                   \
     if (wide) march_lockstep_kernel<SURF_, ATOMIC_, true><<<GRID_, MARCH_THREADS, tab_bytes, STREAM_>>>(                 \
-        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out, TAB_);  \
+        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out, TAB_, TABB_);  \
     else march_lockstep_kernel<SURF_, ATOMIC_, false><<<GRID_, MARCH_THREADS, tab_bytes, STREAM_>>>(                     \
-        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out, TAB_);  \
+        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out, TAB_, TABB_);  \
   } while (0)
 
 // Enqueues one update_tsdf on the handle's stream; the work counters (and the device-side pose) land in
@@ -2119,6 +2140,13 @@ void ws_update_enqueue(ws_handle *h, ws_pt *d_pts, int n, const int scanner_pos_
   P.n_points = n;
   P.far_len = far_start_len(h->res, P.dz_per_distance);
   P.far_block = (P.far_len > 1 ? (P.far_len - 2) / P.half_res + 1 : 0) / LS_BLOCK;      // block of the first far step
+  {
+    // share of the near-field blocks that waits for the far-field launch (WS_NEAR_SPLIT: eighths of the near field
+    // that stay beside the surface phase; 8 = all of it).  Same-box A/B, scans/s end to end: 8 -> 880, 5 -> 873 with
+    // two far-field CTAs per SM, 5 -> 892 with three (the default), 4 -> 880
+    static const int keep8 = [] { const char *e = std::getenv("WS_NEAR_SPLIT"); const int v = e ? std::atoi(e) : 5; return v < 0 ? 0 : (v > 8 ? 8 : v); }();
+    P.near_split_block = (P.far_block * keep8 + 4) / 8;
+  }
   resident_x_intervals(h, P);
 
   cudaStream_t s = h->stream;
@@ -2150,8 +2178,8 @@ void ws_update_enqueue(ws_handle *h, ws_pt *d_pts, int n, const int scanner_pos_
       const size_t want = std::max<size_t>((size_t)n, 1 << 17);
       h->grp_cap = want / 32 + 1;
       WS_CUDA_OK(cudaMalloc(&h->d_rays, want * sizeof(RaySetup)));
-      WS_CUDA_OK(cudaMalloc(&h->d_grp_info, 3 * h->grp_cap * sizeof(uint2)));
-      WS_CUDA_OK(cudaMalloc(&h->d_item_off, 3 * (h->grp_cap + 1) * sizeof(unsigned)));
+      WS_CUDA_OK(cudaMalloc(&h->d_grp_info, 4 * h->grp_cap * sizeof(uint2)));
+      WS_CUDA_OK(cudaMalloc(&h->d_item_off, 4 * (h->grp_cap + 1) * sizeof(unsigned)));
       WS_CUDA_OK(cudaMalloc(&h->d_gen_list, want * sizeof(unsigned)));
       h->rays_cap = want;
     }
@@ -2171,7 +2199,7 @@ void ws_update_enqueue(ws_handle *h, ws_pt *d_pts, int n, const int scanner_pos_
     }
     cudaStream_t s2 = h->stream2;
     setup_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, d_pts, rays, h->d_grp_info, n_groups, h->d_gen_list, h->d_counters, d_pose, d_xform);
-    item_scan_kernel<<<3, 1024, 0, s>>>(h->d_grp_info, n_groups, h->d_item_off, h->d_counters);
+    item_scan_kernel<<<4, 1024, 0, s>>>(h->d_grp_info, n_groups, h->d_item_off, h->d_counters);
     ws_timer_end(h);
     // Two streams from here.  Surface phase (this stream): keys, record, merge -> parked voxels.  The near-field part
     // of the free-space phase needs nothing from it and runs beside it on the second stream (both marches are
@@ -2203,7 +2231,7 @@ void ws_update_enqueue(ws_handle *h, ws_pt *d_pts, int n, const int scanner_pos_
     ws_timer_end(h, h->stream3);
     WS_CUDA_OK(cudaEventRecord(h->ev_scanned, h->stream3));
     ws_timer_begin(h, WS_TIMER_MARCH);
-    LS_LAUNCH_GRID(false, true, 2u, s, h->sm_count * ls_ctas_env("WS_LS_GRID_F", 2));
+    LS_LAUNCH_GRID2(false, true, 2u, 3u, s, h->sm_count * ls_ctas_env("WS_LS_GRID_F", 3));
     ws_timer_end(h);
     WS_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
     WS_CUDA_OK(cudaStreamWaitEvent(s, h->ev_scanned, 0));
@@ -2265,7 +2293,7 @@ void ws_update_finish(ws_handle *h, UpdateCounters *h_ctr, void *h_pose_out, cud
       LS_LAUNCH_ON(true, false, 0u, s);
       march_kernel<false><<<march_blocks, MARCH_THREADS, 0, s>>>(h->g, P, rays, h->d_gen_list, h->d_counters, h->d_rec,
                                                                  h->d_chunk_fill, cap_chunks, d_pose);
-      LS_LAUNCH_ON(false, true, 2u, s);
+      LS_LAUNCH_GRID2(false, true, 2u, 3u, s, lockstep_blocks);
       launch_replay_scan(h, s);
       launch_replay(h, P);
       fmerge_kernel<<<h->sm_count * FMERGE_CTAS, 256, 0, s>>>(h->g, P, h->d_counters);

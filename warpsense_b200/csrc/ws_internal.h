@@ -24,6 +24,7 @@ struct UpdateParams
   int n_points;
   int far_len;         // march lengths >= far_len can meet an interpolated winner: their candidates are recorded
   int far_block;       // first step block (LS_BLOCK steps) that holds a far-field step
+  int near_split_block; // near-field blocks from this one on are marched beside the far field (item table 3), the ones before beside the surface phase (table 1)
   // fast path of the march (march_math.cuh)
   FastDiv div_half;    // / (map_resolution / 2)
   FastDiv32 div_res32; // / map_resolution, 32-bit magic
@@ -120,12 +121,12 @@ struct UpdateCounters
   unsigned rounds;
   unsigned n_parked;         // voxels parked by the merge pass (before any replay round)
   unsigned n_work;
-  unsigned n_items[3];       // (ray group, step block) work items of the lockstep march: surface / free space near / free space far
+  unsigned n_items[4];       // (ray group, step block) work items of the lockstep march: surface / free space near (first part) / free space far / free space near (second part)
   unsigned n_general;        // rays outside the 32-bit fast path: marched by the literal-arithmetic kernel
   unsigned gen_counter;      // ... and its dynamic fetch counter
-  unsigned pad0[13];
-  unsigned item_counter[3];  // dynamic item fetch of the persistent march warps, per item table (own 128-byte line)
-  unsigned pad1[29];
+  unsigned pad0[12];
+  unsigned item_counter[4];  // dynamic item fetch of the persistent march warps, per item table (own 128-byte line)
+  unsigned pad1[28];
   unsigned n_chunks;         // record chunks handed out (own 128-byte line)
   unsigned pad2[31];
   unsigned rec_overflow;     // the record did not fit its buffer
