@@ -11,7 +11,7 @@ tail -c 600 $out/${tag}_bench.json; echo
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 70 -c 200 --csv --log-file $out/${tag}_launches.csv \
    python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-extra > $out/${tag}_ncu_launch.log 2>&1
 bash tools/gpu_list.sh $tag --no-extra > $out/${tag}_list.txt 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"setup_kernel|item_scan|march|merge|brick_list|replay|reg_loop" -s 24 -c 12 -f -o $out/${tag}_prof \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"setup_kernel|item_scan|march|merge|replay|reg_loop" -s 22 -c 11 -f -o $out/${tag}_prof \
    python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-extra > $out/${tag}_ncu_full.log 2>&1
 tail -2 $out/${tag}_ncu_full.log
 ls -la $out | grep $tag

@@ -1169,7 +1169,7 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
                       const uint2 *__restrict__ grp_info, const unsigned *__restrict__ item_off, const unsigned n_groups,
                       UpdateCounters *__restrict__ ctr, Rec *__restrict__ rec, unsigned *__restrict__ chunk_fill,
                       const unsigned cap_chunks, const PoseDev *__restrict__ pose, const LsOut out, const unsigned tab,
-                      const unsigned tab_b)
+                      const unsigned tab_b, const unsigned warp_offset, const unsigned total_warps)
 {
   extern __shared__ unsigned s_tab[];               // size[0] + size[1] + size[2] address parts
   __shared__ int4 s_ray[MARCH_WARPS][64];
@@ -1216,7 +1216,8 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
   int pos_mm[3];
 #pragma unroll
   for (int a = 0; a < 3; a++) pos_mm[a] = pose ? pose->pos_mm[a] : P.pos_mm[a];
-  const unsigned total_warps = gridDim.x * MARCH_WARPS;
+  // (warp_offset / total_warps: a phase may be marched by two launches that share the item counters -- the far field:
+  // two CTAs per SM at once, a third one when the replay's record pass has left the SMs)
 
   LsWarp W;
   if (SURF) rec_init(W.rw, ctr, lane);
@@ -1236,7 +1237,7 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
   const uint2 *ginfo = grp_info + (size_t)tb * n_groups;
   const unsigned *ioff = item_off + (size_t)tb * (n_groups + 1u);
   // items: the first one by warp index, the others from a global counter, fetched one item ahead
-  unsigned k_cur = blockIdx.x * MARCH_WARPS + wib;
+  unsigned k_cur = warp_offset + blockIdx.x * MARCH_WARPS + wib;
   unsigned k_nxt = 0;
   if (lane == 0) k_nxt = atomicAdd(counter, 1u);
   k_nxt = total_warps + __shfl_sync(FULL, k_nxt, 0);
@@ -2078,12 +2079,16 @@ void ws_launch_pose(ws_handle *h, const float *d_X, const float *prior, int comp
 
 #define LS_LAUNCH_ON(SURF_, ATOMIC_, TAB_, STREAM_) LS_LAUNCH_GRID(SURF_, ATOMIC_, TAB_, STREAM_, lockstep_blocks)
 #define LS_LAUNCH_GRID(SURF_, ATOMIC_, TAB_, STREAM_, GRID_) LS_LAUNCH_GRID2(SURF_, ATOMIC_, TAB_, LS_NO_TAB, STREAM_, GRID_)
-#define LS_LAUNCH_GRID2(SURF_, ATOMIC_, TAB_, TABB_, STREAM_, GRID_)                                                     \
+#define LS_LAUNCH_GRID2(SURF_, ATOMIC_, TAB_, TABB_, STREAM_, GRID_) LS_LAUNCH_PART(SURF_, ATOMIC_, TAB_, TABB_, STREAM_, GRID_, 0, GRID_)
+// one of several launches that share a phase's item counters: CTAs [FIRST_, FIRST_ + GRID_) of ALL_
+#define LS_LAUNCH_PART(SURF_, ATOMIC_, TAB_, TABB_, STREAM_, GRID_, FIRST_, ALL_)                                        \
   do {                                                                                                                   \
     if (wide) march_lockstep_kernel<SURF_, ATOMIC_, true><<<GRID_, MARCH_THREADS, tab_bytes, STREAM_>>>(                 \
-        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out, TAB_, TABB_);  \
+        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out, TAB_, TABB_, \
+        (unsigned)(FIRST_) * MARCH_WARPS, (unsigned)(ALL_) * MARCH_WARPS);                                               \
     else march_lockstep_kernel<SURF_, ATOMIC_, false><<<GRID_, MARCH_THREADS, tab_bytes, STREAM_>>>(                     \
-        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out, TAB_, TABB_);  \
+        h->g, P, rays, h->d_grp_info, h->d_item_off, n_groups, h->d_counters, h->d_rec, h->d_chunk_fill, cap_chunks, d_pose, out, TAB_, TABB_, \
+        (unsigned)(FIRST_) * MARCH_WARPS, (unsigned)(ALL_) * MARCH_WARPS);                                               \
   } while (0)
 
 // Enqueues one update_tsdf on the handle's stream; the work counters (and the device-side pose) land in
@@ -2142,9 +2147,10 @@ void ws_update_enqueue(ws_handle *h, ws_pt *d_pts, int n, const int scanner_pos_
   P.far_block = (P.far_len > 1 ? (P.far_len - 2) / P.half_res + 1 : 0) / LS_BLOCK;      // block of the first far step
   {
     // share of the near-field blocks that waits for the far-field launch (WS_NEAR_SPLIT: eighths of the near field
-    // that stay beside the surface phase; 8 = all of it).  Same-box A/B, scans/s end to end: 8 -> 880, 5 -> 873 with
-    // two far-field CTAs per SM, 5 -> 892 with three (the default), 4 -> 880
-    static const int keep8 = [] { const char *e = std::getenv("WS_NEAR_SPLIT"); const int v = e ? std::atoi(e) : 5; return v < 0 ? 0 : (v > 8 ? 8 : v); }();
+    // that stay beside the surface phase; 8 = all of it, the default).  Same-box A/B, scans/s end to end: 8 -> 880,
+    // 5 -> 873, 4 -> 867 with two far-field CTAs per SM: the far-field launch has idle issue slots (57 % issue
+    // active) but more warps do not fill them -- the marches are bound by the ALU pipe
+    static const int keep8 = [] { const char *e = std::getenv("WS_NEAR_SPLIT"); const int v = e ? std::atoi(e) : 8; return v < 0 ? 0 : (v > 8 ? 8 : v); }();
     P.near_split_block = (P.far_block * keep8 + 4) / 8;
   }
   resident_x_intervals(h, P);
@@ -2230,9 +2236,21 @@ void ws_update_enqueue(ws_handle *h, ws_pt *d_pts, int n, const int scanner_pos_
     launch_replay_scan(h, h->stream3);
     ws_timer_end(h, h->stream3);
     WS_CUDA_OK(cudaEventRecord(h->ev_scanned, h->stream3));
+    // The far field: two CTAs per SM -- they leave the record pass the registers of one CTA of its own.  Three from the
+    // start keep the record pass off the SMs until they retire (it then ends after the march and the replay rounds wait
+    // for it: 892 scans/s on one box, 852 on the next); WS_LS_GRID_F2 more per SM can follow on the second stream once the
+    // record pass is through, drawing from the same item counters (measured: no gain, 882 either way -- off by default).
+    const int far_a = h->sm_count * ls_ctas_env("WS_LS_GRID_F", 2), far_b = h->sm_count * ls_ctas_env("WS_LS_GRID_F2", 0);
     ws_timer_begin(h, WS_TIMER_MARCH);
-    LS_LAUNCH_GRID2(false, true, 2u, 3u, s, h->sm_count * ls_ctas_env("WS_LS_GRID_F", 3));
+    LS_LAUNCH_PART(false, true, 2u, 3u, s, far_a, 0, far_a + far_b);
     ws_timer_end(h);
+    if (far_b > 0)
+    {
+      WS_CUDA_OK(cudaStreamWaitEvent(s2, h->ev_scanned, 0));
+      LS_LAUNCH_PART(false, true, 2u, 3u, s2, far_b, far_a, far_a + far_b);
+      WS_CUDA_OK(cudaEventRecord(h->ev_join, s2));
+      h->launches++;
+    }
     WS_CUDA_OK(cudaStreamWaitEvent(s, h->ev_join, 0));
     WS_CUDA_OK(cudaStreamWaitEvent(s, h->ev_scanned, 0));
     // (the replay rounds and the free-space merge write disjoint voxels and could run side by side, but the rounds
