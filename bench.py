@@ -81,6 +81,9 @@ class ClockSampler:
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.sm, self.mx, self.reasons = [], [], set()
+        self.t = []                        # time.perf_counter() of every sample
+        self.t_region = None               # start of the timed region
+        self.first = threading.Event()     # the first sample has landed (NVML is initialised)
         self.stop_flag = threading.Event()
         self.thread = None
         self.source = None
@@ -101,11 +104,13 @@ class ClockSampler:
             while not self.stop_flag.is_set():
                 self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
                 self.mx.append(mx)
+                self.t.append(time.perf_counter())
                 r = int(get_reasons(h))
                 for bit, name in names.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.008)
+                self.first.set()
+                time.sleep(0.004)
         finally:
             nv.nvmlShutdown()
 
@@ -129,8 +134,10 @@ class ClockSampler:
                 if len(parts) >= 9:
                     try:
                         self.sm.append(float(parts[1])); self.mx.append(float(parts[2]))
+                        self.t.append(time.perf_counter())
                     except ValueError:
                         continue
+                    self.first.set()
                     for name, val in zip(names, parts[5:9]):
                         if val.lower().startswith("active"):
                             self.reasons.add(name)
@@ -153,7 +160,10 @@ class ClockSampler:
     def start(self):
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
-        time.sleep(0.02)           # let the first sample land before the timed region begins
+        # NVML initialisation takes tens of milliseconds -- longer than a multi-GPU timed region: wait for the first
+        # sample (taken right after the warm-up scans, clocks still up) before the timed region begins
+        self.first.wait(timeout=5.0)
+        self.t_region = time.perf_counter()
 
     def stop(self):
         self.stop_flag.set()
@@ -161,8 +171,12 @@ class ClockSampler:
             self.thread.join(timeout=3)
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["clock sampling unavailable"]}
-        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": max(self.mx), "samples": len(self.sm),
-                "reasons": sorted(self.reasons), "source": self.source}
+        # the samples that fell inside the timed region; a region shorter than the sampling period keeps the one
+        # taken just before it
+        inside = [v for v, t in zip(self.sm, self.t) if self.t_region is not None and t >= self.t_region]
+        sm = inside if inside else self.sm[-1:]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(self.mx), "samples": len(sm),
+                "samples_before_region": len(self.sm) - len(inside), "reasons": sorted(self.reasons), "source": self.source}
 
 
 def make_frames(args, count):
@@ -588,7 +602,9 @@ def run_native(args):
                     "h2d_bytes_per_step": 12 * N, "d2h_bytes_per_step": 352 + 128 + 64,
                     "note": "ws_track_submit / ws_track_wait with the scan in pinned host memory, two scans in flight: "
                             "H2D on a second stream -> 20 GN iterations -> pose on the device -> update_tsdf -> "
-                            "transform + pose + counters D2H; every scan's results are collected"},
+                            "transform + pose + counters D2H; every scan's results are collected.  The pass continues the "
+                            "stream (scans %d..%d; `value` timed scans %d..%d, which carry ~5 %% more march work)"
+                            % (1 + K + 2 * W, 2 * (K + W), 1 + W, K + W)},
             "gpu_launches": launches,
             "roofline": {
                 "bound": "hbm", "kernel": "update_tsdf = set-up + surface march + surface merge + free-space march + replay + free-space merge (per scan)",
