@@ -100,6 +100,14 @@ WS_HD void dda_advance(DdaAxis &s, unsigned dist)
   if (s.rem >= dist) { s.rem -= dist; s.q++; }
 }
 
+// The DDA's carry without a compare: for rem <= 2 * dist - 2 (the sum of two remainders), floor(rem / dist) -- 0 or 1 --
+// is the high word of rem * (floor(2^32 / dist) + 1), exact for dist <= 65536 (dist * (dist - 1) < 2^32; ray_is_small
+// requires it).  The
+// lockstep march's step phase is bound by the ALU pipe (compares, selects, adds at half rate); this form keeps the
+// whole advance on the multiply-add pipe: IMAD.HI for the carry, two IMADs to apply it.
+WS_HD unsigned dda_carry_magic(unsigned dist) { return dist < 2u ? 0u : (unsigned)((1ull << 32) / dist) + 1u; }
+WS_HD unsigned dda_carry(unsigned rem, unsigned magic) { return ws_umulhi(rem, magic); }
+
 // Bounds under which the fast path is exact for a ray (all products below fit int32 without wrapping and
 // every dividend of a 32-bit magic division stays below 2^32 / res):
 //   max|d| * (distance + tau + 32*h + 1) < 2^31      DDA numerators incl. one stride beyond the last step
@@ -117,7 +125,8 @@ WS_HD bool ray_is_small(const int d[3], const int p[3], int distance, int tau, i
     c = ap > c ? ap : c;
   }
   const i64 L = (i64)distance + tau + 32ll * half_res + 1;
-  return coord_lim > 0 && c < (unsigned)coord_lim && (i64)m * L < (1ll << 31) && (i64)dz * L < (1ll << 30);
+  return coord_lim > 0 && c < (unsigned)coord_lim && (i64)m * L < (1ll << 31) && (i64)dz * L < (1ll << 30) &&
+         distance <= 65536;      // dda_carry (implied by the first product bound: max|d| >= distance / sqrt(3))
 }
 
 // Multi-GPU culling: the march-step ranges [seg[2k], seg[2k+1]) of a ray that can put a candidate into one of
@@ -137,7 +146,9 @@ WS_HD void ray_step_ranges(int n_xiv, const int *xiv_lo, const int *xiv_hi, int 
   for (int kk = 0; kk < n_xiv && n < MAXSEG; kk++)
   {
     const int k = dx >= 0 ? kk : n_xiv - 1 - kk;        // walk the intervals in the ray's direction of travel
-    const double x0 = (double)xiv_lo[k] - (double)pos_x, x1 = (double)xiv_hi[k] - (double)pos_x;
+    // (one millimetre wider on either side: the march truncates (dx * len) / distance, so a step's x may sit up to
+    // 1 mm nearer to the sensor than the real ray -- for a ray that runs almost along y that is many steps)
+    const double x0 = (double)xiv_lo[k] - (double)pos_x - 1.0, x1 = (double)xiv_hi[k] - (double)pos_x + 1.0;
     int i0 = 0, i1 = n_steps;
     if (dx == 0)
     {
