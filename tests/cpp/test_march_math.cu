@@ -67,37 +67,6 @@ int main()
       CHECK(tsdf_weight_fd(v, tau, eps, fw) == tsdf_weight(v, tau, eps), "tsdf_weight tau %d value %d", tau, v);
   }
 
-  // 1d. the DDA carry as a multiplication: floor(rem / dist) for rem = rem_old + drem <= 2 * dist - 2, dist <= 65536
-  for (unsigned dist = 2; dist <= 65536; dist += (dist < 300 ? 1 : 7))
-  {
-    const unsigned magic = dda_carry_magic(dist);
-    const unsigned probe[] = { 0u, 1u, dist / 2, dist - 1, dist, dist + 1, 2 * dist - 3, 2 * dist - 2 };
-    for (unsigned r : probe)
-      if (r <= 2 * dist - 2) CHECK(dda_carry(r, magic) == r / dist, "dda_carry %u / %u", r, dist);
-    for (int t = 0; t < 40; t++)
-    {
-      const unsigned r = (unsigned)uni(0, 2ll * dist - 2);
-      CHECK(dda_carry(r, magic) == r / dist, "dda_carry %u / %u", r, dist);
-    }
-  }
-  for (unsigned dist : { 46341u, 65535u, 65536u })
-    for (unsigned r = 0; r <= 2 * dist - 2; r++) CHECK(dda_carry(r, dda_carry_magic(dist)) == r / dist, "dda_carry %u / %u", r, dist);
-  CHECK(dda_carry(0u, dda_carry_magic(1u)) == 0u, "dda_carry dist 1");
-
-  // 1e. x / 32768 (truncation) as sign-by-mulhi, bias-by-multiply, shift-by-mulhi (update_tsdf.cu div_mr32_m)
-  {
-    auto mr_m = [](int x) {
-      const unsigned sgn = ws_umulhi((unsigned)x, 2u);
-      const int biased = (int)(sgn * 32767u) + x;
-      return (int)(((i64)biased * (i64)(1 << 17)) >> 32);
-    };
-    for (int t = 0; t < 4000000; t++)
-    {
-      const int x = t < 200000 ? t - 100000 : (int)uni(-(1ll << 31) + 40000, (1ll << 31) - 40000);
-      CHECK(mr_m(x) == div_mr32(x) && div_mr32(x) == x / 32768, "div_mr32_m %d", x);
-    }
-  }
-
   // 2. reciprocal-based division with remainder
   for (int t = 0; t < 2000000; t++)
   {

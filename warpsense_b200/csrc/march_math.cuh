@@ -100,14 +100,6 @@ WS_HD void dda_advance(DdaAxis &s, unsigned dist)
   if (s.rem >= dist) { s.rem -= dist; s.q++; }
 }
 
-// The DDA's carry without a compare: for rem <= 2 * dist - 2 (the sum of two remainders), floor(rem / dist) -- 0 or 1 --
-// is the high word of rem * (floor(2^32 / dist) + 1), exact for dist <= 65536 (dist * (dist - 1) < 2^32; ray_is_small
-// requires it).  The
-// lockstep march's step phase is bound by the ALU pipe (compares, selects, adds at half rate); this form keeps the
-// whole advance on the multiply-add pipe: IMAD.HI for the carry, two IMADs to apply it.
-WS_HD unsigned dda_carry_magic(unsigned dist) { return dist < 2u ? 0u : (unsigned)((1ull << 32) / dist) + 1u; }
-WS_HD unsigned dda_carry(unsigned rem, unsigned magic) { return ws_umulhi(rem, magic); }
-
 // Bounds under which the fast path is exact for a ray (all products below fit int32 without wrapping and
 // every dividend of a 32-bit magic division stays below 2^32 / res):
 //   max|d| * (distance + tau + 32*h + 1) < 2^31      DDA numerators incl. one stride beyond the last step
@@ -125,8 +117,7 @@ WS_HD bool ray_is_small(const int d[3], const int p[3], int distance, int tau, i
     c = ap > c ? ap : c;
   }
   const i64 L = (i64)distance + tau + 32ll * half_res + 1;
-  return coord_lim > 0 && c < (unsigned)coord_lim && (i64)m * L < (1ll << 31) && (i64)dz * L < (1ll << 30) &&
-         distance <= 65536;      // dda_carry (implied by the first product bound: max|d| >= distance / sqrt(3))
+  return coord_lim > 0 && c < (unsigned)coord_lim && (i64)m * L < (1ll << 31) && (i64)dz * L < (1ll << 30);
 }
 
 // Multi-GPU culling: the march-step ranges [seg[2k], seg[2k+1]) of a ray that can put a candidate into one of

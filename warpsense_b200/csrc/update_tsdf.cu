@@ -803,37 +803,12 @@ WS_D u64 step_bits(int a, int b)   // bits [a, b) of a 64-bit mask, 0 <= a < b <
   return hi & ~((1ull << a) - 1ull);
 }
 
-// x / MATRIX_RESOLUTION (C++ truncation, div_mr32) on the multiply-add pipe: sign bit by IMAD.HI.U32 with 2, bias
-// 32767 * sign by IMAD, arithmetic >> 15 by IMAD.HI with 2^17.  div_mr32 is three ALU-pipe instructions (SHF, LOP3, SHF)
-// and the march's heavy part runs it six to nine times per batch on the pipe that bounds the kernel.  The two
-// multipliers travel in registers the compiler cannot see through (it would turn the products back into shifts).
-#ifndef WS_MR_ON_FMA
-#define WS_MR_ON_FMA 1
-#endif
-struct MrConst { unsigned two; int k17; };
-WS_D MrConst mr_const()
-{
-  MrConst c; c.two = 2u; c.k17 = 1 << (32 - WS_MR_SHIFT);
-  asm volatile("" : "+r"(c.two), "+r"(c.k17));
-  return c;
-}
-WS_D int div_mr32_m(int x, const MrConst c)
-{
-#if WS_MR_ON_FMA
-  const unsigned sgn = __umulhi((unsigned)x, c.two);
-  return __mulhi((int)(sgn * (unsigned)(WS_MR - 1)) + x, c.k17);
-#else
-  return div_mr32(x);
-#endif
-}
-
 struct LsShared        // per CTA: address tables; per warp: ray table and queue of surviving march steps
 {
   const unsigned *tx, *ty, *tz;     // voxel - lo (0 .. size-1) -> address parts, see the table set-up in the kernel
   int4 *ray;                        // [32][2] per lane of the group: {hit point, distance}, {interpolation vector, -}
   unsigned queue_s;                 // shared-memory address of the warp's queue: [QCAP] {proj x, y, z, march step << 5 | lane}
   unsigned *pd;                     // [3][32] FREE: state words of the previous batch's candidates (cp.async)
-  MrConst mr;                       // div_mr32_m's multipliers
 };
 
 struct LsOut           // where the free-space phase offers candidates that land on parked voxels
@@ -913,7 +888,7 @@ WS_D void free_candidate(const GridDesc &g, const UpdateParams &P, const LsShare
   if (step > 0)
   {
     const int sr = wmul(step, P.res);
-    fx = div_mr32_m(sr * riv[0], sh.mr); fy = div_mr32_m(sr * riv[1], sh.mr); fz = div_mr32_m(sr * riv[2], sh.mr);
+    fx = div_mr32(sr * riv[0]); fy = div_mr32(sr * riv[1]); fz = div_mr32(sr * riv[2]);
   }
   const unsigned tx = (unsigned)(fd32_sdiv_s(low[0] + fx, P.div_res32) + nlo[0]);          // :493
   const unsigned ty = (unsigned)(fd32_sdiv_s(low[1] + fy, P.div_res32) + nlo[1]);
@@ -1002,8 +977,7 @@ WS_D void march_drain(const GridDesc &g, const UpdateParams &P, const LsShared &
   const int iter_steps = (int)fd32_udiv((unsigned)(delta_z * 2), P.div_res32) + 1;           // :486
   const int mid = (int)fd32_udiv((unsigned)delta_z, P.div_res32);                            // :487
   if (have && iter_steps > (1 << WS_SEQ_STEP_BITS)) W.err |= 1u;
-  const int low[3] = { q.x - div_mr32_m(delta_z * riv[0], sh.mr), q.y - div_mr32_m(delta_z * riv[1], sh.mr),
-                       q.z - div_mr32_m(delta_z * riv[2], sh.mr) };                                                             // :488
+  const int low[3] = { q.x - div_mr32(delta_z * riv[0]), q.y - div_mr32(delta_z * riv[1]), q.z - div_mr32(delta_z * riv[2]) };   // :488
   const bool far = len >= P.far_len;
   const int max_steps = __reduce_max_sync(FULL, have ? iter_steps : 0);
 
@@ -1035,7 +1009,7 @@ WS_D void march_drain(const GridDesc &g, const UpdateParams &P, const LsShared &
     if (step > 0)
     {
       const int sr = wmul(step, P.res);
-      fx = div_mr32_m(sr * riv[0], sh.mr); fy = div_mr32_m(sr * riv[1], sh.mr); fz = div_mr32_m(sr * riv[2], sh.mr);
+      fx = div_mr32(sr * riv[0]); fy = div_mr32(sr * riv[1]); fz = div_mr32(sr * riv[2]);
     }
     const unsigned tx = LS_VOX(low[0] + fx, 0), ty = LS_VOX(low[1] + fy, 1), tz = LS_VOX(low[2] + fz, 2);   // :493
     bool valid = have && step < iter_steps &&
@@ -1133,15 +1107,14 @@ WS_D void march_block(const GridDesc &g, const UpdateParams &P, const int pos_mm
       sdq[a] = sgn[a] * (int)dq1[a];
     }
   }
-  // (the carry as a multiplication, march_math.cuh dda_carry: nothing of the advance runs on the ALU pipe)
-  const unsigned carry_magic = dda_carry_magic((unsigned)distance), neg_distance = 0u - (unsigned)distance;
+  // (the carry as a multiplication -- IMAD.HI with floor(2^32 / distance) + 1, then two IMADs -- keeps the advance off
+  // the ALU pipe but is slower: 804 against 818 scans/s, same-box A/B; IMAD.HI does not issue at the rate of the compares)
 #define LS_ADVANCE()                                                                   \
   _Pragma("unroll") for (int a = 0; a < 3; a++)                                        \
   {                                                                                    \
+    proj[a] += sdq[a];                                                                 \
     rem[a] += drem[a];                                                                 \
-    const unsigned cy = dda_carry(rem[a], carry_magic);                                \
-    rem[a] += cy * neg_distance;                                                       \
-    proj[a] += sdq[a] + (int)cy * sgn[a];                                              \
+    if (rem[a] >= (unsigned)distance) { rem[a] -= (unsigned)distance; proj[a] += sgn[a]; } \
   }
   // voxel - lo per axis (the in-bounds test is then one unsigned compare, :460-463)
   const int nlo[3] = { -P.lo[0], -P.lo[1], -P.lo[2] };
@@ -1216,7 +1189,6 @@ march_lockstep_kernel(const GridDesc g, const UpdateParams P, const RaySetup *__
   sh.ray = s_ray[wib]; sh.pd = s_pd[wib];
   sh.queue_s = (unsigned)__cvta_generic_to_shared(s_queue[wib]);
   asm volatile("" : "+r"(sh.queue_s));              // opaque: kept in a register instead of being re-derived every turn
-  sh.mr = mr_const();
   for (int t = threadIdx.x; t < g.size[0] + g.size[1] + g.size[2]; t += blockDim.x)
   {
     // ring coordinate (hdf5_local_map.h:140-151) of voxel lo + t, then its share of the bricked address:
