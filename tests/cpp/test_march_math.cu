@@ -67,6 +67,16 @@ int main()
       CHECK(tsdf_weight_fd(v, tau, eps, fw) == tsdf_weight(v, tau, eps), "tsdf_weight tau %d value %d", tau, v);
   }
 
+  // 1d. (n * r) / 32768 for n >= 0 as the shifted magnitude with r's sign (update_tsdf.cu mr_scaled)
+  for (int t = 0; t < 4000000; t++)
+  {
+    const int r = (int)uni(-WS_MR, WS_MR), n = (int)uni(0, t & 1 ? 60000 : 2000);
+    if ((long long)n * (r < 0 ? -r : r) >= (1ll << 31)) continue;
+    const int ar = r < 0 ? -r : r, sr = r < 0 ? -1 : 1;
+    const int fast = sr * (int)((unsigned)(n * ar) >> WS_MR_SHIFT);
+    CHECK(fast == div_mr32(n * r) && fast == (int)(((long long)n * r) / WS_MR), "mr_scaled %d * %d", n, r);
+  }
+
   // 2. reciprocal-based division with remainder
   for (int t = 0; t < 2000000; t++)
   {

@@ -833,6 +833,27 @@ struct LsWarp          // a warp's running state across work items
   u64 pd_addr[3];
 };
 
+// (n * r) / MATRIX_RESOLUTION (C++ truncation, :488 and :493) for n >= 0: the product has r's sign, so the quotient is
+// the shifted magnitude with r's sign -- IMAD, SHF, IMAD (the last one folds into the addition that follows) instead of
+// div_mr32's IMAD, SHF, LOP3, IADD, SHF: the ALU pipe (SHF / LOP3 at half rate) is what bounds the march.
+// `ar` = |r|, `sr` = +-1; n * |r| < 2^31 on the fast path (march_math.cuh ray_is_small).
+#ifndef WS_FAN_SIGN
+#define WS_FAN_SIGN 1
+#endif
+#ifndef WS_NEAR_CONST
+#define WS_NEAR_CONST 1
+#endif
+WS_D int mr_scaled(int n, int r, int ar, int sr)
+{
+#if WS_FAN_SIGN
+  (void)r;
+  return sr * (int)((unsigned)(n * ar) >> WS_MR_SHIFT);
+#else
+  (void)ar; (void)sr;
+  return div_mr32(n * r);
+#endif
+}
+
 // FREE phase, rare: a free-space candidate (|value| == tau) landed on a parked voxel.  What the replay's first
 // round does for a recorded candidate: offer it to the voxel if it follows the parked winner in the
 // reference's order, and keep it for the later rounds.  Warp-collective (list_append).
@@ -880,15 +901,15 @@ WS_D void free_check_pending(const GridDesc &g, const UpdateParams &P, const LsS
 template <bool WIDE, int SLOT>
 WS_D void free_candidate(const GridDesc &g, const UpdateParams &P, const LsShared &sh, const LsOut &out, LsWarp &W,
                          const bool have, const int step, const int iter_steps, const int mid, const int low[3],
-                         const int riv[3], const int i, const int rl, const unsigned ray_base, const int lane,
-                         UpdateCounters *__restrict__ ctr)
+                         const int riv[3], const int ariv[3], const int sriv[3], const int i, const int rl,
+                         const unsigned ray_base, const int lane, UpdateCounters *__restrict__ ctr)
 {
   const int nlo[3] = { -P.lo[0], -P.lo[1], -P.lo[2] };
   int fx = 0, fy = 0, fz = 0;
   if (step > 0)
   {
     const int sr = wmul(step, P.res);
-    fx = div_mr32(sr * riv[0]); fy = div_mr32(sr * riv[1]); fz = div_mr32(sr * riv[2]);
+    fx = mr_scaled(sr, riv[0], ariv[0], sriv[0]); fy = mr_scaled(sr, riv[1], ariv[1], sriv[1]); fz = mr_scaled(sr, riv[2], ariv[2], sriv[2]);
   }
   const unsigned tx = (unsigned)(fd32_sdiv_s(low[0] + fx, P.div_res32) + nlo[0]);          // :493
   const unsigned ty = (unsigned)(fd32_sdiv_s(low[1] + fy, P.div_res32) + nlo[1]);
@@ -942,6 +963,8 @@ WS_D void march_drain(const GridDesc &g, const UpdateParams &P, const LsShared &
   const int rl = q.w & 31, i = q.w >> 5;
   const int4 r1 = sh.ray[2 * rl + 1];
   const int riv[3] = { r1.x, r1.y, r1.z };
+  const int ariv[3] = { r1.x < 0 ? -r1.x : r1.x, r1.y < 0 ? -r1.y : r1.y, r1.z < 0 ? -r1.z : r1.z };
+  const int sriv[3] = { r1.x < 0 ? -1 : 1, r1.y < 0 ? -1 : 1, r1.z < 0 ? -1 : 1 };
   const int nlo[3] = { -P.lo[0], -P.lo[1], -P.lo[2] };
 #define LS_VOX(x, a) ((unsigned)(fd32_sdiv_s((x), P.div_res32) + nlo[a]))
   const int len = 1 + i * P.half_res;
@@ -973,12 +996,29 @@ WS_D void march_drain(const GridDesc &g, const UpdateParams &P, const LsShared &
   }
 
   // ---- the fan of interpolated voxels around the step (:485-506) -----------------------------------
+#if WS_FAN_SIGN
+  const int delta_z = (int)((unsigned)(P.dz_per_distance * len) >> WS_MR_SHIFT);             // :485 (both factors > 0, product < 2^30)
+#else
   const int delta_z = div_mr32(wmul(P.dz_per_distance, len));                                 // :485
+#endif
+  const bool far = len >= P.far_len;
+#if WS_NEAR_CONST
+  // near field (before far_start_len): delta_z < res / 2 there by the definition of far_len, so the fan is the marched
+  // voxel's one real candidate (iter_steps == 1, mid == 0) -- no divisions (IMAD.HI issues at a quarter of the rate),
+  // no warp reduction; no voxel there can be parked either: the candidate is stored and forgotten
+  if (!SURF && !__any_sync(FULL, have && far))
+  {
+    const int low1[3] = { q.x - mr_scaled(delta_z, riv[0], ariv[0], sriv[0]), q.y - mr_scaled(delta_z, riv[1], ariv[1], sriv[1]),
+                          q.z - mr_scaled(delta_z, riv[2], ariv[2], sriv[2]) };                                                // :488
+    free_candidate<WIDE, -1>(g, P, sh, out, W, have, 0, 1, 0, low1, riv, ariv, sriv, i, rl, ray_base, lane, ctr);
+    return;
+  }
+#endif
   const int iter_steps = (int)fd32_udiv((unsigned)(delta_z * 2), P.div_res32) + 1;           // :486
   const int mid = (int)fd32_udiv((unsigned)delta_z, P.div_res32);                            // :487
   if (have && iter_steps > (1 << WS_SEQ_STEP_BITS)) W.err |= 1u;
-  const int low[3] = { q.x - div_mr32(delta_z * riv[0]), q.y - div_mr32(delta_z * riv[1]), q.z - div_mr32(delta_z * riv[2]) };   // :488
-  const bool far = len >= P.far_len;
+  const int low[3] = { q.x - mr_scaled(delta_z, riv[0], ariv[0], sriv[0]), q.y - mr_scaled(delta_z, riv[1], ariv[1], sriv[1]),
+                       q.z - mr_scaled(delta_z, riv[2], ariv[2], sriv[2]) };                                                   // :488
   const int max_steps = __reduce_max_sync(FULL, have ? iter_steps : 0);
 
   if (!SURF)
@@ -986,19 +1026,19 @@ WS_D void march_drain(const GridDesc &g, const UpdateParams &P, const LsShared &
     // near field (before far_start_len): no voxel there can be parked, the candidates are stored and forgotten
     if (!__any_sync(FULL, have && far))
     {
-      free_candidate<WIDE, -1>(g, P, sh, out, W, have, 0, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
+      free_candidate<WIDE, -1>(g, P, sh, out, W, have, 0, iter_steps, mid, low, riv, ariv, sriv, i, rl, ray_base, lane, ctr);
 #pragma unroll 1
       for (int step = 1; step < max_steps; ++step)
-        free_candidate<WIDE, -1>(g, P, sh, out, W, have, step, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
+        free_candidate<WIDE, -1>(g, P, sh, out, W, have, step, iter_steps, mid, low, riv, ariv, sriv, i, rl, ray_base, lane, ctr);
       return;
     }
     free_check_pending(g, P, sh, out, W, ray_base, lane, ctr);
-    free_candidate<WIDE, 0>(g, P, sh, out, W, have, 0, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
-    if (max_steps > 1) free_candidate<WIDE, 1>(g, P, sh, out, W, have, 1, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
-    if (max_steps > 2) free_candidate<WIDE, 2>(g, P, sh, out, W, have, 2, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
+    free_candidate<WIDE, 0>(g, P, sh, out, W, have, 0, iter_steps, mid, low, riv, ariv, sriv, i, rl, ray_base, lane, ctr);
+    if (max_steps > 1) free_candidate<WIDE, 1>(g, P, sh, out, W, have, 1, iter_steps, mid, low, riv, ariv, sriv, i, rl, ray_base, lane, ctr);
+    if (max_steps > 2) free_candidate<WIDE, 2>(g, P, sh, out, W, have, 2, iter_steps, mid, low, riv, ariv, sriv, i, rl, ray_base, lane, ctr);
 #pragma unroll 1
     for (int step = 3; step < max_steps; ++step)
-      free_candidate<WIDE, 3>(g, P, sh, out, W, have, step, iter_steps, mid, low, riv, i, rl, ray_base, lane, ctr);
+      free_candidate<WIDE, 3>(g, P, sh, out, W, have, step, iter_steps, mid, low, riv, ariv, sriv, i, rl, ray_base, lane, ctr);
     return;
   }
 
@@ -1009,7 +1049,7 @@ WS_D void march_drain(const GridDesc &g, const UpdateParams &P, const LsShared &
     if (step > 0)
     {
       const int sr = wmul(step, P.res);
-      fx = div_mr32(sr * riv[0]); fy = div_mr32(sr * riv[1]); fz = div_mr32(sr * riv[2]);
+      fx = mr_scaled(sr, riv[0], ariv[0], sriv[0]); fy = mr_scaled(sr, riv[1], ariv[1], sriv[1]); fz = mr_scaled(sr, riv[2], ariv[2], sriv[2]);
     }
     const unsigned tx = LS_VOX(low[0] + fx, 0), ty = LS_VOX(low[1] + fy, 1), tz = LS_VOX(low[2] + fz, 2);   // :493
     bool valid = have && step < iter_steps &&
@@ -1107,8 +1147,25 @@ WS_D void march_block(const GridDesc &g, const UpdateParams &P, const int pos_mm
       sdq[a] = sgn[a] * (int)dq1[a];
     }
   }
-  // (the carry as a multiplication -- IMAD.HI with floor(2^32 / distance) + 1, then two IMADs -- keeps the advance off
-  // the ALU pipe but is slower: 804 against 818 scans/s, same-box A/B; IMAD.HI does not issue at the rate of the compares)
+  // Measured issue rates on B200 (tools/ubench/pipes.cu, warp instructions per clock and scheduler): IADD3 0.98, LOP3 / SHF /
+  // ISETP / SEL / IMAD 0.49, IMAD.HI 0.25, POPC 0.12.  The compiler turns the `if` of the advance into two SELs per axis
+  // (ALU pipe, which bounds the step phase); written with predicated adds it is one compare and four full-rate adds.
+  // (The carry as a multiplication -- IMAD.HI with floor(2^32 / distance) + 1 -- was slower: 804 against 818 scans/s.)
+#ifndef WS_STEP_PTX
+#define WS_STEP_PTX 1
+#endif
+
+#if WS_STEP_PTX
+#define LS_ADVANCE()                                                                   \
+  _Pragma("unroll") for (int a = 0; a < 3; a++)                                        \
+    asm("{\n\t.reg .pred p;\n\t"                                                      \
+        "add.u32 %0, %0, %2;\n\t"                                                      \
+        "add.s32 %1, %1, %4;\n\t"                                                      \
+        "setp.ge.u32 p, %0, %3;\n\t"                                                   \
+        "@p sub.u32 %0, %0, %3;\n\t"                                                   \
+        "@p add.s32 %1, %1, %5;\n\t}"                                                  \
+        : "+r"(rem[a]), "+r"(proj[a]) : "r"(drem[a]), "r"((unsigned)distance), "r"(sdq[a]), "r"(sgn[a]));
+#else
 #define LS_ADVANCE()                                                                   \
   _Pragma("unroll") for (int a = 0; a < 3; a++)                                        \
   {                                                                                    \
@@ -1116,9 +1173,13 @@ WS_D void march_block(const GridDesc &g, const UpdateParams &P, const int pos_mm
     rem[a] += drem[a];                                                                 \
     if (rem[a] >= (unsigned)distance) { rem[a] -= (unsigned)distance; proj[a] += sgn[a]; } \
   }
-  // voxel - lo per axis (the in-bounds test is then one unsigned compare, :460-463)
+#endif
+  // voxel - lo per axis (the in-bounds test is then one unsigned compare, :460-463).  (ptxas re-loads the loop's seven
+  // constants from the parameter bank every turn -- six LDC; values made opaque to it are re-derived every turn instead)
   const int nlo[3] = { -P.lo[0], -P.lo[1], -P.lo[2] };
-#define LS_VOX(x, a) ((unsigned)(fd32_sdiv_s((x), P.div_res32) + nlo[a]))
+  const unsigned ext[3] = { (unsigned)P.ext[0], (unsigned)P.ext[1], (unsigned)P.ext[2] };
+  const FastDiv32 dres = P.div_res32;
+#define LS_VOX(x, a) ((unsigned)(fd32_sdiv_s((x), dres) + nlo[a]))
   unsigned px = 0x80000000u, py = 0x80000000u;       // no previous step (update_tsdf.cpp:448)
   if (i0 > 0)
   {
@@ -1134,12 +1195,36 @@ WS_D void march_block(const GridDesc &g, const UpdateParams &P, const int pos_mm
     const int cx = proj[0], cy = proj[1], cz = proj[2];                                         // :452
     LS_ADVANCE();
     const unsigned ix = LS_VOX(cx, 0), iy = LS_VOX(cy, 1), iz = LS_VOX(cz, 2);                  // :453 (- lo)
+#if WS_STEP_PTX
+    // the step's mask bit, the column filter (:455-458) and the bounds test (:460-463) as one chain of predicates and
+    // the ballot on it (the compiler's version keeps `act` in a register: five SELs and a PRMT on the ALU pipe)
+    unsigned m, act_r;
+    {
+      const unsigned mbit = (unsigned)(mask >> (i - s0));
+      asm volatile("{\n\t.reg .pred p;\n\t"
+                   "setp.ne.u32 p, %2, %3;\n\t"
+                   "setp.ne.or.u32 p, %4, %5, p;\n\t"
+                   "setp.le.and.u32 p, %2, %7, p;\n\t"
+                   "setp.le.and.u32 p, %4, %8, p;\n\t"
+                   "setp.le.and.u32 p, %6, %9, p;\n\t"
+                   "and.b32 %1, %10, 1;\n\t"
+                   "setp.ne.and.u32 p, %1, 0, p;\n\t"
+                   "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+                   "selp.u32 %1, 1, 0, p;\n\t}"
+                   : "=r"(m), "=r"(act_r)
+                   : "r"(ix), "r"(px), "r"(iy), "r"(py), "r"(iz), "r"(ext[0]), "r"(ext[1]), "r"(ext[2]), "r"(mbit));
+    }
+    px = ix; py = iy;
+    if (m == 0u) continue;
+    const bool act = act_r != 0u;
+#else
     bool act = ((mask >> (i - s0)) & 1ull) != 0ull;
     if (ix == px && iy == py) act = false;                                                      // :455-458
     px = ix; py = iy;
-    if (ix > (unsigned)P.ext[0] || iy > (unsigned)P.ext[1] || iz > (unsigned)P.ext[2]) act = false;   // :460-463
+    if (ix > ext[0] || iy > ext[1] || iz > ext[2]) act = false;                                   // :460-463
     const unsigned m = __ballot_sync(FULL, act);
     if (m == 0u) continue;
+#endif
     if (act)
       asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};"
                    ::"r"(sh.queue_s + (unsigned)(((qh + qn + __popc(m & lt)) & (QCAP - 1)) << 4)), "r"(cx), "r"(cy), "r"(cz), "r"((i << 5) | lane) : "memory");
