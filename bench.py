@@ -475,6 +475,9 @@ def shift_timing(torch, dist, args):
     wl.barrier()
     out = {}
     pos = np.zeros(3, np.int64)
+    # an untimed 64-voxel shift and back: the staging buffers and the chunk store's first allocations are not what is
+    # being measured (one visit showed 743 ms for the first 8-voxel shift, the next 10 ms)
+    pos[0] += 64; wl.tsdf.shift(pos); pos[0] -= 64; wl.tsdf.shift(pos)
     for d in (1, 8, 64):
         for axis, name in enumerate("xyz"):
             pos[axis] += d

@@ -15,3 +15,4 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:"set
    python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-ref-cuda --no-extra > $out/${tag}_ncu_full.log 2>&1
 tail -2 $out/${tag}_ncu_full.log
 ls -la $out | grep $tag
+timeout 600 python tests/soak.py 60 4242 > $out/${tag}_soak.log 2>&1; tail -2 $out/${tag}_soak.log
