@@ -4,37 +4,46 @@
 // /root/reference) with kernels whose RESULT equals the reference's CPU path
 // (src/cpu/update_tsdf.cpp:397-564), which is the parity target.
 //
-// Pipeline per scan (one stream, one host synchronisation at the end to fetch the work counters):
-//   0. setup_kernel         one THREAD per ray: direction, distance, interpolation vector, DDA increments,
-//                           fast-path flag and -- on a sharded map -- the march-step ranges that can reach this
-//                           rank's columns; 128-byte RaySetup per ray, in scan order.
-//   1. march_kernel<true>   persistent warps, one ray per warp at a time (indices from a global counter, the
-//                           next ray's RaySetup staged to shared memory by cp.async while this one is
-//                           marched).  Lanes stride over the res/2 march steps (exact DDA, 32-bit magics:
-//                           march_math.cuh); the steps that survive the reference's "same (x,y) column as
-//                           the previous step" filter (:455-458) are compacted through a per-warp
-//                           shared-memory queue so the expensive part (value, fan of interpolated voxels,
-//                           addressing) runs with full lanes.  Every candidate (voxel, value,
-//                           real|interpolated, order) is ONE 64-bit atomicMin (RED, no return) on the
-//                           voxel's key -- see ws_common.cuh / DESIGN.md for why min over (|value|,
-//                           interpolated, order) reproduces the sequential rule at :508-512 -- plus a plain
-//                           store that flags the voxel's 8x8x8 brick.  Far-field candidates (the only ones
-//                           that can meet an interpolated winner) are also appended to a record list in
-//                           64-entry chunks owned by the warp.
-//   2./3. merge_kernel      every CTA compacts its share of the touched-brick flags into shared memory, then
-//                           moves those bricks (4 KB keys + 2 KB entries each) through shared memory
-//                           with TMA bulk copies (cp.async.bulk + mbarrier, three stages per CTA), folds final
-//                           winners into the grid (:542-560), resets the keys, and parks the voxels whose
-//                           winner is an interpolated candidate below tau ("pending"): their key word then
-//                           carries the slot rank within the brick and the order of the parked winner.
-//   4. replay_kernel        cooperative (grid-synchronised).  Round 1 streams the record list once and
-//                           keeps, per pending voxel, the minimum key among the candidates that follow the
-//                           parked winner in the reference's order; those candidates are also compacted
-//                           into a short list that later rounds stream instead.  Rounds repeat on the
-//                           device until every pending voxel has its final winner.
-// If the record list overflows its buffer the host grows it and regenerates it with march_kernel<false>
-// (far part of every ray, no atomics) before running replay_kernel again.
-// The scanner pose arrives as kernel parameters or, in the fused per-scan pipeline (ws_track_scan), from
+// Pipeline per scan (three streams that fork from and join the handle's stream; nothing waits on the host):
+//   0. setup_kernel             one THREAD per ray: the registered cloud's transform, direction, distance,
+//                               interpolation vector, DDA increments, fast-path flag, the split between the free-space
+//                               and the surface part of the ray and -- on a sharded map -- the march-step ranges that
+//                               can reach this rank's columns; 128-byte RaySetup per ray, in scan order; per group of
+//                               32 rays the blocks of 64 march steps that hold work, per phase.  item_scan_kernel
+//                               turns the block counts into work items (prefix sums, one CTA per item table).
+//   1. march_lockstep_kernel    one RAY per LANE, a work item = (group of 32 rays, block of 64 steps) from a global
+//      <surface>                counter.  Step phase per lane: exact DDA, 32-bit magic division, the reference's "same
+//                               (x,y) column as the previous step" filter (:455-458) and the bounds test against the
+//                               lane's own previous step; survivors go through a per-warp shared-memory queue so the
+//                               heavy part (value, fan of interpolated voxels, addressing through three shared-memory
+//                               tables) runs on full batches.  Every surface candidate (voxel, value, real |
+//                               interpolated, order) is ONE 64-bit atomicMin (RED, no return) on the voxel's key --
+//                               see ws_common.cuh / DESIGN.md for why min over (|value|, interpolated, order)
+//                               reproduces the sequential rule at :508-512 -- plus a plain store that flags the
+//                               voxel's 8x8x8 brick; far-field candidates (the only ones that can meet an
+//                               interpolated winner) are also appended to a record in 64-entry chunks owned by the warp.
+//      <free space, near field> beside it on the second stream: value == tau by construction, a candidate is one plain
+//                               byte store ("a real / an interpolated free-space candidate arrived"), no key, no record.
+//      march_kernel             the literal wrapping arithmetic for rays outside the 32-bit fast path (none on a sane scan).
+//   2. merge_kernel             every CTA compacts its share of the surface-brick flags, then moves those bricks (4 KB
+//                               keys + 2 KB entries each) through shared memory with TMA bulk copies (cp.async.bulk +
+//                               mbarrier, three stages per CTA), folds final winners into the grid (:542-560), resets the
+//                               keys, and parks the voxels whose winner is an interpolated candidate below tau
+//                               ("pending"): their key word then carries the slot rank within the brick and the order
+//                               of the parked winner.
+//   3. march_lockstep_kernel    <free space, far field>: as the near field, but a candidate that lands on a parked
+//                               voxel is offered to the replay on the spot.  Beside it, on the third stream,
+//      replay_scan_kernel       streams the record once and keeps, per pending voxel, the minimum key among the
+//                               candidates that follow the parked winner in the reference's order; those candidates
+//                               are also compacted into a short list that later rounds stream instead.
+//   4. replay_kernel            cooperative (grid-synchronised): resolve / re-offer rounds on the device until every
+//                               pending voxel has its final winner.
+//   5. fmerge_kernel            every touched brick (flags compacted by the CTAs themselves): voxels that are not closed
+//                               and hold a free-space candidate get (tau, +-WEIGHT_RESOLUTION) folded in; the per-scan
+//                               state is cleared.
+// If the record overflows its buffer the host grows it and regenerates it with the <surface, no atomics> instantiation
+// (far part of every ray) before the far field, the replay and the final merge run again.
+// The scanner pose arrives as kernel parameters or, in the fused per-scan pipeline (ws_track_submit), from
 // device memory written by pose_kernel right after the registration.
 #include <cooperative_groups.h>
 #include <algorithm>
