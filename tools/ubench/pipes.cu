@@ -30,6 +30,10 @@ __global__ void __launch_bounds__(256) k(unsigned *out, unsigned a0, unsigned b0
       if (OP == 8) asm volatile("{.reg .pred p; setp.ge.u32 p, %0, %1; @p sub.u32 %0, %0, %1;}" : "+r"(x[i]) : "r"(b));   // ISETP + predicated IADD
       if (OP == 9) asm volatile("popc.b32 %0, %0;" : "+r"(x[i]));                                              // POPC
       if (OP == 10) asm volatile("{.reg .f32 f; cvt.rn.f32.u32 f, %0; mov.b32 %0, f;}" : "+r"(x[i]));          // I2F
+      if (OP == 11) asm volatile("mad.lo.u32 %0, %0, 1, %1;" : "+r"(x[i]) : "r"(b));                           // ptxas turns it into IADD3
+      if (OP == 12) asm volatile("{.reg .u32 t; shr.u32 t, %0, 31; add.u32 %0, t, %1;}" : "+r"(x[i]) : "r"(b));   // LEA.HI (shift + add)
+      if (OP == 13) asm volatile("prmt.b32 %0, %0, %1, 0x3210;" : "+r"(x[i]) : "r"(b));                        // PRMT
+      if (OP == 14) asm volatile("{.reg .pred p; setp.ne.u32 p, %0, %1; vote.sync.ballot.b32 %0, p, 0xffffffff;}" : "+r"(x[i]) : "r"(b));   // ISETP + VOTE
     }
   }
   unsigned s = 0;
@@ -65,5 +69,7 @@ int main()
   run<0>("IADD3", 1, s, mhz); run<1>("LOP3", 1, s, mhz); run<2>("SHF", 1, s, mhz); run<3>("ISETP + SEL", 2, s, mhz);
   run<8>("ISETP + @p IADD", 2, s, mhz); run<4>("IMAD", 1, s, mhz); run<5>("IMAD.HI.U32", 1, s, mhz); run<6>("IMAD.HI (signed)", 1, s, mhz);
   run<7>("IMAD.WIDE", 1, s, mhz); run<9>("POPC", 1, s, mhz); run<10>("I2F", 1, s, mhz);
+  run<11>("mad x, 1, b (ptxas: IADD3)", 1, s, mhz); run<12>("LEA.HI (x >> 31) + b", 1, s, mhz); run<13>("PRMT", 1, s, mhz);
+  run<14>("ISETP + VOTE", 2, s, mhz);
   return 0;
 }
